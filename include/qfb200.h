@@ -1,0 +1,122 @@
+/*
+ * qfb200.h -- C ABI of libqfb200.so, the B200 (sm_100a) gate-application engine that sits
+ * behind QuantumFlow's backend contract.
+ *
+ * Every entry point replaces one piece of arithmetic that the reference performs in Python/numpy.
+ * Citations are relative to the reference tree (rigetti/quantumflow):
+ *
+ *   bk.tensormul            quantumflow/backend/numpybk.py:159-214   -> qfb_apply_dense / _diag / qfb_run_plan
+ *   bk.inner                quantumflow/backend/numpybk.py:125-128   -> qfb_vdot
+ *   bk.outer (numpy.outer)  quantumflow/backend/numpybk.py:17-21     -> qfb_outer
+ *   bk.productdiag          quantumflow/backend/numpybk.py:150-156   -> qfb_density_diag
+ *   bk.trace on [2^N,2^N]   quantumflow/qubits.py:185-197            -> qfb_density_trace
+ *   bk.transpose (permute)  quantumflow/qubits.py:145-161            -> qfb_permute_bits
+ *   State.norm              quantumflow/qubits.py:180-182            -> qfb_norm2
+ *   State.normalize         quantumflow/states.py:108-111            -> qfb_scale / qfb_scale_rsqrt_dev
+ *   State.probabilities     quantumflow/states.py:113-119            -> qfb_probs
+ *   State.expectation       quantumflow/states.py:131-147            -> qfb_expect_diag
+ *   Measure.run (P0/P1)     quantumflow/stdops.py:53-65              -> qfb_marginal + qfb_collapse
+ *   Circuit.run/evolve loop quantumflow/circuits.py:87-109           -> qfb_run_plan (tiled multi-gate sweeps)
+ *   autograd of tensormul   (TF in the reference, tensorflowbk.py:134-152) -> qfb_gate_grad
+ *
+ * Conventions
+ *   - All state pointers are DEVICE pointers to complex128 (interleaved re,im doubles), C-order flat vectors
+ *     of 2^nbits amplitudes. Tensor axis i of the reference's [2]*n tensor is flat-index bit (n-1-i).
+ *   - `bits[]` are flat-index bit positions, gate qubit 0 first (gate qubit 0 is the MSB of the matrix index,
+ *     quantumflow/qubits.py:70-80).
+ *   - Small operators (`mat`, `diag`) are HOST pointers to row-major complex128; the launcher copies them into
+ *     the kernel parameter block, so there is no hidden device allocation and no sync.
+ *   - `stream` is a cudaStream_t passed as void* (0 = default stream). All calls are asynchronous on that
+ *     stream unless stated; scalar results are written to DEVICE memory (`out_dev`).
+ *   - dst == src means in place (race free: each thread owns a closed group of 2^k addresses).
+ *   - Return value: QFB_OK (0) or an error code; qfb_last_error() returns a thread-local message.
+ *   - `index_hi`: value of the index bits above `nbits` (the rank of a sharded state; 0 when not sharded).
+ *     Diagonal entries and control masks may refer to bit positions >= nbits; they are resolved from index_hi.
+ */
+#ifndef QFB200_H
+#define QFB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define QFB_OK 0
+#define QFB_ERR_ARG 1
+#define QFB_ERR_CUDA 2
+#define QFB_ERR_UNSUPPORTED 3
+
+#define QFB_MAX_DENSE_K 12   /* largest k accepted by qfb_apply_dense (generic path above k=4) */
+#define QFB_MAX_DIAG_K 12
+#define QFB_MAX_CTRL 8
+
+/* ---- library ---- */
+int qfb_version(void);
+const char *qfb_last_error(void);
+/* sm_count, compute capability, opt-in shared memory per block, total device memory of `device` */
+int qfb_device_props(int device, int *sm_count, int *cc_major, int *cc_minor, size_t *smem_optin,
+                     size_t *total_mem);
+
+/* ---- gate application (bk.tensormul) ---- */
+/* out[base|off[r]] = sum_c mat[r][c] * in[base|off[c]] for every group; optional controls: groups whose
+ * control bits are not all 1 are copied (dst != src) or left untouched (dst == src). Control bit positions
+ * >= nbits are resolved from index_hi. */
+int qfb_apply_dense(void *dst, const void *src, int nbits, const double *mat_host, int k, const int *bits,
+                    int nctrl, const int *ctrl_bits, uint64_t index_hi, void *stream);
+/* out[i] = diag[sel(i)] * in[i], sel gathers bits[] (gate qubit 0 = MSB); positions >= nbits use index_hi */
+int qfb_apply_diag(void *dst, const void *src, int nbits, const double *diag_host, int k, const int *bits,
+                   uint64_t index_hi, void *stream);
+
+/* ---- tiled multi-gate executor (Circuit.run / Circuit.evolve) ---- */
+/* `plan_host` is the binary plan produced by the host planner (layout in quantumflow_b200/csrc/qfb_plan.h).
+ * Executes every sweep of the plan in place on `state`. */
+int qfb_run_plan(void *state, int nbits, uint64_t index_hi, const void *plan_host, size_t plan_bytes,
+                 void *stream);
+/* Upload a plan once and replay it (plans are immutable); handle is freed with qfb_plan_destroy. */
+int qfb_plan_upload(const void *plan_host, size_t plan_bytes, void **handle_out, void *stream);
+int qfb_plan_launch(void *handle, void *state, int nbits, uint64_t index_hi, void *stream);
+int qfb_plan_destroy(void *handle);
+/* number of kernel launches performed by this library in this process (bench.py's gpu_launches) */
+uint64_t qfb_launch_count(void);
+
+/* ---- reductions / read-out ---- */
+int qfb_vdot(const void *a, const void *b, uint64_t n, double *out_dev2, void *stream);   /* sum conj(a)*b */
+int qfb_norm2(const void *a, uint64_t n, double *out_dev, void *stream);                  /* sum |a|^2 */
+int qfb_probs(const void *a, uint64_t n, double *out_dev, void *stream);                  /* out[i]=|a[i]|^2 */
+int qfb_expect_diag(const void *a, const double *diag_dev, uint64_t n, double *out_dev, void *stream);
+/* out_dev2 = { sum_{bit=0} |a|^2 , sum_{bit=1} |a|^2 } */
+int qfb_marginal(const void *a, int nbits, int bit, double *out_dev2, void *stream);
+/* dst[i] = (bit(i)==value) ? scale*src[i] : 0 */
+int qfb_collapse(void *dst, const void *src, int nbits, int bit, int value, double scale, void *stream);
+int qfb_scale(void *dst, const void *src, uint64_t n, double scale_re, double scale_im, void *stream);
+/* dst = src * rsqrt(*norm2_dev)  (State.normalize without a host round trip) */
+int qfb_scale_rsqrt_dev(void *dst, const void *src, uint64_t n, const double *norm2_dev, void *stream);
+/* dst = src / (complex at cdiv_dev2)  (Density.normalize: divide by trace) */
+int qfb_scale_cdiv_dev(void *dst, const void *src, uint64_t n, const double *cdiv_dev2, void *stream);
+/* dst = alpha*a + beta*b (complex scalars given as re,im) ; b may be NULL when beta == 0 */
+int qfb_axpby(void *dst, const void *a, double alpha_re, double alpha_im, const void *b, double beta_re,
+              double beta_im, uint64_t n, void *stream);
+/* dst[i*nb + j] = a[i] * (conj_b ? conj(b[j]) : b[j]) */
+int qfb_outer(void *dst, const void *a, uint64_t na, const void *b, uint64_t nb, int conj_b, void *stream);
+int qfb_conj(void *dst, const void *src, uint64_t n, void *stream);
+/* rho is a [2^nq, 2^nq] row-major matrix */
+int qfb_density_diag(const void *rho, int nq, void *out_dev_c128, void *stream);
+int qfb_density_trace(const void *rho, int nq, double *out_dev2, void *stream);
+/* dst index bit j <- src index bit perm[j]  (generalised transpose of a [2]*nbits tensor) */
+int qfb_permute_bits(void *dst, const void *src, int nbits, const int *perm, int conj, void *stream);
+/* cumulative search used by sampling: for each u[j] in [0,total) find smallest i with cdf(i) > u[j];
+ * block-hierarchical, deterministic. probs_dev: float64[n]; u_host: nu uniforms already scaled to [0,1);
+ * out_idx_host: nu indices. Synchronises the stream. */
+int qfb_sample_search(const double *probs_dev, uint64_t n, const double *u_host, int nu, uint64_t *out_idx_host,
+                      void *stream);
+
+/* ---- autograd bridge ---- */
+/* grad_mat[r][c] = sum_groups g[base|off[r]] * conj(psi[base|off[c]])   (k <= 3), written to out_dev (4^k c128) */
+int qfb_gate_grad(const void *g, const void *psi, int nbits, int k, const int *bits, void *out_dev, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* QFB200_H */

@@ -1,0 +1,24 @@
+"""quantumflow_b200 -- a B200-native gate-application engine behind the QuantumFlow API.
+
+`import quantumflow_b200 as qf` gives the hot-path subset of the reference's flat namespace
+(quantumflow/__init__.py:5-23): states, gates, channels, circuits, QAOA helpers and the closeness predicates,
+with `qf.backend` being the b200 tensor backend. Optional-dependency modules of the reference (forest,
+visualization, datasets, cvxpy-based measures) are out of scope and are not imported.
+"""
+from . import backend                       # noqa: F401
+from .config import *                       # noqa: F401,F403
+from .cbits import *                        # noqa: F401,F403
+from .qubits import *                       # noqa: F401,F403
+from .states import *                       # noqa: F401,F403
+from .ops import *                          # noqa: F401,F403
+from .gates import *                        # noqa: F401,F403
+from .stdgates import *                     # noqa: F401,F403
+from .channels import *                     # noqa: F401,F403
+from .stdops import *                       # noqa: F401,F403
+from .circuits import *                     # noqa: F401,F403
+from .dagcircuit import *                   # noqa: F401,F403
+from .measures import *                     # noqa: F401,F403
+from .qaoa import *                         # noqa: F401,F403
+from . import utils, workloads, planner, engine, classify   # noqa: F401
+
+from .config import version as __version__  # noqa: F401

@@ -1,0 +1,491 @@
+// qfb_sweep.cu -- tiled multi-gate executor: the performance path behind Circuit.run / Circuit.evolve
+// (reference loop: quantumflow/circuits.py:87-109, one np.einsum sweep per gate).
+//
+// One launch = one sweep = one read + one write of the state (algorithmic traffic 32 B per amplitude,
+// 32 * 2^n bytes per launch), no matter how many gates the planner packed into it. See qfb_plan.h for the
+// plan layout. Per tile of 2^M amplitudes:
+//
+//   round 0 : coalesced LDG.128 straight into registers (lanes span the low index bits -> every warp
+//             request covers whole 128-byte lines), apply the round's ops on the 2^R register amplitudes
+//   round r : STS.128 -> barrier -> LDS.128 with the next register/thread bit assignment -> barrier -> ops
+//   last    : coalesced STG.128 from registers
+//
+// Shared-memory layout is XOR swizzled at 16-byte granularity: phys = idx ^ fold3(idx >> 3) where fold3 XORs
+// the upper index bits into 3 bits (bit p >= 3 lands on bit (p-3) % 3). The planner assigns lane bits 0..2 of
+// every round to tile bits of three different classes, which makes every quarter-warp LDS/STS.128 hit 8
+// distinct 16-byte bank groups (conflict free) for any choice of register bits.
+//
+// Roofline: HBM bound by design (planner caps the FP64 work per sweep); FP64 FMA pipe and shared-memory
+// bandwidth are the secondary limits ("sweep kernel").
+#include <algorithm>
+#include <vector>
+#include "qfb_common.cuh"
+#include "qfb_plan.h"
+
+namespace qfb {
+
+constexpr int R = QFB_PLAN_REG_BITS;
+constexpr int NE = 1 << R;  // amplitudes per thread
+
+__device__ __forceinline__ uint32_t swz(uint32_t idx) {
+    const uint32_t x = idx >> 3;
+    return idx ^ ((x ^ (x >> 3) ^ (x >> 6) ^ (x >> 9)) & 7u);
+}
+
+template <typename T>
+__device__ __forceinline__ T pick(const T (&s)[R], int e) {
+    T r = 0;
+#pragma unroll
+    for (int i = 0; i < R; ++i)
+        if ((e >> i) & 1) r |= s[i];
+    return r;
+}
+
+// ---- 1-bit operator on register bit J ----
+template <int J>
+__device__ __forceinline__ void g1_apply(c128 (&a)[NE], const double *__restrict__ m, int kind, uint32_t rc) {
+    if (kind == QFB_G1_SWAPX) {
+#pragma unroll
+        for (int p = 0; p < NE / 2; ++p) {
+            const int e0 = ((p >> J) << (J + 1)) | (p & ((1 << J) - 1)), e1 = e0 | (1 << J);
+            if ((e0 & rc) != rc) continue;
+            const c128 t = a[e0];
+            a[e0] = a[e1];
+            a[e1] = t;
+        }
+    } else if (kind == QFB_G1_REAL) {
+        const double m00 = m[0], m01 = m[2], m10 = m[4], m11 = m[6];
+#pragma unroll
+        for (int p = 0; p < NE / 2; ++p) {
+            const int e0 = ((p >> J) << (J + 1)) | (p & ((1 << J) - 1)), e1 = e0 | (1 << J);
+            if ((e0 & rc) != rc) continue;
+            const c128 x = a[e0], y = a[e1];
+            a[e0] = cmake(fma(m00, x.re, m01 * y.re), fma(m00, x.im, m01 * y.im));
+            a[e1] = cmake(fma(m10, x.re, m11 * y.re), fma(m10, x.im, m11 * y.im));
+        }
+    } else if (kind == QFB_G1_RXLIKE) {
+        const double d0 = m[0], o01 = m[3], o10 = m[5], d1 = m[6];
+#pragma unroll
+        for (int p = 0; p < NE / 2; ++p) {
+            const int e0 = ((p >> J) << (J + 1)) | (p & ((1 << J) - 1)), e1 = e0 | (1 << J);
+            if ((e0 & rc) != rc) continue;
+            const c128 x = a[e0], y = a[e1];
+            // (d0) x + (i o01) y ; (i o10) x + (d1) y
+            a[e0] = cmake(fma(d0, x.re, -o01 * y.im), fma(d0, x.im, o01 * y.re));
+            a[e1] = cmake(fma(d1, y.re, -o10 * x.im), fma(d1, y.im, o10 * x.re));
+        }
+    } else if (kind == QFB_G1_ANTIDIAG) {
+        const c128 m01 = cmake(m[2], m[3]), m10 = cmake(m[4], m[5]);
+#pragma unroll
+        for (int p = 0; p < NE / 2; ++p) {
+            const int e0 = ((p >> J) << (J + 1)) | (p & ((1 << J) - 1)), e1 = e0 | (1 << J);
+            if ((e0 & rc) != rc) continue;
+            const c128 x = a[e0], y = a[e1];
+            a[e0] = cmul(m01, y);
+            a[e1] = cmul(m10, x);
+        }
+    } else {
+        const c128 m00 = cmake(m[0], m[1]), m01 = cmake(m[2], m[3]), m10 = cmake(m[4], m[5]),
+                   m11 = cmake(m[6], m[7]);
+#pragma unroll
+        for (int p = 0; p < NE / 2; ++p) {
+            const int e0 = ((p >> J) << (J + 1)) | (p & ((1 << J) - 1)), e1 = e0 | (1 << J);
+            if ((e0 & rc) != rc) continue;
+            const c128 x = a[e0], y = a[e1];
+            c128 u = cmul(m00, x), v = cmul(m10, x);
+            cfma(u, m01, y);
+            cfma(v, m11, y);
+            a[e0] = u;
+            a[e1] = v;
+        }
+    }
+}
+
+// ---- 2-bit operator on register bits J0 > J1 (operator index = bit(J0) << 1 | bit(J1)) ----
+template <int J0, int J1>
+__device__ __forceinline__ void g2_apply(c128 (&a)[NE], const double *__restrict__ m, uint32_t nz, uint32_t rc) {
+    static_assert(J0 > J1, "planner normalises j0 > j1");
+    // the two register bits that enumerate the 4 independent groups
+    constexpr int O0 = (J1 != 0) ? 0 : ((J0 != 1) ? 1 : 2);
+    constexpr int O1 = 6 - J0 - J1 - O0;  // bits sum to 0+1+2+3
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+        const int eb = ((g & 1) << O0) | ((g >> 1) << O1);
+        if ((eb & rc) != rc) continue;
+        const int id[4] = {eb, eb | (1 << J1), eb | (1 << J0), eb | (1 << J0) | (1 << J1)};
+        const c128 in0 = a[id[0]], in1 = a[id[1]], in2 = a[id[2]], in3 = a[id[3]];
+        const c128 in[4] = {in0, in1, in2, in3};
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            c128 acc = cmake(0.0, 0.0);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                if ((nz >> (4 * r + c)) & 1u) cfma(acc, cmake(m[2 * (4 * r + c)], m[2 * (4 * r + c) + 1]), in[c]);
+            }
+            a[id[r]] = acc;
+        }
+    }
+}
+
+// ---- diagonal operator over any bits of the full index ----
+__device__ __forceinline__ void d_apply(c128 (&a)[NE], const uint8_t *__restrict__ payload, int nb,
+                                        uint64_t tfull) {
+    const uint8_t *pos = payload;
+    const c128 *table = reinterpret_cast<const c128 *>(payload + 16);
+    uint32_t selt = 0;
+    for (int q = 0; q < nb; ++q) {
+        const uint32_t p = pos[q];
+        if (p != 0xFFu) selt |= (uint32_t)((tfull >> p) & 1ull) << (nb - 1 - q);
+    }
+    const uint32_t ec[R] = {payload[8], payload[9], payload[10], payload[11]};
+    if ((ec[0] | ec[1] | ec[2] | ec[3]) == 0u) {
+        const c128 d = table[selt];
+#pragma unroll
+        for (int e = 0; e < NE; ++e) a[e] = cmul(d, a[e]);
+    } else {
+#pragma unroll
+        for (int e = 0; e < NE; ++e) a[e] = cmul(table[selt | pick(ec, e)], a[e]);
+    }
+}
+
+template <int M>
+struct SweepCfg {
+    static constexpr int T = 1 << (M - R);                 // threads per CTA
+    static constexpr int MINB = (M >= 13) ? 1 : ((M == 12) ? 2 : ((M == 11) ? 4 : 8));
+    static constexpr int TILE_BYTES = 16 << M;
+};
+
+template <int M>
+__global__ void __launch_bounds__(SweepCfg<M>::T, SweepCfg<M>::MINB)
+sweep_kernel(c128 *__restrict__ state, const uint8_t *__restrict__ rec_g, uint32_t rec_bytes, int nholes,
+             uint64_t hi_shifted) {
+    constexpr int T = SweepCfg<M>::T;
+    constexpr int TB = M - R;  // thread bits
+    extern __shared__ __align__(16) uint8_t smem[];
+    c128 *tile = reinterpret_cast<c128 *>(smem);
+    uint8_t *rec = smem + SweepCfg<M>::TILE_BYTES;
+    const int tid = threadIdx.x;
+    {
+        const uint4 *s4 = reinterpret_cast<const uint4 *>(rec_g);
+        uint4 *d4 = reinterpret_cast<uint4 *>(rec);
+        for (uint32_t i = tid; i < rec_bytes / 16; i += T) d4[i] = s4[i];
+    }
+    __syncthreads();
+    const qfb_sweep_header *sh = reinterpret_cast<const qfb_sweep_header *>(rec);
+    const int nrounds = (int)sh->nrounds;
+    const uint64_t ntiles = 1ull << nholes;
+
+    for (uint64_t tile_id = blockIdx.x; tile_id < ntiles; tile_id += gridDim.x) {
+        uint64_t gb = 0;
+        for (int i = 0; i < nholes; ++i) gb |= ((tile_id >> i) & 1ull) << sh->hole[i];
+
+        c128 a[NE];
+        const uint8_t *rp = rec + sizeof(qfb_sweep_header);
+        for (int round = 0; round < nrounds; ++round) {
+            const qfb_round_header *rh = reinterpret_cast<const qfb_round_header *>(rp);
+            // tile-local index of this thread (register bits zero) and its global image
+            uint32_t tb = 0;
+            uint64_t tg = 0;
+#pragma unroll
+            for (int t = 0; t < TB; ++t) {
+                const uint32_t bit = (tid >> t) & 1u;
+                const uint32_t tp = rh->thrpos[t];
+                tb |= bit << tp;
+                tg |= (uint64_t)bit << sh->gpos[tp];
+            }
+            uint32_t ps[R];  // swizzled image of each register bit
+#pragma unroll
+            for (int i = 0; i < R; ++i) ps[i] = swz(1u << rh->regpos[i]);
+            const uint32_t ptb = swz(tb);  // swz is linear over XOR and tb, register offsets are disjoint
+
+            if (round == 0) {
+                uint64_t sg[R];
+#pragma unroll
+                for (int i = 0; i < R; ++i) sg[i] = 1ull << sh->gpos[rh->regpos[i]];
+                const c128 *src = state + (gb | tg);
+#pragma unroll
+                for (int e = 0; e < NE; ++e) a[e] = ldg_stream(src + pick(sg, e));
+            } else {
+#pragma unroll
+                for (int e = 0; e < NE; ++e) a[e] = tile[ptb ^ pick(ps, e)];
+                __syncthreads();  // everyone has read before anyone overwrites the tile again
+            }
+
+            const uint64_t tfull = hi_shifted | gb | tg;
+            const uint8_t *op = rp + sizeof(qfb_round_header);
+            const int nops = (int)rh->nops;
+            for (int o = 0; o < nops; ++o) {
+                const qfb_op_header *oh = reinterpret_cast<const qfb_op_header *>(op);
+                const uint8_t *payload = op + sizeof(qfb_op_header);
+                const int type = oh->type;
+                if (type == QFB_OP_D) {
+                    d_apply(a, payload, oh->nb, tfull);
+                } else if ((tfull & oh->idx_cmask) == oh->idx_cmask) {
+                    const double *m = reinterpret_cast<const double *>(payload);
+                    const uint32_t rc = oh->reg_cmask;
+                    if (type == QFB_OP_G1) {
+                        const int kind = oh->kind;
+                        switch (oh->j0) {
+                            case 0: g1_apply<0>(a, m, kind, rc); break;
+                            case 1: g1_apply<1>(a, m, kind, rc); break;
+                            case 2: g1_apply<2>(a, m, kind, rc); break;
+                            default: g1_apply<3>(a, m, kind, rc); break;
+                        }
+                    } else {
+                        const uint32_t nz = *reinterpret_cast<const uint32_t *>(payload + 256);
+                        switch (oh->j0 * 4 + oh->j1) {
+                            case 1 * 4 + 0: g2_apply<1, 0>(a, m, nz, rc); break;
+                            case 2 * 4 + 0: g2_apply<2, 0>(a, m, nz, rc); break;
+                            case 2 * 4 + 1: g2_apply<2, 1>(a, m, nz, rc); break;
+                            case 3 * 4 + 0: g2_apply<3, 0>(a, m, nz, rc); break;
+                            case 3 * 4 + 1: g2_apply<3, 1>(a, m, nz, rc); break;
+                            default: g2_apply<3, 2>(a, m, nz, rc); break;
+                        }
+                    }
+                }
+                op += oh->bytes;
+            }
+
+            if (round + 1 < nrounds) {
+#pragma unroll
+                for (int e = 0; e < NE; ++e) tile[ptb ^ pick(ps, e)] = a[e];
+                __syncthreads();
+            } else {
+                uint64_t sg[R];
+#pragma unroll
+                for (int i = 0; i < R; ++i) sg[i] = 1ull << sh->gpos[rh->regpos[i]];
+                c128 *dst = state + (gb | tg);
+#pragma unroll
+                for (int e = 0; e < NE; ++e) stg_stream(dst + pick(sg, e), a[e]);
+            }
+            rp += rh->bytes;
+        }
+    }
+}
+
+// ---- host side ----
+struct SweepInfo {
+    size_t offset;  // byte offset of the sweep record inside the device copy
+    uint32_t bytes;
+};
+
+struct PlanHandle {
+    uint32_t magic;
+    int nbits, tile_bits, device;
+    std::vector<SweepInfo> sweeps;
+    void *dev;
+    size_t dev_bytes;
+};
+
+static int validate_plan(const uint8_t *p, size_t nbytes, std::vector<SweepInfo> &sweeps, int &nbits, int &M) {
+    QFB_CHECK_ARG(p && nbytes >= sizeof(qfb_plan_header), "plan: too small");
+    qfb_plan_header h;
+    memcpy(&h, p, sizeof(h));
+    QFB_CHECK_ARG(h.magic == QFB_PLAN_MAGIC && h.version == QFB_PLAN_VERSION, "plan: bad magic/version");
+    QFB_CHECK_ARG(h.total_bytes == nbytes, "plan: size mismatch (%llu vs %llu)", (unsigned long long)h.total_bytes,
+                  (unsigned long long)nbytes);
+    QFB_CHECK_ARG(h.reg_bits == (uint32_t)R, "plan: reg_bits=%u unsupported", h.reg_bits);
+    QFB_CHECK_ARG(h.tile_bits >= QFB_PLAN_MIN_TILE_BITS && h.tile_bits <= QFB_PLAN_MAX_TILE_BITS &&
+                      h.tile_bits <= h.nbits,
+                  "plan: tile_bits=%u unsupported (nbits=%u)", h.tile_bits, h.nbits);
+    QFB_CHECK_ARG(h.nbits - h.tile_bits <= QFB_PLAN_MAX_HOLES, "plan: nbits=%u too large", h.nbits);
+    nbits = (int)h.nbits;
+    M = (int)h.tile_bits;
+    size_t off = sizeof(h);
+    for (uint32_t s = 0; s < h.nsweeps; ++s) {
+        QFB_CHECK_ARG(off + sizeof(qfb_sweep_header) <= nbytes, "plan: truncated sweep %u", s);
+        qfb_sweep_header sh;
+        memcpy(&sh, p + off, sizeof(sh));
+        QFB_CHECK_ARG(sh.bytes % 16 == 0 && sh.bytes >= sizeof(sh) && off + sh.bytes <= nbytes &&
+                          sh.bytes <= QFB_PLAN_MAX_SWEEP_BYTES,
+                      "plan: sweep %u has bad size %u", s, sh.bytes);
+        QFB_CHECK_ARG(sh.nrounds >= 1, "plan: sweep %u has no rounds", s);
+        // tile bits and holes must partition [0, nbits)
+        uint64_t seen = 0;
+        for (int j = 0; j < M; ++j) {
+            QFB_CHECK_ARG(sh.gpos[j] < h.nbits && !((seen >> sh.gpos[j]) & 1ull), "plan: sweep %u bad gpos", s);
+            seen |= 1ull << sh.gpos[j];
+        }
+        for (uint32_t i = 0; i < h.nbits - h.tile_bits; ++i) {
+            QFB_CHECK_ARG(sh.hole[i] < h.nbits && !((seen >> sh.hole[i]) & 1ull), "plan: sweep %u bad hole", s);
+            seen |= 1ull << sh.hole[i];
+        }
+        size_t roff = off + sizeof(sh);
+        const size_t send = off + sh.bytes;
+        for (uint32_t r = 0; r < sh.nrounds; ++r) {
+            QFB_CHECK_ARG(roff + sizeof(qfb_round_header) <= send, "plan: sweep %u truncated round %u", s, r);
+            qfb_round_header rh;
+            memcpy(&rh, p + roff, sizeof(rh));
+            QFB_CHECK_ARG(rh.bytes % 16 == 0 && rh.bytes >= sizeof(rh) && roff + rh.bytes <= send,
+                          "plan: sweep %u round %u bad size", s, r);
+            uint32_t tseen = 0;
+            for (int i = 0; i < R; ++i) {
+                QFB_CHECK_ARG(rh.regpos[i] < M && !((tseen >> rh.regpos[i]) & 1u), "plan: bad regpos");
+                tseen |= 1u << rh.regpos[i];
+            }
+            for (int t = 0; t < M - R; ++t) {
+                QFB_CHECK_ARG(rh.thrpos[t] < M && !((tseen >> rh.thrpos[t]) & 1u), "plan: bad thrpos");
+                tseen |= 1u << rh.thrpos[t];
+            }
+            size_t ooff = roff + sizeof(rh);
+            const size_t rend = roff + rh.bytes;
+            for (uint32_t o = 0; o < rh.nops; ++o) {
+                QFB_CHECK_ARG(ooff + sizeof(qfb_op_header) <= rend, "plan: truncated op");
+                qfb_op_header oh;
+                memcpy(&oh, p + ooff, sizeof(oh));
+                QFB_CHECK_ARG(oh.bytes % 16 == 0 && oh.bytes >= sizeof(oh) && ooff + oh.bytes <= rend,
+                              "plan: op bad size");
+                if (oh.type == QFB_OP_G1) {
+                    QFB_CHECK_ARG(oh.bytes == 16 + 64 && oh.j0 < R && oh.kind <= QFB_G1_ANTIDIAG &&
+                                      !((oh.reg_cmask >> oh.j0) & 1) && oh.reg_cmask < NE,
+                                  "plan: bad G1 op");
+                } else if (oh.type == QFB_OP_G2) {
+                    QFB_CHECK_ARG(oh.bytes == 16 + 272 && oh.j0 < R && oh.j1 < oh.j0 &&
+                                      !((oh.reg_cmask >> oh.j0) & 1) && !((oh.reg_cmask >> oh.j1) & 1) &&
+                                      oh.reg_cmask < NE,
+                                  "plan: bad G2 op");
+                } else if (oh.type == QFB_OP_D) {
+                    QFB_CHECK_ARG(oh.nb >= 1 && oh.nb <= QFB_PLAN_MAX_DIAG_BITS &&
+                                      oh.bytes == 16 + 16 + (32u << oh.nb),
+                                  "plan: bad D op");
+                } else {
+                    QFB_CHECK_ARG(false, "plan: unknown op type %u", oh.type);
+                }
+                ooff += oh.bytes;
+            }
+            QFB_CHECK_ARG(ooff == rend, "plan: round size mismatch");
+            roff += rh.bytes;
+        }
+        QFB_CHECK_ARG(roff == send, "plan: sweep size mismatch");
+        sweeps.push_back(SweepInfo{off, sh.bytes});
+        off += sh.bytes;
+    }
+    QFB_CHECK_ARG(off == nbytes, "plan: trailing bytes");
+    return QFB_OK;
+}
+
+template <int M>
+static int launch_sweep(c128 *state, const uint8_t *rec_dev, uint32_t rec_bytes, int nbits, uint64_t index_hi,
+                        cudaStream_t st) {
+    constexpr int T = SweepCfg<M>::T;
+    const size_t smem = (size_t)SweepCfg<M>::TILE_BYTES + rec_bytes;
+    static thread_local size_t configured[64] = {0};
+    static thread_local int occ[64] = {0};
+    int dev = 0;
+    QFB_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64) dev = 0;
+    if (smem > configured[dev]) {
+        // grow in 8 KiB steps so the attribute is set a handful of times per process
+        const size_t want = std::min<size_t>(((smem + 8191) / 8192) * 8192, 227 * 1024);
+        QFB_CHECK_ARG(smem <= want, "sweep: %zu bytes of shared memory exceed the 227 KiB limit", smem);
+        QFB_CUDA(cudaFuncSetAttribute(sweep_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)want));
+        configured[dev] = want;
+        occ[dev] = 0;
+    }
+    if (occ[dev] == 0) {
+        int nb = 0;
+        QFB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, sweep_kernel<M>, T, configured[dev]));
+        occ[dev] = std::max(1, nb);
+    }
+    const int nholes = nbits - M;
+    const uint64_t ntiles = 1ull << nholes;
+    const uint64_t cap = (uint64_t)sm_count_cached() * occ[dev];
+    const int grid = (int)std::min<uint64_t>(ntiles, cap);
+    const uint64_t hi_shifted = (nbits >= 64) ? 0ull : (index_hi << nbits);
+    sweep_kernel<M><<<grid, T, smem, st>>>(state, rec_dev, rec_bytes, nholes, hi_shifted);
+    QFB_LAUNCH_CHECK();
+    return QFB_OK;
+}
+
+static int launch_sweep_dispatch(int M, c128 *state, const uint8_t *rec_dev, uint32_t rec_bytes, int nbits,
+                                 uint64_t index_hi, cudaStream_t st) {
+    switch (M) {
+        case 5: return launch_sweep<5>(state, rec_dev, rec_bytes, nbits, index_hi, st);
+        case 6: return launch_sweep<6>(state, rec_dev, rec_bytes, nbits, index_hi, st);
+        case 7: return launch_sweep<7>(state, rec_dev, rec_bytes, nbits, index_hi, st);
+        case 8: return launch_sweep<8>(state, rec_dev, rec_bytes, nbits, index_hi, st);
+        case 9: return launch_sweep<9>(state, rec_dev, rec_bytes, nbits, index_hi, st);
+        case 10: return launch_sweep<10>(state, rec_dev, rec_bytes, nbits, index_hi, st);
+        case 11: return launch_sweep<11>(state, rec_dev, rec_bytes, nbits, index_hi, st);
+        case 12: return launch_sweep<12>(state, rec_dev, rec_bytes, nbits, index_hi, st);
+        case 13: return launch_sweep<13>(state, rec_dev, rec_bytes, nbits, index_hi, st);
+        default: break;
+    }
+    set_error("sweep: tile_bits=%d unsupported", M);
+    return QFB_ERR_UNSUPPORTED;
+}
+
+constexpr uint32_t HANDLE_MAGIC = 0x48424651u;
+
+}  // namespace qfb
+
+using namespace qfb;
+
+extern "C" {
+
+int qfb_plan_upload(const void *plan_host, size_t plan_bytes, void **handle_out, void *stream) {
+    QFB_CHECK_ARG(handle_out, "qfb_plan_upload: null handle_out");
+    *handle_out = nullptr;
+    PlanHandle *h = new PlanHandle();
+    h->magic = HANDLE_MAGIC;
+    h->dev = nullptr;
+    int rc = validate_plan((const uint8_t *)plan_host, plan_bytes, h->sweeps, h->nbits, h->tile_bits);
+    if (rc != QFB_OK) {
+        delete h;
+        return rc;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaError_t e = cudaGetDevice(&h->device);
+    if (e == cudaSuccess) e = cudaMalloc(&h->dev, plan_bytes);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(h->dev, plan_host, plan_bytes, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);  // pageable source
+    if (e != cudaSuccess) {
+        set_error("qfb_plan_upload: %s", cudaGetErrorString(e));
+        if (h->dev) cudaFree(h->dev);
+        delete h;
+        return QFB_ERR_CUDA;
+    }
+    h->dev_bytes = plan_bytes;
+    *handle_out = h;
+    return QFB_OK;
+}
+
+int qfb_plan_launch(void *handle, void *state, int nbits, uint64_t index_hi, void *stream) {
+    PlanHandle *h = (PlanHandle *)handle;
+    QFB_CHECK_ARG(h && h->magic == HANDLE_MAGIC, "qfb_plan_launch: bad handle");
+    QFB_CHECK_ARG(state, "qfb_plan_launch: null state");
+    QFB_CHECK_ARG(nbits == h->nbits, "qfb_plan_launch: plan built for %d bits, state has %d", h->nbits, nbits);
+    for (const SweepInfo &s : h->sweeps) {
+        int rc = launch_sweep_dispatch(h->tile_bits, (c128 *)state, (const uint8_t *)h->dev + s.offset, s.bytes,
+                                       nbits, index_hi, (cudaStream_t)stream);
+        if (rc != QFB_OK) return rc;
+    }
+    return QFB_OK;
+}
+
+int qfb_plan_destroy(void *handle) {
+    PlanHandle *h = (PlanHandle *)handle;
+    QFB_CHECK_ARG(h && h->magic == HANDLE_MAGIC, "qfb_plan_destroy: bad handle");
+    h->magic = 0;
+    if (h->dev) cudaFree(h->dev);
+    delete h;
+    return QFB_OK;
+}
+
+int qfb_run_plan(void *state, int nbits, uint64_t index_hi, const void *plan_host, size_t plan_bytes,
+                 void *stream) {
+    void *h = nullptr;
+    int rc = qfb_plan_upload(plan_host, plan_bytes, &h, stream);
+    if (rc != QFB_OK) return rc;
+    rc = qfb_plan_launch(h, state, nbits, index_hi, stream);
+    // the device copy must outlive the queued kernels
+    cudaError_t e = cudaStreamSynchronize((cudaStream_t)stream);
+    qfb_plan_destroy(h);
+    if (rc == QFB_OK && e != cudaSuccess) {
+        set_error("qfb_run_plan: %s", cudaGetErrorString(e));
+        return QFB_ERR_CUDA;
+    }
+    return rc;
+}
+
+}  // extern "C"
