@@ -108,6 +108,7 @@ class Circuit(Operation):
 
     def run(self, ket: State = None) -> State:
         """Apply the circuit to a state (default |0...0> on the circuit's qubits)."""
+        owned = ket is None          # an engine-created buffer may be updated in place
         if ket is None:
             ket = zero_state(qubits=self.qubits)
         flat = self._flat_elements()
@@ -125,21 +126,22 @@ class Circuit(Operation):
                     return [(g.matrix(), [count - 1 - qubits.index(q) for q in g.qubits]) for g in gates]
 
                 segments = self._segments(flat[i:j], ('run', tuple(qubits)), count, bitops)
-                tensor = ket.tensor.clone()
+                tensor = ket.tensor if owned else ket.tensor.clone()
                 self._execute(segments, tensor)
                 ket = State(tensor, ket.qubits, ket.memory)
-                i = j
-            elif j > i:
-                for elem in flat[i:j]:
-                    ket = elem.run(ket)
+                owned = True
                 i = j
             else:
-                ket = flat[i].run(ket)
-                i += 1
+                for elem in flat[i:max(j, i + 1)]:
+                    before = ket.tensor.data_ptr()
+                    ket = elem.run(ket)
+                    owned = owned or ket.tensor.data_ptr() != before
+                i = max(j, i + 1)
         return ket
 
     def evolve(self, rho: Density = None) -> Density:
         """Apply the circuit to a density matrix (default |0...0><0...0|)."""
+        owned = rho is None
         if rho is None:
             rho = zero_state(qubits=self.qubits).asdensity()
         flat = self._flat_elements()
@@ -179,21 +181,21 @@ class Circuit(Operation):
                     return out
 
                 segments = self._segments(flat[i:j], ('evolve', tuple(qubits)), 2 * count, bitops)
-                tensor = rho.tensor.clone()
+                tensor = rho.tensor if owned else rho.tensor.clone()
                 self._execute(segments, tensor)
                 # Kraus.evolve drops classical memory in the reference (channels.py:85)
                 memory = rho.memory
                 if any(hasattr(e, 'superoperator_matrix') for e in flat[i:j]):
                     memory = None
                 rho = Density(tensor, rho.qubits, memory)
-                i = j
-            elif j > i:
-                for elem in flat[i:j]:
-                    rho = elem.evolve(rho)
+                owned = True
                 i = j
             else:
-                rho = flat[i].evolve(rho)
-                i += 1
+                for elem in flat[i:max(j, i + 1)]:
+                    before = rho.tensor.data_ptr()
+                    rho = elem.evolve(rho)
+                    owned = owned or rho.tensor.data_ptr() != before
+                i = max(j, i + 1)
         return rho
 
     def asgate(self) -> Gate:

@@ -41,6 +41,15 @@ __device__ __forceinline__ T pick(const T (&s)[R], int e) {
     return r;
 }
 
+// XOR-combine (swizzled offsets overlap in their low bits, so OR would be wrong)
+__device__ __forceinline__ uint32_t pick_xor(const uint32_t (&s)[R], int e) {
+    uint32_t r = 0;
+#pragma unroll
+    for (int i = 0; i < R; ++i)
+        if ((e >> i) & 1) r ^= s[i];
+    return r;
+}
+
 // ---- 1-bit operator on register bit J ----
 template <int J>
 __device__ __forceinline__ void g1_apply(c128 (&a)[NE], const double *__restrict__ m, int kind, uint32_t rc) {
@@ -207,7 +216,7 @@ sweep_kernel(c128 *__restrict__ state, const uint8_t *__restrict__ rec_g, uint32
                 for (int e = 0; e < NE; ++e) a[e] = ldg_stream(src + pick(sg, e));
             } else {
 #pragma unroll
-                for (int e = 0; e < NE; ++e) a[e] = tile[ptb ^ pick(ps, e)];
+                for (int e = 0; e < NE; ++e) a[e] = tile[ptb ^ pick_xor(ps, e)];
                 __syncthreads();  // everyone has read before anyone overwrites the tile again
             }
 
@@ -248,7 +257,7 @@ sweep_kernel(c128 *__restrict__ state, const uint8_t *__restrict__ rec_g, uint32
 
             if (round + 1 < nrounds) {
 #pragma unroll
-                for (int e = 0; e < NE; ++e) tile[ptb ^ pick(ps, e)] = a[e];
+                for (int e = 0; e < NE; ++e) tile[ptb ^ pick_xor(ps, e)] = a[e];
                 __syncthreads();
             } else {
                 uint64_t sg[R];
@@ -370,7 +379,6 @@ static int launch_sweep(c128 *state, const uint8_t *rec_dev, uint32_t rec_bytes,
     constexpr int T = SweepCfg<M>::T;
     const size_t smem = (size_t)SweepCfg<M>::TILE_BYTES + rec_bytes;
     static thread_local size_t configured[64] = {0};
-    static thread_local int occ[64] = {0};
     int dev = 0;
     QFB_CUDA(cudaGetDevice(&dev));
     if (dev < 0 || dev >= 64) dev = 0;
@@ -380,16 +388,13 @@ static int launch_sweep(c128 *state, const uint8_t *rec_dev, uint32_t rec_bytes,
         QFB_CHECK_ARG(smem <= want, "sweep: %zu bytes of shared memory exceed the 227 KiB limit", smem);
         QFB_CUDA(cudaFuncSetAttribute(sweep_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)want));
         configured[dev] = want;
-        occ[dev] = 0;
     }
-    if (occ[dev] == 0) {
-        int nb = 0;
-        QFB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, sweep_kernel<M>, T, configured[dev]));
-        occ[dev] = std::max(1, nb);
-    }
+    int resident = 0;  // CTAs per SM for this launch's shared-memory footprint (host-side arithmetic)
+    QFB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, sweep_kernel<M>, T, smem));
+    resident = std::max(1, resident);
     const int nholes = nbits - M;
     const uint64_t ntiles = 1ull << nholes;
-    const uint64_t cap = (uint64_t)sm_count_cached() * occ[dev];
+    const uint64_t cap = (uint64_t)sm_count_cached() * resident;
     const int grid = (int)std::min<uint64_t>(ntiles, cap);
     const uint64_t hi_shifted = (nbits >= 64) ? 0ull : (index_hi << nbits);
     sweep_kernel<M><<<grid, T, smem, st>>>(state, rec_dev, rec_bytes, nholes, hi_shifted);

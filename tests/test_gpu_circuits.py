@@ -1,0 +1,242 @@
+"""GPU parity of Circuit.run / Circuit.evolve (planner + tiled sweep executor) against fixtures produced by the
+reference on the same circuits and seeds, and -- at BASELINE.json's full sizes -- through size-independent
+properties (unitarity round trip, norm, agreement of independent execution paths)."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import quantumflow_b200 as qf
+from quantumflow_b200 import engine, planner, workloads
+from oracle import c_oracle
+from oracle import qf_oracle as O
+
+from conftest import AMP_TOL, GOLDEN
+
+pytestmark = pytest.mark.gpu
+
+
+def amps(state):
+    return qf.asarray(state.tensor).reshape(-1)
+
+
+@pytest.mark.parametrize('seed', [0, 1, 2])
+def test_wb12_matches_reference(golden, seed):
+    want = golden('workloads.npz')['wb12_seed{}'.format(seed)]
+    circ = workloads.wb_circuit(qf, 12, 20, seed)
+    got = amps(circ.run())
+    assert np.abs(got - want).max() < AMP_TOL
+    # gate-by-gate path (one kernel per Gate.run, the reference's own loop structure) agrees as well
+    ket = qf.zero_state(12)
+    for elem in circ.elements:
+        ket = elem.run(ket)
+    assert np.abs(amps(ket) - want).max() < AMP_TOL
+
+
+def test_wa_wb16_and_library_circuits_match_reference(golden):
+    data = golden('workloads.npz')
+    assert np.abs(amps(workloads.wa_circuit(qf, 12, 0).run()) - data['wa12_seed0']).max() < AMP_TOL
+    assert np.abs(amps(workloads.wa_circuit(qf, 16, 1).run()) - data['wa16_seed1']).max() < AMP_TOL
+    assert np.abs(amps(workloads.wb_circuit(qf, 16, 8, 3).run()) - data['wb16_d8_seed3']).max() < AMP_TOL
+    ket = qf.qft_circuit([0, 1, 2]).run(qf.X(2).run(qf.zero_state(3)))
+    assert np.abs(amps(ket) - data['qft3_of_001']).max() < AMP_TOL
+    ket = qf.qft_circuit([0, 1, 2, 3, 4]).run(qf.State(data['qft5_random_in']))
+    assert np.abs(amps(ket) - data['qft5_random']).max() < AMP_TOL
+    assert np.abs(amps(qf.ghz_circuit(range(12)).run()) - data['ghz12']).max() < AMP_TOL
+    add = qf.addition_circuit([0, 1, 2], [3, 4, 5], [6, 7])
+    ket = qf.Circuit([qf.X(0), qf.X(2), qf.X(4), qf.X(5)]).run(qf.zero_state(8))
+    assert np.abs(amps(add.run(ket)) - data['adder3_state']).max() < AMP_TOL
+    pe = qf.phase_estimation_circuit(qf.RZ(-4 * np.pi * 0.25, 4), range(4))
+    assert np.abs(amps(pe.run()) - data['phase_est']).max() < AMP_TOL
+
+
+def test_reference_test_vectors():
+    # 2-qubit QAOA ket, reference tests/test_circuits.py:19-24, 43-60 (and density version test_channels:183-200)
+    pi = np.pi
+    true_ket = qf.State(np.array([0.00167784 + 1.00210180e-05j, 0.5 - 4.99997185e-01j,
+                                  0.5 - 4.99997185e-01j, 0.00167784 + 1.00210180e-05j]).reshape(2, 2))
+    circ = qf.Circuit([qf.RY(pi / 2, 0), qf.RX(pi, 0), qf.RY(pi / 2, 1), qf.RX(pi, 1), qf.CNOT(0, 1),
+                       qf.RX(-pi / 2, 1), qf.RY(4.71572463191, 1), qf.RX(pi / 2, 1), qf.CNOT(0, 1),
+                       qf.RX(-2 * 2.74973750579, 0), qf.RX(-2 * 2.74973750579, 1)])
+    assert qf.states_close(circ.run(qf.zero_state(2)), true_ket)
+    assert qf.densities_close(circ.evolve(), true_ket.asdensity())
+    # inverse circuit, reference tests/test_circuits.py:119-148
+    circ = workloads.wb_circuit(qf, 7, 4, 5)
+    back = circ.H.run(circ.run())
+    assert qf.states_close(back, qf.zero_state(7))
+    # adder truth table through measure(), reference tests/test_circuits.py:298-350 (2-bit version)
+    from quantumflow_b200.utils import bitlist_to_int, int_to_bitlist
+    add = qf.addition_circuit([0, 1], [2, 3], [4, 5])
+    for a in range(4):
+        for b in range(4):
+            bits = tuple(int_to_bitlist(a, 2)) + tuple(int_to_bitlist(b, 2)) + (0, 0)
+            ket = qf.Circuit([qf.X(i) for i, v in enumerate(bits) if v]).run(qf.zero_state(6)) \
+                if any(bits) else qf.zero_state(6)
+            res = add.run(ket).measure()
+            total = bitlist_to_int([res[5]] + list(res[2:4]))
+            assert total == a + b
+
+
+def test_mixed_arity_circuit_matches_reference(golden):
+    import random
+    rnd = random.Random(11)
+    circ = qf.Circuit()
+    names1 = ['H', 'S', 'T', 'X', 'Y', 'Z', 'S_H', 'T_H']
+    for d in range(12):
+        for q in range(9):
+            circ += getattr(qf, rnd.choice(names1))(q)
+        a, b, c = rnd.sample(range(9), 3)
+        circ += qf.CCNOT(a, b, c)
+        a, b, c = rnd.sample(range(9), 3)
+        circ += qf.CSWAP(a, b, c)
+        a, b = rnd.sample(range(9), 2)
+        circ += qf.CAN(rnd.random(), rnd.random(), rnd.random(), a, b)
+        a, b = rnd.sample(range(9), 2)
+        circ += qf.PISWAP(rnd.random(), a, b)
+        a, b = rnd.sample(range(9), 2)
+        circ += qf.ISWAP(a, b)
+        a, b = rnd.sample(range(9), 2)
+        circ += qf.CPHASE(rnd.random(), a, b)
+        a, b = rnd.sample(range(9), 2)
+        circ += qf.SWAP(a, b)
+        circ += qf.TX(rnd.random(), rnd.randrange(9))
+        circ += qf.ZYZ(rnd.random(), rnd.random(), rnd.random(), rnd.randrange(9))
+    want = golden('workloads.npz')['mixed9_seed11']
+    assert np.abs(amps(circ.run()) - want).max() < AMP_TOL
+    # nested circuits, a dense 3-qubit gate in the middle (planner fallback segment), and a barrier element
+    np.random.seed(2)
+    rand3 = qf.random_gate([4, 0, 7])
+    nested = qf.Circuit([qf.Circuit(circ.elements[:30]), rand3, qf.Barrier(0, 1), qf.Circuit(circ.elements[30:60])])
+    ket = qf.zero_state(9)
+    for elem in list(circ.elements[:30]) + [rand3] + list(circ.elements[30:60]):
+        ket = elem.run(ket)
+    assert np.abs(amps(nested.run()) - amps(ket)).max() < AMP_TOL
+
+
+@pytest.mark.parametrize('tile', [5, 6, 7, 8, 9, 10, 11, 12, 13])
+def test_every_tile_size_of_the_sweep_kernel(tile):
+    n = 14
+    specs = workloads.wb_gate_list(n, 6, tile)
+    ops = [(O.gate_matrix(nm, p), [n - 1 - q for q in qs]) for nm, p, qs in specs]
+    segments = planner.build_segments(n, ops, tile_bits=tile)
+    state = torch.zeros(1 << n, dtype=torch.complex128, device='cuda')
+    state[0] = 1
+    qf.Circuit._execute(segments, state)
+    want = c_oracle.run_specs(specs, n, O.gate_matrix)
+    assert np.abs(state.cpu().numpy() - want).max() < AMP_TOL
+    # the one-call entry point of the C ABI (upload + launch + free)
+    from quantumflow_b200 import _lib
+    import ctypes
+    state2 = torch.zeros(1 << n, dtype=torch.complex128, device='cuda')
+    state2[0] = 1
+    for seg in segments:
+        buf = ctypes.create_string_buffer(seg.blob, len(seg.blob))
+        _lib.check(_lib.load().qfb_run_plan(state2.data_ptr(), n, 0, ctypes.cast(buf, ctypes.c_void_p),
+                                            len(seg.blob), torch.cuda.current_stream().cuda_stream))
+    assert torch.equal(state, state2)
+
+
+def test_config_c1_wb20_matches_reference(golden):
+    """BASELINE.json configs[0]: 20 qubits, depth 20, 620 gates."""
+    data = golden('workloads.npz')
+    meta = json.load(open(os.path.join(GOLDEN, 'workloads_meta.json')))['wb20_seed0']
+    circ = workloads.wb_circuit(qf, 20, 20, 0)
+    assert circ.size() == 620
+    ket = circ.run()
+    got = amps(ket)
+    assert np.abs(got[meta['indices']] - data['wb20_seed0_amps']).max() < AMP_TOL
+    assert np.abs(got[::4099] - data['wb20_seed0_stride']).max() < AMP_TOL
+    assert abs(float(qf.asarray(ket.norm())) - meta['norm']) < 1e-12
+    probs = ket.probabilities().reshape(-1)
+    idx = torch.arange(probs.numel(), device=probs.device, dtype=torch.float64)
+    assert abs(float((idx * probs).sum() / probs.numel()) - meta['mean_index']) < 1e-10
+    # full-vector check against the C oracle (itself pinned to the reference in test_oracle.py)
+    want = c_oracle.run_specs(workloads.wb_gate_list(20, 20, 0), 20, O.gate_matrix)
+    assert np.abs(got - want).max() < AMP_TOL
+
+
+def test_wb24_full_vector_against_c_oracle():
+    n, depth, seed = 24, 10, 4
+    got = amps(workloads.wb_circuit(qf, n, depth, seed).run())
+    want = c_oracle.run_specs(workloads.wb_gate_list(n, depth, seed), n, O.gate_matrix)
+    assert np.abs(got - want).max() < AMP_TOL
+
+
+def test_density_workloads_match_reference(golden):
+    data = golden('workloads.npz')
+    for kraus in (True, False):
+        rho = workloads.wd_circuit(qf, 6, 20, 0, kraus=kraus).evolve()
+        want = data['wd6_seed0_kraus' if kraus else 'wd6_seed0_chan']
+        assert np.abs(qf.asarray(rho.asoperator()) - want).max() < AMP_TOL
+        assert abs(complex(qf.asarray(rho.trace())) - 1) < 1e-12
+    # SURVEY Appendix G golden values
+    assert abs(float(qf.asarray(qf.purity(rho))) - 0.104522702942447) < 1e-12
+    rho = workloads.wd_circuit(qf, 8, 4, 1, kraus=True).evolve()
+    assert np.abs(qf.asarray(rho.asoperator()) - data['wd8_d4_seed1_kraus']).max() < AMP_TOL
+    import math
+    import random
+    rnd = random.Random(5)
+    circ = qf.Circuit()
+    for d in range(6):
+        for q in range(5):
+            circ += qf.RY(rnd.uniform(0, 2 * math.pi), q)
+        for q in range(0, 4, 2):
+            circ += qf.CNOT(q, q + 1)
+        for q in range(5):
+            circ += qf.Damping(0.05, q)
+    assert np.abs(qf.asarray(circ.evolve().asoperator()) - data['damping5_seed5']).max() < AMP_TOL
+    # element-by-element evolution (Gate.evolve / Kraus.evolve kernels) agrees with the planned sweeps
+    rho = qf.zero_state(5).asdensity()
+    for elem in circ.elements:
+        rho = elem.evolve(rho)
+    assert np.abs(qf.asarray(rho.asoperator()) - data['damping5_seed5']).max() < AMP_TOL
+    # CCNOT decomposition on densities, reference tests/test_circuits.py:248-260
+    rho0 = qf.random_density(3)
+    assert qf.densities_close(qf.CCNOT(0, 1, 2).evolve(rho0), qf.ccnot_circuit([0, 1, 2]).evolve(rho0))
+
+
+def test_density_11q_properties():
+    """A 22-bit density (64 MiB): trace 1, Hermitian, purity never increases under depolarizing noise."""
+    n = 11
+    prev = 1.0 + 1e-12
+    rho = qf.zero_state(n).asdensity()
+    specs = workloads.wd_gate_list(n, 3, 2)
+    per_layer = len(specs) // 3
+    for layer in range(3):
+        circ = workloads.circuit_from_specs(qf, specs[layer * per_layer:(layer + 1) * per_layer])
+        rho = circ.evolve(rho)
+        assert abs(complex(qf.asarray(rho.trace())) - 1) < 1e-10
+        pur = float(qf.asarray(qf.purity(rho)))
+        assert pur <= prev
+        prev = pur
+    op = rho.asoperator()
+    assert float((op - op.conj().T).abs().max()) < 1e-12
+
+
+@pytest.mark.parametrize('n,depth', [(28, 20), (30, 20)])
+def test_full_size_round_trip(n, depth):
+    """BASELINE.json configs[3] scale: U then U^dagger returns |0...0>; the norm stays 1 in between. Both are
+    size independent properties (the oracle cannot run at this size in seconds)."""
+    free, _ = torch.cuda.mem_get_info()
+    if free < 3 * (16 << n):
+        pytest.skip('not enough device memory')
+    circ = workloads.wb_circuit(qf, n, depth, 0)
+    ket = circ.run()
+    assert abs(float(qf.asarray(ket.norm())) - 1) < 1e-9
+    # spot amplitudes equal the per-gate kernels' result on the same state? too slow at 930 sweeps; instead
+    # check a second independent plan shape (different tile size) gives the same amplitudes
+    specs = workloads.wb_gate_list(n, depth, 0)
+    ops = [(O.gate_matrix(nm, p), [n - 1 - q for q in qs]) for nm, p, qs in specs]
+    alt = torch.zeros(1 << n, dtype=torch.complex128, device='cuda')
+    alt[0] = 1
+    qf.Circuit._execute(planner.build_segments(n, ops, tile_bits=11, low_bits=4), alt)
+    diff = float((alt - ket.tensor.reshape(-1)).abs().max())
+    assert diff < AMP_TOL
+    del alt
+    back = circ.H.run(ket)
+    del ket
+    vec = back.tensor.reshape(-1)
+    assert abs(complex(vec[0].item()) - 1) < 1e-9
+    assert abs(float(qf.asarray(back.norm())) - 1) < 1e-9

@@ -1,0 +1,194 @@
+"""Planner + binary plan format, verified on the CPU with the plan emulator (tests/plan_emulator.py walks a
+plan the way sweep_kernel does) against the oracle. The GPU tests then only have to establish that the kernel
+implements the same walk."""
+import random
+
+import numpy as np
+import pytest
+
+import plan_emulator as E
+from oracle import qf_oracle as O
+from quantumflow_b200 import planner, workloads
+
+from conftest import AMP_TOL
+
+
+def bitops_of(specs, n):
+    return [(O.gate_matrix(name, params), [n - 1 - q for q in qubits]) for name, params, qubits in specs]
+
+
+def run_segments(segments, state, index_hi=0):
+    state = np.array(state, dtype=np.complex128).reshape(-1)
+    for seg in segments:
+        if seg.kind == 'plan':
+            state = E.execute(seg.blob, state, index_hi)
+        else:
+            state = O.tensormul_flat(seg.mat, state, list(seg.bits))
+    return state
+
+
+def zero(n):
+    v = np.zeros(1 << n, dtype=np.complex128)
+    v[0] = 1
+    return v
+
+
+@pytest.mark.parametrize('n,depth,seed,tile', [(12, 20, 0, 12), (12, 6, 1, 8), (11, 5, 2, 11), (10, 5, 2, 10),
+                                                (9, 4, 3, 6), (8, 6, 4, 5), (13, 3, 5, 13), (7, 9, 6, 7)])
+def test_wb_plan_matches_oracle(n, depth, seed, tile):
+    specs = workloads.wb_gate_list(n, depth, seed)
+    segments = planner.build_segments(n, bitops_of(specs, n), tile_bits=tile)
+    assert all(s.kind == 'plan' for s in segments)
+    got = run_segments(segments, zero(n))
+    want = O.run_specs(specs, n).reshape(-1)
+    assert np.abs(got - want).max() < AMP_TOL
+    stats = planner.plan_stats(segments)
+    assert stats['ops'] == len(specs) and stats['sweeps'] < len(specs) / 4
+
+
+def test_plan_matches_reference_fixture(golden):
+    want = golden('workloads.npz')['wb12_seed1']
+    specs = workloads.wb_gate_list(12, 20, 1)
+    got = run_segments(planner.build_segments(12, bitops_of(specs, 12)), zero(12))
+    assert np.abs(got - want).max() < AMP_TOL
+
+
+def test_controls_three_qubit_gates_and_fallback(golden):
+    """CCNOT/CSWAP become controlled 1-/2-bit ops, CAN/PISWAP dense 2-bit ops, ISWAP/SWAP permutation ops."""
+    rnd = random.Random(11)
+    specs = []
+    names1 = ['H', 'S', 'T', 'X', 'Y', 'Z', 'S_H', 'T_H']
+    for d in range(12):
+        for q in range(9):
+            specs.append((rnd.choice(names1), (), (q,)))
+        a, b, c = rnd.sample(range(9), 3)
+        specs.append(('CCNOT', (), (a, b, c)))
+        a, b, c = rnd.sample(range(9), 3)
+        specs.append(('CSWAP', (), (a, b, c)))
+        a, b = rnd.sample(range(9), 2)
+        specs.append(('CAN', (rnd.random(), rnd.random(), rnd.random()), (a, b)))
+        a, b = rnd.sample(range(9), 2)
+        specs.append(('PISWAP', (rnd.random(),), (a, b)))
+        a, b = rnd.sample(range(9), 2)
+        specs.append(('ISWAP', (), (a, b)))
+        a, b = rnd.sample(range(9), 2)
+        specs.append(('CPHASE', (rnd.random(),), (a, b)))
+        a, b = rnd.sample(range(9), 2)
+        specs.append(('SWAP', (), (a, b)))
+        specs.append(('TX', (rnd.random(),), (rnd.randrange(9),)))
+        specs.append(('ZYZ', (rnd.random(), rnd.random(), rnd.random()), (rnd.randrange(9),)))
+    want = golden('workloads.npz')['mixed9_seed11']          # produced by the reference with the same `random`
+    for tile in (9, 7, 5):
+        segments = planner.build_segments(9, bitops_of(specs, 9), tile_bits=tile)
+        got = run_segments(segments, zero(9))
+        assert np.abs(got - want).max() < AMP_TOL, tile
+    # a dense 3-qubit operator cannot be expressed by the executor: it becomes its own segment
+    rng = np.random.RandomState(3)
+    u3 = np.linalg.qr(rng.normal(size=(8, 8)) + 1j * rng.normal(size=(8, 8)))[0]
+    ops = bitops_of(specs[:20], 9) + [(u3, [7, 2, 4])] + bitops_of(specs[20:40], 9)
+    segments = planner.build_segments(9, ops)
+    assert [s.kind for s in segments] == ['plan', 'op', 'plan']
+    want = zero(9)
+    for m, bits in ops:
+        want = O.tensormul_flat(m, want, bits)
+    assert np.abs(run_segments(segments, zero(9)) - want).max() < AMP_TOL
+
+
+def test_density_bitops_plan(golden):
+    """Circuit.evolve as bit-level ops on the 2N-bit vector: U on ket bits, conj(U) on bra bits, channels as
+    2-bit superoperators (reference ops.py:354-363)."""
+    n = 6
+    specs = workloads.wd_gate_list(n, 20, 0)
+    ops = []
+    for name, params, qubits in specs:
+        ket_bits = [2 * n - 1 - q for q in qubits]
+        bra_bits = [n - 1 - q for q in qubits]
+        if name == 'DEPOLARIZING':
+            ops.append((O.depolarizing_superop(params[0]), ket_bits + bra_bits))
+        else:
+            u = O.gate_matrix(name, params)
+            ops.append((u, ket_bits))
+            ops.append((u.conj(), bra_bits))
+    segments = planner.build_segments(2 * n, ops)
+    got = run_segments(segments, zero(2 * n)).reshape(64, 64)
+    want = golden('workloads.npz')['wd6_seed0_kraus']
+    assert np.abs(got - want).max() < AMP_TOL
+    assert planner.plan_stats(segments)['sweeps'] <= 12
+
+
+def test_sharded_plan_uses_rank_bits_for_diagonals_and_controls():
+    """With the top p bits held in the rank (index_hi), diagonal operators and controls on those bits need no
+    communication: the plan resolves them from index_hi."""
+    n, p = 11, 2
+    nl = n - p
+    rnd = random.Random(5)
+    specs = []
+    for q in range(n):
+        specs.append(('H', (), (q,)))
+    for _ in range(40):
+        kind = rnd.choice(['T', 'RZ', 'CZ', 'CNOT', 'ZZ', 'CCNOT', 'RX'])
+        if kind in ('T', 'RZ'):
+            q = rnd.randrange(n)
+            specs.append((kind, (rnd.random(),) if kind == 'RZ' else (), (q,)))
+        elif kind == 'RX':
+            specs.append((kind, (rnd.random(),), (rnd.randrange(p, n),)))          # local target only
+        elif kind in ('CZ', 'ZZ'):
+            a, b = rnd.sample(range(n), 2)
+            specs.append((kind, (rnd.random(),) if kind == 'ZZ' else (), (a, b)))
+        elif kind == 'CNOT':
+            c = rnd.randrange(n)
+            t = rnd.choice([q for q in range(p, n) if q != c])
+            specs.append((kind, (), (c, t)))
+        else:
+            t = rnd.randrange(p, n)
+            c0, c1 = rnd.sample([q for q in range(n) if q != t], 2)
+            specs.append((kind, (), (c0, c1, t)))
+    # the initial H layer on the global qubits cannot be done locally: start from a random full state instead
+    specs = specs[n:]
+    rng = np.random.RandomState(0)
+    full = rng.normal(size=1 << n) + 1j * rng.normal(size=1 << n)
+    want = O.run_specs(specs, n, full.reshape([2] * n)).reshape(-1)
+    ops = bitops_of(specs, n)                     # bit positions in the FULL index; >= nl means rank bit
+    segments = planner.build_segments(nl, ops)
+    got = np.empty_like(full)
+    for rank in range(1 << p):
+        shard = full[rank << nl: (rank + 1) << nl]
+        got[rank << nl: (rank + 1) << nl] = run_segments(segments, shard, index_hi=rank)
+    assert np.abs(got - want).max() < AMP_TOL
+    with pytest.raises(ValueError):
+        planner.build_segments(nl, [(O.gate_matrix('H'), [n - 1])])      # mixing a rank bit needs a remap
+
+
+def test_layout_invariants():
+    specs = workloads.wb_gate_list(14, 6, 7)
+    segments = planner.build_segments(14, bitops_of(specs, 14))
+    plan = E.parse(segments[0].blob)
+    assert plan['M'] == 12
+    worst = 1
+    for sweep in plan['sweeps']:
+        assert sweep['gpos'][:3] == [0, 1, 2]                       # low bits always in the tile
+        assert sweep['gpos'] == sorted(sweep['gpos'])
+        nr = len(sweep['rounds'])
+        for r, rd in enumerate(sweep['rounds']):
+            if r in (0, nr - 1):
+                assert min(rd['regpos']) >= 3                       # lanes keep the low bits on edge rounds
+                assert rd['thrpos'][:3] == [0, 1, 2]
+            worst = max(worst, E.conflict_degree(rd, plan['M']))
+    assert worst == 1                                               # swizzle + lane assignment: conflict free
+    # executes correctly with 4 tiles
+    got = run_segments(segments, zero(14))
+    assert np.abs(got - O.run_specs(specs, 14, flat=True).reshape(-1)).max() < AMP_TOL
+
+
+def test_identity_and_global_phase_ops():
+    ops = [(np.eye(2), [0]), (np.exp(0.3j) * np.eye(2), [3]), (O.gate_matrix('H'), [2]), (np.eye(4), [1, 2])]
+    segments = planner.build_segments(6, ops)
+    got = run_segments(segments, zero(6))
+    want = O.tensormul_flat(O.gate_matrix('H'), zero(6), [2]) * np.exp(0.3j)
+    assert np.abs(got - want).max() < 1e-15
+    assert planner.build_segments(6, [(np.eye(2), [0])]) == []
+
+
+def test_planner_rejects_tiny_states():
+    with pytest.raises(ValueError):
+        planner.build_segments(3, [(O.gate_matrix('H'), [0])])
