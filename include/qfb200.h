@@ -74,6 +74,8 @@ int qfb_apply_diag(void *dst, const void *src, int nbits, const double *diag_hos
  * Executes every sweep of the plan in place on `state`. */
 int qfb_run_plan(void *state, int nbits, uint64_t index_hi, const void *plan_host, size_t plan_bytes,
                  void *stream);
+/* Structural validation of a plan (pure host code, no CUDA call): sizes, bit partitions, op records. */
+int qfb_plan_validate(const void *plan_host, size_t plan_bytes);
 /* Upload a plan once and replay it (plans are immutable); handle is freed with qfb_plan_destroy. */
 int qfb_plan_upload(const void *plan_host, size_t plan_bytes, void **handle_out, void *stream);
 int qfb_plan_launch(void *handle, void *state, int nbits, uint64_t index_hi, void *stream);

@@ -21,6 +21,7 @@ PROTOTYPES = {
                                 c_uint64, c_void_p]),
     'qfb_apply_diag': (c_int, [c_void_p, c_void_p, c_int, _c_double_p, c_int, _c_int_p, c_uint64, c_void_p]),
     'qfb_run_plan': (c_int, [c_void_p, c_int, c_uint64, c_void_p, c_size_t, c_void_p]),
+    'qfb_plan_validate': (c_int, [c_void_p, c_size_t]),
     'qfb_plan_upload': (c_int, [c_void_p, c_size_t, POINTER(c_void_p), c_void_p]),
     'qfb_plan_launch': (c_int, [c_void_p, c_void_p, c_int, c_uint64, c_void_p]),
     'qfb_plan_destroy': (c_int, [c_void_p]),

@@ -6,10 +6,18 @@
  * positions chosen by the planner (gpos[], ascending; the low bits are always included so that every global
  * access is a full 128-byte line). A tile is processed in ROUNDS. In a round each thread holds 2^R amplitudes
  * in registers: R "register bits" (regpos[], tile-bit positions) enumerate the amplitudes of one thread and
- * the remaining M-R tile bits (thrpos[]) enumerate the threads. Ops of a round act on register bits only
- * (dense 1- and 2-bit operators, optionally controlled) or are diagonal (any bit of the full index, including
- * tile-id bits and the rank bits of a sharded state). Between rounds the tile is exchanged through shared
- * memory (XOR-swizzled, see qfb_sweep.cu). Round 0 loads from HBM, the last round stores to HBM.
+ * the remaining M-R tile bits (thrpos[]) enumerate the threads. Ops of a round are
+ *
+ *   G1   dense 1-bit operator on a register bit, optionally controlled
+ *   G2   dense 2-bit operator on two register bits, optionally controlled
+ *   CPH  one term of a diagonal operator in phase-polynomial form: multiply the amplitude by `factor` when all
+ *        bits of a mask are 1. Mask bits may be ANY bit of the full index (register bits, thread bits, tile-id
+ *        bits, rank bits of a sharded state), so diagonal gates never constrain tiling. A term without register
+ *        bits is a per-thread scalar: it is accumulated into one running factor and applied once per round.
+ *
+ * Controls are split the same way: `reg_cmask` over the register index, `idx_cmask` over the full index.
+ * Between rounds the tile is exchanged through shared memory (XOR-swizzled, see qfb_sweep.cu). Round 0 loads
+ * from HBM, the last round stores to HBM.
  *
  * All records are multiples of 16 bytes; integers little endian. The Python planner
  * (quantumflow_b200/planner.py) writes this layout with struct.pack; keep the two in sync.
@@ -19,13 +27,12 @@
 #include <stdint.h>
 
 #define QFB_PLAN_MAGIC 0x50424651u /* "QFBP" */
-#define QFB_PLAN_VERSION 2u
+#define QFB_PLAN_VERSION 3u
 #define QFB_PLAN_REG_BITS 4
 #define QFB_PLAN_MAX_TILE_BITS 13
 #define QFB_PLAN_MIN_TILE_BITS 5
 #define QFB_PLAN_MAX_HOLES 48
 #define QFB_PLAN_MAX_SWEEP_BYTES (40 * 1024)
-#define QFB_PLAN_MAX_DIAG_BITS 6
 
 typedef struct {
     uint32_t magic;
@@ -51,36 +58,40 @@ typedef struct {
     uint32_t bytes;     /* whole round record including this header */
     uint8_t regpos[4];  /* tile-bit position of register bit i */
     uint8_t thrpos[12]; /* tile-bit position of thread bit t, t < M-R */
-    uint8_t pad[8];
+    uint8_t has_scalar; /* 1 when the round holds CPH terms without register bits */
+    uint8_t pad[7];
 } qfb_round_header; /* 32 bytes */
 
-enum { QFB_OP_G1 = 1, QFB_OP_G2 = 2, QFB_OP_D = 3 };
+enum { QFB_OP_G1 = 1, QFB_OP_G2 = 2, QFB_OP_CPH = 3 };
 /* kinds of QFB_OP_G1 (structure of the 2x2 operator, chosen by the planner to save FP64 work) */
 enum {
     QFB_G1_GENERAL = 0,
-    QFB_G1_REAL = 1,     /* all entries real (H, RY) */
+    QFB_G1_REAL = 1,     /* all entries real (RY) */
     QFB_G1_RXLIKE = 2,   /* real diagonal, imaginary off-diagonal (RX) */
     QFB_G1_SWAPX = 3,    /* Pauli X: swap, no arithmetic */
-    QFB_G1_ANTIDIAG = 4  /* zero diagonal (Y, phased X) */
+    QFB_G1_ANTIDIAG = 4, /* zero diagonal (Y, phased X) */
+    QFB_G1_HLIKE = 5     /* h * [[+-1, +-1], [+-1, +-1]] (Hadamard): sums first, one multiply, so that
+                            destructive interference gives exact zeros like the reference's h*x + h*y */
 };
+/* kinds of QFB_OP_CPH */
+enum { QFB_CPH_FACTOR = 0, QFB_CPH_NEG = 1 /* factor == -1: sign flip, no arithmetic */ };
 
 typedef struct {
     uint8_t type;
     uint8_t kind;
     uint8_t j0;        /* register bit of gate qubit 0 (MSB of the operator index) */
     uint8_t j1;        /* register bit of gate qubit 1 (G2 only; j0 > j1) */
-    uint8_t reg_cmask; /* control mask over the register index */
-    uint8_t nb;        /* QFB_OP_D: number of table bits */
+    uint8_t reg_cmask; /* control / phase mask over the register index */
+    uint8_t pad;
     uint16_t bytes;    /* whole op record including this header */
-    uint64_t idx_cmask; /* control mask over thread-level bits of the FULL index (incl. rank bits) */
+    uint64_t idx_cmask; /* control / phase mask over thread-level bits of the FULL index (incl. rank bits) */
 } qfb_op_header; /* 16 bytes */
 
 /* payloads (follow the header)
- *   G1: double m[8]                 row-major 2x2 complex                         (64 B)
- *   G2: double m[32]; uint32 nzmask; uint32 pad[3]   row-major 4x4 complex, bit (4r+c) of nzmask set
- *                                   when entry (r,c) is non-zero                  (272 B)
- *   D : uint8 pos[8]; uint8 econtrib[4]; uint8 pad[4]; double table[2 << nb]
- *       pos[q]     full-index position of table bit q when it is thread-level, 0xFF otherwise
- *       econtrib[i] weight (1 << (nb-1-q)) contributed by register bit i, 0 if it is not a table bit
+ *   G1 : double m[8]   row-major 2x2 complex (64 B). HLIKE: m[0] = h, signs packed in m[1]'s place are NOT used:
+ *                      the kernel reads the signs of the four real parts.
+ *   G2 : double m[32]; uint32 nzmask; uint32 pad[3]   row-major 4x4 complex, bit (4r+c) of nzmask set when
+ *                      entry (r,c) is non-zero (272 B)
+ *   CPH: double factor[2]  (16 B)
  */
 #endif

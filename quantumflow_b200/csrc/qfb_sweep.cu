@@ -50,56 +50,62 @@ __device__ __forceinline__ uint32_t pick_xor(const uint32_t (&s)[R], int e) {
     return r;
 }
 
-// ---- 1-bit operator on register bit J ----
-template <int J>
+// In-place complex product a *= f (two temporaries, no register shuffling at the join points)
+__device__ __forceinline__ void cmul_inplace(c128 &a, double fr, double fi) {
+    const double t0 = fi * a.im, t1 = fi * a.re;
+    a.re = fma(fr, a.re, -t0);
+    a.im = fma(fr, a.im, t1);
+}
+__device__ __forceinline__ double flip_sign(double x) {
+    return __longlong_as_double(__double_as_longlong(x) ^ (long long)0x8000000000000000ull);
+}
+
+// ---- 1-bit operator on register bit J; RC: honour the register control mask ----
+template <int J, bool RC>
 __device__ __forceinline__ void g1_apply(c128 (&a)[NE], const double *__restrict__ m, int kind, uint32_t rc) {
-    if (kind == QFB_G1_SWAPX) {
-#pragma unroll
-        for (int p = 0; p < NE / 2; ++p) {
-            const int e0 = ((p >> J) << (J + 1)) | (p & ((1 << J) - 1)), e1 = e0 | (1 << J);
-            if ((e0 & rc) != rc) continue;
-            const c128 t = a[e0];
-            a[e0] = a[e1];
-            a[e1] = t;
+#define QFB_PAIR_LOOP                                                                      \
+    _Pragma("unroll") for (int p = 0; p < NE / 2; ++p) {                                   \
+        const int e0 = ((p >> J) << (J + 1)) | (p & ((1 << J) - 1)), e1 = e0 | (1 << J);   \
+        if (RC && (e0 & rc) != rc) continue;
+    if (!RC && kind == QFB_G1_HLIKE) {  // controlled operators only come as SWAPX or GENERAL
+        const double h0 = m[0], r0 = m[1], h1 = m[4], r1 = m[5];  // out0 = h0 (x + r0 y), out1 = h1 (x + r1 y)
+        QFB_PAIR_LOOP
+            const c128 x = a[e0], y = a[e1];
+            a[e0] = cmake(h0 * fma(r0, y.re, x.re), h0 * fma(r0, y.im, x.im));
+            a[e1] = cmake(h1 * fma(r1, y.re, x.re), h1 * fma(r1, y.im, x.im));
         }
-    } else if (kind == QFB_G1_REAL) {
+    } else if (!RC && kind == QFB_G1_REAL) {
         const double m00 = m[0], m01 = m[2], m10 = m[4], m11 = m[6];
-#pragma unroll
-        for (int p = 0; p < NE / 2; ++p) {
-            const int e0 = ((p >> J) << (J + 1)) | (p & ((1 << J) - 1)), e1 = e0 | (1 << J);
-            if ((e0 & rc) != rc) continue;
+        QFB_PAIR_LOOP
             const c128 x = a[e0], y = a[e1];
             a[e0] = cmake(fma(m00, x.re, m01 * y.re), fma(m00, x.im, m01 * y.im));
             a[e1] = cmake(fma(m10, x.re, m11 * y.re), fma(m10, x.im, m11 * y.im));
         }
-    } else if (kind == QFB_G1_RXLIKE) {
+    } else if (!RC && kind == QFB_G1_RXLIKE) {
         const double d0 = m[0], o01 = m[3], o10 = m[5], d1 = m[6];
-#pragma unroll
-        for (int p = 0; p < NE / 2; ++p) {
-            const int e0 = ((p >> J) << (J + 1)) | (p & ((1 << J) - 1)), e1 = e0 | (1 << J);
-            if ((e0 & rc) != rc) continue;
+        QFB_PAIR_LOOP
             const c128 x = a[e0], y = a[e1];
             // (d0) x + (i o01) y ; (i o10) x + (d1) y
             a[e0] = cmake(fma(d0, x.re, -o01 * y.im), fma(d0, x.im, o01 * y.re));
             a[e1] = cmake(fma(d1, y.re, -o10 * x.im), fma(d1, y.im, o10 * x.re));
         }
-    } else if (kind == QFB_G1_ANTIDIAG) {
-        const c128 m01 = cmake(m[2], m[3]), m10 = cmake(m[4], m[5]);
-#pragma unroll
-        for (int p = 0; p < NE / 2; ++p) {
-            const int e0 = ((p >> J) << (J + 1)) | (p & ((1 << J) - 1)), e1 = e0 | (1 << J);
-            if ((e0 & rc) != rc) continue;
+    } else if (kind == QFB_G1_SWAPX) {
+        QFB_PAIR_LOOP
+            const c128 t = a[e0];
+            a[e0] = a[e1];
+            a[e1] = t;
+        }
+    } else if (!RC && kind == QFB_G1_ANTIDIAG) {
+        const double ar = m[2], ai = m[3], br = m[4], bi = m[5];
+        QFB_PAIR_LOOP
             const c128 x = a[e0], y = a[e1];
-            a[e0] = cmul(m01, y);
-            a[e1] = cmul(m10, x);
+            a[e0] = cmake(fma(ar, y.re, -ai * y.im), fma(ar, y.im, ai * y.re));
+            a[e1] = cmake(fma(br, x.re, -bi * x.im), fma(br, x.im, bi * x.re));
         }
     } else {
         const c128 m00 = cmake(m[0], m[1]), m01 = cmake(m[2], m[3]), m10 = cmake(m[4], m[5]),
                    m11 = cmake(m[6], m[7]);
-#pragma unroll
-        for (int p = 0; p < NE / 2; ++p) {
-            const int e0 = ((p >> J) << (J + 1)) | (p & ((1 << J) - 1)), e1 = e0 | (1 << J);
-            if ((e0 & rc) != rc) continue;
+        QFB_PAIR_LOOP
             const c128 x = a[e0], y = a[e1];
             c128 u = cmul(m00, x), v = cmul(m10, x);
             cfma(u, m01, y);
@@ -108,6 +114,7 @@ __device__ __forceinline__ void g1_apply(c128 (&a)[NE], const double *__restrict
             a[e1] = v;
         }
     }
+#undef QFB_PAIR_LOOP
 }
 
 // ---- 2-bit operator on register bits J0 > J1 (operator index = bit(J0) << 1 | bit(J1)) ----
@@ -136,24 +143,37 @@ __device__ __forceinline__ void g2_apply(c128 (&a)[NE], const double *__restrict
     }
 }
 
-// ---- diagonal operator over any bits of the full index ----
-__device__ __forceinline__ void d_apply(c128 (&a)[NE], const uint8_t *__restrict__ payload, int nb,
-                                        uint64_t tfull) {
-    const uint8_t *pos = payload;
-    const c128 *table = reinterpret_cast<const c128 *>(payload + 16);
-    uint32_t selt = 0;
-    for (int q = 0; q < nb; ++q) {
-        const uint32_t p = pos[q];
-        if (p != 0xFFu) selt |= (uint32_t)((tfull >> p) & 1ull) << (nb - 1 - q);
-    }
-    const uint32_t ec[R] = {payload[8], payload[9], payload[10], payload[11]};
-    if ((ec[0] | ec[1] | ec[2] | ec[3]) == 0u) {
-        const c128 d = table[selt];
+// ---- controlled phase on the register elements whose index contains MASK ----
+template <int MASK>
+__device__ __forceinline__ void cph_apply(c128 (&a)[NE], double fr, double fi, bool neg) {
+    if (neg) {
 #pragma unroll
-        for (int e = 0; e < NE; ++e) a[e] = cmul(d, a[e]);
+        for (int e = 0; e < NE; ++e)
+            if ((e & MASK) == MASK) a[e] = cmake(flip_sign(a[e].re), flip_sign(a[e].im));
     } else {
 #pragma unroll
-        for (int e = 0; e < NE; ++e) a[e] = cmul(table[selt | pick(ec, e)], a[e]);
+        for (int e = 0; e < NE; ++e)
+            if ((e & MASK) == MASK) cmul_inplace(a[e], fr, fi);
+    }
+}
+
+__device__ __forceinline__ void cph_dispatch(c128 (&a)[NE], uint32_t rc, double fr, double fi, bool neg) {
+    switch (rc) {
+        case 1: cph_apply<1>(a, fr, fi, neg); break;
+        case 2: cph_apply<2>(a, fr, fi, neg); break;
+        case 3: cph_apply<3>(a, fr, fi, neg); break;
+        case 4: cph_apply<4>(a, fr, fi, neg); break;
+        case 5: cph_apply<5>(a, fr, fi, neg); break;
+        case 6: cph_apply<6>(a, fr, fi, neg); break;
+        case 7: cph_apply<7>(a, fr, fi, neg); break;
+        case 8: cph_apply<8>(a, fr, fi, neg); break;
+        case 9: cph_apply<9>(a, fr, fi, neg); break;
+        case 10: cph_apply<10>(a, fr, fi, neg); break;
+        case 11: cph_apply<11>(a, fr, fi, neg); break;
+        case 12: cph_apply<12>(a, fr, fi, neg); break;
+        case 13: cph_apply<13>(a, fr, fi, neg); break;
+        case 14: cph_apply<14>(a, fr, fi, neg); break;
+        default: cph_apply<15>(a, fr, fi, neg); break;
     }
 }
 
@@ -221,28 +241,47 @@ sweep_kernel(c128 *__restrict__ state, const uint8_t *__restrict__ rec_g, uint32
             }
 
             const uint64_t tfull = hi_shifted | gb | tg;
+            double phr = 1.0, phi = 0.0;  // running per-thread scalar phase of this round
             const uint8_t *op = rp + sizeof(qfb_round_header);
             const int nops = (int)rh->nops;
             for (int o = 0; o < nops; ++o) {
-                const qfb_op_header *oh = reinterpret_cast<const qfb_op_header *>(op);
-                const uint8_t *payload = op + sizeof(qfb_op_header);
-                const int type = oh->type;
-                if (type == QFB_OP_D) {
-                    d_apply(a, payload, oh->nb, tfull);
-                } else if ((tfull & oh->idx_cmask) == oh->idx_cmask) {
-                    const double *m = reinterpret_cast<const double *>(payload);
-                    const uint32_t rc = oh->reg_cmask;
+                const uint4 hw = *reinterpret_cast<const uint4 *>(op);
+                const uint32_t type = hw.x & 0xffu, kind = (hw.x >> 8) & 0xffu, j0 = (hw.x >> 16) & 0xffu,
+                               j1 = hw.x >> 24, rc = hw.y & 0xffu, bytes = hw.y >> 16;
+                const uint64_t cm = ((uint64_t)hw.w << 32) | hw.z;
+                const double *m = reinterpret_cast<const double *>(op + sizeof(qfb_op_header));
+                const bool on = (tfull & cm) == cm;
+                if (type == QFB_OP_CPH) {
+                    if (on) {
+                        const double fr = m[0], fi = m[1];
+                        if (rc == 0u) {
+                            const double t0 = fi * phi, t1 = fi * phr;
+                            phr = fma(fr, phr, -t0);
+                            phi = fma(fr, phi, t1);
+                        } else {
+                            cph_dispatch(a, rc, fr, fi, kind == QFB_CPH_NEG);
+                        }
+                    }
+                } else if (on) {
                     if (type == QFB_OP_G1) {
-                        const int kind = oh->kind;
-                        switch (oh->j0) {
-                            case 0: g1_apply<0>(a, m, kind, rc); break;
-                            case 1: g1_apply<1>(a, m, kind, rc); break;
-                            case 2: g1_apply<2>(a, m, kind, rc); break;
-                            default: g1_apply<3>(a, m, kind, rc); break;
+                        if (rc == 0u) {
+                            switch (j0) {
+                                case 0: g1_apply<0, false>(a, m, kind, 0u); break;
+                                case 1: g1_apply<1, false>(a, m, kind, 0u); break;
+                                case 2: g1_apply<2, false>(a, m, kind, 0u); break;
+                                default: g1_apply<3, false>(a, m, kind, 0u); break;
+                            }
+                        } else {
+                            switch (j0) {
+                                case 0: g1_apply<0, true>(a, m, kind, rc); break;
+                                case 1: g1_apply<1, true>(a, m, kind, rc); break;
+                                case 2: g1_apply<2, true>(a, m, kind, rc); break;
+                                default: g1_apply<3, true>(a, m, kind, rc); break;
+                            }
                         }
                     } else {
-                        const uint32_t nz = *reinterpret_cast<const uint32_t *>(payload + 256);
-                        switch (oh->j0 * 4 + oh->j1) {
+                        const uint32_t nz = *reinterpret_cast<const uint32_t *>(op + sizeof(qfb_op_header) + 256);
+                        switch (j0 * 4 + j1) {
                             case 1 * 4 + 0: g2_apply<1, 0>(a, m, nz, rc); break;
                             case 2 * 4 + 0: g2_apply<2, 0>(a, m, nz, rc); break;
                             case 2 * 4 + 1: g2_apply<2, 1>(a, m, nz, rc); break;
@@ -252,7 +291,11 @@ sweep_kernel(c128 *__restrict__ state, const uint8_t *__restrict__ rec_g, uint32
                         }
                     }
                 }
-                op += oh->bytes;
+                op += bytes;
+            }
+            if (rh->has_scalar) {
+#pragma unroll
+                for (int e = 0; e < NE; ++e) cmul_inplace(a[e], phr, phi);
             }
 
             if (round + 1 < nrounds) {
@@ -345,7 +388,7 @@ static int validate_plan(const uint8_t *p, size_t nbytes, std::vector<SweepInfo>
                 QFB_CHECK_ARG(oh.bytes % 16 == 0 && oh.bytes >= sizeof(oh) && ooff + oh.bytes <= rend,
                               "plan: op bad size");
                 if (oh.type == QFB_OP_G1) {
-                    QFB_CHECK_ARG(oh.bytes == 16 + 64 && oh.j0 < R && oh.kind <= QFB_G1_ANTIDIAG &&
+                    QFB_CHECK_ARG(oh.bytes == 16 + 64 && oh.j0 < R && oh.kind <= QFB_G1_HLIKE &&
                                       !((oh.reg_cmask >> oh.j0) & 1) && oh.reg_cmask < NE,
                                   "plan: bad G1 op");
                 } else if (oh.type == QFB_OP_G2) {
@@ -353,10 +396,10 @@ static int validate_plan(const uint8_t *p, size_t nbytes, std::vector<SweepInfo>
                                       !((oh.reg_cmask >> oh.j0) & 1) && !((oh.reg_cmask >> oh.j1) & 1) &&
                                       oh.reg_cmask < NE,
                                   "plan: bad G2 op");
-                } else if (oh.type == QFB_OP_D) {
-                    QFB_CHECK_ARG(oh.nb >= 1 && oh.nb <= QFB_PLAN_MAX_DIAG_BITS &&
-                                      oh.bytes == 16 + 16 + (32u << oh.nb),
-                                  "plan: bad D op");
+                } else if (oh.type == QFB_OP_CPH) {
+                    QFB_CHECK_ARG(oh.bytes == 16 + 16 && oh.reg_cmask < NE && oh.kind <= QFB_CPH_NEG &&
+                                      (oh.reg_cmask != 0 || rh.has_scalar == 1),
+                                  "plan: bad CPH op");
                 } else {
                     QFB_CHECK_ARG(false, "plan: unknown op type %u", oh.type);
                 }
@@ -427,6 +470,12 @@ constexpr uint32_t HANDLE_MAGIC = 0x48424651u;
 using namespace qfb;
 
 extern "C" {
+
+int qfb_plan_validate(const void *plan_host, size_t plan_bytes) {
+    std::vector<SweepInfo> sweeps;
+    int nbits = 0, M = 0;
+    return validate_plan((const uint8_t *)plan_host, plan_bytes, sweeps, nbits, M);
+}
 
 int qfb_plan_upload(const void *plan_host, size_t plan_bytes, void **handle_out, void *stream) {
     QFB_CHECK_ARG(handle_out, "qfb_plan_upload: null handle_out");

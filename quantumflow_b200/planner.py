@@ -24,19 +24,19 @@ import numpy as np
 from . import classify
 
 PLAN_MAGIC = 0x50424651
-PLAN_VERSION = 2
+PLAN_VERSION = 3
 REG_BITS = 4
 MAX_TILE_BITS = 13
 MIN_TILE_BITS = 5
 MAX_HOLES = 48
 MAX_SWEEP_BYTES = 40 * 1024
-MAX_DIAG_BITS = 6
-OP_G1, OP_G2, OP_D = 1, 2, 3
+MAX_DIAG_BITS = 5
+OP_G1, OP_G2, OP_CPH = 1, 2, 3
 
 DEFAULT_TILE_BITS = 12
 DEFAULT_LOW_BITS = 3
 # cost units ~ FP64 work per amplitude relative to a dense 1-bit operator
-COST = {'G1': 1.0, 'G1_cheap': 0.5, 'G1_swap': 0.15, 'G2': 2.5, 'D': 0.5}
+COST = {'G1': 1.0, 'G1_cheap': 0.5, 'G1_swap': 0.2, 'G2': 2.5, 'P': 0.15}
 DEFAULT_MAX_COST = 28.0
 
 
@@ -66,45 +66,87 @@ class Fallback:
         self.bits = tuple(int(b) for b in bits)
 
 
+def phase_polynomial(table: np.ndarray, k: int):
+    """Diagonal operator -> list of (qubit subset mask over the k table bits, factor) with
+    d[s] = prod over subsets T of s of factor[T]; bit q of the table index has weight 1 << (k-1-q).
+    Requires every entry to be non-zero."""
+    phi = {}
+    for s in range(1 << k):
+        val = complex(table[s])
+        for t in range(s):
+            if (t & s) == t and t in phi:
+                val = val / phi[t]
+        phi[s] = val
+    return phi
+
+
 def classify_op(mat: np.ndarray, bits: Sequence[int], gate_index: int = -1):
-    """Turn (matrix, bits) into a POp, a Fallback, or None (identity)."""
+    """Turn (matrix, bits) into a list of POps, a Fallback, or None (identity)."""
     k = len(bits)
     mat = classify.as_matrix(mat, k)
     if classify.is_identity(mat):
         return None
     if classify.is_diagonal(mat):
-        if k > MAX_DIAG_BITS:
-            return Fallback(mat, bits)
-        # drop bits the table does not depend on
         table = np.ascontiguousarray(np.diagonal(mat))
-        keep = []
-        t = table.reshape([2] * k)
-        for q in range(k):
-            a, b = np.take(t, 0, axis=q), np.take(t, 1, axis=q)
-            if not np.array_equal(a, b):
-                keep.append(q)
-        if len(keep) < k:
-            idx = tuple(slice(None) if q in keep else 0 for q in range(k))
-            table = np.ascontiguousarray(t[idx]).reshape(-1)
-            bits = [bits[q] for q in keep]
-            if not keep:   # global phase
-                return POp('D', dbits=(), mat=table.reshape(1), cost=COST['D'], gate_index=gate_index)
-        return POp('D', dbits=bits, mat=table, cost=COST['D'], gate_index=gate_index)
+        if np.all(table != 0) and k <= MAX_DIAG_BITS:
+            terms = []
+            for sub, factor in phase_polynomial(table, k).items():
+                if factor == 1:
+                    continue
+                tbits = [bits[q] for q in range(k) if (sub >> (k - 1 - q)) & 1]
+                terms.append(POp('P', dbits=tbits, mat=complex(factor), cost=COST['P'], gate_index=gate_index))
+            return terms or None
+        if k > 2:
+            return Fallback(mat, bits)
+        # singular diagonal (projectors): a dense 1- or 2-bit operator
+        cost = COST['G1_cheap'] if k == 1 else COST['G2'] * 0.25 + 0.3
+        return [POp('G', mix=bits, ctrl=(), mat=mat, cost=cost, gate_index=gate_index)]
     controls, targets, reduced = ([], list(range(k)), mat) if k == 1 else classify.peel_controls(mat, k)
     if len(targets) > 2:
         return Fallback(mat, bits)
     cbits = [bits[q] for q in controls]
     tbits = [bits[q] for q in targets]
     if len(targets) == 1:
-        kind = classify.g1_kind(reduced)
-        if classify.is_diagonal(reduced):
-            # controlled phase that was not caught as fully diagonal cannot happen (diag checked first)
-            pass
-        cost = COST['G1_swap'] if kind == 3 else (COST['G1_cheap'] if kind in (1, 2, 4) else COST['G1'])
-        return POp('G', mix=tbits, ctrl=cbits, mat=reduced, cost=cost, gate_index=gate_index)
+        kind = g1_kind(reduced, bool(cbits))
+        cost = COST['G1_swap'] if kind == 3 else (COST['G1_cheap'] if kind in (1, 2, 4, 5) else COST['G1'])
+        return [POp('G', mix=tbits, ctrl=cbits, mat=reduced, cost=cost, gate_index=gate_index)]
     nnz = int(np.count_nonzero(reduced))
-    return POp('G', mix=tbits, ctrl=cbits, mat=reduced, cost=COST['G2'] * max(nnz, 4) / 16.0 + 0.3,
-               gate_index=gate_index)
+    return [POp('G', mix=tbits, ctrl=cbits, mat=reduced, cost=COST['G2'] * max(nnz, 4) / 16.0 + 0.3,
+                gate_index=gate_index)]
+
+
+def g1_kind(m: np.ndarray, controlled: bool) -> int:
+    """QFB_G1_* kind of a 2x2 operator; controlled operators only use SWAPX / GENERAL (fewer kernel variants)."""
+    kind = classify.g1_kind(m)
+    m = np.asarray(m).reshape(2, 2)
+    if kind == 1 and np.all(m.real != 0) and len({abs(v) for v in m.real.reshape(-1)}) == 1:
+        kind = 5   # HLIKE
+    if controlled and kind not in (0, 3):
+        kind = 0
+    return kind
+
+
+def merge_phase_terms(ops: List[POp]) -> List[POp]:
+    """Multiply together phase terms with the same bit mask when no mixing operator on those bits sits between
+    them (phase terms commute with each other and with controls). Terms that become 1 are dropped."""
+    out: List[POp] = []
+    open_terms: Dict[frozenset, int] = {}
+    for op in ops:
+        if op.kind == 'P':
+            key = op.diagset
+            pos = open_terms.get(key)
+            if pos is not None:
+                prev = out[pos]
+                out[pos] = POp('P', dbits=prev.dbits, mat=prev.mat * op.mat, cost=prev.cost,
+                               gate_index=prev.gate_index)
+            else:
+                open_terms[key] = len(out)
+                out.append(op)
+        else:
+            for key in [k for k in open_terms if k & op.mixset]:
+                del open_terms[key]
+            out.append(op)
+    return [op for op in out if not (op.kind == 'P' and op.mat == 1)]
 
 
 def _conflicts(op: POp, def_any: set, def_mix: set) -> bool:
@@ -161,8 +203,7 @@ class Planner:
                     ok = False
             if ok and cost + op.cost > self.max_cost and chosen:
                 ok = False
-            opbytes = 16 + (64 if (op.kind == 'G' and len(op.mix) == 1) else
-                            272 if op.kind == 'G' else 16 + (32 << max(1, len(op.dbits))))
+            opbytes = 16 + (64 if (op.kind == 'G' and len(op.mix) == 1) else 272 if op.kind == 'G' else 16)
             if ok and nbytes + opbytes + 32 * 8 > MAX_SWEEP_BYTES:
                 ok = False
                 full = True
@@ -263,7 +304,7 @@ class Planner:
             chosen, remaining, tile = self._form_sweep(remaining)
             if not chosen:
                 raise RuntimeError('planner made no progress')
-            sweep = SweepPlan(tile, chosen)
+            sweep = SweepPlan(tile, merge_phase_terms(chosen))
             self._form_rounds(sweep)
             sweeps.append(sweep)
         return sweeps
@@ -277,26 +318,19 @@ class Planner:
             p = pos_of.get(bit)
             return reg_of.get(p) if p is not None else None
 
-        if op.kind == 'D':
-            nb = len(op.dbits)
-            if nb == 0:   # global phase: a 1-bit table on bit 0 with equal entries
-                table = np.array([op.mat[0], op.mat[0]], dtype=np.complex128)
-                dbits = (0,)
-                nb = 1
-            else:
-                table = np.asarray(op.mat, dtype=np.complex128)
-                dbits = op.dbits
-            pos = [0xFF] * 8
-            econ = [0] * 4
-            for q, bit in enumerate(dbits):
+        if op.kind == 'P':
+            reg_cmask = 0
+            idx_cmask = 0
+            for bit in op.dbits:
                 ri = reg_index(bit)
                 if ri is None:
-                    pos[q] = bit
+                    idx_cmask |= 1 << bit
                 else:
-                    econ[ri] = 1 << (nb - 1 - q)
-            payload = struct.pack('<8B4B4x', *pos, *econ) + table.tobytes()
-            header = struct.pack('<BBBBBBHQ', OP_D, 0, 0, 0, 0, nb, 16 + len(payload), 0)
-            return header + payload
+                    reg_cmask |= 1 << ri
+            factor = complex(op.mat)
+            kind = 1 if (factor == -1 and reg_cmask != 0) else 0
+            payload = struct.pack('<dd', factor.real, factor.imag)
+            return struct.pack('<BBBBBBHQ', OP_CPH, kind, 0, 0, reg_cmask, 0, 16 + len(payload), idx_cmask) + payload
         reg_cmask = 0
         idx_cmask = 0
         for c in op.ctrl:
@@ -307,9 +341,13 @@ class Planner:
                 reg_cmask |= 1 << ri
         if len(op.mix) == 1:
             j0 = reg_index(op.mix[0])
-            mat = np.ascontiguousarray(op.mat, dtype=np.complex128).reshape(2, 2)
-            kind = classify.g1_kind(mat)
-            payload = mat.tobytes()
+            mat = np.array(op.mat, dtype=np.complex128).reshape(2, 2)
+            kind = g1_kind(mat, bool(op.ctrl))
+            if kind == 5:   # HLIKE: out0 = h0 (x + r0 y), out1 = h1 (x + r1 y); ratios ride in the imaginary slots
+                h0, h1 = mat[0, 0].real, mat[1, 0].real
+                mat[0, 0] = complex(h0, mat[0, 1].real / h0)
+                mat[1, 0] = complex(h1, mat[1, 1].real / h1)
+            payload = np.ascontiguousarray(mat).tobytes()
             header = struct.pack('<BBBBBBHQ', OP_G1, kind, j0, 0, reg_cmask, 0, 16 + len(payload), idx_cmask)
             return header + payload
         j0, j1 = reg_index(op.mix[0]), reg_index(op.mix[1])
@@ -333,10 +371,13 @@ class Planner:
             rounds_blob = b''
             nops = 0
             for regs, thr, ops in sweep.rounds:
-                ops_blob = b''.join(self._emit_op(op, sweep, regs) for op in ops)
+                emitted = [self._emit_op(op, sweep, regs) for op in ops]
+                ops_blob = b''.join(emitted)
                 nops += len(ops)
+                has_scalar = int(any(e[0] == OP_CPH and e[4] == 0 for e in emitted))
                 thrpad = list(thr) + [0] * (12 - len(thr))
-                rounds_blob += struct.pack('<II4B12B8x', len(ops), 32 + len(ops_blob), *regs, *thrpad) + ops_blob
+                rounds_blob += struct.pack('<II4B12BB7x', len(ops), 32 + len(ops_blob), *regs, *thrpad,
+                                           has_scalar) + ops_blob
             holes = [b for b in range(self.nbits) if b not in sweep.tile]
             gpos = list(sweep.tile) + [0] * (16 - len(sweep.tile))
             hole = holes + [0] * (MAX_HOLES - len(holes))
@@ -375,7 +416,8 @@ def build_segments(nbits: int, bitops: Sequence[Tuple[np.ndarray, Sequence[int]]
         if pending:
             sweeps = planner.plan(pending)
             blob = planner.serialise(sweeps)
-            segments.append(Segment('plan', blob=blob, nsweeps=len(sweeps), nops=len(pending),
+            segments.append(Segment('plan', blob=blob, nsweeps=len(sweeps),
+                                    nops=len({op.gate_index for op in pending}),
                                     nrounds=sum(len(s.rounds) for s in sweeps)))
             pending.clear()
 
@@ -387,7 +429,7 @@ def build_segments(nbits: int, bitops: Sequence[Tuple[np.ndarray, Sequence[int]]
             flush()
             segments.append(Segment('op', mat=item.mat, bits=item.bits, nsweeps=1, nops=1))
         else:
-            pending.append(item)
+            pending.extend(item)
     flush()
     return segments
 

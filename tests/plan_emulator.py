@@ -20,7 +20,7 @@ def swz(idx):
 
 def parse(blob: bytes):
     magic, version, nbits, M, rbits, nsweeps, total = struct.unpack_from('<IIIIIIQ', blob, 0)
-    assert magic == 0x50424651 and version == 2 and rbits == R and total == len(blob)
+    assert magic == 0x50424651 and version == 3 and rbits == R and total == len(blob)
     off = 32
     sweeps = []
     for _ in range(nsweeps):
@@ -33,6 +33,7 @@ def parse(blob: bytes):
             rn, rbytes = struct.unpack_from('<II', blob, roff)
             regpos = list(blob[roff + 8: roff + 12])
             thrpos = list(blob[roff + 12: roff + 12 + (M - R)])
+            has_scalar = blob[roff + 24]
             ooff = roff + 32
             ops = []
             for _o in range(rn):
@@ -42,7 +43,7 @@ def parse(blob: bytes):
                                 payload=payload))
                 ooff += obytes
             assert ooff == roff + rbytes
-            rounds.append(dict(regpos=regpos, thrpos=thrpos, ops=ops))
+            rounds.append(dict(regpos=regpos, thrpos=thrpos, ops=ops, has_scalar=has_scalar))
             roff += rbytes
         assert roff == off + size
         sweeps.append(dict(gpos=gpos, hole=hole, rounds=rounds))
@@ -71,6 +72,9 @@ def _apply_g1(a, op):
         elif op['kind'] == 4:    # ANTIDIAG
             a[e0] = m[0, 1] * y
             a[e1] = m[1, 0] * x
+        elif op['kind'] == 5:    # HLIKE: ratios ride in the imaginary slots of m00 / m10
+            a[e0] = m[0, 0].real * (x + m[0, 0].imag * y)
+            a[e1] = m[1, 0].real * (x + m[1, 0].imag * y)
         else:
             a[e0] = m[0, 0] * x + m[0, 1] * y
             a[e1] = m[1, 0] * x + m[1, 1] * y
@@ -98,21 +102,22 @@ def _apply_g2(a, op):
             a[ids[r]] = acc
 
 
-def _apply_d(a, op, tfull):
-    nb = op['nb']
-    pos = op['payload'][0:8]
-    ec = op['payload'][8:12]
-    table = np.frombuffer(op['payload'], dtype=np.complex128, count=1 << nb, offset=16)
-    selt = 0
-    for q in range(nb):
-        if pos[q] != 0xFF:
-            selt |= ((tfull >> pos[q]) & 1) << (nb - 1 - q)
+def _apply_cph(a, op, on, scalar):
+    """Returns the updated per-thread scalar."""
+    factor = complex(*struct.unpack_from('<dd', op['payload'], 0))
+    rc = op['reg_cmask']
+    if not on:
+        return scalar
+    if rc == 0:
+        return scalar * factor
     for e in range(NE):
-        sel = selt
-        for i in range(R):
-            if (e >> i) & 1:
-                sel |= ec[i]
-        a[e] = table[sel] * a[e]
+        if (e & rc) == rc:
+            if op['kind'] == 1:
+                assert factor == -1
+                a[e] = -a[e]
+            else:
+                a[e] = factor * a[e]
+    return scalar
 
 
 def conflict_degree(plan_round, M):
@@ -178,14 +183,22 @@ def execute(blob: bytes, state: np.ndarray, index_hi: int = 0, check_layout: boo
                         else:
                             a[e] = tile[swz(tb | toff)]
                     tfull = (index_hi << nbits) | gb | tg
+                    scalar = 1.0 + 0j
                     for op in rd['ops']:
+                        on = (tfull & op['idx_cmask']) == op['idx_cmask']
                         if op['type'] == 3:
-                            _apply_d(a, op, tfull)
-                        elif (tfull & op['idx_cmask']) == op['idx_cmask']:
+                            assert op['reg_cmask'] != 0 or rd['has_scalar'] == 1
+                            scalar = _apply_cph(a, op, on, scalar)
+                        elif on:
                             if op['type'] == 1:
+                                assert op['reg_cmask'] == 0 or op['kind'] in (0, 3)
                                 _apply_g1(a, op)
                             else:
                                 _apply_g2(a, op)
+                    if rd['has_scalar']:
+                        a = a * scalar
+                    else:
+                        assert scalar == 1
                     regs_all[tid] = a
                 # all threads have read the tile before anyone writes it (the kernel's barriers)
                 for tid in range(T):

@@ -119,7 +119,7 @@ def test_inplace_controls_diag_and_generic_paths(engine):
     # errors: library reports, python raises
     from quantumflow_b200._lib import QfbError
     with pytest.raises(QfbError):
-        engine.apply_operator(dev(psi), np.eye(2), [n])
+        engine.apply_operator(dev(psi), O.gate_matrix('H'), [n])
     with pytest.raises(QfbError):
         engine.apply_operator(dev(psi), m2 := np.ones((4, 4)), [3, 3])
 

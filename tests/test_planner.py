@@ -17,10 +17,21 @@ def bitops_of(specs, n):
     return [(O.gate_matrix(name, params), [n - 1 - q for q in qubits]) for name, params, qubits in specs]
 
 
+def validate_with_library(blob):
+    """The library's own structural validation (host code of qfb_plan_upload; no GPU needed)."""
+    import ctypes
+    from quantumflow_b200 import _lib
+    lib = _lib.load()
+    buf = ctypes.create_string_buffer(blob, len(blob))
+    rc = lib.qfb_plan_validate(ctypes.cast(buf, ctypes.c_void_p), len(blob))
+    assert rc == 0, lib.qfb_last_error()
+
+
 def run_segments(segments, state, index_hi=0):
     state = np.array(state, dtype=np.complex128).reshape(-1)
     for seg in segments:
         if seg.kind == 'plan':
+            validate_with_library(seg.blob)
             state = E.execute(seg.blob, state, index_hi)
         else:
             state = O.tensormul_flat(seg.mat, state, list(seg.bits))
