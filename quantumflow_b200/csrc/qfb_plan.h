@@ -27,7 +27,7 @@
 #include <stdint.h>
 
 #define QFB_PLAN_MAGIC 0x50424651u /* "QFBP" */
-#define QFB_PLAN_VERSION 3u
+#define QFB_PLAN_VERSION 4u
 #define QFB_PLAN_REG_BITS 4
 #define QFB_PLAN_MAX_TILE_BITS 13
 #define QFB_PLAN_MIN_TILE_BITS 5
@@ -54,24 +54,42 @@ typedef struct {
 } qfb_sweep_header; /* 80 bytes */
 
 typedef struct {
+    uint32_t tb;  /* tile-local index contribution (register bits zero) */
+    uint32_t pad;
+    uint64_t tg;  /* the same bits at their index-bit positions */
+} qfb_thread_lut; /* 16 bytes */
+
+#define QFB_PLAN_LUT_LO 16 /* entries indexed by the low 4 thread bits */
+#define QFB_PLAN_LUT_HI 32 /* entries indexed by the remaining (M-R-4 <= 5) thread bits */
+
+typedef struct {
     uint32_t nops;
-    uint32_t bytes;     /* whole round record including this header */
+    uint32_t bytes;     /* whole round record: header + thread LUTs + ops */
     uint8_t regpos[4];  /* tile-bit position of register bit i */
     uint8_t thrpos[12]; /* tile-bit position of thread bit t, t < M-R */
     uint8_t has_scalar; /* 1 when the round holds CPH terms without register bits */
-    uint8_t pad[7];
-} qfb_round_header; /* 32 bytes */
+    uint8_t has_g2;     /* 1 when the round holds G2 ops (selects the kernel variant for the whole plan) */
+    uint8_t pad[6];
+    /* thread id -> (tb, tg) in two table look-ups instead of a per-bit deposit loop:
+     * tb = lut_lo[tid & 15].tb | lut_hi[tid >> 4].tb, same for tg */
+    qfb_thread_lut lut_lo[QFB_PLAN_LUT_LO];
+    qfb_thread_lut lut_hi[QFB_PLAN_LUT_HI];
+} qfb_round_header; /* 32 + 768 bytes */
 
 enum { QFB_OP_G1 = 1, QFB_OP_G2 = 2, QFB_OP_CPH = 3 };
-/* kinds of QFB_OP_G1 (structure of the 2x2 operator, chosen by the planner to save FP64 work) */
+/* kinds of QFB_OP_G1: structure of the 2x2 operator, chosen by the planner to save FP64 work. The "pivoted"
+ * kinds apply the operator divided by its (0,0) entry; the planner multiplies the pivots of a sweep into one
+ * uniform scalar that rides on the sweep's unconditional CPH term. (x, y) = the pair of amplitudes. */
 enum {
-    QFB_G1_GENERAL = 0,
-    QFB_G1_REAL = 1,     /* all entries real (RY) */
-    QFB_G1_RXLIKE = 2,   /* real diagonal, imaginary off-diagonal (RX) */
+    QFB_G1_GENERAL = 0,  /* 16 FP64 per pair */
+    QFB_G1_REAL = 1,     /* all entries real: 8 per pair */
+    QFB_G1_RXLIKE = 2,   /* real diagonal, imaginary off-diagonal: 8 per pair */
     QFB_G1_SWAPX = 3,    /* Pauli X: swap, no arithmetic */
-    QFB_G1_ANTIDIAG = 4, /* zero diagonal (Y, phased X) */
-    QFB_G1_HLIKE = 5     /* h * [[+-1, +-1], [+-1, +-1]] (Hadamard): sums first, one multiply, so that
-                            destructive interference gives exact zeros like the reference's h*x + h*y */
+    QFB_G1_ANTIDIAG = 4, /* zero diagonal (Y, phased X): 8 per pair */
+    QFB_G1_SUMDIFF = 5,  /* pivoted Hadamard-like: x' = x + r0 y, y' = x + r1 y with r = +-1 (m[0], m[1]); sums only,
+                            so destructive interference gives exact zeros like the reference's h*x + h*y: 4 per pair */
+    QFB_G1_ROT_R = 6,    /* pivoted real rotation (RY): x' = x + r y, y' = y + s x  (m[0], m[1]): 4 per pair */
+    QFB_G1_ROT_I = 7     /* pivoted RX-like: x' = x + i a y, y' = y + i b x  (m[0], m[1]): 4 per pair */
 };
 /* kinds of QFB_OP_CPH */
 enum { QFB_CPH_FACTOR = 0, QFB_CPH_NEG = 1 /* factor == -1: sign flip, no arithmetic */ };
@@ -88,8 +106,7 @@ typedef struct {
 } qfb_op_header; /* 16 bytes */
 
 /* payloads (follow the header)
- *   G1 : double m[8]   row-major 2x2 complex (64 B). HLIKE: m[0] = h, signs packed in m[1]'s place are NOT used:
- *                      the kernel reads the signs of the four real parts.
+ *   G1 : double m[8]   row-major 2x2 complex (64 B); pivoted kinds use m[0], m[1] as described above
  *   G2 : double m[32]; uint32 nzmask; uint32 pad[3]   row-major 4x4 complex, bit (4r+c) of nzmask set when
  *                      entry (r,c) is non-zero (272 B)
  *   CPH: double factor[2]  (16 B)

@@ -50,14 +50,51 @@ __device__ __forceinline__ uint32_t pick_xor(const uint32_t (&s)[R], int e) {
     return r;
 }
 
-// In-place complex product a *= f (two temporaries, no register shuffling at the join points)
-__device__ __forceinline__ void cmul_inplace(c128 &a, double fr, double fi) {
-    const double t0 = fi * a.im, t1 = fi * a.re;
-    a.re = fma(fr, a.re, -t0);
-    a.im = fma(fr, a.im, t1);
+// ---------------------------------------------------------------------------------------------------------
+// Two-address FP64 primitives. Every update of a register amplitude goes through one of these: the tied
+// "+d" operand keeps each amplitude component in ONE virtual register for the whole op loop. Written as plain
+// C++ (new SSA value per update) the compiler renames the 2^R amplitudes inside handlers and then re-copies all
+// of them at every merge point of the interpreter loop: 58% of all executed instructions were MOVs in the
+// first profile (profiles/r1_sweep_v1_summary.txt).
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void ip_mul(double &x, double s) {            // x = x * s
+    asm("mul.f64 %0, %0, %1;" : "+d"(x) : "d"(s));
 }
-__device__ __forceinline__ double flip_sign(double x) {
-    return __longlong_as_double(__double_as_longlong(x) ^ (long long)0x8000000000000000ull);
+__device__ __forceinline__ void ip_fma_acc(double &acc, double a, double b) {   // acc = a * b + acc
+    asm("fma.rn.f64 %0, %1, %2, %0;" : "+d"(acc) : "d"(a), "d"(b));
+}
+__device__ __forceinline__ void ip_fma_scale(double &x, double s, double c) {   // x = x * s + c
+    asm("fma.rn.f64 %0, %0, %1, %2;" : "+d"(x) : "d"(s), "d"(c));
+}
+__device__ __forceinline__ void ip_set(double &x, double v) {             // x = v (keeps x's register)
+    asm("mov.f64 %0, %1;" : "+d"(x) : "d"(v));
+}
+__device__ __forceinline__ void ip_neg(double &x) {                       // x = -x (sign-bit flip, ALU pipe)
+    asm("xor.b64 %0, %0, 0x8000000000000000;" : "+d"(x));
+}
+__device__ __forceinline__ void ip_swap(double &x, double &y) {
+    asm("{\n\t.reg .f64 t;\n\tmov.f64 t, %0;\n\tmov.f64 %0, %1;\n\tmov.f64 %1, t;\n\t}" : "+d"(x), "+d"(y));
+}
+// a *= (fr + i fi)
+__device__ __forceinline__ void cmul_inplace(c128 &a, double fr, double fi) {
+    const double t0 = -fi * a.im, t1 = fi * a.re;
+    ip_fma_scale(a.re, fr, t0);
+    ip_fma_scale(a.im, fr, t1);
+}
+// (x, y) <- (m00 x + m01 y, m10 x + m11 y), all complex; 16 FP64 ops, cross terms first
+__device__ __forceinline__ void pair_general(c128 &x, c128 &y, const double *__restrict__ m) {
+    const double m00r = m[0], m00i = m[1], m01r = m[2], m01i = m[3], m10r = m[4], m10i = m[5], m11r = m[6],
+                 m11i = m[7];
+    const double pr = fma(m01r, y.re, -m01i * y.im), pi = fma(m01r, y.im, m01i * y.re);   // m01 y
+    const double qr = fma(m10r, x.re, -m10i * x.im), qi = fma(m10r, x.im, m10i * x.re);   // m10 x
+    const double rx = fma(m00i, x.re, pi);   // imaginary part of m00 x + m01 y, minus m00r x.im
+    const double ry = fma(m11i, y.re, qi);
+    ip_fma_scale(x.re, m00r, pr);
+    ip_fma_acc(x.re, -m00i, x.im);
+    ip_fma_scale(x.im, m00r, rx);
+    ip_fma_scale(y.re, m11r, qr);
+    ip_fma_acc(y.re, -m11i, y.im);
+    ip_fma_scale(y.im, m11r, ry);
 }
 
 // ---- 1-bit operator on register bit J; RC: honour the register control mask ----
@@ -67,51 +104,77 @@ __device__ __forceinline__ void g1_apply(c128 (&a)[NE], const double *__restrict
     _Pragma("unroll") for (int p = 0; p < NE / 2; ++p) {                                   \
         const int e0 = ((p >> J) << (J + 1)) | (p & ((1 << J) - 1)), e1 = e0 | (1 << J);   \
         if (RC && (e0 & rc) != rc) continue;
-    if (!RC && kind == QFB_G1_HLIKE) {  // controlled operators only come as SWAPX or GENERAL
-        const double h0 = m[0], r0 = m[1], h1 = m[4], r1 = m[5];  // out0 = h0 (x + r0 y), out1 = h1 (x + r1 y)
+    // controlled operators only come as SWAPX or GENERAL (pivoting needs an unconditional, uniform scalar)
+    if (!RC && kind == QFB_G1_SUMDIFF) {
+        const double r0 = m[0], r1 = m[1];  // x' = x + r0 y, y' = x + r1 y, r = +-1: exact sums
         QFB_PAIR_LOOP
-            const c128 x = a[e0], y = a[e1];
-            a[e0] = cmake(h0 * fma(r0, y.re, x.re), h0 * fma(r0, y.im, x.im));
-            a[e1] = cmake(h1 * fma(r1, y.re, x.re), h1 * fma(r1, y.im, x.im));
+            c128 &x = a[e0], &y = a[e1];
+            const double sr = fma(r1, y.re, x.re), si = fma(r1, y.im, x.im);
+            ip_fma_acc(x.re, r0, y.re);
+            ip_fma_acc(x.im, r0, y.im);
+            ip_set(y.re, sr);
+            ip_set(y.im, si);
+        }
+    } else if (!RC && kind == QFB_G1_ROT_R) {
+        const double r = m[0], s = m[1];    // x' = x + r y, y' = y + s x
+        QFB_PAIR_LOOP
+            c128 &x = a[e0], &y = a[e1];
+            const double xr = x.re, xi = x.im;
+            ip_fma_acc(x.re, r, y.re);
+            ip_fma_acc(x.im, r, y.im);
+            ip_fma_acc(y.re, s, xr);
+            ip_fma_acc(y.im, s, xi);
+        }
+    } else if (!RC && kind == QFB_G1_ROT_I) {
+        const double ca = m[0], cb = m[1];  // x' = x + i ca y, y' = y + i cb x
+        QFB_PAIR_LOOP
+            c128 &x = a[e0], &y = a[e1];
+            const double xr = x.re, xi = x.im;
+            ip_fma_acc(x.re, -ca, y.im);
+            ip_fma_acc(x.im, ca, y.re);
+            ip_fma_acc(y.re, -cb, xi);
+            ip_fma_acc(y.im, cb, xr);
         }
     } else if (!RC && kind == QFB_G1_REAL) {
         const double m00 = m[0], m01 = m[2], m10 = m[4], m11 = m[6];
         QFB_PAIR_LOOP
-            const c128 x = a[e0], y = a[e1];
-            a[e0] = cmake(fma(m00, x.re, m01 * y.re), fma(m00, x.im, m01 * y.im));
-            a[e1] = cmake(fma(m10, x.re, m11 * y.re), fma(m10, x.im, m11 * y.im));
+            c128 &x = a[e0], &y = a[e1];
+            const double pr = m01 * y.re, pi = m01 * y.im, qr = m10 * x.re, qi = m10 * x.im;
+            ip_fma_scale(x.re, m00, pr);
+            ip_fma_scale(x.im, m00, pi);
+            ip_fma_scale(y.re, m11, qr);
+            ip_fma_scale(y.im, m11, qi);
         }
     } else if (!RC && kind == QFB_G1_RXLIKE) {
         const double d0 = m[0], o01 = m[3], o10 = m[5], d1 = m[6];
         QFB_PAIR_LOOP
-            const c128 x = a[e0], y = a[e1];
+            c128 &x = a[e0], &y = a[e1];
             // (d0) x + (i o01) y ; (i o10) x + (d1) y
-            a[e0] = cmake(fma(d0, x.re, -o01 * y.im), fma(d0, x.im, o01 * y.re));
-            a[e1] = cmake(fma(d1, y.re, -o10 * x.im), fma(d1, y.im, o10 * x.re));
+            const double pr = -o01 * y.im, pi = o01 * y.re, qr = -o10 * x.im, qi = o10 * x.re;
+            ip_fma_scale(x.re, d0, pr);
+            ip_fma_scale(x.im, d0, pi);
+            ip_fma_scale(y.re, d1, qr);
+            ip_fma_scale(y.im, d1, qi);
         }
     } else if (kind == QFB_G1_SWAPX) {
         QFB_PAIR_LOOP
-            const c128 t = a[e0];
-            a[e0] = a[e1];
-            a[e1] = t;
+            ip_swap(a[e0].re, a[e1].re);
+            ip_swap(a[e0].im, a[e1].im);
         }
     } else if (!RC && kind == QFB_G1_ANTIDIAG) {
         const double ar = m[2], ai = m[3], br = m[4], bi = m[5];
         QFB_PAIR_LOOP
-            const c128 x = a[e0], y = a[e1];
-            a[e0] = cmake(fma(ar, y.re, -ai * y.im), fma(ar, y.im, ai * y.re));
-            a[e1] = cmake(fma(br, x.re, -bi * x.im), fma(br, x.im, bi * x.re));
+            c128 &x = a[e0], &y = a[e1];
+            const double qr = fma(br, x.re, -bi * x.im), qi = fma(br, x.im, bi * x.re);   // b x
+            const double pr = fma(ar, y.re, -ai * y.im), pi = fma(ar, y.im, ai * y.re);   // a y
+            ip_set(x.re, pr);
+            ip_set(x.im, pi);
+            ip_set(y.re, qr);
+            ip_set(y.im, qi);
         }
     } else {
-        const c128 m00 = cmake(m[0], m[1]), m01 = cmake(m[2], m[3]), m10 = cmake(m[4], m[5]),
-                   m11 = cmake(m[6], m[7]);
         QFB_PAIR_LOOP
-            const c128 x = a[e0], y = a[e1];
-            c128 u = cmul(m00, x), v = cmul(m10, x);
-            cfma(u, m01, y);
-            cfma(v, m11, y);
-            a[e0] = u;
-            a[e1] = v;
+            pair_general(a[e0], a[e1], m);
         }
     }
 #undef QFB_PAIR_LOOP
@@ -129,16 +192,27 @@ __device__ __forceinline__ void g2_apply(c128 (&a)[NE], const double *__restrict
         const int eb = ((g & 1) << O0) | ((g >> 1) << O1);
         if ((eb & rc) != rc) continue;
         const int id[4] = {eb, eb | (1 << J1), eb | (1 << J0), eb | (1 << J0) | (1 << J1)};
-        const c128 in0 = a[id[0]], in1 = a[id[1]], in2 = a[id[2]], in3 = a[id[3]];
-        const c128 in[4] = {in0, in1, in2, in3};
+        double outr[4], outi[4];
 #pragma unroll
         for (int r = 0; r < 4; ++r) {
-            c128 acc = cmake(0.0, 0.0);
+            double accr = 0.0, acci = 0.0;
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
-                if ((nz >> (4 * r + c)) & 1u) cfma(acc, cmake(m[2 * (4 * r + c)], m[2 * (4 * r + c) + 1]), in[c]);
+                if ((nz >> (4 * r + c)) & 1u) {
+                    const double mr = m[2 * (4 * r + c)], mi = m[2 * (4 * r + c) + 1];
+                    accr = fma(mr, a[id[c]].re, accr);
+                    accr = fma(-mi, a[id[c]].im, accr);
+                    acci = fma(mr, a[id[c]].im, acci);
+                    acci = fma(mi, a[id[c]].re, acci);
+                }
             }
-            a[id[r]] = acc;
+            outr[r] = accr;
+            outi[r] = acci;
+        }
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            ip_set(a[id[r]].re, outr[r]);
+            ip_set(a[id[r]].im, outi[r]);
         }
     }
 }
@@ -149,7 +223,10 @@ __device__ __forceinline__ void cph_apply(c128 (&a)[NE], double fr, double fi, b
     if (neg) {
 #pragma unroll
         for (int e = 0; e < NE; ++e)
-            if ((e & MASK) == MASK) a[e] = cmake(flip_sign(a[e].re), flip_sign(a[e].im));
+            if ((e & MASK) == MASK) {
+                ip_neg(a[e].re);
+                ip_neg(a[e].im);
+            }
     } else {
 #pragma unroll
         for (int e = 0; e < NE; ++e)
@@ -184,12 +261,13 @@ struct SweepCfg {
     static constexpr int TILE_BYTES = 16 << M;
 };
 
-template <int M>
+// HAS_G2 = false drops the dense 2-bit handlers (40% of the code): circuits made of 1-bit, controlled-1-bit and
+// diagonal gates (every workload of BASELINE.json) run the smaller kernel, which is kinder to the instruction cache.
+template <int M, bool HAS_G2>
 __global__ void __launch_bounds__(SweepCfg<M>::T, SweepCfg<M>::MINB)
 sweep_kernel(c128 *__restrict__ state, const uint8_t *__restrict__ rec_g, uint32_t rec_bytes, int nholes,
              uint64_t hi_shifted) {
     constexpr int T = SweepCfg<M>::T;
-    constexpr int TB = M - R;  // thread bits
     extern __shared__ __align__(16) uint8_t smem[];
     c128 *tile = reinterpret_cast<c128 *>(smem);
     uint8_t *rec = smem + SweepCfg<M>::TILE_BYTES;
@@ -212,16 +290,11 @@ sweep_kernel(c128 *__restrict__ state, const uint8_t *__restrict__ rec_g, uint32
         const uint8_t *rp = rec + sizeof(qfb_sweep_header);
         for (int round = 0; round < nrounds; ++round) {
             const qfb_round_header *rh = reinterpret_cast<const qfb_round_header *>(rp);
-            // tile-local index of this thread (register bits zero) and its global image
-            uint32_t tb = 0;
-            uint64_t tg = 0;
-#pragma unroll
-            for (int t = 0; t < TB; ++t) {
-                const uint32_t bit = (tid >> t) & 1u;
-                const uint32_t tp = rh->thrpos[t];
-                tb |= bit << tp;
-                tg |= (uint64_t)bit << sh->gpos[tp];
-            }
+            // tile-local index of this thread (register bits zero) and its global image: two table look-ups
+            const uint4 l0 = *reinterpret_cast<const uint4 *>(&rh->lut_lo[tid & 15]);
+            const uint4 l1 = *reinterpret_cast<const uint4 *>(&rh->lut_hi[(tid >> 4) & 31]);
+            const uint32_t tb = l0.x | l1.x;
+            const uint64_t tg = (((uint64_t)l0.w << 32) | l0.z) | (((uint64_t)l1.w << 32) | l1.z);
             uint32_t ps[R];  // swizzled image of each register bit
 #pragma unroll
             for (int i = 0; i < R; ++i) ps[i] = swz(1u << rh->regpos[i]);
@@ -244,8 +317,10 @@ sweep_kernel(c128 *__restrict__ state, const uint8_t *__restrict__ rec_g, uint32
             double phr = 1.0, phi = 0.0;  // running per-thread scalar phase of this round
             const uint8_t *op = rp + sizeof(qfb_round_header);
             const int nops = (int)rh->nops;
+            uint4 hw_next = *reinterpret_cast<const uint4 *>(op);  // rounds end with a 16-byte guard record
             for (int o = 0; o < nops; ++o) {
-                const uint4 hw = *reinterpret_cast<const uint4 *>(op);
+                const uint4 hw = hw_next;
+                hw_next = *reinterpret_cast<const uint4 *>(op + (hw.y >> 16));   // prefetch the next op header
                 const uint32_t type = hw.x & 0xffu, kind = (hw.x >> 8) & 0xffu, j0 = (hw.x >> 16) & 0xffu,
                                j1 = hw.x >> 24, rc = hw.y & 0xffu, bytes = hw.y >> 16;
                 const uint64_t cm = ((uint64_t)hw.w << 32) | hw.z;
@@ -279,7 +354,7 @@ sweep_kernel(c128 *__restrict__ state, const uint8_t *__restrict__ rec_g, uint32
                                 default: g1_apply<3, true>(a, m, kind, rc); break;
                             }
                         }
-                    } else {
+                    } else if (HAS_G2) {
                         const uint32_t nz = *reinterpret_cast<const uint32_t *>(op + sizeof(qfb_op_header) + 256);
                         switch (j0 * 4 + j1) {
                             case 1 * 4 + 0: g2_apply<1, 0>(a, m, nz, rc); break;
@@ -319,6 +394,7 @@ sweep_kernel(c128 *__restrict__ state, const uint8_t *__restrict__ rec_g, uint32
 struct SweepInfo {
     size_t offset;  // byte offset of the sweep record inside the device copy
     uint32_t bytes;
+    bool has_g2;    // selects the kernel variant with the dense 2-bit handlers
 };
 
 struct PlanHandle {
@@ -364,12 +440,29 @@ static int validate_plan(const uint8_t *p, size_t nbytes, std::vector<SweepInfo>
         }
         size_t roff = off + sizeof(sh);
         const size_t send = off + sh.bytes;
+        bool sweep_g2 = false;
         for (uint32_t r = 0; r < sh.nrounds; ++r) {
             QFB_CHECK_ARG(roff + sizeof(qfb_round_header) <= send, "plan: sweep %u truncated round %u", s, r);
             qfb_round_header rh;
             memcpy(&rh, p + roff, sizeof(rh));
             QFB_CHECK_ARG(rh.bytes % 16 == 0 && rh.bytes >= sizeof(rh) && roff + rh.bytes <= send,
                           "plan: sweep %u round %u bad size", s, r);
+            sweep_g2 = sweep_g2 || rh.has_g2;
+            // thread LUTs must reproduce the deposit of the thread bits through thrpos / gpos
+            for (int t = 0; t < (1 << (M - R)); ++t) {
+                uint32_t tb = 0;
+                uint64_t tg = 0;
+                for (int b = 0; b < M - R; ++b) {
+                    if ((t >> b) & 1) {
+                        QFB_CHECK_ARG(rh.thrpos[b] < M, "plan: bad thrpos");
+                        tb |= 1u << rh.thrpos[b];
+                        tg |= 1ull << sh.gpos[rh.thrpos[b]];
+                    }
+                }
+                const qfb_thread_lut &lo = rh.lut_lo[t & 15], &hi = rh.lut_hi[(t >> 4) & 31];
+                QFB_CHECK_ARG((lo.tb | hi.tb) == tb && (lo.tg | hi.tg) == tg, "plan: sweep %u round %u bad thread LUT",
+                              s, r);
+            }
             uint32_t tseen = 0;
             for (int i = 0; i < R; ++i) {
                 QFB_CHECK_ARG(rh.regpos[i] < M && !((tseen >> rh.regpos[i]) & 1u), "plan: bad regpos");
@@ -388,11 +481,12 @@ static int validate_plan(const uint8_t *p, size_t nbytes, std::vector<SweepInfo>
                 QFB_CHECK_ARG(oh.bytes % 16 == 0 && oh.bytes >= sizeof(oh) && ooff + oh.bytes <= rend,
                               "plan: op bad size");
                 if (oh.type == QFB_OP_G1) {
-                    QFB_CHECK_ARG(oh.bytes == 16 + 64 && oh.j0 < R && oh.kind <= QFB_G1_HLIKE &&
+                    QFB_CHECK_ARG(oh.bytes == 16 + 64 && oh.j0 < R && oh.kind <= QFB_G1_ROT_I &&
+                                      (oh.reg_cmask == 0 || oh.kind == QFB_G1_GENERAL || oh.kind == QFB_G1_SWAPX) &&
                                       !((oh.reg_cmask >> oh.j0) & 1) && oh.reg_cmask < NE,
                                   "plan: bad G1 op");
                 } else if (oh.type == QFB_OP_G2) {
-                    QFB_CHECK_ARG(oh.bytes == 16 + 272 && oh.j0 < R && oh.j1 < oh.j0 &&
+                    QFB_CHECK_ARG(rh.has_g2 == 1 && oh.bytes == 16 + 272 && oh.j0 < R && oh.j1 < oh.j0 &&
                                       !((oh.reg_cmask >> oh.j0) & 1) && !((oh.reg_cmask >> oh.j1) & 1) &&
                                       oh.reg_cmask < NE,
                                   "plan: bad G2 op");
@@ -409,18 +503,19 @@ static int validate_plan(const uint8_t *p, size_t nbytes, std::vector<SweepInfo>
             roff += rh.bytes;
         }
         QFB_CHECK_ARG(roff == send, "plan: sweep size mismatch");
-        sweeps.push_back(SweepInfo{off, sh.bytes});
+        sweeps.push_back(SweepInfo{off, sh.bytes, sweep_g2});
         off += sh.bytes;
     }
     QFB_CHECK_ARG(off == nbytes, "plan: trailing bytes");
     return QFB_OK;
 }
 
-template <int M>
+template <int M, bool G2>
 static int launch_sweep(c128 *state, const uint8_t *rec_dev, uint32_t rec_bytes, int nbits, uint64_t index_hi,
                         cudaStream_t st) {
     constexpr int T = SweepCfg<M>::T;
-    const size_t smem = (size_t)SweepCfg<M>::TILE_BYTES + rec_bytes;
+    // +16: the op loop prefetches one header past the last op of a round
+    const size_t smem = (size_t)SweepCfg<M>::TILE_BYTES + rec_bytes + 16;
     static thread_local size_t configured[64] = {0};
     int dev = 0;
     QFB_CUDA(cudaGetDevice(&dev));
@@ -429,34 +524,39 @@ static int launch_sweep(c128 *state, const uint8_t *rec_dev, uint32_t rec_bytes,
         // grow in 8 KiB steps so the attribute is set a handful of times per process
         const size_t want = std::min<size_t>(((smem + 8191) / 8192) * 8192, 227 * 1024);
         QFB_CHECK_ARG(smem <= want, "sweep: %zu bytes of shared memory exceed the 227 KiB limit", smem);
-        QFB_CUDA(cudaFuncSetAttribute(sweep_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)want));
+        QFB_CUDA(cudaFuncSetAttribute(sweep_kernel<M, G2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)want));
         configured[dev] = want;
     }
     int resident = 0;  // CTAs per SM for this launch's shared-memory footprint (host-side arithmetic)
-    QFB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, sweep_kernel<M>, T, smem));
+    QFB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, sweep_kernel<M, G2>, T, smem));
     resident = std::max(1, resident);
     const int nholes = nbits - M;
     const uint64_t ntiles = 1ull << nholes;
     const uint64_t cap = (uint64_t)sm_count_cached() * resident;
     const int grid = (int)std::min<uint64_t>(ntiles, cap);
     const uint64_t hi_shifted = (nbits >= 64) ? 0ull : (index_hi << nbits);
-    sweep_kernel<M><<<grid, T, smem, st>>>(state, rec_dev, rec_bytes, nholes, hi_shifted);
+    sweep_kernel<M, G2><<<grid, T, smem, st>>>(state, rec_dev, rec_bytes, nholes, hi_shifted);
     QFB_LAUNCH_CHECK();
     return QFB_OK;
 }
 
-static int launch_sweep_dispatch(int M, c128 *state, const uint8_t *rec_dev, uint32_t rec_bytes, int nbits,
-                                 uint64_t index_hi, cudaStream_t st) {
+#define QFB_SWEEP_CASE(MM)                                                                          \
+    case MM:                                                                                        \
+        return g2 ? launch_sweep<MM, true>(state, rec_dev, rec_bytes, nbits, index_hi, st)          \
+                  : launch_sweep<MM, false>(state, rec_dev, rec_bytes, nbits, index_hi, st);
+
+static int launch_sweep_dispatch(int M, bool g2, c128 *state, const uint8_t *rec_dev, uint32_t rec_bytes,
+                                 int nbits, uint64_t index_hi, cudaStream_t st) {
     switch (M) {
-        case 5: return launch_sweep<5>(state, rec_dev, rec_bytes, nbits, index_hi, st);
-        case 6: return launch_sweep<6>(state, rec_dev, rec_bytes, nbits, index_hi, st);
-        case 7: return launch_sweep<7>(state, rec_dev, rec_bytes, nbits, index_hi, st);
-        case 8: return launch_sweep<8>(state, rec_dev, rec_bytes, nbits, index_hi, st);
-        case 9: return launch_sweep<9>(state, rec_dev, rec_bytes, nbits, index_hi, st);
-        case 10: return launch_sweep<10>(state, rec_dev, rec_bytes, nbits, index_hi, st);
-        case 11: return launch_sweep<11>(state, rec_dev, rec_bytes, nbits, index_hi, st);
-        case 12: return launch_sweep<12>(state, rec_dev, rec_bytes, nbits, index_hi, st);
-        case 13: return launch_sweep<13>(state, rec_dev, rec_bytes, nbits, index_hi, st);
+        QFB_SWEEP_CASE(5)
+        QFB_SWEEP_CASE(6)
+        QFB_SWEEP_CASE(7)
+        QFB_SWEEP_CASE(8)
+        QFB_SWEEP_CASE(9)
+        QFB_SWEEP_CASE(10)
+        QFB_SWEEP_CASE(11)
+        QFB_SWEEP_CASE(12)
+        QFB_SWEEP_CASE(13)
         default: break;
     }
     set_error("sweep: tile_bits=%d unsupported", M);
@@ -510,7 +610,7 @@ int qfb_plan_launch(void *handle, void *state, int nbits, uint64_t index_hi, voi
     QFB_CHECK_ARG(state, "qfb_plan_launch: null state");
     QFB_CHECK_ARG(nbits == h->nbits, "qfb_plan_launch: plan built for %d bits, state has %d", h->nbits, nbits);
     for (const SweepInfo &s : h->sweeps) {
-        int rc = launch_sweep_dispatch(h->tile_bits, (c128 *)state, (const uint8_t *)h->dev + s.offset, s.bytes,
+        int rc = launch_sweep_dispatch(h->tile_bits, s.has_g2, (c128 *)state, (const uint8_t *)h->dev + s.offset, s.bytes,
                                        nbits, index_hi, (cudaStream_t)stream);
         if (rc != QFB_OK) return rc;
     }

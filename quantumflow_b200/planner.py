@@ -5,16 +5,23 @@ Input  : a list of bit-level operators (matrix, index-bit positions) in program 
 Output : segments, each either a binary plan (csrc/qfb_plan.h) executed by qfb_plan_launch, or a single operator
          that the executor cannot express (>2 mixing bits) and that goes through qfb_apply_dense.
 
-Three greedy passes, all order preserving up to commutation:
+Passes, all order preserving up to commutation:
 
-1. classify   every operator becomes D (diagonal over any bits), or G (1 or 2 mixing bits + any number of
-              control bits, controls peeled by classify.peel_controls). Diagonal uses and control uses of a bit
-              commute with each other, so they never constrain tiling.
+1. classify   a diagonal operator becomes phase-polynomial terms P(mask, factor): multiply by `factor` where all
+              mask bits are 1 (any bits of the full index, so diagonal gates never constrain tiling; terms with
+              factor 1 vanish, e.g. CZ is the single term P({a,b}, -1)). Everything else becomes G: 1 or 2
+              mixing bits + any number of control bits (controls peeled by classify.peel_controls). Diagonal uses
+              and control uses of a bit commute with each other.
 2. sweeps     walk the list; an operator joins the current sweep when it does not conflict with a deferred
               operator and its mixing bits fit into the tile (M bits, the L lowest index bits are always members
-              so that global accesses are whole 128-byte lines). A cost cap keeps a sweep HBM-bound.
+              so that global accesses are whole 128-byte lines). A cost cap keeps a sweep close to HBM-bound.
 3. rounds     inside a sweep the same walk assigns operators to rounds of R=4 register bits; the first and
-              last round keep the low tile bits on the lanes (coalesced LDG/STG).
+              last round keep the low tile bits on the lanes (coalesced LDG/STG). Phase terms are then moved,
+              inside their commutation window, to the round where they are cheapest: a term whose bits are all
+              thread-level is a per-thread scalar (4 FP64 ops instead of up to 64).
+4. encode     1-bit operators are divided by their (0,0) entry when that exposes a cheaper form (Hadamard:
+              sums only; RX / RY: two fused multiply-adds per amplitude); the pivots of a sweep are multiplied
+              into one uniform scalar that is applied once.
 """
 import struct
 from typing import Dict, List, Optional, Sequence, Tuple
@@ -24,7 +31,7 @@ import numpy as np
 from . import classify
 
 PLAN_MAGIC = 0x50424651
-PLAN_VERSION = 3
+PLAN_VERSION = 4
 REG_BITS = 4
 MAX_TILE_BITS = 13
 MIN_TILE_BITS = 5
@@ -32,16 +39,23 @@ MAX_HOLES = 48
 MAX_SWEEP_BYTES = 40 * 1024
 MAX_DIAG_BITS = 5
 OP_G1, OP_G2, OP_CPH = 1, 2, 3
+ROUND_HEADER_BYTES = 32 + 16 * (16 + 32)
+
+# QFB_G1_* kinds (csrc/qfb_plan.h)
+K_GENERAL, K_REAL, K_RXLIKE, K_SWAPX, K_ANTIDIAG, K_SUMDIFF, K_ROT_R, K_ROT_I = range(8)
 
 DEFAULT_TILE_BITS = 12
 DEFAULT_LOW_BITS = 3
-# cost units ~ FP64 work per amplitude relative to a dense 1-bit operator
-COST = {'G1': 1.0, 'G1_cheap': 0.5, 'G1_swap': 0.2, 'G2': 2.5, 'P': 0.15}
+# cost units ~ FP64 work per amplitude relative to a dense 1-bit operator (16 FP64 ops per amplitude pair)
+COST = {K_GENERAL: 1.0, K_REAL: 0.5, K_RXLIKE: 0.5, K_SWAPX: 0.2, K_ANTIDIAG: 0.5, K_SUMDIFF: 0.25, K_ROT_R: 0.25,
+        K_ROT_I: 0.25, 'G2': 2.5, 'P': 0.1}
 DEFAULT_MAX_COST = 28.0
+# pivot on the (0,0) entry unless it is this much smaller than the largest entry
+PIVOT_RATIO = 1e-3
 
 
 class POp:
-    """A classified operator."""
+    """A classified operator: kind 'G' (mixing) or 'P' (phase term)."""
     __slots__ = ('kind', 'mix', 'ctrl', 'dbits', 'mat', 'cost', 'mixset', 'diagset', 'anyset', 'gate_index')
 
     def __init__(self, kind, mix=(), ctrl=(), dbits=(), mat=None, cost=1.0, gate_index=-1):
@@ -66,18 +80,54 @@ class Fallback:
         self.bits = tuple(int(b) for b in bits)
 
 
-def phase_polynomial(table: np.ndarray, k: int):
-    """Diagonal operator -> list of (qubit subset mask over the k table bits, factor) with
-    d[s] = prod over subsets T of s of factor[T]; bit q of the table index has weight 1 << (k-1-q).
-    Requires every entry to be non-zero."""
-    phi = {}
+# ---------------------------------------------------------------------------------------------------------
+# pass 1: classification
+# ---------------------------------------------------------------------------------------------------------
+
+def phase_polynomial(table: np.ndarray, k: int) -> Dict[int, complex]:
+    """Diagonal operator -> {subset mask over the k table bits: factor} with d[s] = prod_{T subset of s} factor[T];
+    bit q of the table index has weight 1 << (k-1-q). Requires every entry to be non-zero."""
+    phi: Dict[int, complex] = {}
     for s in range(1 << k):
         val = complex(table[s])
         for t in range(s):
-            if (t & s) == t and t in phi:
+            if (t & s) == t:
                 val = val / phi[t]
         phi[s] = val
     return phi
+
+
+def encode_g1(mat: np.ndarray, controlled: bool) -> Tuple[int, np.ndarray, Optional[complex]]:
+    """(kind, 8-double payload, pivot) for a 2x2 operator. `pivot` is the uniform scalar that has been divided
+    out (None when the operator is applied as is)."""
+    m = np.array(mat, dtype=np.complex128).reshape(2, 2)
+    plain = np.ascontiguousarray(m).view(np.float64).reshape(-1).copy()
+    base = classify.g1_kind(m)            # 0 general, 1 real, 2 rxlike, 3 swapx, 4 antidiag
+    if base == K_SWAPX:
+        return K_SWAPX, plain, None
+    if controlled:
+        return K_GENERAL, plain, None
+    if base == K_ANTIDIAG:
+        return K_ANTIDIAG, plain, None
+    big = np.abs(m).max()
+    m00 = m[0, 0]
+    pivotable = m00 != 0 and abs(m00) >= PIVOT_RATIO * big
+    if base == K_REAL and pivotable:
+        p = m00.real
+        r, s, t = m[0, 1].real / p, m[1, 0].real / p, m[1, 1].real / p
+        payload = np.zeros(8)
+        if s == 1.0 and abs(r) == 1.0 and abs(t) == 1.0:
+            payload[0], payload[1] = r, t
+            return K_SUMDIFF, payload, complex(p)
+        if t == 1.0:
+            payload[0], payload[1] = r, s
+            return K_ROT_R, payload, complex(p)
+    if base == K_RXLIKE and pivotable and m[1, 1] == m00:
+        p = m00.real
+        payload = np.zeros(8)
+        payload[0], payload[1] = m[0, 1].imag / p, m[1, 0].imag / p
+        return K_ROT_I, payload, complex(p)
+    return base, plain, None
 
 
 def classify_op(mat: np.ndarray, bits: Sequence[int], gate_index: int = -1):
@@ -99,7 +149,7 @@ def classify_op(mat: np.ndarray, bits: Sequence[int], gate_index: int = -1):
         if k > 2:
             return Fallback(mat, bits)
         # singular diagonal (projectors): a dense 1- or 2-bit operator
-        cost = COST['G1_cheap'] if k == 1 else COST['G2'] * 0.25 + 0.3
+        cost = COST[K_REAL] if k == 1 else COST['G2'] * 0.25 + 0.3
         return [POp('G', mix=bits, ctrl=(), mat=mat, cost=cost, gate_index=gate_index)]
     controls, targets, reduced = ([], list(range(k)), mat) if k == 1 else classify.peel_controls(mat, k)
     if len(targets) > 2:
@@ -107,23 +157,11 @@ def classify_op(mat: np.ndarray, bits: Sequence[int], gate_index: int = -1):
     cbits = [bits[q] for q in controls]
     tbits = [bits[q] for q in targets]
     if len(targets) == 1:
-        kind = g1_kind(reduced, bool(cbits))
-        cost = COST['G1_swap'] if kind == 3 else (COST['G1_cheap'] if kind in (1, 2, 4, 5) else COST['G1'])
-        return [POp('G', mix=tbits, ctrl=cbits, mat=reduced, cost=cost, gate_index=gate_index)]
+        kind = encode_g1(reduced, bool(cbits))[0]
+        return [POp('G', mix=tbits, ctrl=cbits, mat=reduced, cost=COST[kind], gate_index=gate_index)]
     nnz = int(np.count_nonzero(reduced))
     return [POp('G', mix=tbits, ctrl=cbits, mat=reduced, cost=COST['G2'] * max(nnz, 4) / 16.0 + 0.3,
                 gate_index=gate_index)]
-
-
-def g1_kind(m: np.ndarray, controlled: bool) -> int:
-    """QFB_G1_* kind of a 2x2 operator; controlled operators only use SWAPX / GENERAL (fewer kernel variants)."""
-    kind = classify.g1_kind(m)
-    m = np.asarray(m).reshape(2, 2)
-    if kind == 1 and np.all(m.real != 0) and len({abs(v) for v in m.real.reshape(-1)}) == 1:
-        kind = 5   # HLIKE
-    if controlled and kind not in (0, 3):
-        kind = 0
-    return kind
 
 
 def merge_phase_terms(ops: List[POp]) -> List[POp]:
@@ -158,13 +196,22 @@ def swizzle_class(pos: int) -> int:
     return pos if pos < 3 else (pos - 3) % 3
 
 
+class Round:
+    __slots__ = ('regs', 'thr', 'ops')
+
+    def __init__(self, regs, thr, ops):
+        self.regs = regs   # tile positions of register bits 0..3
+        self.thr = thr     # tile positions of thread bits 0..M-5
+        self.ops = ops     # POps in execution order
+
+
 class SweepPlan:
     __slots__ = ('tile', 'ops', 'rounds', 'cost')
 
     def __init__(self, tile: List[int], ops: List[POp]):
         self.tile = tile      # index-bit positions, ascending, length M
         self.ops = ops
-        self.rounds = []      # list of (regpos[4], thrpos[M-4], [POp])
+        self.rounds: List[Round] = []
         self.cost = sum(o.cost for o in ops)
 
 
@@ -190,7 +237,7 @@ class Planner:
         def_any: set = set()
         def_mix: set = set()
         cost = 0.0
-        nbytes = 80
+        nbytes = 80 + 8 * ROUND_HEADER_BYTES
         full = False
         for op in ops:
             ok = not full and not _conflicts(op, def_any, def_mix)
@@ -204,7 +251,7 @@ class Planner:
             if ok and cost + op.cost > self.max_cost and chosen:
                 ok = False
             opbytes = 16 + (64 if (op.kind == 'G' and len(op.mix) == 1) else 272 if op.kind == 'G' else 16)
-            if ok and nbytes + opbytes + 32 * 8 > MAX_SWEEP_BYTES:
+            if ok and nbytes + opbytes > MAX_SWEEP_BYTES - 4 * ROUND_HEADER_BYTES:
                 ok = False
                 full = True
             if ok:
@@ -266,9 +313,6 @@ class Planner:
                     deferred.append(op)
                     def_any |= op.anyset
                     def_mix |= op.mixset
-            if not chosen and first:
-                # nothing can run with the low bits on the lanes; open a pure load round
-                pass
             rounds.append((regs, chosen))
             remaining = deferred
             first = False
@@ -280,7 +324,7 @@ class Planner:
         # drop an empty first round when the sweep has another round that can serve as the load round
         if len(rounds) > 1 and not rounds[0][1] and not any(p < self.L for p in rounds[1][0]):
             rounds.pop(0)
-        final = []
+        final: List[Round] = []
         nr = len(rounds)
         for r, (regs, chosen) in enumerate(rounds):
             edge = (r == 0) or (r == nr - 1)
@@ -293,8 +337,89 @@ class Planner:
                 cand.sort(key=lambda p: (counts[swizzle_class(p)], -p))
                 regs.append(cand.pop(0))
             regs.sort()
-            final.append((regs, self._thread_order(regs, edge), chosen))
+            final.append(Round(regs, self._thread_order(regs, edge), chosen))
         sweep.rounds = final
+        self._relocate_phase_terms(sweep)
+
+    def _relocate_phase_terms(self, sweep: SweepPlan) -> None:
+        """Move every phase term, inside its commutation window, to the round where it is cheapest."""
+        pos_of = {b: j for j, b in enumerate(sweep.tile)}
+        rounds = sweep.rounds
+        nr = len(rounds)
+        placed: List[List[POp]] = [[op for op in rd.ops if op.kind == 'G'] for rd in rounds]
+        terms: List[Tuple[POp, Tuple[int, int], Tuple[int, int]]] = []
+        for r, rd in enumerate(rounds):
+            gcount = 0
+            for op in rd.ops:
+                if op.kind == 'G':
+                    gcount += 1
+                    continue
+                # window: after the last conflicting G op before the term, before the first one after it
+                lo = (-1, -1)
+                for rr in range(r, -1, -1):
+                    glist = placed[rr]
+                    upto = gcount if rr == r else len(glist)
+                    hit = [i for i in range(upto) if glist[i].mixset & op.diagset]
+                    if hit:
+                        lo = (rr, hit[-1])
+                        break
+                hi = (nr, 0)
+                for rr in range(r, nr):
+                    glist = placed[rr]
+                    start = gcount if rr == r else 0
+                    hit = [i for i in range(start, len(glist)) if glist[i].mixset & op.diagset]
+                    if hit:
+                        hi = (rr, hit[0])
+                        break
+                terms.append((op, lo, hi))
+
+        def reg_mask(op: POp, r: int) -> int:
+            mask = 0
+            for b in op.dbits:
+                p = pos_of.get(b)
+                if p is not None and p in rounds[r].regs:
+                    mask |= 1 << rounds[r].regs.index(p)
+            return mask
+
+        def legal_rounds(lo, hi):
+            return range(max(lo[0], 0), min(hi[0], nr - 1) + 1)
+
+        # the round that can host most terms as per-thread scalars becomes the sweep's scalar round
+        votes = [0] * nr
+        for op, lo, hi in terms:
+            for r in legal_rounds(lo, hi):
+                if reg_mask(op, r) == 0:
+                    votes[r] += 1
+        scalar_rounds = {max(range(nr), key=lambda r: (votes[r], -r))} if terms else set()
+        # after[r][i]: terms that run right after G op i of round r (i = -1: at the start of the round)
+        after: List[Dict[int, List[POp]]] = [dict() for _ in range(nr)]
+        for op, lo, hi in terms:
+            best = None
+            for r in legal_rounds(lo, hi):
+                mask = reg_mask(op, r)
+                if mask == 0:
+                    cost = 0.05 if r in scalar_rounds else 1.05
+                else:
+                    touched = 16 >> bin(mask).count('1')
+                    cost = (0.1 if op.mat == -1 else 0.5) * touched / 8.0
+                if best is None or cost < best[0]:
+                    best = (cost, r, mask)
+            _, r, mask = best
+            if mask == 0:
+                scalar_rounds.add(r)
+            if r == lo[0]:
+                anchor = lo[1]                     # right after the conflicting predecessor
+            elif r == hi[0]:
+                anchor = hi[1] - 1                 # right before the conflicting successor
+            else:
+                anchor = len(placed[r]) - 1        # anywhere: at the end
+            after[r].setdefault(anchor, []).append(op)
+        for r, rd in enumerate(rounds):
+            ops: List[POp] = list(after[r].get(-1, []))
+            for i, g in enumerate(placed[r]):
+                ops.append(g)
+                ops.extend(after[r].get(i, []))
+            rd.ops = ops
 
     # ---- driver -----------------------------------------------------------------------------------
     def plan(self, pops: List[POp]) -> List[SweepPlan]:
@@ -309,28 +434,29 @@ class Planner:
             sweeps.append(sweep)
         return sweeps
 
-    # ---- serialisation ----------------------------------------------------------------------------
-    def _emit_op(self, op: POp, sweep: SweepPlan, regs: Sequence[int]) -> bytes:
-        pos_of = {b: j for j, b in enumerate(sweep.tile)}
-        reg_of = {p: i for i, p in enumerate(regs)}   # tile position -> register bit
+    # ---- pass 4: encoding -------------------------------------------------------------------------
+    @staticmethod
+    def _emit_phase(bits: Sequence[int], factor: complex, pos_of, reg_of) -> bytes:
+        reg_cmask = 0
+        idx_cmask = 0
+        for bit in bits:
+            p = pos_of.get(bit)
+            ri = reg_of.get(p) if p is not None else None
+            if ri is None:
+                idx_cmask |= 1 << bit
+            else:
+                reg_cmask |= 1 << ri
+        factor = complex(factor)
+        kind = 1 if (factor == -1 and reg_cmask != 0) else 0
+        payload = struct.pack('<dd', factor.real, factor.imag)
+        return struct.pack('<BBBBBBHQ', OP_CPH, kind, 0, 0, reg_cmask, 0, 16 + len(payload), idx_cmask) + payload
 
+    @staticmethod
+    def _emit_gate(op: POp, pos_of, reg_of) -> Tuple[bytes, Optional[complex]]:
         def reg_index(bit: int) -> Optional[int]:
             p = pos_of.get(bit)
             return reg_of.get(p) if p is not None else None
 
-        if op.kind == 'P':
-            reg_cmask = 0
-            idx_cmask = 0
-            for bit in op.dbits:
-                ri = reg_index(bit)
-                if ri is None:
-                    idx_cmask |= 1 << bit
-                else:
-                    reg_cmask |= 1 << ri
-            factor = complex(op.mat)
-            kind = 1 if (factor == -1 and reg_cmask != 0) else 0
-            payload = struct.pack('<dd', factor.real, factor.imag)
-            return struct.pack('<BBBBBBHQ', OP_CPH, kind, 0, 0, reg_cmask, 0, 16 + len(payload), idx_cmask) + payload
         reg_cmask = 0
         idx_cmask = 0
         for c in op.ctrl:
@@ -340,16 +466,11 @@ class Planner:
             else:
                 reg_cmask |= 1 << ri
         if len(op.mix) == 1:
-            j0 = reg_index(op.mix[0])
-            mat = np.array(op.mat, dtype=np.complex128).reshape(2, 2)
-            kind = g1_kind(mat, bool(op.ctrl))
-            if kind == 5:   # HLIKE: out0 = h0 (x + r0 y), out1 = h1 (x + r1 y); ratios ride in the imaginary slots
-                h0, h1 = mat[0, 0].real, mat[1, 0].real
-                mat[0, 0] = complex(h0, mat[0, 1].real / h0)
-                mat[1, 0] = complex(h1, mat[1, 1].real / h1)
-            payload = np.ascontiguousarray(mat).tobytes()
-            header = struct.pack('<BBBBBBHQ', OP_G1, kind, j0, 0, reg_cmask, 0, 16 + len(payload), idx_cmask)
-            return header + payload
+            kind, payload, pivot = encode_g1(op.mat, bool(op.ctrl))
+            blob = payload.tobytes()
+            header = struct.pack('<BBBBBBHQ', OP_G1, kind, reg_index(op.mix[0]), 0, reg_cmask, 0, 16 + len(blob),
+                                 idx_cmask)
+            return header + blob, pivot
         j0, j1 = reg_index(op.mix[0]), reg_index(op.mix[1])
         mat = np.ascontiguousarray(op.mat, dtype=np.complex128).reshape(2, 2, 2, 2)
         if j0 < j1:   # kernel wants the operator's MSB qubit on the higher register bit
@@ -361,23 +482,60 @@ class Planner:
             for c in range(4):
                 if mat[r, c] != 0:
                     nz |= 1 << (4 * r + c)
-        payload = mat.tobytes() + struct.pack('<I12x', nz)
-        header = struct.pack('<BBBBBBHQ', OP_G2, 0, j0, j1, reg_cmask, 0, 16 + len(payload), idx_cmask)
-        return header + payload
+        blob = mat.tobytes() + struct.pack('<I12x', nz)
+        header = struct.pack('<BBBBBBHQ', OP_G2, 0, j0, j1, reg_cmask, 0, 16 + len(blob), idx_cmask)
+        return header + blob, None
+
+    @staticmethod
+    def _thread_luts(sweep: SweepPlan, thr: Sequence[int]) -> bytes:
+        """lut_lo[v] deposits thread bits 0..3 of v, lut_hi[v] thread bits 4.. of (v << 4)."""
+        def entry(value: int, first: int) -> bytes:
+            tb = tg = 0
+            for t, p in enumerate(thr):
+                if t >= first and t < first + (4 if first == 0 else 8) and (value >> (t - first)) & 1:
+                    tb |= 1 << p
+                    tg |= 1 << sweep.tile[p]
+            return struct.pack('<IIQ', tb, 0, tg)
+
+        return b''.join(entry(v, 0) for v in range(16)) + b''.join(entry(v, 4) for v in range(32))
 
     def serialise(self, sweeps: List[SweepPlan]) -> bytes:
         body = b''
         for sweep in sweeps:
+            pos_of = {b: j for j, b in enumerate(sweep.tile)}
+            encoded: List[Tuple[Round, List[bytes]]] = []
+            scalar = 1.0 + 0j
+            for rd in sweep.rounds:
+                reg_of = {p: i for i, p in enumerate(rd.regs)}
+                blobs: List[bytes] = []
+                for op in rd.ops:
+                    if op.kind == 'P':
+                        if not op.dbits:          # global phase: joins the sweep scalar
+                            scalar *= complex(op.mat)
+                            continue
+                        blobs.append(self._emit_phase(op.dbits, op.mat, pos_of, reg_of))
+                    else:
+                        blob, pivot = self._emit_gate(op, pos_of, reg_of)
+                        if pivot is not None:
+                            scalar *= pivot
+                        blobs.append(blob)
+                encoded.append((rd, blobs))
+            if scalar != 1:
+                # one unconditional per-thread scalar term; put it where a scalar is applied anyway
+                target = next((i for i, (_, bl) in enumerate(encoded)
+                               if any(b[0] == OP_CPH and b[4] == 0 for b in bl)), len(encoded) - 1)
+                encoded[target][1].append(self._emit_phase((), scalar, pos_of, {}))
             rounds_blob = b''
             nops = 0
-            for regs, thr, ops in sweep.rounds:
-                emitted = [self._emit_op(op, sweep, regs) for op in ops]
-                ops_blob = b''.join(emitted)
-                nops += len(ops)
-                has_scalar = int(any(e[0] == OP_CPH and e[4] == 0 for e in emitted))
-                thrpad = list(thr) + [0] * (12 - len(thr))
-                rounds_blob += struct.pack('<II4B12BB7x', len(ops), 32 + len(ops_blob), *regs, *thrpad,
-                                           has_scalar) + ops_blob
+            for rd, blobs in encoded:
+                ops_blob = b''.join(blobs)
+                nops += len(blobs)
+                has_scalar = int(any(b[0] == OP_CPH and b[4] == 0 for b in blobs))
+                has_g2 = int(any(b[0] == OP_G2 for b in blobs))
+                thrpad = list(rd.thr) + [0] * (12 - len(rd.thr))
+                rounds_blob += struct.pack('<II4B12BBB6x', len(blobs), ROUND_HEADER_BYTES + len(ops_blob), *rd.regs,
+                                           *thrpad, has_scalar, has_g2)
+                rounds_blob += self._thread_luts(sweep, rd.thr) + ops_blob
             holes = [b for b in range(self.nbits) if b not in sweep.tile]
             gpos = list(sweep.tile) + [0] * (16 - len(sweep.tile))
             hole = holes + [0] * (MAX_HOLES - len(holes))

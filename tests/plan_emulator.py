@@ -20,7 +20,7 @@ def swz(idx):
 
 def parse(blob: bytes):
     magic, version, nbits, M, rbits, nsweeps, total = struct.unpack_from('<IIIIIIQ', blob, 0)
-    assert magic == 0x50424651 and version == 3 and rbits == R and total == len(blob)
+    assert magic == 0x50424651 and version == 4 and rbits == R and total == len(blob)
     off = 32
     sweeps = []
     for _ in range(nsweeps):
@@ -33,8 +33,18 @@ def parse(blob: bytes):
             rn, rbytes = struct.unpack_from('<II', blob, roff)
             regpos = list(blob[roff + 8: roff + 12])
             thrpos = list(blob[roff + 12: roff + 12 + (M - R)])
-            has_scalar = blob[roff + 24]
-            ooff = roff + 32
+            has_scalar, has_g2 = blob[roff + 24], blob[roff + 25]
+            # thread LUTs (16 + 32 entries of <IIQ): must reproduce the deposit of the thread bits
+            lut = [struct.unpack_from('<IIQ', blob, roff + 32 + 16 * i) for i in range(48)]
+            for tid in range(1 << (M - R)):
+                tb = tg = 0
+                for t in range(M - R):
+                    if (tid >> t) & 1:
+                        tb |= 1 << thrpos[t]
+                        tg |= 1 << gpos[thrpos[t]]
+                lo, hi = lut[tid & 15], lut[16 + ((tid >> 4) & 31)]
+                assert (lo[0] | hi[0], lo[2] | hi[2]) == (tb, tg), 'bad thread LUT'
+            ooff = roff + 32 + 768
             ops = []
             for _o in range(rn):
                 typ, kind, j0, j1, rcm, nb, obytes, icm = struct.unpack_from('<BBBBBBHQ', blob, ooff)
@@ -43,6 +53,7 @@ def parse(blob: bytes):
                                 payload=payload))
                 ooff += obytes
             assert ooff == roff + rbytes
+            assert has_g2 == int(any(o['type'] == 2 for o in ops))
             rounds.append(dict(regpos=regpos, thrpos=thrpos, ops=ops, has_scalar=has_scalar))
             roff += rbytes
         assert roff == off + size
@@ -72,9 +83,17 @@ def _apply_g1(a, op):
         elif op['kind'] == 4:    # ANTIDIAG
             a[e0] = m[0, 1] * y
             a[e1] = m[1, 0] * x
-        elif op['kind'] == 5:    # HLIKE: ratios ride in the imaginary slots of m00 / m10
-            a[e0] = m[0, 0].real * (x + m[0, 0].imag * y)
-            a[e1] = m[1, 0].real * (x + m[1, 0].imag * y)
+        elif op['kind'] == 5:    # SUMDIFF (pivoted): x' = x + r0 y, y' = x + r1 y
+            r0, r1 = m[0, 0].real, m[0, 0].imag
+            assert abs(r0) == 1 and abs(r1) == 1
+            a[e0] = x + r0 * y
+            a[e1] = x + r1 * y
+        elif op['kind'] == 6:    # ROT_R (pivoted): x' = x + r y, y' = y + s x
+            a[e0] = x + m[0, 0].real * y
+            a[e1] = y + m[0, 0].imag * x
+        elif op['kind'] == 7:    # ROT_I (pivoted): x' = x + i a y, y' = y + i b x
+            a[e0] = x + 1j * m[0, 0].real * y
+            a[e1] = y + 1j * m[0, 0].imag * x
         else:
             a[e0] = m[0, 0] * x + m[0, 1] * y
             a[e1] = m[1, 0] * x + m[1, 1] * y
