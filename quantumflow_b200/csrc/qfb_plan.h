@@ -27,7 +27,7 @@
 #include <stdint.h>
 
 #define QFB_PLAN_MAGIC 0x50424651u /* "QFBP" */
-#define QFB_PLAN_VERSION 4u
+#define QFB_PLAN_VERSION 5u
 #define QFB_PLAN_REG_BITS 4
 #define QFB_PLAN_MAX_TILE_BITS 13
 #define QFB_PLAN_MIN_TILE_BITS 5
@@ -76,7 +76,6 @@ typedef struct {
     qfb_thread_lut lut_hi[QFB_PLAN_LUT_HI];
 } qfb_round_header; /* 32 + 768 bytes */
 
-enum { QFB_OP_G1 = 1, QFB_OP_G2 = 2, QFB_OP_CPH = 3 };
 /* kinds of QFB_OP_G1: structure of the 2x2 operator, chosen by the planner to save FP64 work. The "pivoted"
  * kinds apply the operator divided by its (0,0) entry; the planner multiplies the pivots of a sweep into one
  * uniform scalar that rides on the sweep's unconditional CPH term. (x, y) = the pair of amplitudes. */
@@ -91,17 +90,31 @@ enum {
     QFB_G1_ROT_R = 6,    /* pivoted real rotation (RY): x' = x + r y, y' = y + s x  (m[0], m[1]): 4 per pair */
     QFB_G1_ROT_I = 7     /* pivoted RX-like: x' = x + i a y, y' = y + i b x  (m[0], m[1]): 4 per pair */
 };
-/* kinds of QFB_OP_CPH */
-enum { QFB_CPH_FACTOR = 0, QFB_CPH_NEG = 1 /* factor == -1: sign flip, no arithmetic */ };
+/* Handler ids: one dense switch (a jump table) in the kernel's op interpreter.
+ *   QFB_H_G1 + 4*kind + j          uncontrolled 1-bit operator of the given kind on register bit j
+ *   QFB_H_G1C_GENERAL + j          controlled dense 1-bit operator   (reg_cmask / idx_cmask)
+ *   QFB_H_G1C_SWAPX + j            controlled X (CNOT, CCNOT ...)
+ *   QFB_H_CPH_SCALAR               phase term without register bits: accumulates into the round's scalar
+ *   QFB_H_CPH_REG / QFB_H_CPH_NEG  phase term on the register elements selected by reg_cmask (NEG: factor -1)
+ *   QFB_H_G2 + pair                dense 2-bit operator, (j0, j1) = (1,0) (2,0) (2,1) (3,0) (3,1) (3,2)
+ *   QFB_H_END                      terminates the round's op list */
+enum {
+    QFB_H_G1 = 0,
+    QFB_H_G1C_GENERAL = 32,
+    QFB_H_G1C_SWAPX = 36,
+    QFB_H_CPH_SCALAR = 40,
+    QFB_H_CPH_REG = 41,
+    QFB_H_CPH_NEG = 42,
+    QFB_H_G2 = 43,
+    QFB_H_END = 49
+};
 
 typedef struct {
-    uint8_t type;
-    uint8_t kind;
-    uint8_t j0;        /* register bit of gate qubit 0 (MSB of the operator index) */
-    uint8_t j1;        /* register bit of gate qubit 1 (G2 only; j0 > j1) */
+    uint8_t handler;
     uint8_t reg_cmask; /* control / phase mask over the register index */
-    uint8_t pad;
-    uint16_t bytes;    /* whole op record including this header */
+    uint8_t size16;    /* whole op record including this header, in 16-byte units */
+    uint8_t pad0;
+    uint32_t pad1;
     uint64_t idx_cmask; /* control / phase mask over thread-level bits of the FULL index (incl. rank bits) */
 } qfb_op_header; /* 16 bytes */
 
@@ -110,5 +123,6 @@ typedef struct {
  *   G2 : double m[32]; uint32 nzmask; uint32 pad[3]   row-major 4x4 complex, bit (4r+c) of nzmask set when
  *                      entry (r,c) is non-zero (272 B)
  *   CPH: double factor[2]  (16 B)
+ *   END: none
  */
 #endif

@@ -98,14 +98,14 @@ __device__ __forceinline__ void pair_general(c128 &x, c128 &y, const double *__r
 }
 
 // ---- 1-bit operator on register bit J; RC: honour the register control mask ----
-template <int J, bool RC>
-__device__ __forceinline__ void g1_apply(c128 (&a)[NE], const double *__restrict__ m, int kind, uint32_t rc) {
+template <int J, int KIND, bool RC>
+__device__ __forceinline__ void g1_apply(c128 (&a)[NE], const double *__restrict__ m, uint32_t rc) {
 #define QFB_PAIR_LOOP                                                                      \
     _Pragma("unroll") for (int p = 0; p < NE / 2; ++p) {                                   \
         const int e0 = ((p >> J) << (J + 1)) | (p & ((1 << J) - 1)), e1 = e0 | (1 << J);   \
         if (RC && (e0 & rc) != rc) continue;
     // controlled operators only come as SWAPX or GENERAL (pivoting needs an unconditional, uniform scalar)
-    if (!RC && kind == QFB_G1_SUMDIFF) {
+    if constexpr (KIND == QFB_G1_SUMDIFF) {
         const double r0 = m[0], r1 = m[1];  // x' = x + r0 y, y' = x + r1 y, r = +-1: exact sums
         QFB_PAIR_LOOP
             c128 &x = a[e0], &y = a[e1];
@@ -115,7 +115,7 @@ __device__ __forceinline__ void g1_apply(c128 (&a)[NE], const double *__restrict
             ip_set(y.re, sr);
             ip_set(y.im, si);
         }
-    } else if (!RC && kind == QFB_G1_ROT_R) {
+    } else if constexpr (KIND == QFB_G1_ROT_R) {
         const double r = m[0], s = m[1];    // x' = x + r y, y' = y + s x
         QFB_PAIR_LOOP
             c128 &x = a[e0], &y = a[e1];
@@ -125,7 +125,7 @@ __device__ __forceinline__ void g1_apply(c128 (&a)[NE], const double *__restrict
             ip_fma_acc(y.re, s, xr);
             ip_fma_acc(y.im, s, xi);
         }
-    } else if (!RC && kind == QFB_G1_ROT_I) {
+    } else if constexpr (KIND == QFB_G1_ROT_I) {
         const double ca = m[0], cb = m[1];  // x' = x + i ca y, y' = y + i cb x
         QFB_PAIR_LOOP
             c128 &x = a[e0], &y = a[e1];
@@ -135,7 +135,7 @@ __device__ __forceinline__ void g1_apply(c128 (&a)[NE], const double *__restrict
             ip_fma_acc(y.re, -cb, xi);
             ip_fma_acc(y.im, cb, xr);
         }
-    } else if (!RC && kind == QFB_G1_REAL) {
+    } else if constexpr (KIND == QFB_G1_REAL) {
         const double m00 = m[0], m01 = m[2], m10 = m[4], m11 = m[6];
         QFB_PAIR_LOOP
             c128 &x = a[e0], &y = a[e1];
@@ -145,7 +145,7 @@ __device__ __forceinline__ void g1_apply(c128 (&a)[NE], const double *__restrict
             ip_fma_scale(y.re, m11, qr);
             ip_fma_scale(y.im, m11, qi);
         }
-    } else if (!RC && kind == QFB_G1_RXLIKE) {
+    } else if constexpr (KIND == QFB_G1_RXLIKE) {
         const double d0 = m[0], o01 = m[3], o10 = m[5], d1 = m[6];
         QFB_PAIR_LOOP
             c128 &x = a[e0], &y = a[e1];
@@ -156,12 +156,12 @@ __device__ __forceinline__ void g1_apply(c128 (&a)[NE], const double *__restrict
             ip_fma_scale(y.re, d1, qr);
             ip_fma_scale(y.im, d1, qi);
         }
-    } else if (kind == QFB_G1_SWAPX) {
+    } else if constexpr (KIND == QFB_G1_SWAPX) {
         QFB_PAIR_LOOP
             ip_swap(a[e0].re, a[e1].re);
             ip_swap(a[e0].im, a[e1].im);
         }
-    } else if (!RC && kind == QFB_G1_ANTIDIAG) {
+    } else if constexpr (KIND == QFB_G1_ANTIDIAG) {
         const double ar = m[2], ai = m[3], br = m[4], bi = m[5];
         QFB_PAIR_LOOP
             c128 &x = a[e0], &y = a[e1];
@@ -315,58 +315,73 @@ sweep_kernel(c128 *__restrict__ state, const uint8_t *__restrict__ rec_g, uint32
 
             const uint64_t tfull = hi_shifted | gb | tg;
             double phr = 1.0, phi = 0.0;  // running per-thread scalar phase of this round
+            // ---- op interpreter: one table jump per op; the next header is in flight while a handler runs ----
             const uint8_t *op = rp + sizeof(qfb_round_header);
-            const int nops = (int)rh->nops;
-            uint4 hw_next = *reinterpret_cast<const uint4 *>(op);  // rounds end with a 16-byte guard record
-            for (int o = 0; o < nops; ++o) {
-                const uint4 hw = hw_next;
-                hw_next = *reinterpret_cast<const uint4 *>(op + (hw.y >> 16));   // prefetch the next op header
-                const uint32_t type = hw.x & 0xffu, kind = (hw.x >> 8) & 0xffu, j0 = (hw.x >> 16) & 0xffu,
-                               j1 = hw.x >> 24, rc = hw.y & 0xffu, bytes = hw.y >> 16;
+            uint4 hw = *reinterpret_cast<const uint4 *>(op);
+            for (;;) {
+                const uint32_t handler = hw.x & 0xffu;
+                if (handler == QFB_H_END) break;
+                const uint32_t rc = (hw.x >> 8) & 0xffu;
                 const uint64_t cm = ((uint64_t)hw.w << 32) | hw.z;
                 const double *m = reinterpret_cast<const double *>(op + sizeof(qfb_op_header));
-                const bool on = (tfull & cm) == cm;
-                if (type == QFB_OP_CPH) {
-                    if (on) {
-                        const double fr = m[0], fi = m[1];
-                        if (rc == 0u) {
+                op += ((hw.x >> 16) & 0xffu) << 4;
+                const uint4 hwn = *reinterpret_cast<const uint4 *>(op);   // every round ends with an END record
+#define QFB_G1_CASES(KIND)                                                                     \
+    case QFB_H_G1 + 4 * KIND + 0: g1_apply<0, KIND, false>(a, m, 0u); break;                   \
+    case QFB_H_G1 + 4 * KIND + 1: g1_apply<1, KIND, false>(a, m, 0u); break;                   \
+    case QFB_H_G1 + 4 * KIND + 2: g1_apply<2, KIND, false>(a, m, 0u); break;                   \
+    case QFB_H_G1 + 4 * KIND + 3: g1_apply<3, KIND, false>(a, m, 0u); break;
+#define QFB_G1C_CASES(BASE, KIND)                                                              \
+    case BASE + 0: if ((tfull & cm) == cm) g1_apply<0, KIND, true>(a, m, rc); break;           \
+    case BASE + 1: if ((tfull & cm) == cm) g1_apply<1, KIND, true>(a, m, rc); break;           \
+    case BASE + 2: if ((tfull & cm) == cm) g1_apply<2, KIND, true>(a, m, rc); break;           \
+    case BASE + 3: if ((tfull & cm) == cm) g1_apply<3, KIND, true>(a, m, rc); break;
+#define QFB_G2_CASE(IDX, J0, J1)                                                               \
+    case QFB_H_G2 + IDX:                                                                       \
+        if (HAS_G2 && (tfull & cm) == cm)                                                      \
+            g2_apply<J0, J1>(a, m, *reinterpret_cast<const uint32_t *>(m + 32), rc);           \
+        break;
+                switch (handler) {
+                    QFB_G1_CASES(QFB_G1_GENERAL)
+                    QFB_G1_CASES(QFB_G1_REAL)
+                    QFB_G1_CASES(QFB_G1_RXLIKE)
+                    QFB_G1_CASES(QFB_G1_SWAPX)
+                    QFB_G1_CASES(QFB_G1_ANTIDIAG)
+                    QFB_G1_CASES(QFB_G1_SUMDIFF)
+                    QFB_G1_CASES(QFB_G1_ROT_R)
+                    QFB_G1_CASES(QFB_G1_ROT_I)
+                    QFB_G1C_CASES(QFB_H_G1C_GENERAL, QFB_G1_GENERAL)
+                    QFB_G1C_CASES(QFB_H_G1C_SWAPX, QFB_G1_SWAPX)
+                    case QFB_H_CPH_SCALAR:
+                        if ((tfull & cm) == cm) {
+                            const double fr = m[0], fi = m[1];
                             const double t0 = fi * phi, t1 = fi * phr;
                             phr = fma(fr, phr, -t0);
                             phi = fma(fr, phi, t1);
-                        } else {
-                            cph_dispatch(a, rc, fr, fi, kind == QFB_CPH_NEG);
                         }
-                    }
-                } else if (on) {
-                    if (type == QFB_OP_G1) {
-                        if (rc == 0u) {
-                            switch (j0) {
-                                case 0: g1_apply<0, false>(a, m, kind, 0u); break;
-                                case 1: g1_apply<1, false>(a, m, kind, 0u); break;
-                                case 2: g1_apply<2, false>(a, m, kind, 0u); break;
-                                default: g1_apply<3, false>(a, m, kind, 0u); break;
-                            }
-                        } else {
-                            switch (j0) {
-                                case 0: g1_apply<0, true>(a, m, kind, rc); break;
-                                case 1: g1_apply<1, true>(a, m, kind, rc); break;
-                                case 2: g1_apply<2, true>(a, m, kind, rc); break;
-                                default: g1_apply<3, true>(a, m, kind, rc); break;
-                            }
-                        }
-                    } else if (HAS_G2) {
-                        const uint32_t nz = *reinterpret_cast<const uint32_t *>(op + sizeof(qfb_op_header) + 256);
-                        switch (j0 * 4 + j1) {
-                            case 1 * 4 + 0: g2_apply<1, 0>(a, m, nz, rc); break;
-                            case 2 * 4 + 0: g2_apply<2, 0>(a, m, nz, rc); break;
-                            case 2 * 4 + 1: g2_apply<2, 1>(a, m, nz, rc); break;
-                            case 3 * 4 + 0: g2_apply<3, 0>(a, m, nz, rc); break;
-                            case 3 * 4 + 1: g2_apply<3, 1>(a, m, nz, rc); break;
-                            default: g2_apply<3, 2>(a, m, nz, rc); break;
-                        }
-                    }
+                        break;
+                    case QFB_H_CPH_REG:
+                        if ((tfull & cm) == cm) cph_dispatch(a, rc, m[0], m[1], false);
+                        break;
+                    case QFB_H_CPH_NEG:
+                        if ((tfull & cm) == cm) cph_dispatch(a, rc, 0.0, 0.0, true);
+                        break;
+                    QFB_G2_CASE(0, 1, 0)
+                    QFB_G2_CASE(1, 2, 0)
+                    QFB_G2_CASE(2, 2, 1)
+                    QFB_G2_CASE(3, 3, 0)
+                    QFB_G2_CASE(4, 3, 1)
+                    QFB_G2_CASE(5, 3, 2)
+                    default: break;
                 }
-                op += bytes;
+#undef QFB_G1_CASES
+#undef QFB_G1C_CASES
+#undef QFB_G2_CASE
+                // hand the prefetched header over at the very end (volatile: keeps the copy, and with it the
+                // wait for the load, below the handler instead of right behind the LDS)
+                asm volatile("mov.b32 %0, %4;\n\tmov.b32 %1, %5;\n\tmov.b32 %2, %6;\n\tmov.b32 %3, %7;"
+                             : "=r"(hw.x), "=r"(hw.y), "=r"(hw.z), "=r"(hw.w)
+                             : "r"(hwn.x), "r"(hwn.y), "r"(hwn.z), "r"(hwn.w));
             }
             if (rh->has_scalar) {
 #pragma unroll
@@ -474,31 +489,39 @@ static int validate_plan(const uint8_t *p, size_t nbytes, std::vector<SweepInfo>
             }
             size_t ooff = roff + sizeof(rh);
             const size_t rend = roff + rh.bytes;
-            for (uint32_t o = 0; o < rh.nops; ++o) {
+            bool ended = false;
+            for (uint32_t o = 0; o <= rh.nops; ++o) {
                 QFB_CHECK_ARG(ooff + sizeof(qfb_op_header) <= rend, "plan: truncated op");
                 qfb_op_header oh;
                 memcpy(&oh, p + ooff, sizeof(oh));
-                QFB_CHECK_ARG(oh.bytes % 16 == 0 && oh.bytes >= sizeof(oh) && ooff + oh.bytes <= rend,
-                              "plan: op bad size");
-                if (oh.type == QFB_OP_G1) {
-                    QFB_CHECK_ARG(oh.bytes == 16 + 64 && oh.j0 < R && oh.kind <= QFB_G1_ROT_I &&
-                                      (oh.reg_cmask == 0 || oh.kind == QFB_G1_GENERAL || oh.kind == QFB_G1_SWAPX) &&
-                                      !((oh.reg_cmask >> oh.j0) & 1) && oh.reg_cmask < NE,
-                                  "plan: bad G1 op");
-                } else if (oh.type == QFB_OP_G2) {
-                    QFB_CHECK_ARG(rh.has_g2 == 1 && oh.bytes == 16 + 272 && oh.j0 < R && oh.j1 < oh.j0 &&
-                                      !((oh.reg_cmask >> oh.j0) & 1) && !((oh.reg_cmask >> oh.j1) & 1) &&
-                                      oh.reg_cmask < NE,
+                const uint32_t bytes = (uint32_t)oh.size16 * 16u;
+                QFB_CHECK_ARG(bytes >= sizeof(oh) && ooff + bytes <= rend, "plan: op bad size");
+                const int h = oh.handler;
+                if (o == rh.nops) {
+                    QFB_CHECK_ARG(h == QFB_H_END && bytes == 16, "plan: round does not end with an END record");
+                    ended = true;
+                } else if (h >= QFB_H_G1 && h < QFB_H_G1 + 32) {
+                    QFB_CHECK_ARG(bytes == 16 + 64 && oh.reg_cmask == 0 && oh.idx_cmask == 0, "plan: bad G1 op");
+                } else if (h >= QFB_H_G1C_GENERAL && h < QFB_H_G1C_SWAPX + 4) {
+                    const int j = (h - QFB_H_G1C_GENERAL) & 3;
+                    QFB_CHECK_ARG(bytes == 16 + 64 && !((oh.reg_cmask >> j) & 1) && oh.reg_cmask < NE,
+                                  "plan: bad controlled G1 op");
+                } else if (h == QFB_H_CPH_SCALAR) {
+                    QFB_CHECK_ARG(bytes == 32 && oh.reg_cmask == 0 && rh.has_scalar == 1, "plan: bad scalar CPH op");
+                } else if (h == QFB_H_CPH_REG || h == QFB_H_CPH_NEG) {
+                    QFB_CHECK_ARG(bytes == 32 && oh.reg_cmask > 0 && oh.reg_cmask < NE, "plan: bad CPH op");
+                } else if (h >= QFB_H_G2 && h < QFB_H_G2 + 6) {
+                    static const int J0[6] = {1, 2, 2, 3, 3, 3}, J1[6] = {0, 0, 1, 0, 1, 2};
+                    const int j0 = J0[h - QFB_H_G2], j1 = J1[h - QFB_H_G2];
+                    QFB_CHECK_ARG(rh.has_g2 == 1 && bytes == 16 + 272 && !((oh.reg_cmask >> j0) & 1) &&
+                                      !((oh.reg_cmask >> j1) & 1) && oh.reg_cmask < NE,
                                   "plan: bad G2 op");
-                } else if (oh.type == QFB_OP_CPH) {
-                    QFB_CHECK_ARG(oh.bytes == 16 + 16 && oh.reg_cmask < NE && oh.kind <= QFB_CPH_NEG &&
-                                      (oh.reg_cmask != 0 || rh.has_scalar == 1),
-                                  "plan: bad CPH op");
                 } else {
-                    QFB_CHECK_ARG(false, "plan: unknown op type %u", oh.type);
+                    QFB_CHECK_ARG(false, "plan: unknown handler %d", h);
                 }
-                ooff += oh.bytes;
+                ooff += bytes;
             }
+            QFB_CHECK_ARG(ended, "plan: missing END record");
             QFB_CHECK_ARG(ooff == rend, "plan: round size mismatch");
             roff += rh.bytes;
         }

@@ -31,14 +31,28 @@ import numpy as np
 from . import classify
 
 PLAN_MAGIC = 0x50424651
-PLAN_VERSION = 4
+PLAN_VERSION = 5
 REG_BITS = 4
 MAX_TILE_BITS = 13
 MIN_TILE_BITS = 5
 MAX_HOLES = 48
 MAX_SWEEP_BYTES = 40 * 1024
 MAX_DIAG_BITS = 5
-OP_G1, OP_G2, OP_CPH = 1, 2, 3
+# handler ids (csrc/qfb_plan.h)
+H_G1, H_G1C_GENERAL, H_G1C_SWAPX, H_CPH_SCALAR, H_CPH_REG, H_CPH_NEG, H_G2, H_END = 0, 32, 36, 40, 41, 42, 43, 49
+G2_PAIRS = [(1, 0), (2, 0), (2, 1), (3, 0), (3, 1), (3, 2)]
+
+
+def _op_record(handler: int, reg_cmask: int, idx_cmask: int, payload: bytes = b'') -> bytes:
+    size = 16 + len(payload)
+    assert size % 16 == 0 and size // 16 < 256
+    return struct.pack('<BBBBIQ', handler, reg_cmask, size // 16, 0, 0, idx_cmask) + payload
+
+
+def is_scalar_term(record: bytes) -> bool:
+    return record[0] == H_CPH_SCALAR
+
+
 ROUND_HEADER_BYTES = 32 + 16 * (16 + 32)
 
 # QFB_G1_* kinds (csrc/qfb_plan.h)
@@ -447,9 +461,8 @@ class Planner:
             else:
                 reg_cmask |= 1 << ri
         factor = complex(factor)
-        kind = 1 if (factor == -1 and reg_cmask != 0) else 0
-        payload = struct.pack('<dd', factor.real, factor.imag)
-        return struct.pack('<BBBBBBHQ', OP_CPH, kind, 0, 0, reg_cmask, 0, 16 + len(payload), idx_cmask) + payload
+        handler = H_CPH_SCALAR if reg_cmask == 0 else (H_CPH_NEG if factor == -1 else H_CPH_REG)
+        return _op_record(handler, reg_cmask, idx_cmask, struct.pack('<dd', factor.real, factor.imag))
 
     @staticmethod
     def _emit_gate(op: POp, pos_of, reg_of) -> Tuple[bytes, Optional[complex]]:
@@ -467,10 +480,12 @@ class Planner:
                 reg_cmask |= 1 << ri
         if len(op.mix) == 1:
             kind, payload, pivot = encode_g1(op.mat, bool(op.ctrl))
-            blob = payload.tobytes()
-            header = struct.pack('<BBBBBBHQ', OP_G1, kind, reg_index(op.mix[0]), 0, reg_cmask, 0, 16 + len(blob),
-                                 idx_cmask)
-            return header + blob, pivot
+            j = reg_index(op.mix[0])
+            if op.ctrl:
+                handler = (H_G1C_SWAPX if kind == K_SWAPX else H_G1C_GENERAL) + j
+            else:
+                handler = H_G1 + 4 * kind + j
+            return _op_record(handler, reg_cmask, idx_cmask, payload.tobytes()), pivot
         j0, j1 = reg_index(op.mix[0]), reg_index(op.mix[1])
         mat = np.ascontiguousarray(op.mat, dtype=np.complex128).reshape(2, 2, 2, 2)
         if j0 < j1:   # kernel wants the operator's MSB qubit on the higher register bit
@@ -482,9 +497,8 @@ class Planner:
             for c in range(4):
                 if mat[r, c] != 0:
                     nz |= 1 << (4 * r + c)
-        blob = mat.tobytes() + struct.pack('<I12x', nz)
-        header = struct.pack('<BBBBBBHQ', OP_G2, 0, j0, j1, reg_cmask, 0, 16 + len(blob), idx_cmask)
-        return header + blob, None
+        return _op_record(H_G2 + G2_PAIRS.index((j0, j1)), reg_cmask, idx_cmask,
+                          mat.tobytes() + struct.pack('<I12x', nz)), None
 
     @staticmethod
     def _thread_luts(sweep: SweepPlan, thr: Sequence[int]) -> bytes:
@@ -522,16 +536,16 @@ class Planner:
                 encoded.append((rd, blobs))
             if scalar != 1:
                 # one unconditional per-thread scalar term; put it where a scalar is applied anyway
-                target = next((i for i, (_, bl) in enumerate(encoded)
-                               if any(b[0] == OP_CPH and b[4] == 0 for b in bl)), len(encoded) - 1)
+                target = next((i for i, (_, bl) in enumerate(encoded) if any(is_scalar_term(b) for b in bl)),
+                              len(encoded) - 1)
                 encoded[target][1].append(self._emit_phase((), scalar, pos_of, {}))
             rounds_blob = b''
             nops = 0
             for rd, blobs in encoded:
-                ops_blob = b''.join(blobs)
+                ops_blob = b''.join(blobs) + _op_record(H_END, 0, 0)
                 nops += len(blobs)
-                has_scalar = int(any(b[0] == OP_CPH and b[4] == 0 for b in blobs))
-                has_g2 = int(any(b[0] == OP_G2 for b in blobs))
+                has_scalar = int(any(is_scalar_term(b) for b in blobs))
+                has_g2 = int(any(H_G2 <= b[0] < H_G2 + 6 for b in blobs))
                 thrpad = list(rd.thr) + [0] * (12 - len(rd.thr))
                 rounds_blob += struct.pack('<II4B12BBB6x', len(blobs), ROUND_HEADER_BYTES + len(ops_blob), *rd.regs,
                                            *thrpad, has_scalar, has_g2)

@@ -20,7 +20,7 @@ def swz(idx):
 
 def parse(blob: bytes):
     magic, version, nbits, M, rbits, nsweeps, total = struct.unpack_from('<IIIIIIQ', blob, 0)
-    assert magic == 0x50424651 and version == 4 and rbits == R and total == len(blob)
+    assert magic == 0x50424651 and version == 5 and rbits == R and total == len(blob)
     off = 32
     sweeps = []
     for _ in range(nsweeps):
@@ -46,12 +46,27 @@ def parse(blob: bytes):
                 assert (lo[0] | hi[0], lo[2] | hi[2]) == (tb, tg), 'bad thread LUT'
             ooff = roff + 32 + 768
             ops = []
-            for _o in range(rn):
-                typ, kind, j0, j1, rcm, nb, obytes, icm = struct.unpack_from('<BBBBBBHQ', blob, ooff)
+            for _o in range(rn + 1):
+                handler, rcm, size16, _p0, _p1, icm = struct.unpack_from('<BBBBIQ', blob, ooff)
+                obytes = 16 * size16
                 payload = blob[ooff + 16: ooff + obytes]
-                ops.append(dict(type=typ, kind=kind, j0=j0, j1=j1, reg_cmask=rcm, nb=nb, idx_cmask=icm,
-                                payload=payload))
                 ooff += obytes
+                if _o == rn:
+                    assert handler == 49 and obytes == 16, 'round must end with an END record'
+                    break
+                if handler < 32:
+                    assert rcm == 0 and icm == 0
+                    typ, kind, j0, j1 = 1, handler // 4, handler % 4, 0
+                elif handler < 40:
+                    typ, kind, j0, j1 = 1, (0 if handler < 36 else 3), handler % 4, 0
+                elif handler in (40, 41, 42):
+                    typ, kind, j0, j1 = 3, int(handler == 42), 0, 0
+                    assert (handler == 40) == (rcm == 0)
+                else:
+                    assert 43 <= handler < 49
+                    typ, kind = 2, 0
+                    j0, j1 = [(1, 0), (2, 0), (2, 1), (3, 0), (3, 1), (3, 2)][handler - 43]
+                ops.append(dict(type=typ, kind=kind, j0=j0, j1=j1, reg_cmask=rcm, idx_cmask=icm, payload=payload))
             assert ooff == roff + rbytes
             assert has_g2 == int(any(o['type'] == 2 for o in ops))
             rounds.append(dict(regpos=regpos, thrpos=thrpos, ops=ops, has_scalar=has_scalar))
