@@ -98,15 +98,17 @@ __device__ __forceinline__ void pair_general(c128 &x, c128 &y, const double *__r
 }
 
 // ---- 1-bit operator on register bit J; RC: honour the register control mask ----
+// p0, p1: the first two payload doubles, prefetched together with the op header
 template <int J, int KIND, bool RC>
-__device__ __forceinline__ void g1_apply(c128 (&a)[NE], const double *__restrict__ m, uint32_t rc) {
+__device__ __forceinline__ void g1_apply(c128 (&a)[NE], const double *__restrict__ m, double p0, double p1,
+                                         uint32_t rc) {
 #define QFB_PAIR_LOOP                                                                      \
     _Pragma("unroll") for (int p = 0; p < NE / 2; ++p) {                                   \
         const int e0 = ((p >> J) << (J + 1)) | (p & ((1 << J) - 1)), e1 = e0 | (1 << J);   \
         if (RC && (e0 & rc) != rc) continue;
     // controlled operators only come as SWAPX or GENERAL (pivoting needs an unconditional, uniform scalar)
     if constexpr (KIND == QFB_G1_SUMDIFF) {
-        const double r0 = m[0], r1 = m[1];  // x' = x + r0 y, y' = x + r1 y, r = +-1: exact sums
+        const double r0 = p0, r1 = p1;  // x' = x + r0 y, y' = x + r1 y, r = +-1: exact sums
         QFB_PAIR_LOOP
             c128 &x = a[e0], &y = a[e1];
             const double sr = fma(r1, y.re, x.re), si = fma(r1, y.im, x.im);
@@ -116,7 +118,7 @@ __device__ __forceinline__ void g1_apply(c128 (&a)[NE], const double *__restrict
             ip_set(y.im, si);
         }
     } else if constexpr (KIND == QFB_G1_ROT_R) {
-        const double r = m[0], s = m[1];    // x' = x + r y, y' = y + s x
+        const double r = p0, s = p1;    // x' = x + r y, y' = y + s x
         QFB_PAIR_LOOP
             c128 &x = a[e0], &y = a[e1];
             const double xr = x.re, xi = x.im;
@@ -126,7 +128,7 @@ __device__ __forceinline__ void g1_apply(c128 (&a)[NE], const double *__restrict
             ip_fma_acc(y.im, s, xi);
         }
     } else if constexpr (KIND == QFB_G1_ROT_I) {
-        const double ca = m[0], cb = m[1];  // x' = x + i ca y, y' = y + i cb x
+        const double ca = p0, cb = p1;  // x' = x + i ca y, y' = y + i cb x
         QFB_PAIR_LOOP
             c128 &x = a[e0], &y = a[e1];
             const double xr = x.re, xi = x.im;
@@ -318,6 +320,7 @@ sweep_kernel(c128 *__restrict__ state, const uint8_t *__restrict__ rec_g, uint32
             // ---- op interpreter: one table jump per op; the next header is in flight while a handler runs ----
             const uint8_t *op = rp + sizeof(qfb_round_header);
             uint4 hw = *reinterpret_cast<const uint4 *>(op);
+            double2 pw = *reinterpret_cast<const double2 *>(op + sizeof(qfb_op_header));
             for (;;) {
                 const uint32_t handler = hw.x & 0xffu;
                 if (handler == QFB_H_END) break;
@@ -326,16 +329,17 @@ sweep_kernel(c128 *__restrict__ state, const uint8_t *__restrict__ rec_g, uint32
                 const double *m = reinterpret_cast<const double *>(op + sizeof(qfb_op_header));
                 op += ((hw.x >> 16) & 0xffu) << 4;
                 const uint4 hwn = *reinterpret_cast<const uint4 *>(op);   // every round ends with an END record
+                const double2 pwn = *reinterpret_cast<const double2 *>(op + sizeof(qfb_op_header));
 #define QFB_G1_CASES(KIND)                                                                     \
-    case QFB_H_G1 + 4 * KIND + 0: g1_apply<0, KIND, false>(a, m, 0u); break;                   \
-    case QFB_H_G1 + 4 * KIND + 1: g1_apply<1, KIND, false>(a, m, 0u); break;                   \
-    case QFB_H_G1 + 4 * KIND + 2: g1_apply<2, KIND, false>(a, m, 0u); break;                   \
-    case QFB_H_G1 + 4 * KIND + 3: g1_apply<3, KIND, false>(a, m, 0u); break;
+    case QFB_H_G1 + 4 * KIND + 0: g1_apply<0, KIND, false>(a, m, pw.x, pw.y, 0u); break;                   \
+    case QFB_H_G1 + 4 * KIND + 1: g1_apply<1, KIND, false>(a, m, pw.x, pw.y, 0u); break;                   \
+    case QFB_H_G1 + 4 * KIND + 2: g1_apply<2, KIND, false>(a, m, pw.x, pw.y, 0u); break;                   \
+    case QFB_H_G1 + 4 * KIND + 3: g1_apply<3, KIND, false>(a, m, pw.x, pw.y, 0u); break;
 #define QFB_G1C_CASES(BASE, KIND)                                                              \
-    case BASE + 0: if ((tfull & cm) == cm) g1_apply<0, KIND, true>(a, m, rc); break;           \
-    case BASE + 1: if ((tfull & cm) == cm) g1_apply<1, KIND, true>(a, m, rc); break;           \
-    case BASE + 2: if ((tfull & cm) == cm) g1_apply<2, KIND, true>(a, m, rc); break;           \
-    case BASE + 3: if ((tfull & cm) == cm) g1_apply<3, KIND, true>(a, m, rc); break;
+    case BASE + 0: if ((tfull & cm) == cm) g1_apply<0, KIND, true>(a, m, pw.x, pw.y, rc); break;           \
+    case BASE + 1: if ((tfull & cm) == cm) g1_apply<1, KIND, true>(a, m, pw.x, pw.y, rc); break;           \
+    case BASE + 2: if ((tfull & cm) == cm) g1_apply<2, KIND, true>(a, m, pw.x, pw.y, rc); break;           \
+    case BASE + 3: if ((tfull & cm) == cm) g1_apply<3, KIND, true>(a, m, pw.x, pw.y, rc); break;
 #define QFB_G2_CASE(IDX, J0, J1)                                                               \
     case QFB_H_G2 + IDX:                                                                       \
         if (HAS_G2 && (tfull & cm) == cm)                                                      \
@@ -343,10 +347,7 @@ sweep_kernel(c128 *__restrict__ state, const uint8_t *__restrict__ rec_g, uint32
         break;
                 switch (handler) {
                     QFB_G1_CASES(QFB_G1_GENERAL)
-                    QFB_G1_CASES(QFB_G1_REAL)
-                    QFB_G1_CASES(QFB_G1_RXLIKE)
                     QFB_G1_CASES(QFB_G1_SWAPX)
-                    QFB_G1_CASES(QFB_G1_ANTIDIAG)
                     QFB_G1_CASES(QFB_G1_SUMDIFF)
                     QFB_G1_CASES(QFB_G1_ROT_R)
                     QFB_G1_CASES(QFB_G1_ROT_I)
@@ -354,14 +355,14 @@ sweep_kernel(c128 *__restrict__ state, const uint8_t *__restrict__ rec_g, uint32
                     QFB_G1C_CASES(QFB_H_G1C_SWAPX, QFB_G1_SWAPX)
                     case QFB_H_CPH_SCALAR:
                         if ((tfull & cm) == cm) {
-                            const double fr = m[0], fi = m[1];
+                            const double fr = pw.x, fi = pw.y;
                             const double t0 = fi * phi, t1 = fi * phr;
                             phr = fma(fr, phr, -t0);
                             phi = fma(fr, phi, t1);
                         }
                         break;
                     case QFB_H_CPH_REG:
-                        if ((tfull & cm) == cm) cph_dispatch(a, rc, m[0], m[1], false);
+                        if ((tfull & cm) == cm) cph_dispatch(a, rc, pw.x, pw.y, false);
                         break;
                     case QFB_H_CPH_NEG:
                         if ((tfull & cm) == cm) cph_dispatch(a, rc, 0.0, 0.0, true);
@@ -382,6 +383,7 @@ sweep_kernel(c128 *__restrict__ state, const uint8_t *__restrict__ rec_g, uint32
                 asm volatile("mov.b32 %0, %4;\n\tmov.b32 %1, %5;\n\tmov.b32 %2, %6;\n\tmov.b32 %3, %7;"
                              : "=r"(hw.x), "=r"(hw.y), "=r"(hw.z), "=r"(hw.w)
                              : "r"(hwn.x), "r"(hwn.y), "r"(hwn.z), "r"(hwn.w));
+                asm volatile("mov.f64 %0, %2;\n\tmov.f64 %1, %3;" : "=d"(pw.x), "=d"(pw.y) : "d"(pwn.x), "d"(pwn.y));
             }
             if (rh->has_scalar) {
 #pragma unroll
@@ -501,7 +503,12 @@ static int validate_plan(const uint8_t *p, size_t nbytes, std::vector<SweepInfo>
                     QFB_CHECK_ARG(h == QFB_H_END && bytes == 16, "plan: round does not end with an END record");
                     ended = true;
                 } else if (h >= QFB_H_G1 && h < QFB_H_G1 + 32) {
-                    QFB_CHECK_ARG(bytes == 16 + 64 && oh.reg_cmask == 0 && oh.idx_cmask == 0, "plan: bad G1 op");
+                    const int kind = (h - QFB_H_G1) >> 2;
+                    // REAL / RXLIKE / ANTIDIAG are reserved: the planner folds them into GENERAL (they are rare
+                    // once rotations are pivoted, and their handlers only cost instruction-cache space)
+                    QFB_CHECK_ARG(bytes == 16 + 64 && oh.reg_cmask == 0 && oh.idx_cmask == 0 &&
+                                      kind != QFB_G1_REAL && kind != QFB_G1_RXLIKE && kind != QFB_G1_ANTIDIAG,
+                                  "plan: bad G1 op");
                 } else if (h >= QFB_H_G1C_GENERAL && h < QFB_H_G1C_SWAPX + 4) {
                     const int j = (h - QFB_H_G1C_GENERAL) & 3;
                     QFB_CHECK_ARG(bytes == 16 + 64 && !((oh.reg_cmask >> j) & 1) && oh.reg_cmask < NE,
@@ -537,8 +544,8 @@ template <int M, bool G2>
 static int launch_sweep(c128 *state, const uint8_t *rec_dev, uint32_t rec_bytes, int nbits, uint64_t index_hi,
                         cudaStream_t st) {
     constexpr int T = SweepCfg<M>::T;
-    // +16: the op loop prefetches one header past the last op of a round
-    const size_t smem = (size_t)SweepCfg<M>::TILE_BYTES + rec_bytes + 16;
+    // +32: the op loop prefetches one header + 16 payload bytes past the END record of a round
+    const size_t smem = (size_t)SweepCfg<M>::TILE_BYTES + rec_bytes + 32;
     static thread_local size_t configured[64] = {0};
     int dev = 0;
     QFB_CUDA(cudaGetDevice(&dev));

@@ -122,7 +122,7 @@ def encode_g1(mat: np.ndarray, controlled: bool) -> Tuple[int, np.ndarray, Optio
     if controlled:
         return K_GENERAL, plain, None
     if base == K_ANTIDIAG:
-        return K_ANTIDIAG, plain, None
+        return K_GENERAL, plain, None
     big = np.abs(m).max()
     m00 = m[0, 0]
     pivotable = m00 != 0 and abs(m00) >= PIVOT_RATIO * big
@@ -141,7 +141,8 @@ def encode_g1(mat: np.ndarray, controlled: bool) -> Tuple[int, np.ndarray, Optio
         payload = np.zeros(8)
         payload[0], payload[1] = m[0, 1].imag / p, m[1, 0].imag / p
         return K_ROT_I, payload, complex(p)
-    return base, plain, None
+    # REAL / RXLIKE / ANTIDIAG operators that could not be pivoted are rare; they share the GENERAL handler
+    return (K_SWAPX if base == K_SWAPX else K_GENERAL), plain, None
 
 
 def classify_op(mat: np.ndarray, bits: Sequence[int], gate_index: int = -1):

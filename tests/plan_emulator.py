@@ -57,6 +57,7 @@ def parse(blob: bytes):
                 if handler < 32:
                     assert rcm == 0 and icm == 0
                     typ, kind, j0, j1 = 1, handler // 4, handler % 4, 0
+                    assert kind in (0, 3, 5, 6, 7), 'reserved G1 kind'
                 elif handler < 40:
                     typ, kind, j0, j1 = 1, (0 if handler < 36 else 3), handler % 4, 0
                 elif handler in (40, 41, 42):
