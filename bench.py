@@ -281,10 +281,11 @@ def main():
         state[0] = 1.0
 
     def step():
+        nonlocal state
         if runner is None:
             qf.Circuit._execute(segments, state)
         else:
-            runner.execute(state)
+            state = runner.execute(state)     # remaps swap the shard with the runner's scratch buffer
 
     def barrier():
         if world > 1:
@@ -294,6 +295,8 @@ def main():
     for _ in range(args.warmup):
         step()
     barrier()
+    if runner is not None:
+        runner.reset_comm_counters()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
@@ -358,8 +361,7 @@ def main():
                 out = circ.run(ket)                                     # public API: plans (cached) + sweeps
                 host_out.copy_(out.tensor.reshape(-1), non_blocking=False)   # D2H of the result
             else:
-                dstate = host_in.to(dev, non_blocking=False)
-                runner.execute(dstate)
+                dstate = runner.execute(host_in.to(dev, non_blocking=False))
                 host_out.copy_(dstate, non_blocking=False)
 
         e2e_step()      # warm-up (first Circuit.run also builds and uploads the plan)
