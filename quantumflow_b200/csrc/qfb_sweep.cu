@@ -284,9 +284,37 @@ sweep_kernel(c128 *__restrict__ state, const uint8_t *__restrict__ rec_g, uint32
     const int nrounds = (int)sh->nrounds;
     const uint64_t ntiles = 1ull << nholes;
 
-    for (uint64_t tile_id = blockIdx.x; tile_id < ntiles; tile_id += gridDim.x) {
+    // ---- asynchronous tile loader: the NEXT tile streams into the exchange buffer (cp.async, 16 B per request,
+    // L1 bypass) while the last round of the current tile computes and stores. Thread t moves tile-local elements
+    // t + c*T, c = 0..NE-1: consecutive threads read consecutive 16-byte words, i.e. whole 128-byte lines.
+    uint64_t lin_tg = 0;   // index-bit image of the tile-local bits carried by the thread id
+#pragma unroll
+    for (int b = 0; b < M - R; ++b) lin_tg |= (uint64_t)((tid >> b) & 1) << sh->gpos[b];
+    uint64_t lin_cg[R];    // index-bit image of tile-local bits M-R .. M-1 (the chunk number c)
+#pragma unroll
+    for (int i = 0; i < R; ++i) lin_cg[i] = 1ull << sh->gpos[M - R + i];
+    const uint32_t lin_sw = swz((uint32_t)tid);
+    const uint32_t tile_smem = (uint32_t)__cvta_generic_to_shared(tile);
+    auto tile_base = [&](uint64_t tile_id) {
         uint64_t gb = 0;
         for (int i = 0; i < nholes; ++i) gb |= ((tile_id >> i) & 1ull) << sh->hole[i];
+        return gb;
+    };
+    auto prefetch_tile = [&](uint64_t gb) {
+        const c128 *src = state + (gb | lin_tg);
+#pragma unroll
+        for (int c = 0; c < NE; ++c) {
+            const uint32_t dst = tile_smem + ((lin_sw ^ swz((uint32_t)c << (M - R))) << 4);
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src + pick(lin_cg, c)) : "memory");
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    if ((uint64_t)blockIdx.x < ntiles) prefetch_tile(tile_base(blockIdx.x));
+
+    for (uint64_t tile_id = blockIdx.x; tile_id < ntiles; tile_id += gridDim.x) {
+        const uint64_t gb = tile_base(tile_id);
+        asm volatile("cp.async.wait_all;" ::: "memory");
+        __syncthreads();   // the whole tile has landed in shared memory
 
         c128 a[NE];
         const uint8_t *rp = rec + sizeof(qfb_sweep_header);
@@ -302,18 +330,11 @@ sweep_kernel(c128 *__restrict__ state, const uint8_t *__restrict__ rec_g, uint32
             for (int i = 0; i < R; ++i) ps[i] = swz(1u << rh->regpos[i]);
             const uint32_t ptb = swz(tb);  // swz is linear over XOR and tb, register offsets are disjoint
 
-            if (round == 0) {
-                uint64_t sg[R];
 #pragma unroll
-                for (int i = 0; i < R; ++i) sg[i] = 1ull << sh->gpos[rh->regpos[i]];
-                const c128 *src = state + (gb | tg);
-#pragma unroll
-                for (int e = 0; e < NE; ++e) a[e] = ldg_stream(src + pick(sg, e));
-            } else {
-#pragma unroll
-                for (int e = 0; e < NE; ++e) a[e] = tile[ptb ^ pick_xor(ps, e)];
-                __syncthreads();  // everyone has read before anyone overwrites the tile again
-            }
+            for (int e = 0; e < NE; ++e) a[e] = tile[ptb ^ pick_xor(ps, e)];
+            __syncthreads();  // everyone has read before anyone overwrites the tile again
+            if (round + 1 == nrounds && tile_id + gridDim.x < ntiles)
+                prefetch_tile(tile_base(tile_id + gridDim.x));   // buffer is free until the next tile starts
 
             const uint64_t tfull = hi_shifted | gb | tg;
             double phr = 1.0, phi = 0.0;  // running per-thread scalar phase of this round

@@ -15,8 +15,8 @@ Passes, all order preserving up to commutation:
 2. sweeps     walk the list; an operator joins the current sweep when it does not conflict with a deferred
               operator and its mixing bits fit into the tile (M bits, the L lowest index bits are always members
               so that global accesses are whole 128-byte lines). A cost cap keeps a sweep close to HBM-bound.
-3. rounds     inside a sweep the same walk assigns operators to rounds of R=4 register bits; the first and
-              last round keep the low tile bits on the lanes (coalesced LDG/STG). Phase terms are then moved,
+3. rounds     inside a sweep the same walk assigns operators to rounds of R=4 register bits; the last round
+              keeps the low tile bits on the lanes (coalesced STG; tiles are loaded by cp.async, any layout). Phase terms are then moved,
               inside their commutation window, to the round where they are cheapest: a term whose bits are all
               thread-level is a per-thread scalar (4 FP64 ops instead of up to 64).
 4. encode     1-bit operators are divided by their (0,0) entry when that exposes a cheaper form (Hadamard:
@@ -305,7 +305,6 @@ class Planner:
         pos_of = {b: j for j, b in enumerate(sweep.tile)}
         remaining = list(sweep.ops)
         rounds: List[Tuple[List[int], List[POp]]] = []
-        first = True
         while remaining:
             regs: List[int] = []
             chosen: List[POp] = []
@@ -316,9 +315,7 @@ class Planner:
                 ok = not _conflicts(op, def_any, def_mix)
                 if ok and op.kind == 'G':
                     need = [pos_of[b] for b in op.mix if pos_of[b] not in regs]
-                    if first and any(pos_of[b] < self.L for b in op.mix):
-                        ok = False
-                    elif len(regs) + len(need) > REG_BITS:
+                    if len(regs) + len(need) > REG_BITS:
                         ok = False
                     else:
                         regs += need
@@ -330,19 +327,15 @@ class Planner:
                     def_mix |= op.mixset
             rounds.append((regs, chosen))
             remaining = deferred
-            first = False
         if not rounds:
             rounds.append(([], []))
         # the last round stores to HBM: its register bits must avoid the low tile positions
         if any(p < self.L for p in rounds[-1][0]):
             rounds.append(([], []))
-        # drop an empty first round when the sweep has another round that can serve as the load round
-        if len(rounds) > 1 and not rounds[0][1] and not any(p < self.L for p in rounds[1][0]):
-            rounds.pop(0)
         final: List[Round] = []
         nr = len(rounds)
         for r, (regs, chosen) in enumerate(rounds):
-            edge = (r == 0) or (r == nr - 1)
+            edge = (r == nr - 1)     # only the storing round needs the low bits on the lanes (loads are cp.async)
             regs = list(regs)
             # fill up to R register bits with high free positions (never low ones on edge rounds)
             cand = [p for p in range(self.M - 1, -1, -1) if p not in regs and (p >= self.L or not edge)]

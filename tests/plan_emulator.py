@@ -192,10 +192,16 @@ def execute(blob: bytes, state: np.ndarray, index_hi: int = 0, check_layout: boo
             for i, h in enumerate(hole):
                 gb |= ((tile_id >> i) & 1) << h
             tile = np.zeros(1 << M, dtype=np.complex128)   # "shared memory", indexed by swizzled tile index
+            # asynchronous tile loader: tile-local index i <- state[gb | deposit(i through gpos)]
+            for i in range(1 << M):
+                g = 0
+                for j in range(M):
+                    g |= ((i >> j) & 1) << gpos[j]
+                tile[swz(i)] = state[gb | g]
             for rnd, rd in enumerate(sweep['rounds']):
                 regpos, thrpos = rd['regpos'], rd['thrpos']
                 assert sorted(regpos + thrpos) == list(range(M))
-                if check_layout and (rnd == 0 or rnd == nrounds - 1):
+                if check_layout and rnd == nrounds - 1:
                     # edge rounds: lanes must walk the lowest index bits (coalesced 128-byte lines)
                     nlow = min(3, M - R)
                     assert [gpos[thrpos[t]] for t in range(nlow)] == list(range(nlow)), 'uncoalesced edge round'
@@ -213,10 +219,7 @@ def execute(blob: bytes, state: np.ndarray, index_hi: int = 0, check_layout: boo
                             if (e >> i) & 1:
                                 toff |= 1 << regpos[i]
                                 goff |= 1 << gpos[regpos[i]]
-                        if rnd == 0:
-                            a[e] = state[gb | tg | goff]
-                        else:
-                            a[e] = tile[swz(tb | toff)]
+                        a[e] = tile[swz(tb | toff)]
                     tfull = (index_hi << nbits) | gb | tg
                     scalar = 1.0 + 0j
                     for op in rd['ops']:
