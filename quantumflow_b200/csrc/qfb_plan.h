@@ -27,7 +27,7 @@
 #include <stdint.h>
 
 #define QFB_PLAN_MAGIC 0x50424651u /* "QFBP" */
-#define QFB_PLAN_VERSION 5u
+#define QFB_PLAN_VERSION 6u
 #define QFB_PLAN_REG_BITS 4
 #define QFB_PLAN_MAX_TILE_BITS 13
 #define QFB_PLAN_MIN_TILE_BITS 5
@@ -90,23 +90,33 @@ enum {
     QFB_G1_ROT_R = 6,    /* pivoted real rotation (RY): x' = x + r y, y' = y + s x  (m[0], m[1]): 4 per pair */
     QFB_G1_ROT_I = 7     /* pivoted RX-like: x' = x + i a y, y' = y + i b x  (m[0], m[1]): 4 per pair */
 };
-/* Handler ids: one dense switch (a jump table) in the kernel's op interpreter.
- *   QFB_H_G1 + 4*kind + j          uncontrolled 1-bit operator of the given kind on register bit j
- *   QFB_H_G1C_GENERAL + j          controlled dense 1-bit operator   (reg_cmask / idx_cmask)
- *   QFB_H_G1C_SWAPX + j            controlled X (CNOT, CCNOT ...)
- *   QFB_H_CPH_SCALAR               phase term without register bits: accumulates into the round's scalar
- *   QFB_H_CPH_REG / QFB_H_CPH_NEG  phase term on the register elements selected by reg_cmask (NEG: factor -1)
- *   QFB_H_G2 + pair                dense 2-bit operator, (j0, j1) = (1,0) (2,0) (2,1) (3,0) (3,1) (3,2)
- *   QFB_H_END                      terminates the round's op list */
+/* Handler ids: ONE DENSE switch in the kernel's op interpreter (dense ids let ptxas emit a jump table, BRX,
+ * instead of a compare tree whose serial branches cost ~15 cycles per level).
+ *   QFB_H_G1_GENERAL + j  uncontrolled dense 1-bit operator on register bit j (16 FP64 per pair)
+ *   QFB_H_G1_SWAPX + j    X
+ *   QFB_H_G1_SUMDIFF + j  pivoted Hadamard-like
+ *   QFB_H_G1_ROT_R + j    pivoted real rotation (RY)
+ *   QFB_H_G1_ROT_I + j    pivoted RX-like
+ *   QFB_H_G1C_GENERAL + j controlled dense 1-bit operator   (reg_cmask / idx_cmask)
+ *   QFB_H_G1C_SWAPX + j   controlled X (CNOT, CCNOT ...)
+ *   QFB_H_CPH_SCALAR      phase term without register bits: accumulates into the round's scalar
+ *   QFB_H_CPH_REG / _NEG  phase term on the register elements selected by reg_cmask (NEG: factor -1)
+ *   QFB_H_G2 + pair       dense 2-bit operator, (j0, j1) = (1,0) (2,0) (2,1) (3,0) (3,1) (3,2)
+ *   QFB_H_END             terminates the round's op list */
 enum {
-    QFB_H_G1 = 0,
-    QFB_H_G1C_GENERAL = 32,
-    QFB_H_G1C_SWAPX = 36,
-    QFB_H_CPH_SCALAR = 40,
-    QFB_H_CPH_REG = 41,
-    QFB_H_CPH_NEG = 42,
-    QFB_H_G2 = 43,
-    QFB_H_END = 49
+    QFB_H_G1_GENERAL = 0,
+    QFB_H_G1_SWAPX = 4,
+    QFB_H_G1_SUMDIFF = 8,
+    QFB_H_G1_ROT_R = 12,
+    QFB_H_G1_ROT_I = 16,
+    QFB_H_G1C_GENERAL = 20,
+    QFB_H_G1C_SWAPX = 24,
+    QFB_H_CPH_SCALAR = 28,
+    QFB_H_CPH_REG = 29,
+    QFB_H_CPH_NEG = 30,
+    QFB_H_G2 = 31,
+    QFB_H_END = 37,
+    QFB_H_COUNT = 38
 };
 
 typedef struct {

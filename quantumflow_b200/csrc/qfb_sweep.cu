@@ -17,6 +17,7 @@
 //
 // Roofline: HBM bound by design (planner caps the FP64 work per sweep); FP64 FMA pipe and shared-memory
 // bandwidth are the secondary limits ("sweep kernel").
+#include <stdlib.h>
 #include <algorithm>
 #include <vector>
 #include "qfb_common.cuh"
@@ -108,14 +109,16 @@ __device__ __forceinline__ void g1_apply(c128 (&a)[NE], const double *__restrict
         if (RC && (e0 & rc) != rc) continue;
     // controlled operators only come as SWAPX or GENERAL (pivoting needs an unconditional, uniform scalar)
     if constexpr (KIND == QFB_G1_SUMDIFF) {
-        const double r0 = p0, r1 = p1;  // x' = x + r0 y, y' = x + r1 y, r = +-1: exact sums
+        // x' = x + r0 y, y' = x + r1 y with r = +-1. y' is formed from x' (y' = x' + (r1 - r0) y) so that no
+        // temporary copy is needed: 4 FP64 per pair, nothing else. Exact zeros under destructive interference
+        // are kept: x = -r0 y gives x' = 0 exactly, x = -r1 y gives x' = (r0 - r1) y exactly and y' = 0.
+        const double r0 = p0, d = p1 - p0;
         QFB_PAIR_LOOP
             c128 &x = a[e0], &y = a[e1];
-            const double sr = fma(r1, y.re, x.re), si = fma(r1, y.im, x.im);
             ip_fma_acc(x.re, r0, y.re);
             ip_fma_acc(x.im, r0, y.im);
-            ip_set(y.re, sr);
-            ip_set(y.im, si);
+            ip_fma_scale(y.re, d, x.re);
+            ip_fma_scale(y.im, d, x.im);
         }
     } else if constexpr (KIND == QFB_G1_ROT_R) {
         const double r = p0, s = p1;    // x' = x + r y, y' = y + s x
@@ -237,7 +240,9 @@ __device__ __forceinline__ void cph_apply(c128 (&a)[NE], double fr, double fi, b
 }
 
 __device__ __forceinline__ void cph_dispatch(c128 (&a)[NE], uint32_t rc, double fr, double fi, bool neg) {
-    switch (rc) {
+    uint32_t opaque0;   // see the op interpreter: forces a jump table instead of a compare tree
+    asm volatile("mov.u32 %0, 0;" : "=r"(opaque0));
+    switch (rc + opaque0) {
         case 1: cph_apply<1>(a, fr, fi, neg); break;
         case 2: cph_apply<2>(a, fr, fi, neg); break;
         case 3: cph_apply<3>(a, fr, fi, neg); break;
@@ -268,7 +273,7 @@ struct SweepCfg {
 template <int M, bool HAS_G2>
 __global__ void __launch_bounds__(SweepCfg<M>::T, SweepCfg<M>::MINB)
 sweep_kernel(c128 *__restrict__ state, const uint8_t *__restrict__ rec_g, uint32_t rec_bytes, int nholes,
-             uint64_t hi_shifted) {
+             uint64_t hi_shifted, int async_load) {
     constexpr int T = SweepCfg<M>::T;
     extern __shared__ __align__(16) uint8_t smem[];
     c128 *tile = reinterpret_cast<c128 *>(smem);
@@ -309,12 +314,25 @@ sweep_kernel(c128 *__restrict__ state, const uint8_t *__restrict__ rec_g, uint32
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
-    if ((uint64_t)blockIdx.x < ntiles) prefetch_tile(tile_base(blockIdx.x));
+    // Two loaders (launch parameter): async_load = 1 streams the next tile into the exchange buffer (above);
+    // async_load = 0 loads round 0 with LDG straight into registers and only warms L2 with the next tile's lines
+    // (no extra shared-memory pass, but round 0 must keep the low bits on the lanes).
+    auto prefetch_l2 = [&](uint64_t gb) {
+        const c128 *src = state + (gb | lin_tg);
+        if ((tid & 7) == 0) {   // one request per 128-byte line
+#pragma unroll
+            for (int c = 0; c < NE; ++c)
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(src + pick(lin_cg, c)));
+        }
+    };
+    if (async_load && (uint64_t)blockIdx.x < ntiles) prefetch_tile(tile_base(blockIdx.x));
 
     for (uint64_t tile_id = blockIdx.x; tile_id < ntiles; tile_id += gridDim.x) {
         const uint64_t gb = tile_base(tile_id);
-        asm volatile("cp.async.wait_all;" ::: "memory");
-        __syncthreads();   // the whole tile has landed in shared memory
+        if (async_load) {
+            asm volatile("cp.async.wait_all;" ::: "memory");
+            __syncthreads();   // the whole tile has landed in shared memory
+        }
 
         c128 a[NE];
         const uint8_t *rp = rec + sizeof(qfb_sweep_header);
@@ -330,11 +348,22 @@ sweep_kernel(c128 *__restrict__ state, const uint8_t *__restrict__ rec_g, uint32
             for (int i = 0; i < R; ++i) ps[i] = swz(1u << rh->regpos[i]);
             const uint32_t ptb = swz(tb);  // swz is linear over XOR and tb, register offsets are disjoint
 
+            if (round == 0 && !async_load) {
+                uint64_t sg[R];
 #pragma unroll
-            for (int e = 0; e < NE; ++e) a[e] = tile[ptb ^ pick_xor(ps, e)];
-            __syncthreads();  // everyone has read before anyone overwrites the tile again
-            if (round + 1 == nrounds && tile_id + gridDim.x < ntiles)
-                prefetch_tile(tile_base(tile_id + gridDim.x));   // buffer is free until the next tile starts
+                for (int i = 0; i < R; ++i) sg[i] = 1ull << sh->gpos[rh->regpos[i]];
+                const c128 *src = state + (gb | tg);
+#pragma unroll
+                for (int e = 0; e < NE; ++e) a[e] = ldg_stream(src + pick(sg, e));
+            } else {
+#pragma unroll
+                for (int e = 0; e < NE; ++e) a[e] = tile[ptb ^ pick_xor(ps, e)];
+                __syncthreads();  // everyone has read before anyone overwrites the tile again
+            }
+            if (round + 1 == nrounds && tile_id + gridDim.x < ntiles) {
+                if (async_load) prefetch_tile(tile_base(tile_id + gridDim.x));   // buffer is free until the next tile
+                else prefetch_l2(tile_base(tile_id + gridDim.x));
+            }
 
             const uint64_t tfull = hi_shifted | gb | tg;
             double phr = 1.0, phi = 0.0;  // running per-thread scalar phase of this round
@@ -343,7 +372,13 @@ sweep_kernel(c128 *__restrict__ state, const uint8_t *__restrict__ rec_g, uint32
             uint4 hw = *reinterpret_cast<const uint4 *>(op);
             double2 pw = *reinterpret_cast<const double2 *>(op + sizeof(qfb_op_header));
             for (;;) {
-                const uint32_t handler = hw.x & 0xffu;
+                // `opaque0` is 0, but the compiler cannot know and must treat the handler id as per-thread data:
+                // for warp-uniform values ptxas only builds compare trees (~15 cycles per level of serial
+                // branches, profiles/r1_microbench_v5.jsonl: a CZ sign flip cost as much as a Hadamard), for
+                // per-thread values it emits jump tables (BRX).
+                uint32_t opaque0;
+                asm volatile("mov.u32 %0, 0;" : "=r"(opaque0));
+                const uint32_t handler = (hw.x & 0xffu) + opaque0;
                 if (handler == QFB_H_END) break;
                 const uint32_t rc = (hw.x >> 8) & 0xffu;
                 const uint64_t cm = ((uint64_t)hw.w << 32) | hw.z;
@@ -351,11 +386,11 @@ sweep_kernel(c128 *__restrict__ state, const uint8_t *__restrict__ rec_g, uint32
                 op += ((hw.x >> 16) & 0xffu) << 4;
                 const uint4 hwn = *reinterpret_cast<const uint4 *>(op);   // every round ends with an END record
                 const double2 pwn = *reinterpret_cast<const double2 *>(op + sizeof(qfb_op_header));
-#define QFB_G1_CASES(KIND)                                                                     \
-    case QFB_H_G1 + 4 * KIND + 0: g1_apply<0, KIND, false>(a, m, pw.x, pw.y, 0u); break;                   \
-    case QFB_H_G1 + 4 * KIND + 1: g1_apply<1, KIND, false>(a, m, pw.x, pw.y, 0u); break;                   \
-    case QFB_H_G1 + 4 * KIND + 2: g1_apply<2, KIND, false>(a, m, pw.x, pw.y, 0u); break;                   \
-    case QFB_H_G1 + 4 * KIND + 3: g1_apply<3, KIND, false>(a, m, pw.x, pw.y, 0u); break;
+#define QFB_G1_CASES(BASE, KIND)                                                               \
+    case BASE + 0: g1_apply<0, KIND, false>(a, m, pw.x, pw.y, 0u); break;                      \
+    case BASE + 1: g1_apply<1, KIND, false>(a, m, pw.x, pw.y, 0u); break;                      \
+    case BASE + 2: g1_apply<2, KIND, false>(a, m, pw.x, pw.y, 0u); break;                      \
+    case BASE + 3: g1_apply<3, KIND, false>(a, m, pw.x, pw.y, 0u); break;
 #define QFB_G1C_CASES(BASE, KIND)                                                              \
     case BASE + 0: if ((tfull & cm) == cm) g1_apply<0, KIND, true>(a, m, pw.x, pw.y, rc); break;           \
     case BASE + 1: if ((tfull & cm) == cm) g1_apply<1, KIND, true>(a, m, pw.x, pw.y, rc); break;           \
@@ -367,11 +402,11 @@ sweep_kernel(c128 *__restrict__ state, const uint8_t *__restrict__ rec_g, uint32
             g2_apply<J0, J1>(a, m, *reinterpret_cast<const uint32_t *>(m + 32), rc);           \
         break;
                 switch (handler) {
-                    QFB_G1_CASES(QFB_G1_GENERAL)
-                    QFB_G1_CASES(QFB_G1_SWAPX)
-                    QFB_G1_CASES(QFB_G1_SUMDIFF)
-                    QFB_G1_CASES(QFB_G1_ROT_R)
-                    QFB_G1_CASES(QFB_G1_ROT_I)
+                    QFB_G1_CASES(QFB_H_G1_GENERAL, QFB_G1_GENERAL)
+                    QFB_G1_CASES(QFB_H_G1_SWAPX, QFB_G1_SWAPX)
+                    QFB_G1_CASES(QFB_H_G1_SUMDIFF, QFB_G1_SUMDIFF)
+                    QFB_G1_CASES(QFB_H_G1_ROT_R, QFB_G1_ROT_R)
+                    QFB_G1_CASES(QFB_H_G1_ROT_I, QFB_G1_ROT_I)
                     QFB_G1C_CASES(QFB_H_G1C_GENERAL, QFB_G1_GENERAL)
                     QFB_G1C_CASES(QFB_H_G1C_SWAPX, QFB_G1_SWAPX)
                     case QFB_H_CPH_SCALAR:
@@ -523,13 +558,8 @@ static int validate_plan(const uint8_t *p, size_t nbytes, std::vector<SweepInfo>
                 if (o == rh.nops) {
                     QFB_CHECK_ARG(h == QFB_H_END && bytes == 16, "plan: round does not end with an END record");
                     ended = true;
-                } else if (h >= QFB_H_G1 && h < QFB_H_G1 + 32) {
-                    const int kind = (h - QFB_H_G1) >> 2;
-                    // REAL / RXLIKE / ANTIDIAG are reserved: the planner folds them into GENERAL (they are rare
-                    // once rotations are pivoted, and their handlers only cost instruction-cache space)
-                    QFB_CHECK_ARG(bytes == 16 + 64 && oh.reg_cmask == 0 && oh.idx_cmask == 0 &&
-                                      kind != QFB_G1_REAL && kind != QFB_G1_RXLIKE && kind != QFB_G1_ANTIDIAG,
-                                  "plan: bad G1 op");
+                } else if (h >= QFB_H_G1_GENERAL && h < QFB_H_G1C_GENERAL) {
+                    QFB_CHECK_ARG(bytes == 16 + 64 && oh.reg_cmask == 0 && oh.idx_cmask == 0, "plan: bad G1 op");
                 } else if (h >= QFB_H_G1C_GENERAL && h < QFB_H_G1C_SWAPX + 4) {
                     const int j = (h - QFB_H_G1C_GENERAL) & 3;
                     QFB_CHECK_ARG(bytes == 16 + 64 && !((oh.reg_cmask >> j) & 1) && oh.reg_cmask < NE,
@@ -586,7 +616,11 @@ static int launch_sweep(c128 *state, const uint8_t *rec_dev, uint32_t rec_bytes,
     const uint64_t cap = (uint64_t)sm_count_cached() * resident;
     const int grid = (int)std::min<uint64_t>(ntiles, cap);
     const uint64_t hi_shifted = (nbits >= 64) ? 0ull : (index_hi << nbits);
-    sweep_kernel<M, G2><<<grid, T, smem, st>>>(state, rec_dev, rec_bytes, nholes, hi_shifted);
+    static const int async_load = [] {
+        const char *v = getenv("QFB_LOADER");
+        return (v && strcmp(v, "async") == 0) ? 1 : 0;
+    }();
+    sweep_kernel<M, G2><<<grid, T, smem, st>>>(state, rec_dev, rec_bytes, nholes, hi_shifted, async_load);
     QFB_LAUNCH_CHECK();
     return QFB_OK;
 }

@@ -15,8 +15,8 @@ Passes, all order preserving up to commutation:
 2. sweeps     walk the list; an operator joins the current sweep when it does not conflict with a deferred
               operator and its mixing bits fit into the tile (M bits, the L lowest index bits are always members
               so that global accesses are whole 128-byte lines). A cost cap keeps a sweep close to HBM-bound.
-3. rounds     inside a sweep the same walk assigns operators to rounds of R=4 register bits; the last round
-              keeps the low tile bits on the lanes (coalesced STG; tiles are loaded by cp.async, any layout). Phase terms are then moved,
+3. rounds     inside a sweep the same walk assigns operators to rounds of R=4 register bits; the first and
+              last round keep the low tile bits on the lanes (coalesced LDG/STG). Phase terms are then moved,
               inside their commutation window, to the round where they are cheapest: a term whose bits are all
               thread-level is a per-thread scalar (4 FP64 ops instead of up to 64).
 4. encode     1-bit operators are divided by their (0,0) entry when that exposes a cheaper form (Hadamard:
@@ -31,7 +31,7 @@ import numpy as np
 from . import classify
 
 PLAN_MAGIC = 0x50424651
-PLAN_VERSION = 5
+PLAN_VERSION = 6
 REG_BITS = 4
 MAX_TILE_BITS = 13
 MIN_TILE_BITS = 5
@@ -39,7 +39,9 @@ MAX_HOLES = 48
 MAX_SWEEP_BYTES = 40 * 1024
 MAX_DIAG_BITS = 5
 # handler ids (csrc/qfb_plan.h)
-H_G1, H_G1C_GENERAL, H_G1C_SWAPX, H_CPH_SCALAR, H_CPH_REG, H_CPH_NEG, H_G2, H_END = 0, 32, 36, 40, 41, 42, 43, 49
+H_G1C_GENERAL, H_G1C_SWAPX, H_CPH_SCALAR, H_CPH_REG, H_CPH_NEG, H_G2, H_END = 20, 24, 28, 29, 30, 31, 37
+# uncontrolled 1-bit handlers by QFB_G1_* kind
+H_G1_OF_KIND = {0: 0, 3: 4, 5: 8, 6: 12, 7: 16}
 G2_PAIRS = [(1, 0), (2, 0), (2, 1), (3, 0), (3, 1), (3, 2)]
 
 
@@ -305,6 +307,7 @@ class Planner:
         pos_of = {b: j for j, b in enumerate(sweep.tile)}
         remaining = list(sweep.ops)
         rounds: List[Tuple[List[int], List[POp]]] = []
+        first = True
         while remaining:
             regs: List[int] = []
             chosen: List[POp] = []
@@ -315,7 +318,9 @@ class Planner:
                 ok = not _conflicts(op, def_any, def_mix)
                 if ok and op.kind == 'G':
                     need = [pos_of[b] for b in op.mix if pos_of[b] not in regs]
-                    if len(regs) + len(need) > REG_BITS:
+                    if first and any(pos_of[b] < self.L for b in op.mix):
+                        ok = False
+                    elif len(regs) + len(need) > REG_BITS:
                         ok = False
                     else:
                         regs += need
@@ -327,15 +332,19 @@ class Planner:
                     def_mix |= op.mixset
             rounds.append((regs, chosen))
             remaining = deferred
+            first = False
         if not rounds:
             rounds.append(([], []))
         # the last round stores to HBM: its register bits must avoid the low tile positions
         if any(p < self.L for p in rounds[-1][0]):
             rounds.append(([], []))
+        # drop an empty first round when the sweep has another round that can serve as the load round
+        if len(rounds) > 1 and not rounds[0][1] and not any(p < self.L for p in rounds[1][0]):
+            rounds.pop(0)
         final: List[Round] = []
         nr = len(rounds)
         for r, (regs, chosen) in enumerate(rounds):
-            edge = (r == nr - 1)     # only the storing round needs the low bits on the lanes (loads are cp.async)
+            edge = (r == 0) or (r == nr - 1)   # rounds that touch HBM keep the low bits on the lanes
             regs = list(regs)
             # fill up to R register bits with high free positions (never low ones on edge rounds)
             cand = [p for p in range(self.M - 1, -1, -1) if p not in regs and (p >= self.L or not edge)]
@@ -478,7 +487,7 @@ class Planner:
             if op.ctrl:
                 handler = (H_G1C_SWAPX if kind == K_SWAPX else H_G1C_GENERAL) + j
             else:
-                handler = H_G1 + 4 * kind + j
+                handler = H_G1_OF_KIND[kind] + j
             return _op_record(handler, reg_cmask, idx_cmask, payload.tobytes()), pivot
         j0, j1 = reg_index(op.mix[0]), reg_index(op.mix[1])
         mat = np.ascontiguousarray(op.mat, dtype=np.complex128).reshape(2, 2, 2, 2)

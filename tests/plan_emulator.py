@@ -20,7 +20,7 @@ def swz(idx):
 
 def parse(blob: bytes):
     magic, version, nbits, M, rbits, nsweeps, total = struct.unpack_from('<IIIIIIQ', blob, 0)
-    assert magic == 0x50424651 and version == 5 and rbits == R and total == len(blob)
+    assert magic == 0x50424651 and version == 6 and rbits == R and total == len(blob)
     off = 32
     sweeps = []
     for _ in range(nsweeps):
@@ -52,21 +52,20 @@ def parse(blob: bytes):
                 payload = blob[ooff + 16: ooff + obytes]
                 ooff += obytes
                 if _o == rn:
-                    assert handler == 49 and obytes == 16, 'round must end with an END record'
+                    assert handler == 37 and obytes == 16, 'round must end with an END record'
                     break
-                if handler < 32:
+                if handler < 20:
                     assert rcm == 0 and icm == 0
-                    typ, kind, j0, j1 = 1, handler // 4, handler % 4, 0
-                    assert kind in (0, 3, 5, 6, 7), 'reserved G1 kind'
-                elif handler < 40:
-                    typ, kind, j0, j1 = 1, (0 if handler < 36 else 3), handler % 4, 0
-                elif handler in (40, 41, 42):
-                    typ, kind, j0, j1 = 3, int(handler == 42), 0, 0
-                    assert (handler == 40) == (rcm == 0)
+                    typ, kind, j0, j1 = 1, [0, 3, 5, 6, 7][handler // 4], handler % 4, 0
+                elif handler < 28:
+                    typ, kind, j0, j1 = 1, (0 if handler < 24 else 3), handler % 4, 0
+                elif handler in (28, 29, 30):
+                    typ, kind, j0, j1 = 3, int(handler == 30), 0, 0
+                    assert (handler == 28) == (rcm == 0)
                 else:
-                    assert 43 <= handler < 49
+                    assert 31 <= handler < 37
                     typ, kind = 2, 0
-                    j0, j1 = [(1, 0), (2, 0), (2, 1), (3, 0), (3, 1), (3, 2)][handler - 43]
+                    j0, j1 = [(1, 0), (2, 0), (2, 1), (3, 0), (3, 1), (3, 2)][handler - 31]
                 ops.append(dict(type=typ, kind=kind, j0=j0, j1=j1, reg_cmask=rcm, idx_cmask=icm, payload=payload))
             assert ooff == roff + rbytes
             assert has_g2 == int(any(o['type'] == 2 for o in ops))
@@ -103,7 +102,7 @@ def _apply_g1(a, op):
             r0, r1 = m[0, 0].real, m[0, 0].imag
             assert abs(r0) == 1 and abs(r1) == 1
             a[e0] = x + r0 * y
-            a[e1] = x + r1 * y
+            a[e1] = a[e0] + (r1 - r0) * y      # formed from x' like the kernel does
         elif op['kind'] == 6:    # ROT_R (pivoted): x' = x + r y, y' = y + s x
             a[e0] = x + m[0, 0].real * y
             a[e1] = y + m[0, 0].imag * x
@@ -201,7 +200,7 @@ def execute(blob: bytes, state: np.ndarray, index_hi: int = 0, check_layout: boo
             for rnd, rd in enumerate(sweep['rounds']):
                 regpos, thrpos = rd['regpos'], rd['thrpos']
                 assert sorted(regpos + thrpos) == list(range(M))
-                if check_layout and rnd == nrounds - 1:
+                if check_layout and (rnd == 0 or rnd == nrounds - 1):
                     # edge rounds: lanes must walk the lowest index bits (coalesced 128-byte lines)
                     nlow = min(3, M - R)
                     assert [gpos[thrpos[t]] for t in range(nlow)] == list(range(nlow)), 'uncoalesced edge round'

@@ -181,8 +181,8 @@ def test_layout_invariants():
         assert sweep['gpos'] == sorted(sweep['gpos'])
         nr = len(sweep['rounds'])
         for r, rd in enumerate(sweep['rounds']):
-            if r == nr - 1:
-                assert min(rd['regpos']) >= 3                       # lanes keep the low bits on the storing round
+            if r in (0, nr - 1):
+                assert min(rd['regpos']) >= 3                       # lanes keep the low bits on rounds touching HBM
                 assert rd['thrpos'][:3] == [0, 1, 2]
             worst = max(worst, E.conflict_degree(rd, plan['M']))
     assert worst == 1                                               # swizzle + lane assignment: conflict free

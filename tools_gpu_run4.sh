@@ -1,0 +1,21 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 1200 python -m pytest tests -m gpu -q --timeout 900 -p no:cacheprovider -x > gpurun_out/pytest.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest.log
+tail -n 3 gpurun_out/pytest.log
+for L in ldg async; do
+  echo "== loader $L"
+  QFB_LOADER=$L python tools_microbench.py 30 12 2>&1 | tee gpurun_out/microbench_$L.jsonl | python -c "
+import sys, json
+for l in sys.stdin:
+    try: d=json.loads(l)
+    except Exception: print(l.strip()); continue
+    print('%-62s %7.2f ms rounds %d' % (d['case'][:62], d['ms'], d['rounds']))"
+  for cfg in "12 3 28" "11 3 28"; do
+    set -- $cfg
+    QFB_LOADER=$L timeout 600 python bench.py --steps 3 --warmup 2 --no-e2e --no-cpu-baseline --tile-bits $1 --low-bits $2 --max-cost $3 2>> gpurun_out/sweep_knobs.err | python -c "
+import sys, json
+for l in sys.stdin:
+    d=json.loads(l)
+    print('BENCH', d['plan']['tile_bits'], d['plan']['sweeps'], d['plan']['rounds'], 'ms/step %.1f gates/s %.0f frac %.3f sweep_ms %.2f'%(d['ms_per_step'], d['value'], d['roofline']['frac'], d['roofline']['avg_launch_ms']))"
+  done
+done
