@@ -19,6 +19,11 @@
  * Between rounds the tile is exchanged through shared memory (XOR-swizzled, see qfb_sweep.cu). Round 0 loads
  * from HBM, the last round stores to HBM.
  *
+ * Pauli-X gates are never executed: the planner tracks them as a pending bit-flip mask of the sweep, rewrites
+ * the operators that follow (operator conjugated by X on its flipped bits) and hands the mask to the kernel as
+ * `store_xor`: the last round stores amplitude i to address i ^ store_xor (tile bits only, so the permutation
+ * stays inside the CTA's tile and inside whole 128-byte lines).
+ *
  * All records are multiples of 16 bytes; integers little endian. The Python planner
  * (quantumflow_b200/planner.py) writes this layout with struct.pack; keep the two in sync.
  */
@@ -27,7 +32,7 @@
 #include <stdint.h>
 
 #define QFB_PLAN_MAGIC 0x50424651u /* "QFBP" */
-#define QFB_PLAN_VERSION 6u
+#define QFB_PLAN_VERSION 7u
 #define QFB_PLAN_REG_BITS 4
 #define QFB_PLAN_MAX_TILE_BITS 13
 #define QFB_PLAN_MIN_TILE_BITS 5
@@ -44,18 +49,23 @@ typedef struct {
     uint64_t total_bytes;
 } qfb_plan_header; /* 32 bytes */
 
+#define QFB_SWEEP_FLAG_G2 1u          /* some round holds G2 ops (selects the kernel variant) */
+#define QFB_SWEEP_FLAG_STORE_SYNC 2u  /* single-round sweep with store_xor != 0: barrier between loads and stores */
+
 typedef struct {
     uint32_t bytes; /* whole sweep record including this header */
     uint32_t nrounds;
     uint32_t nops; /* informational */
-    uint32_t reserved;
+    uint32_t flags;
     uint8_t gpos[16]; /* gpos[j] = index bit position of tile bit j (ascending) */
     uint8_t hole[QFB_PLAN_MAX_HOLES]; /* hole[i] = index bit position of tile-id bit i (ascending) */
-} qfb_sweep_header; /* 80 bytes */
+    uint64_t store_xor; /* pending X flips of the sweep (index-bit mask, subset of the tile bits) */
+    uint8_t pad[8];
+} qfb_sweep_header; /* 96 bytes */
 
 typedef struct {
+    uint32_t stb; /* byte offset of the thread's first amplitude in the swizzled exchange buffer: swz(tb) << 4 */
     uint32_t tb;  /* tile-local index contribution (register bits zero) */
-    uint32_t pad;
     uint64_t tg;  /* the same bits at their index-bit positions */
 } qfb_thread_lut; /* 16 bytes */
 
@@ -68,68 +78,71 @@ typedef struct {
     uint8_t regpos[4];  /* tile-bit position of register bit i */
     uint8_t thrpos[12]; /* tile-bit position of thread bit t, t < M-R */
     uint8_t has_scalar; /* 1 when the round holds CPH terms without register bits */
-    uint8_t has_g2;     /* 1 when the round holds G2 ops (selects the kernel variant for the whole plan) */
+    uint8_t has_g2;     /* 1 when the round holds G2 ops */
     uint8_t pad[6];
-    /* thread id -> (tb, tg) in two table look-ups instead of a per-bit deposit loop:
-     * tb = lut_lo[tid & 15].tb | lut_hi[tid >> 4].tb, same for tg */
+    uint32_t ps_b[4];   /* swz(1 << regpos[i]) << 4: byte offset of register bit i in the exchange buffer */
+    int64_t rgb[4];     /* 16 << gpos[regpos[i]]: byte distance in the state between register bit i = 0 and 1 */
+    int64_t rst[4];     /* the same for the final store: negative when store_xor flips that bit */
+    /* thread id -> (stb, tb, tg) in two table look-ups instead of a per-bit deposit loop:
+     * x = lut_lo[tid & 15].x ^ lut_hi[tid >> 4].x (the bit sets are disjoint and swz is linear over XOR) */
     qfb_thread_lut lut_lo[QFB_PLAN_LUT_LO];
     qfb_thread_lut lut_hi[QFB_PLAN_LUT_HI];
-} qfb_round_header; /* 32 + 768 bytes */
+} qfb_round_header; /* 112 + 768 bytes */
 
-/* kinds of QFB_OP_G1: structure of the 2x2 operator, chosen by the planner to save FP64 work. The "pivoted"
- * kinds apply the operator divided by its (0,0) entry; the planner multiplies the pivots of a sweep into one
- * uniform scalar that rides on the sweep's unconditional CPH term. (x, y) = the pair of amplitudes. */
-enum {
-    QFB_G1_GENERAL = 0,  /* 16 FP64 per pair */
-    QFB_G1_REAL = 1,     /* all entries real: 8 per pair */
-    QFB_G1_RXLIKE = 2,   /* real diagonal, imaginary off-diagonal: 8 per pair */
-    QFB_G1_SWAPX = 3,    /* Pauli X: swap, no arithmetic */
-    QFB_G1_ANTIDIAG = 4, /* zero diagonal (Y, phased X): 8 per pair */
-    QFB_G1_SUMDIFF = 5,  /* pivoted Hadamard-like: x' = x + r0 y, y' = x + r1 y with r = +-1 (m[0], m[1]); sums only,
-                            so destructive interference gives exact zeros like the reference's h*x + h*y: 4 per pair */
-    QFB_G1_ROT_R = 6,    /* pivoted real rotation (RY): x' = x + r y, y' = y + s x  (m[0], m[1]): 4 per pair */
-    QFB_G1_ROT_I = 7     /* pivoted RX-like: x' = x + i a y, y' = y + i b x  (m[0], m[1]): 4 per pair */
-};
-/* Handler ids: ONE DENSE switch in the kernel's op interpreter (dense ids let ptxas emit a jump table, BRX,
- * instead of a compare tree whose serial branches cost ~15 cycles per level).
+/* kinds of dense 1-bit operators: structure of the 2x2 operator, chosen by the planner to save FP64 work and
+ * register copies; (x, y) = the pair of amplitudes, every update is in place.
+ *   GENERAL  16 FP64 per pair
+ *   SWAPX    Pauli X: swap, no arithmetic (only as a controlled operator; uncontrolled X is store_xor)
+ *   SUMDIFF  Hadamard-like divided by its (0,0) entry ("pivot"; the planner multiplies the pivots of a sweep into
+ *            one uniform scalar that rides on a CPH term): x' = x + r0 y, y' = x' + (r1 - r0) y with r = +-1.
+ *            Sums only, so destructive interference gives exact zeros like the reference's h*x + h*y. 4 per pair.
+ *   ROT_R    real rotation [[c, -s], [s, c]] (RY) as three shears  x += a y; y += b x; x += a y  with
+ *            a = -tan(phi/2), b = sin(phi): exact determinant 1, |a| <= 1 (the planner folds a half turn into
+ *            the sign of the sweep scalar), no pivot, no temporaries. 6 per pair.
+ *   ROT_I    [[c, i s], [i s, c]] (RX) the same way with imaginary shears  x += i a y; y += i b x; x += i a y. */
+/* Handler ids: ONE DENSE switch in the kernel's op interpreter (a jump table, BRX).
  *   QFB_H_G1_GENERAL + j  uncontrolled dense 1-bit operator on register bit j (16 FP64 per pair)
- *   QFB_H_G1_SWAPX + j    X
  *   QFB_H_G1_SUMDIFF + j  pivoted Hadamard-like
- *   QFB_H_G1_ROT_R + j    pivoted real rotation (RY)
- *   QFB_H_G1_ROT_I + j    pivoted RX-like
+ *   QFB_H_G1_ROT_R + j    real rotation (RY), three shears
+ *   QFB_H_G1_ROT_I + j    RX-like rotation, three imaginary shears
  *   QFB_H_G1C_GENERAL + j controlled dense 1-bit operator   (reg_cmask / idx_cmask)
  *   QFB_H_G1C_SWAPX + j   controlled X (CNOT, CCNOT ...)
  *   QFB_H_CPH_SCALAR      phase term without register bits: accumulates into the round's scalar
- *   QFB_H_CPH_REG / _NEG  phase term on the register elements selected by reg_cmask (NEG: factor -1)
+ *   QFB_H_CPH_REG1 + j    phase term on register bit j (and idx_cmask)
+ *   QFB_H_CPH_NEG1 + j    the same with factor -1 (sign flip, no FP64 work)
+ *   QFB_H_CPH_NEG2 + pair factor -1 on two register bits, pair as for G2 (CZ between register bits)
+ *   QFB_H_CPH_REGM / NEGM any other register mask (reg_cmask)
  *   QFB_H_G2 + pair       dense 2-bit operator, (j0, j1) = (1,0) (2,0) (2,1) (3,0) (3,1) (3,2)
  *   QFB_H_END             terminates the round's op list */
 enum {
     QFB_H_G1_GENERAL = 0,
-    QFB_H_G1_SWAPX = 4,
-    QFB_H_G1_SUMDIFF = 8,
-    QFB_H_G1_ROT_R = 12,
-    QFB_H_G1_ROT_I = 16,
-    QFB_H_G1C_GENERAL = 20,
-    QFB_H_G1C_SWAPX = 24,
-    QFB_H_CPH_SCALAR = 28,
-    QFB_H_CPH_REG = 29,
-    QFB_H_CPH_NEG = 30,
-    QFB_H_G2 = 31,
-    QFB_H_END = 37,
-    QFB_H_COUNT = 38
+    QFB_H_G1_SUMDIFF = 4,
+    QFB_H_G1_ROT_R = 8,
+    QFB_H_G1_ROT_I = 12,
+    QFB_H_G1C_GENERAL = 16,
+    QFB_H_G1C_SWAPX = 20,
+    QFB_H_CPH_SCALAR = 24,
+    QFB_H_CPH_REG1 = 25,
+    QFB_H_CPH_NEG1 = 29,
+    QFB_H_CPH_NEG2 = 33,
+    QFB_H_CPH_REGM = 39,
+    QFB_H_CPH_NEGM = 40,
+    QFB_H_END = 41,
+    QFB_H_G2 = 42,
+    QFB_H_COUNT = 48
 };
 
 typedef struct {
-    uint8_t handler;
+    uint32_t handler;
+    uint16_t bytes;    /* whole op record including this header (multiple of 16) */
     uint8_t reg_cmask; /* control / phase mask over the register index */
-    uint8_t size16;    /* whole op record including this header, in 16-byte units */
-    uint8_t pad0;
-    uint32_t pad1;
+    uint8_t pad;
     uint64_t idx_cmask; /* control / phase mask over thread-level bits of the FULL index (incl. rank bits) */
 } qfb_op_header; /* 16 bytes */
 
 /* payloads (follow the header)
- *   G1 : double m[8]   row-major 2x2 complex (64 B); pivoted kinds use m[0], m[1] as described above
+ *   G1 GENERAL / G1C: double m[8]   row-major 2x2 complex (64 B)
+ *   G1 SUMDIFF: double r[2] = (r0, r1); ROT_R / ROT_I: double (a, b)   (16 B)
  *   G2 : double m[32]; uint32 nzmask; uint32 pad[3]   row-major 4x4 complex, bit (4r+c) of nzmask set when
  *                      entry (r,c) is non-zero (272 B)
  *   CPH: double factor[2]  (16 B)

@@ -22,243 +22,24 @@
 #include <vector>
 #include "qfb_common.cuh"
 #include "qfb_plan.h"
+#include "qfb_oploop.inc"
 
 namespace qfb {
 
 constexpr int R = QFB_PLAN_REG_BITS;
 constexpr int NE = 1 << R;  // amplitudes per thread
 
-__device__ __forceinline__ uint32_t swz(uint32_t idx) {
-    const uint32_t x = idx >> 3;
-    return idx ^ ((x ^ (x >> 3) ^ (x >> 6) ^ (x >> 9)) & 7u);
-}
-
-template <typename T>
-__device__ __forceinline__ T pick(const T (&s)[R], int e) {
-    T r = 0;
-#pragma unroll
-    for (int i = 0; i < R; ++i)
-        if ((e >> i) & 1) r |= s[i];
-    return r;
-}
-
-// XOR-combine (swizzled offsets overlap in their low bits, so OR would be wrong)
-__device__ __forceinline__ uint32_t pick_xor(const uint32_t (&s)[R], int e) {
-    uint32_t r = 0;
-#pragma unroll
-    for (int i = 0; i < R; ++i)
-        if ((e >> i) & 1) r ^= s[i];
-    return r;
-}
-
-// ---------------------------------------------------------------------------------------------------------
-// Two-address FP64 primitives. Every update of a register amplitude goes through one of these: the tied
-// "+d" operand keeps each amplitude component in ONE virtual register for the whole op loop. Written as plain
-// C++ (new SSA value per update) the compiler renames the 2^R amplitudes inside handlers and then re-copies all
-// of them at every merge point of the interpreter loop: 58% of all executed instructions were MOVs in the
-// first profile (profiles/r1_sweep_v1_summary.txt).
-// ---------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void ip_mul(double &x, double s) {            // x = x * s
-    asm("mul.f64 %0, %0, %1;" : "+d"(x) : "d"(s));
-}
-__device__ __forceinline__ void ip_fma_acc(double &acc, double a, double b) {   // acc = a * b + acc
-    asm("fma.rn.f64 %0, %1, %2, %0;" : "+d"(acc) : "d"(a), "d"(b));
-}
-__device__ __forceinline__ void ip_fma_scale(double &x, double s, double c) {   // x = x * s + c
+// x = x * s + c with the result in x's own register. The amplitudes are pinned to registers for the whole tile
+// (the op interpreter is PTX with tied operands, qfb_oploop.inc); the few C++ updates go through the same form so
+// that the compiler has no reason to rename them around the interpreter.
+__device__ __forceinline__ void ip_fma_scale(double &x, double s, double c) {
     asm("fma.rn.f64 %0, %0, %1, %2;" : "+d"(x) : "d"(s), "d"(c));
-}
-__device__ __forceinline__ void ip_set(double &x, double v) {             // x = v (keeps x's register)
-    asm("mov.f64 %0, %1;" : "+d"(x) : "d"(v));
-}
-__device__ __forceinline__ void ip_neg(double &x) {                       // x = -x (sign-bit flip, ALU pipe)
-    asm("xor.b64 %0, %0, 0x8000000000000000;" : "+d"(x));
-}
-__device__ __forceinline__ void ip_swap(double &x, double &y) {
-    asm("{\n\t.reg .f64 t;\n\tmov.f64 t, %0;\n\tmov.f64 %0, %1;\n\tmov.f64 %1, t;\n\t}" : "+d"(x), "+d"(y));
 }
 // a *= (fr + i fi)
 __device__ __forceinline__ void cmul_inplace(c128 &a, double fr, double fi) {
     const double t0 = -fi * a.im, t1 = fi * a.re;
     ip_fma_scale(a.re, fr, t0);
     ip_fma_scale(a.im, fr, t1);
-}
-// (x, y) <- (m00 x + m01 y, m10 x + m11 y), all complex; 16 FP64 ops, cross terms first
-__device__ __forceinline__ void pair_general(c128 &x, c128 &y, const double *__restrict__ m) {
-    const double m00r = m[0], m00i = m[1], m01r = m[2], m01i = m[3], m10r = m[4], m10i = m[5], m11r = m[6],
-                 m11i = m[7];
-    const double pr = fma(m01r, y.re, -m01i * y.im), pi = fma(m01r, y.im, m01i * y.re);   // m01 y
-    const double qr = fma(m10r, x.re, -m10i * x.im), qi = fma(m10r, x.im, m10i * x.re);   // m10 x
-    const double rx = fma(m00i, x.re, pi);   // imaginary part of m00 x + m01 y, minus m00r x.im
-    const double ry = fma(m11i, y.re, qi);
-    ip_fma_scale(x.re, m00r, pr);
-    ip_fma_acc(x.re, -m00i, x.im);
-    ip_fma_scale(x.im, m00r, rx);
-    ip_fma_scale(y.re, m11r, qr);
-    ip_fma_acc(y.re, -m11i, y.im);
-    ip_fma_scale(y.im, m11r, ry);
-}
-
-// ---- 1-bit operator on register bit J; RC: honour the register control mask ----
-// p0, p1: the first two payload doubles, prefetched together with the op header
-template <int J, int KIND, bool RC>
-__device__ __forceinline__ void g1_apply(c128 (&a)[NE], const double *__restrict__ m, double p0, double p1,
-                                         uint32_t rc) {
-#define QFB_PAIR_LOOP                                                                      \
-    _Pragma("unroll") for (int p = 0; p < NE / 2; ++p) {                                   \
-        const int e0 = ((p >> J) << (J + 1)) | (p & ((1 << J) - 1)), e1 = e0 | (1 << J);   \
-        if (RC && (e0 & rc) != rc) continue;
-    // controlled operators only come as SWAPX or GENERAL (pivoting needs an unconditional, uniform scalar)
-    if constexpr (KIND == QFB_G1_SUMDIFF) {
-        // x' = x + r0 y, y' = x + r1 y with r = +-1. y' is formed from x' (y' = x' + (r1 - r0) y) so that no
-        // temporary copy is needed: 4 FP64 per pair, nothing else. Exact zeros under destructive interference
-        // are kept: x = -r0 y gives x' = 0 exactly, x = -r1 y gives x' = (r0 - r1) y exactly and y' = 0.
-        const double r0 = p0, d = p1 - p0;
-        QFB_PAIR_LOOP
-            c128 &x = a[e0], &y = a[e1];
-            ip_fma_acc(x.re, r0, y.re);
-            ip_fma_acc(x.im, r0, y.im);
-            ip_fma_scale(y.re, d, x.re);
-            ip_fma_scale(y.im, d, x.im);
-        }
-    } else if constexpr (KIND == QFB_G1_ROT_R) {
-        const double r = p0, s = p1;    // x' = x + r y, y' = y + s x
-        QFB_PAIR_LOOP
-            c128 &x = a[e0], &y = a[e1];
-            const double xr = x.re, xi = x.im;
-            ip_fma_acc(x.re, r, y.re);
-            ip_fma_acc(x.im, r, y.im);
-            ip_fma_acc(y.re, s, xr);
-            ip_fma_acc(y.im, s, xi);
-        }
-    } else if constexpr (KIND == QFB_G1_ROT_I) {
-        const double ca = p0, cb = p1;  // x' = x + i ca y, y' = y + i cb x
-        QFB_PAIR_LOOP
-            c128 &x = a[e0], &y = a[e1];
-            const double xr = x.re, xi = x.im;
-            ip_fma_acc(x.re, -ca, y.im);
-            ip_fma_acc(x.im, ca, y.re);
-            ip_fma_acc(y.re, -cb, xi);
-            ip_fma_acc(y.im, cb, xr);
-        }
-    } else if constexpr (KIND == QFB_G1_REAL) {
-        const double m00 = m[0], m01 = m[2], m10 = m[4], m11 = m[6];
-        QFB_PAIR_LOOP
-            c128 &x = a[e0], &y = a[e1];
-            const double pr = m01 * y.re, pi = m01 * y.im, qr = m10 * x.re, qi = m10 * x.im;
-            ip_fma_scale(x.re, m00, pr);
-            ip_fma_scale(x.im, m00, pi);
-            ip_fma_scale(y.re, m11, qr);
-            ip_fma_scale(y.im, m11, qi);
-        }
-    } else if constexpr (KIND == QFB_G1_RXLIKE) {
-        const double d0 = m[0], o01 = m[3], o10 = m[5], d1 = m[6];
-        QFB_PAIR_LOOP
-            c128 &x = a[e0], &y = a[e1];
-            // (d0) x + (i o01) y ; (i o10) x + (d1) y
-            const double pr = -o01 * y.im, pi = o01 * y.re, qr = -o10 * x.im, qi = o10 * x.re;
-            ip_fma_scale(x.re, d0, pr);
-            ip_fma_scale(x.im, d0, pi);
-            ip_fma_scale(y.re, d1, qr);
-            ip_fma_scale(y.im, d1, qi);
-        }
-    } else if constexpr (KIND == QFB_G1_SWAPX) {
-        QFB_PAIR_LOOP
-            ip_swap(a[e0].re, a[e1].re);
-            ip_swap(a[e0].im, a[e1].im);
-        }
-    } else if constexpr (KIND == QFB_G1_ANTIDIAG) {
-        const double ar = m[2], ai = m[3], br = m[4], bi = m[5];
-        QFB_PAIR_LOOP
-            c128 &x = a[e0], &y = a[e1];
-            const double qr = fma(br, x.re, -bi * x.im), qi = fma(br, x.im, bi * x.re);   // b x
-            const double pr = fma(ar, y.re, -ai * y.im), pi = fma(ar, y.im, ai * y.re);   // a y
-            ip_set(x.re, pr);
-            ip_set(x.im, pi);
-            ip_set(y.re, qr);
-            ip_set(y.im, qi);
-        }
-    } else {
-        QFB_PAIR_LOOP
-            pair_general(a[e0], a[e1], m);
-        }
-    }
-#undef QFB_PAIR_LOOP
-}
-
-// ---- 2-bit operator on register bits J0 > J1 (operator index = bit(J0) << 1 | bit(J1)) ----
-template <int J0, int J1>
-__device__ __forceinline__ void g2_apply(c128 (&a)[NE], const double *__restrict__ m, uint32_t nz, uint32_t rc) {
-    static_assert(J0 > J1, "planner normalises j0 > j1");
-    // the two register bits that enumerate the 4 independent groups
-    constexpr int O0 = (J1 != 0) ? 0 : ((J0 != 1) ? 1 : 2);
-    constexpr int O1 = 6 - J0 - J1 - O0;  // bits sum to 0+1+2+3
-#pragma unroll
-    for (int g = 0; g < 4; ++g) {
-        const int eb = ((g & 1) << O0) | ((g >> 1) << O1);
-        if ((eb & rc) != rc) continue;
-        const int id[4] = {eb, eb | (1 << J1), eb | (1 << J0), eb | (1 << J0) | (1 << J1)};
-        double outr[4], outi[4];
-#pragma unroll
-        for (int r = 0; r < 4; ++r) {
-            double accr = 0.0, acci = 0.0;
-#pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                if ((nz >> (4 * r + c)) & 1u) {
-                    const double mr = m[2 * (4 * r + c)], mi = m[2 * (4 * r + c) + 1];
-                    accr = fma(mr, a[id[c]].re, accr);
-                    accr = fma(-mi, a[id[c]].im, accr);
-                    acci = fma(mr, a[id[c]].im, acci);
-                    acci = fma(mi, a[id[c]].re, acci);
-                }
-            }
-            outr[r] = accr;
-            outi[r] = acci;
-        }
-#pragma unroll
-        for (int r = 0; r < 4; ++r) {
-            ip_set(a[id[r]].re, outr[r]);
-            ip_set(a[id[r]].im, outi[r]);
-        }
-    }
-}
-
-// ---- controlled phase on the register elements whose index contains MASK ----
-template <int MASK>
-__device__ __forceinline__ void cph_apply(c128 (&a)[NE], double fr, double fi, bool neg) {
-    if (neg) {
-#pragma unroll
-        for (int e = 0; e < NE; ++e)
-            if ((e & MASK) == MASK) {
-                ip_neg(a[e].re);
-                ip_neg(a[e].im);
-            }
-    } else {
-#pragma unroll
-        for (int e = 0; e < NE; ++e)
-            if ((e & MASK) == MASK) cmul_inplace(a[e], fr, fi);
-    }
-}
-
-__device__ __forceinline__ void cph_dispatch(c128 (&a)[NE], uint32_t rc, double fr, double fi, bool neg) {
-    uint32_t opaque0;   // see the op interpreter: forces a jump table instead of a compare tree
-    asm volatile("mov.u32 %0, 0;" : "=r"(opaque0));
-    switch (rc + opaque0) {
-        case 1: cph_apply<1>(a, fr, fi, neg); break;
-        case 2: cph_apply<2>(a, fr, fi, neg); break;
-        case 3: cph_apply<3>(a, fr, fi, neg); break;
-        case 4: cph_apply<4>(a, fr, fi, neg); break;
-        case 5: cph_apply<5>(a, fr, fi, neg); break;
-        case 6: cph_apply<6>(a, fr, fi, neg); break;
-        case 7: cph_apply<7>(a, fr, fi, neg); break;
-        case 8: cph_apply<8>(a, fr, fi, neg); break;
-        case 9: cph_apply<9>(a, fr, fi, neg); break;
-        case 10: cph_apply<10>(a, fr, fi, neg); break;
-        case 11: cph_apply<11>(a, fr, fi, neg); break;
-        case 12: cph_apply<12>(a, fr, fi, neg); break;
-        case 13: cph_apply<13>(a, fr, fi, neg); break;
-        case 14: cph_apply<14>(a, fr, fi, neg); break;
-        default: cph_apply<15>(a, fr, fi, neg); break;
-    }
 }
 
 template <int M>
@@ -268,16 +49,33 @@ struct SweepCfg {
     static constexpr int TILE_BYTES = 16 << M;
 };
 
-// HAS_G2 = false drops the dense 2-bit handlers (40% of the code): circuits made of 1-bit, controlled-1-bit and
-// diagonal gates (every workload of BASELINE.json) run the smaller kernel, which is kinder to the instruction cache.
+// HAS_G2 = false drops the dense 2-bit handlers: circuits made of 1-bit, controlled-1-bit and diagonal gates
+// (every workload of BASELINE.json except the density channels) run the smaller kernel, which is kinder to the
+// instruction cache.
+// q[e] for all 2^R register indices from a base and one step per register bit: 2^R - 1 operations instead of
+// recombining the steps for every e
+template <typename T, typename S, typename F>
+__device__ __forceinline__ void spread(T (&q)[NE], T base, const S (&step)[R], F combine) {
+    q[0] = base;
+#pragma unroll
+    for (int i = 0; i < R; ++i)
+#pragma unroll
+        for (int e = 0; e < (1 << i); ++e) q[e | (1 << i)] = combine(q[e], step[i]);
+}
+
+constexpr int HLUT_BITS = 6;                                  // tile-id bits per look-up
+constexpr int HLUT_MAX = (QFB_PLAN_MAX_HOLES + HLUT_BITS - 1) / HLUT_BITS;
+constexpr int HLUT_BYTES = HLUT_MAX * (1 << HLUT_BITS) * 8;   // 4 KiB
+
 template <int M, bool HAS_G2>
 __global__ void __launch_bounds__(SweepCfg<M>::T, SweepCfg<M>::MINB)
 sweep_kernel(c128 *__restrict__ state, const uint8_t *__restrict__ rec_g, uint32_t rec_bytes, int nholes,
-             uint64_t hi_shifted, int async_load) {
+             uint64_t hi_shifted) {
     constexpr int T = SweepCfg<M>::T;
     extern __shared__ __align__(16) uint8_t smem[];
-    c128 *tile = reinterpret_cast<c128 *>(smem);
-    uint8_t *rec = smem + SweepCfg<M>::TILE_BYTES;
+    uint8_t *tile = smem;
+    uint64_t *hlut = reinterpret_cast<uint64_t *>(smem + SweepCfg<M>::TILE_BYTES);
+    uint8_t *rec = smem + SweepCfg<M>::TILE_BYTES + HLUT_BYTES;
     const int tid = threadIdx.x;
     {
         const uint4 *s4 = reinterpret_cast<const uint4 *>(rec_g);
@@ -288,177 +86,119 @@ sweep_kernel(c128 *__restrict__ state, const uint8_t *__restrict__ rec_g, uint32
     const qfb_sweep_header *sh = reinterpret_cast<const qfb_sweep_header *>(rec);
     const int nrounds = (int)sh->nrounds;
     const uint64_t ntiles = 1ull << nholes;
-
-    // ---- asynchronous tile loader: the NEXT tile streams into the exchange buffer (cp.async, 16 B per request,
-    // L1 bypass) while the last round of the current tile computes and stores. Thread t moves tile-local elements
-    // t + c*T, c = 0..NE-1: consecutive threads read consecutive 16-byte words, i.e. whole 128-byte lines.
-    uint64_t lin_tg = 0;   // index-bit image of the tile-local bits carried by the thread id
-#pragma unroll
-    for (int b = 0; b < M - R; ++b) lin_tg |= (uint64_t)((tid >> b) & 1) << sh->gpos[b];
-    uint64_t lin_cg[R];    // index-bit image of tile-local bits M-R .. M-1 (the chunk number c)
-#pragma unroll
-    for (int i = 0; i < R; ++i) lin_cg[i] = 1ull << sh->gpos[M - R + i];
-    const uint32_t lin_sw = swz((uint32_t)tid);
-    const uint32_t tile_smem = (uint32_t)__cvta_generic_to_shared(tile);
+    const uint64_t store_xor = sh->store_xor;
+    const bool store_sync = (sh->flags & QFB_SWEEP_FLAG_STORE_SYNC) != 0;
+    // tile id -> index bits (deposit through hole[]): HLUT_BITS tile-id bits per table look-up
+    const int nlut = (nholes + HLUT_BITS - 1) / HLUT_BITS;
+    for (int i = tid; i < nlut << HLUT_BITS; i += T) {
+        const int k = i >> HLUT_BITS;
+        uint64_t v = 0;
+        for (int b = 0; b < HLUT_BITS && k * HLUT_BITS + b < nholes; ++b)
+            v |= (uint64_t)((i >> b) & 1) << sh->hole[k * HLUT_BITS + b];
+        hlut[i] = v;
+    }
+    __syncthreads();
     auto tile_base = [&](uint64_t tile_id) {
         uint64_t gb = 0;
-        for (int i = 0; i < nholes; ++i) gb |= ((tile_id >> i) & 1ull) << sh->hole[i];
+        for (int k = 0; k < nlut; ++k) gb |= hlut[(k << HLUT_BITS) | ((tile_id >> (k * HLUT_BITS)) & ((1 << HLUT_BITS) - 1))];
         return gb;
     };
-    auto prefetch_tile = [&](uint64_t gb) {
-        const c128 *src = state + (gb | lin_tg);
-#pragma unroll
-        for (int c = 0; c < NE; ++c) {
-            const uint32_t dst = tile_smem + ((lin_sw ^ swz((uint32_t)c << (M - R))) << 4);
-            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src + pick(lin_cg, c)) : "memory");
-        }
-        asm volatile("cp.async.commit_group;" ::: "memory");
-    };
-    // Two loaders (launch parameter): async_load = 1 streams the next tile into the exchange buffer (above);
-    // async_load = 0 loads round 0 with LDG straight into registers and only warms L2 with the next tile's lines
-    // (no extra shared-memory pass, but round 0 must keep the low bits on the lanes).
-    auto prefetch_l2 = [&](uint64_t gb) {
-        const c128 *src = state + (gb | lin_tg);
-        if ((tid & 7) == 0) {   // one request per 128-byte line
-#pragma unroll
-            for (int c = 0; c < NE; ++c)
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(src + pick(lin_cg, c)));
-        }
-    };
-    if (async_load && (uint64_t)blockIdx.x < ntiles) prefetch_tile(tile_base(blockIdx.x));
+    const auto add64 = [](const char *p, int64_t s) { return p + s; };
+    const auto xor32 = [](uint32_t x, uint32_t s) { return x ^ s; };
 
     for (uint64_t tile_id = blockIdx.x; tile_id < ntiles; tile_id += gridDim.x) {
         const uint64_t gb = tile_base(tile_id);
-        if (async_load) {
-            asm volatile("cp.async.wait_all;" ::: "memory");
-            __syncthreads();   // the whole tile has landed in shared memory
-        }
-
-        c128 a[NE];
         const uint8_t *rp = rec + sizeof(qfb_sweep_header);
-        for (int round = 0; round < nrounds; ++round) {
-            const qfb_round_header *rh = reinterpret_cast<const qfb_round_header *>(rp);
-            // tile-local index of this thread (register bits zero) and its global image: two table look-ups
+        const qfb_round_header *rh = reinterpret_cast<const qfb_round_header *>(rp);
+        // thread id -> exchange-buffer offset and index-bit image of the thread bits: two table look-ups
+        uint32_t stb;
+        uint64_t tg;
+        {
             const uint4 l0 = *reinterpret_cast<const uint4 *>(&rh->lut_lo[tid & 15]);
             const uint4 l1 = *reinterpret_cast<const uint4 *>(&rh->lut_hi[(tid >> 4) & 31]);
-            const uint32_t tb = l0.x | l1.x;
-            const uint64_t tg = (((uint64_t)l0.w << 32) | l0.z) | (((uint64_t)l1.w << 32) | l1.z);
-            uint32_t ps[R];  // swizzled image of each register bit
+            stb = l0.x ^ l1.x;
+            tg = (((uint64_t)l0.w << 32) | l0.z) | (((uint64_t)l1.w << 32) | l1.z);
+        }
+        c128 a[NE];
+        {   // round 0: coalesced LDG.128 straight into registers
+            int64_t step[R];
 #pragma unroll
-            for (int i = 0; i < R; ++i) ps[i] = swz(1u << rh->regpos[i]);
-            const uint32_t ptb = swz(tb);  // swz is linear over XOR and tb, register offsets are disjoint
-
-            if (round == 0 && !async_load) {
-                uint64_t sg[R];
+            for (int i = 0; i < R; ++i) step[i] = rh->rgb[i];
+            const char *p[NE];
+            spread(p, reinterpret_cast<const char *>(state + (gb | tg)), step, add64);
 #pragma unroll
-                for (int i = 0; i < R; ++i) sg[i] = 1ull << sh->gpos[rh->regpos[i]];
-                const c128 *src = state + (gb | tg);
+            for (int e = 0; e < NE; ++e) a[e] = ldg_stream(reinterpret_cast<const c128 *>(p[e]));
+            if (tile_id + gridDim.x < ntiles && (tid & 7) == 0) {
+                // warm L2 with the next tile's lines (one request per 128-byte line)
+                const int64_t delta = (int64_t)(tile_base(tile_id + gridDim.x) - gb) * 16;
 #pragma unroll
-                for (int e = 0; e < NE; ++e) a[e] = ldg_stream(src + pick(sg, e));
-            } else {
-#pragma unroll
-                for (int e = 0; e < NE; ++e) a[e] = tile[ptb ^ pick_xor(ps, e)];
-                __syncthreads();  // everyone has read before anyone overwrites the tile again
+                for (int e = 0; e < NE; ++e) asm volatile("prefetch.global.L2 [%0];" ::"l"(p[e] + delta));
             }
-            if (round + 1 == nrounds && tile_id + gridDim.x < ntiles) {
-                if (async_load) prefetch_tile(tile_base(tile_id + gridDim.x));   // buffer is free until the next tile
-                else prefetch_l2(tile_base(tile_id + gridDim.x));
-            }
+        }
 
+        int round = 0;
+        for (;;) {
             const uint64_t tfull = hi_shifted | gb | tg;
             double phr = 1.0, phi = 0.0;  // running per-thread scalar phase of this round
-            // ---- op interpreter: one table jump per op; the next header is in flight while a handler runs ----
-            const uint8_t *op = rp + sizeof(qfb_round_header);
-            uint4 hw = *reinterpret_cast<const uint4 *>(op);
-            double2 pw = *reinterpret_cast<const double2 *>(op + sizeof(qfb_op_header));
-            for (;;) {
-                // `opaque0` is 0, but the compiler cannot know and must treat the handler id as per-thread data:
-                // for warp-uniform values ptxas only builds compare trees (~15 cycles per level of serial
-                // branches, profiles/r1_microbench_v5.jsonl: a CZ sign flip cost as much as a Hadamard), for
-                // per-thread values it emits jump tables (BRX).
-                uint32_t opaque0;
-                asm volatile("mov.u32 %0, 0;" : "=r"(opaque0));
-                const uint32_t handler = (hw.x & 0xffu) + opaque0;
-                if (handler == QFB_H_END) break;
-                const uint32_t rc = (hw.x >> 8) & 0xffu;
-                const uint64_t cm = ((uint64_t)hw.w << 32) | hw.z;
-                const double *m = reinterpret_cast<const double *>(op + sizeof(qfb_op_header));
-                op += ((hw.x >> 16) & 0xffu) << 4;
-                const uint4 hwn = *reinterpret_cast<const uint4 *>(op);   // every round ends with an END record
-                const double2 pwn = *reinterpret_cast<const double2 *>(op + sizeof(qfb_op_header));
-#define QFB_G1_CASES(BASE, KIND)                                                               \
-    case BASE + 0: g1_apply<0, KIND, false>(a, m, pw.x, pw.y, 0u); break;                      \
-    case BASE + 1: g1_apply<1, KIND, false>(a, m, pw.x, pw.y, 0u); break;                      \
-    case BASE + 2: g1_apply<2, KIND, false>(a, m, pw.x, pw.y, 0u); break;                      \
-    case BASE + 3: g1_apply<3, KIND, false>(a, m, pw.x, pw.y, 0u); break;
-#define QFB_G1C_CASES(BASE, KIND)                                                              \
-    case BASE + 0: if ((tfull & cm) == cm) g1_apply<0, KIND, true>(a, m, pw.x, pw.y, rc); break;           \
-    case BASE + 1: if ((tfull & cm) == cm) g1_apply<1, KIND, true>(a, m, pw.x, pw.y, rc); break;           \
-    case BASE + 2: if ((tfull & cm) == cm) g1_apply<2, KIND, true>(a, m, pw.x, pw.y, rc); break;           \
-    case BASE + 3: if ((tfull & cm) == cm) g1_apply<3, KIND, true>(a, m, pw.x, pw.y, rc); break;
-#define QFB_G2_CASE(IDX, J0, J1)                                                               \
-    case QFB_H_G2 + IDX:                                                                       \
-        if (HAS_G2 && (tfull & cm) == cm)                                                      \
-            g2_apply<J0, J1>(a, m, *reinterpret_cast<const uint32_t *>(m + 32), rc);           \
-        break;
-                switch (handler) {
-                    QFB_G1_CASES(QFB_H_G1_GENERAL, QFB_G1_GENERAL)
-                    QFB_G1_CASES(QFB_H_G1_SWAPX, QFB_G1_SWAPX)
-                    QFB_G1_CASES(QFB_H_G1_SUMDIFF, QFB_G1_SUMDIFF)
-                    QFB_G1_CASES(QFB_H_G1_ROT_R, QFB_G1_ROT_R)
-                    QFB_G1_CASES(QFB_H_G1_ROT_I, QFB_G1_ROT_I)
-                    QFB_G1C_CASES(QFB_H_G1C_GENERAL, QFB_G1_GENERAL)
-                    QFB_G1C_CASES(QFB_H_G1C_SWAPX, QFB_G1_SWAPX)
-                    case QFB_H_CPH_SCALAR:
-                        if ((tfull & cm) == cm) {
-                            const double fr = pw.x, fi = pw.y;
-                            const double t0 = fi * phi, t1 = fi * phr;
-                            phr = fma(fr, phr, -t0);
-                            phi = fma(fr, phi, t1);
-                        }
-                        break;
-                    case QFB_H_CPH_REG:
-                        if ((tfull & cm) == cm) cph_dispatch(a, rc, pw.x, pw.y, false);
-                        break;
-                    case QFB_H_CPH_NEG:
-                        if ((tfull & cm) == cm) cph_dispatch(a, rc, 0.0, 0.0, true);
-                        break;
-                    QFB_G2_CASE(0, 1, 0)
-                    QFB_G2_CASE(1, 2, 0)
-                    QFB_G2_CASE(2, 2, 1)
-                    QFB_G2_CASE(3, 3, 0)
-                    QFB_G2_CASE(4, 3, 1)
-                    QFB_G2_CASE(5, 3, 2)
-                    default: break;
-                }
-#undef QFB_G1_CASES
-#undef QFB_G1C_CASES
-#undef QFB_G2_CASE
-                // hand the prefetched header over at the very end (volatile: keeps the copy, and with it the
-                // wait for the load, below the handler instead of right behind the LDS)
-                asm volatile("mov.b32 %0, %4;\n\tmov.b32 %1, %5;\n\tmov.b32 %2, %6;\n\tmov.b32 %3, %7;"
-                             : "=r"(hw.x), "=r"(hw.y), "=r"(hw.z), "=r"(hw.w)
-                             : "r"(hwn.x), "r"(hwn.y), "r"(hwn.z), "r"(hwn.w));
-                asm volatile("mov.f64 %0, %2;\n\tmov.f64 %1, %3;" : "=d"(pw.x), "=d"(pw.y) : "d"(pwn.x), "d"(pwn.y));
+            // ---- op interpreter (PTX, qfb_oploop.inc): one brx.idx per op, amplitudes pinned to registers ----
+            uint32_t op = (uint32_t)__cvta_generic_to_shared(rp + sizeof(qfb_round_header));
+#define QFB_AMP(e) "+d"(a[e].re), "+d"(a[e].im)
+#define QFB_OPLOOP_OPERANDS                                                                                   \
+    QFB_AMP(0), QFB_AMP(1), QFB_AMP(2), QFB_AMP(3), QFB_AMP(4), QFB_AMP(5), QFB_AMP(6), QFB_AMP(7), QFB_AMP(8),    \
+        QFB_AMP(9), QFB_AMP(10), QFB_AMP(11), QFB_AMP(12), QFB_AMP(13), QFB_AMP(14), QFB_AMP(15), "+d"(phr),     \
+        "+d"(phi), "+r"(op)                                                                                   \
+        : "l"(tfull)
+            if constexpr (HAS_G2) {
+                asm volatile(QFB_OPLOOP_PTX_G2 : QFB_OPLOOP_OPERANDS);
+            } else {
+                asm volatile(QFB_OPLOOP_PTX : QFB_OPLOOP_OPERANDS);
             }
+#undef QFB_AMP
+#undef QFB_OPLOOP_OPERANDS
             if (rh->has_scalar) {
 #pragma unroll
                 for (int e = 0; e < NE; ++e) cmul_inplace(a[e], phr, phi);
             }
+            if (++round == nrounds) break;
 
-            if (round + 1 < nrounds) {
+            // ---- exchange: this round's assignment out, the next round's in (swizzled, conflict free) ----
+            {
+                uint32_t ps[R], q[NE];
 #pragma unroll
-                for (int e = 0; e < NE; ++e) tile[ptb ^ pick_xor(ps, e)] = a[e];
-                __syncthreads();
-            } else {
-                uint64_t sg[R];
+                for (int i = 0; i < R; ++i) ps[i] = rh->ps_b[i];
+                spread(q, stb, ps, xor32);
 #pragma unroll
-                for (int i = 0; i < R; ++i) sg[i] = 1ull << sh->gpos[rh->regpos[i]];
-                c128 *dst = state + (gb | tg);
-#pragma unroll
-                for (int e = 0; e < NE; ++e) stg_stream(dst + pick(sg, e), a[e]);
+                for (int e = 0; e < NE; ++e) *reinterpret_cast<c128 *>(tile + q[e]) = a[e];
             }
+            __syncthreads();
             rp += rh->bytes;
+            rh = reinterpret_cast<const qfb_round_header *>(rp);
+            {
+                const uint4 l0 = *reinterpret_cast<const uint4 *>(&rh->lut_lo[tid & 15]);
+                const uint4 l1 = *reinterpret_cast<const uint4 *>(&rh->lut_hi[(tid >> 4) & 31]);
+                stb = l0.x ^ l1.x;
+                tg = (((uint64_t)l0.w << 32) | l0.z) | (((uint64_t)l1.w << 32) | l1.z);
+                uint32_t ps[R], q[NE];
+#pragma unroll
+                for (int i = 0; i < R; ++i) ps[i] = rh->ps_b[i];
+                spread(q, stb, ps, xor32);
+#pragma unroll
+                for (int e = 0; e < NE; ++e) a[e] = *reinterpret_cast<const c128 *>(tile + q[e]);
+            }
+            __syncthreads();  // everyone has read before anyone overwrites the tile again
+        }
+
+        // ---- last round: coalesced STG.128; amplitude i goes to address i ^ store_xor (pending X flips): the
+        // base takes the XOR, the per-register-bit steps of a flipped bit are negative (rst[], set by the planner)
+        if (store_sync) __syncthreads();   // single-round sweep: all loads of the tile precede the permuted stores
+        {
+            int64_t step[R];
+#pragma unroll
+            for (int i = 0; i < R; ++i) step[i] = rh->rst[i];
+            const char *p[NE];
+            spread(p, reinterpret_cast<const char *>(state + ((gb | tg) ^ store_xor)), step, add64);
+#pragma unroll
+            for (int e = 0; e < NE; ++e) stg_stream(reinterpret_cast<c128 *>(const_cast<char *>(p[e])), a[e]);
         }
     }
 }
@@ -478,6 +218,11 @@ struct PlanHandle {
     size_t dev_bytes;
 };
 
+static uint32_t swz_host(uint32_t idx) {
+    const uint32_t x = idx >> 3;
+    return idx ^ ((x ^ (x >> 3) ^ (x >> 6) ^ (x >> 9)) & 7u);
+}
+
 static int validate_plan(const uint8_t *p, size_t nbytes, std::vector<SweepInfo> &sweeps, int &nbits, int &M) {
     QFB_CHECK_ARG(p && nbytes >= sizeof(qfb_plan_header), "plan: too small");
     qfb_plan_header h;
@@ -492,6 +237,7 @@ static int validate_plan(const uint8_t *p, size_t nbytes, std::vector<SweepInfo>
     QFB_CHECK_ARG(h.nbits - h.tile_bits <= QFB_PLAN_MAX_HOLES, "plan: nbits=%u too large", h.nbits);
     nbits = (int)h.nbits;
     M = (int)h.tile_bits;
+    const uint32_t nholes = h.nbits - h.tile_bits;
     size_t off = sizeof(h);
     for (uint32_t s = 0; s < h.nsweeps; ++s) {
         QFB_CHECK_ARG(off + sizeof(qfb_sweep_header) <= nbytes, "plan: truncated sweep %u", s);
@@ -502,15 +248,19 @@ static int validate_plan(const uint8_t *p, size_t nbytes, std::vector<SweepInfo>
                       "plan: sweep %u has bad size %u", s, sh.bytes);
         QFB_CHECK_ARG(sh.nrounds >= 1, "plan: sweep %u has no rounds", s);
         // tile bits and holes must partition [0, nbits)
-        uint64_t seen = 0;
+        uint64_t seen = 0, tilemask = 0;
         for (int j = 0; j < M; ++j) {
             QFB_CHECK_ARG(sh.gpos[j] < h.nbits && !((seen >> sh.gpos[j]) & 1ull), "plan: sweep %u bad gpos", s);
             seen |= 1ull << sh.gpos[j];
         }
-        for (uint32_t i = 0; i < h.nbits - h.tile_bits; ++i) {
+        tilemask = seen;
+        for (uint32_t i = 0; i < nholes; ++i) {
             QFB_CHECK_ARG(sh.hole[i] < h.nbits && !((seen >> sh.hole[i]) & 1ull), "plan: sweep %u bad hole", s);
             seen |= 1ull << sh.hole[i];
         }
+        QFB_CHECK_ARG((sh.store_xor & ~tilemask) == 0, "plan: sweep %u store_xor leaves the tile", s);
+        const bool want_sync = sh.store_xor != 0 && sh.nrounds == 1;
+        QFB_CHECK_ARG(((sh.flags & QFB_SWEEP_FLAG_STORE_SYNC) != 0) == want_sync, "plan: sweep %u bad store-sync flag", s);
         size_t roff = off + sizeof(sh);
         const size_t send = off + sh.bytes;
         bool sweep_g2 = false;
@@ -521,29 +271,33 @@ static int validate_plan(const uint8_t *p, size_t nbytes, std::vector<SweepInfo>
             QFB_CHECK_ARG(rh.bytes % 16 == 0 && rh.bytes >= sizeof(rh) && roff + rh.bytes <= send,
                           "plan: sweep %u round %u bad size", s, r);
             sweep_g2 = sweep_g2 || rh.has_g2;
+            uint32_t tseen = 0;
+            for (int i = 0; i < R; ++i) {
+                QFB_CHECK_ARG(rh.regpos[i] < M && !((tseen >> rh.regpos[i]) & 1u), "plan: bad regpos");
+                tseen |= 1u << rh.regpos[i];
+                const int64_t gbytes = (int64_t)16 << sh.gpos[rh.regpos[i]];
+                const bool flipped = (sh.store_xor >> sh.gpos[rh.regpos[i]]) & 1ull;
+                QFB_CHECK_ARG(rh.ps_b[i] == (swz_host(1u << rh.regpos[i]) << 4) && rh.rgb[i] == gbytes &&
+                                  rh.rst[i] == (flipped ? -gbytes : gbytes),
+                              "plan: sweep %u round %u bad register-bit images", s, r);
+            }
+            for (int t = 0; t < M - R; ++t) {
+                QFB_CHECK_ARG(rh.thrpos[t] < M && !((tseen >> rh.thrpos[t]) & 1u), "plan: bad thrpos");
+                tseen |= 1u << rh.thrpos[t];
+            }
             // thread LUTs must reproduce the deposit of the thread bits through thrpos / gpos
             for (int t = 0; t < (1 << (M - R)); ++t) {
                 uint32_t tb = 0;
                 uint64_t tg = 0;
                 for (int b = 0; b < M - R; ++b) {
                     if ((t >> b) & 1) {
-                        QFB_CHECK_ARG(rh.thrpos[b] < M, "plan: bad thrpos");
                         tb |= 1u << rh.thrpos[b];
                         tg |= 1ull << sh.gpos[rh.thrpos[b]];
                     }
                 }
                 const qfb_thread_lut &lo = rh.lut_lo[t & 15], &hi = rh.lut_hi[(t >> 4) & 31];
-                QFB_CHECK_ARG((lo.tb | hi.tb) == tb && (lo.tg | hi.tg) == tg, "plan: sweep %u round %u bad thread LUT",
-                              s, r);
-            }
-            uint32_t tseen = 0;
-            for (int i = 0; i < R; ++i) {
-                QFB_CHECK_ARG(rh.regpos[i] < M && !((tseen >> rh.regpos[i]) & 1u), "plan: bad regpos");
-                tseen |= 1u << rh.regpos[i];
-            }
-            for (int t = 0; t < M - R; ++t) {
-                QFB_CHECK_ARG(rh.thrpos[t] < M && !((tseen >> rh.thrpos[t]) & 1u), "plan: bad thrpos");
-                tseen |= 1u << rh.thrpos[t];
+                QFB_CHECK_ARG((lo.tb | hi.tb) == tb && (lo.tg | hi.tg) == tg && (lo.stb ^ hi.stb) == (swz_host(tb) << 4),
+                              "plan: sweep %u round %u bad thread LUT", s, r);
             }
             size_t ooff = roff + sizeof(rh);
             const size_t rend = roff + rh.bytes;
@@ -552,30 +306,39 @@ static int validate_plan(const uint8_t *p, size_t nbytes, std::vector<SweepInfo>
                 QFB_CHECK_ARG(ooff + sizeof(qfb_op_header) <= rend, "plan: truncated op");
                 qfb_op_header oh;
                 memcpy(&oh, p + ooff, sizeof(oh));
-                const uint32_t bytes = (uint32_t)oh.size16 * 16u;
-                QFB_CHECK_ARG(bytes >= sizeof(oh) && ooff + bytes <= rend, "plan: op bad size");
-                const int h = oh.handler;
+                const uint32_t bytes = oh.bytes;
+                QFB_CHECK_ARG(bytes % 16 == 0 && bytes >= sizeof(oh) && ooff + bytes <= rend, "plan: op bad size");
+                const int hd = (int)oh.handler;
+                const int rcm = oh.reg_cmask;
                 if (o == rh.nops) {
-                    QFB_CHECK_ARG(h == QFB_H_END && bytes == 16, "plan: round does not end with an END record");
+                    QFB_CHECK_ARG(hd == QFB_H_END && bytes == 16, "plan: round does not end with an END record");
                     ended = true;
-                } else if (h >= QFB_H_G1_GENERAL && h < QFB_H_G1C_GENERAL) {
-                    QFB_CHECK_ARG(bytes == 16 + 64 && oh.reg_cmask == 0 && oh.idx_cmask == 0, "plan: bad G1 op");
-                } else if (h >= QFB_H_G1C_GENERAL && h < QFB_H_G1C_SWAPX + 4) {
-                    const int j = (h - QFB_H_G1C_GENERAL) & 3;
-                    QFB_CHECK_ARG(bytes == 16 + 64 && !((oh.reg_cmask >> j) & 1) && oh.reg_cmask < NE,
-                                  "plan: bad controlled G1 op");
-                } else if (h == QFB_H_CPH_SCALAR) {
-                    QFB_CHECK_ARG(bytes == 32 && oh.reg_cmask == 0 && rh.has_scalar == 1, "plan: bad scalar CPH op");
-                } else if (h == QFB_H_CPH_REG || h == QFB_H_CPH_NEG) {
-                    QFB_CHECK_ARG(bytes == 32 && oh.reg_cmask > 0 && oh.reg_cmask < NE, "plan: bad CPH op");
-                } else if (h >= QFB_H_G2 && h < QFB_H_G2 + 6) {
+                } else if (hd >= QFB_H_G1_GENERAL && hd < QFB_H_G1_SUMDIFF) {
+                    QFB_CHECK_ARG(bytes == 16 + 64 && rcm == 0 && oh.idx_cmask == 0, "plan: bad G1 op");
+                } else if (hd >= QFB_H_G1_SUMDIFF && hd < QFB_H_G1C_GENERAL) {
+                    QFB_CHECK_ARG(bytes == 32 && rcm == 0 && oh.idx_cmask == 0, "plan: bad pivoted G1 op");
+                } else if (hd >= QFB_H_G1C_GENERAL && hd < QFB_H_G1C_SWAPX + 4) {
+                    const int j = (hd - QFB_H_G1C_GENERAL) & 3;
+                    const uint32_t want = hd < QFB_H_G1C_SWAPX ? 16 + 64 : 16;   // controlled X carries no matrix
+                    QFB_CHECK_ARG(bytes == want && !((rcm >> j) & 1) && rcm < NE, "plan: bad controlled G1 op");
+                } else if (hd == QFB_H_CPH_SCALAR) {
+                    QFB_CHECK_ARG(bytes == 32 && rcm == 0 && rh.has_scalar == 1, "plan: bad scalar CPH op");
+                } else if (hd >= QFB_H_CPH_REG1 && hd < QFB_H_CPH_NEG2) {
+                    QFB_CHECK_ARG(bytes == 32 && rcm == (1 << ((hd - QFB_H_CPH_REG1) & 3)), "plan: bad 1-bit CPH op");
+                } else if (hd >= QFB_H_CPH_NEG2 && hd < QFB_H_CPH_REGM) {
                     static const int J0[6] = {1, 2, 2, 3, 3, 3}, J1[6] = {0, 0, 1, 0, 1, 2};
-                    const int j0 = J0[h - QFB_H_G2], j1 = J1[h - QFB_H_G2];
-                    QFB_CHECK_ARG(rh.has_g2 == 1 && bytes == 16 + 272 && !((oh.reg_cmask >> j0) & 1) &&
-                                      !((oh.reg_cmask >> j1) & 1) && oh.reg_cmask < NE,
+                    const int pi = hd - QFB_H_CPH_NEG2;
+                    QFB_CHECK_ARG(bytes == 32 && rcm == ((1 << J0[pi]) | (1 << J1[pi])), "plan: bad 2-bit CPH op");
+                } else if (hd == QFB_H_CPH_REGM || hd == QFB_H_CPH_NEGM) {
+                    QFB_CHECK_ARG(bytes == 32 && rcm > 0 && rcm < NE, "plan: bad CPH op");
+                } else if (hd >= QFB_H_G2 && hd < QFB_H_G2 + 6) {
+                    static const int J0[6] = {1, 2, 2, 3, 3, 3}, J1[6] = {0, 0, 1, 0, 1, 2};
+                    const int j0 = J0[hd - QFB_H_G2], j1 = J1[hd - QFB_H_G2];
+                    QFB_CHECK_ARG(rh.has_g2 == 1 && bytes == 16 + 272 && !((rcm >> j0) & 1) && !((rcm >> j1) & 1) &&
+                                      rcm < NE,
                                   "plan: bad G2 op");
                 } else {
-                    QFB_CHECK_ARG(false, "plan: unknown handler %d", h);
+                    QFB_CHECK_ARG(false, "plan: unknown handler %d", hd);
                 }
                 ooff += bytes;
             }
@@ -584,6 +347,7 @@ static int validate_plan(const uint8_t *p, size_t nbytes, std::vector<SweepInfo>
             roff += rh.bytes;
         }
         QFB_CHECK_ARG(roff == send, "plan: sweep size mismatch");
+        QFB_CHECK_ARG(((sh.flags & QFB_SWEEP_FLAG_G2) != 0) == sweep_g2, "plan: sweep %u bad G2 flag", s);
         sweeps.push_back(SweepInfo{off, sh.bytes, sweep_g2});
         off += sh.bytes;
     }
@@ -595,8 +359,8 @@ template <int M, bool G2>
 static int launch_sweep(c128 *state, const uint8_t *rec_dev, uint32_t rec_bytes, int nbits, uint64_t index_hi,
                         cudaStream_t st) {
     constexpr int T = SweepCfg<M>::T;
-    // +32: the op loop prefetches one header + 16 payload bytes past the END record of a round
-    const size_t smem = (size_t)SweepCfg<M>::TILE_BYTES + rec_bytes + 32;
+    // +16: the op loop prefetches one header past the END record of a round
+    const size_t smem = (size_t)SweepCfg<M>::TILE_BYTES + HLUT_BYTES + rec_bytes + 16;
     static thread_local size_t configured[64] = {0};
     int dev = 0;
     QFB_CUDA(cudaGetDevice(&dev));
@@ -616,11 +380,7 @@ static int launch_sweep(c128 *state, const uint8_t *rec_dev, uint32_t rec_bytes,
     const uint64_t cap = (uint64_t)sm_count_cached() * resident;
     const int grid = (int)std::min<uint64_t>(ntiles, cap);
     const uint64_t hi_shifted = (nbits >= 64) ? 0ull : (index_hi << nbits);
-    static const int async_load = [] {
-        const char *v = getenv("QFB_LOADER");
-        return (v && strcmp(v, "async") == 0) ? 1 : 0;
-    }();
-    sweep_kernel<M, G2><<<grid, T, smem, st>>>(state, rec_dev, rec_bytes, nholes, hi_shifted, async_load);
+    sweep_kernel<M, G2><<<grid, T, smem, st>>>(state, rec_dev, rec_bytes, nholes, hi_shifted);
     QFB_LAUNCH_CHECK();
     return QFB_OK;
 }

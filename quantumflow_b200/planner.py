@@ -31,7 +31,7 @@ import numpy as np
 from . import classify
 
 PLAN_MAGIC = 0x50424651
-PLAN_VERSION = 6
+PLAN_VERSION = 7
 REG_BITS = 4
 MAX_TILE_BITS = 13
 MIN_TILE_BITS = 5
@@ -39,23 +39,30 @@ MAX_HOLES = 48
 MAX_SWEEP_BYTES = 40 * 1024
 MAX_DIAG_BITS = 5
 # handler ids (csrc/qfb_plan.h)
-H_G1C_GENERAL, H_G1C_SWAPX, H_CPH_SCALAR, H_CPH_REG, H_CPH_NEG, H_G2, H_END = 20, 24, 28, 29, 30, 31, 37
-# uncontrolled 1-bit handlers by QFB_G1_* kind
-H_G1_OF_KIND = {0: 0, 3: 4, 5: 8, 6: 12, 7: 16}
+(H_G1_GENERAL, H_G1_SUMDIFF, H_G1_ROT_R, H_G1_ROT_I, H_G1C_GENERAL, H_G1C_SWAPX, H_CPH_SCALAR, H_CPH_REG1,
+ H_CPH_NEG1, H_CPH_NEG2, H_CPH_REGM, H_CPH_NEGM, H_END, H_G2) = 0, 4, 8, 12, 16, 20, 24, 25, 29, 33, 39, 40, 41, 42
 G2_PAIRS = [(1, 0), (2, 0), (2, 1), (3, 0), (3, 1), (3, 2)]
+SWEEP_FLAG_G2, SWEEP_FLAG_STORE_SYNC = 1, 2
 
 
 def _op_record(handler: int, reg_cmask: int, idx_cmask: int, payload: bytes = b'') -> bytes:
     size = 16 + len(payload)
-    assert size % 16 == 0 and size // 16 < 256
-    return struct.pack('<BBBBIQ', handler, reg_cmask, size // 16, 0, 0, idx_cmask) + payload
+    assert size % 16 == 0 and size < 65536
+    return struct.pack('<IHBBQ', handler, size, reg_cmask, 0, idx_cmask) + payload
 
 
 def is_scalar_term(record: bytes) -> bool:
-    return record[0] == H_CPH_SCALAR
+    return struct.unpack_from('<I', record, 0)[0] == H_CPH_SCALAR
 
 
-ROUND_HEADER_BYTES = 32 + 16 * (16 + 32)
+def swz(idx: int) -> int:
+    """XOR swizzle of the exchange buffer (16-byte granularity), see csrc/qfb_sweep.cu."""
+    x = idx >> 3
+    return idx ^ ((x ^ (x >> 3) ^ (x >> 6) ^ (x >> 9)) & 7)
+
+
+SWEEP_HEADER_BYTES = 96
+ROUND_HEADER_BYTES = 112 + 16 * (16 + 32)
 
 # QFB_G1_* kinds (csrc/qfb_plan.h)
 K_GENERAL, K_REAL, K_RXLIKE, K_SWAPX, K_ANTIDIAG, K_SUMDIFF, K_ROT_R, K_ROT_I = range(8)
@@ -63,8 +70,8 @@ K_GENERAL, K_REAL, K_RXLIKE, K_SWAPX, K_ANTIDIAG, K_SUMDIFF, K_ROT_R, K_ROT_I = 
 DEFAULT_TILE_BITS = 12
 DEFAULT_LOW_BITS = 3
 # cost units ~ FP64 work per amplitude relative to a dense 1-bit operator (16 FP64 ops per amplitude pair)
-COST = {K_GENERAL: 1.0, K_REAL: 0.5, K_RXLIKE: 0.5, K_SWAPX: 0.2, K_ANTIDIAG: 0.5, K_SUMDIFF: 0.25, K_ROT_R: 0.25,
-        K_ROT_I: 0.25, 'G2': 2.5, 'P': 0.1}
+COST = {K_GENERAL: 1.0, K_REAL: 1.0, K_RXLIKE: 1.0, K_SWAPX: 0.3, K_ANTIDIAG: 1.0, K_SUMDIFF: 0.25, K_ROT_R: 0.375,
+        K_ROT_I: 0.375, 'G2': 2.5, 'P': 0.1}
 DEFAULT_MAX_COST = 28.0
 # pivot on the (0,0) entry unless it is this much smaller than the largest entry
 PIVOT_RATIO = 1e-3
@@ -113,38 +120,40 @@ def phase_polynomial(table: np.ndarray, k: int) -> Dict[int, complex]:
     return phi
 
 
+ROT_TOL = 8e-16
+
+
 def encode_g1(mat: np.ndarray, controlled: bool) -> Tuple[int, np.ndarray, Optional[complex]]:
-    """(kind, 8-double payload, pivot) for a 2x2 operator. `pivot` is the uniform scalar that has been divided
-    out (None when the operator is applied as is)."""
+    """(kind, payload doubles, scalar) for a 2x2 operator. `scalar` is the uniform factor that has been divided
+    out (None when the operator is applied as is); payload: 8 doubles (row-major matrix) for GENERAL / SWAPX,
+    2 doubles for the structured kinds (csrc/qfb_plan.h)."""
     m = np.array(mat, dtype=np.complex128).reshape(2, 2)
     plain = np.ascontiguousarray(m).view(np.float64).reshape(-1).copy()
     base = classify.g1_kind(m)            # 0 general, 1 real, 2 rxlike, 3 swapx, 4 antidiag
     if base == K_SWAPX:
         return K_SWAPX, plain, None
-    if controlled:
+    if controlled or base == K_ANTIDIAG:
         return K_GENERAL, plain, None
-    if base == K_ANTIDIAG:
-        return K_GENERAL, plain, None
-    big = np.abs(m).max()
-    m00 = m[0, 0]
-    pivotable = m00 != 0 and abs(m00) >= PIVOT_RATIO * big
-    if base == K_REAL and pivotable:
-        p = m00.real
-        r, s, t = m[0, 1].real / p, m[1, 0].real / p, m[1, 1].real / p
-        payload = np.zeros(8)
-        if s == 1.0 and abs(r) == 1.0 and abs(t) == 1.0:
-            payload[0], payload[1] = r, t
-            return K_SUMDIFF, payload, complex(p)
-        if t == 1.0:
-            payload[0], payload[1] = r, s
-            return K_ROT_R, payload, complex(p)
-    if base == K_RXLIKE and pivotable and m[1, 1] == m00:
-        p = m00.real
-        payload = np.zeros(8)
-        payload[0], payload[1] = m[0, 1].imag / p, m[1, 0].imag / p
-        return K_ROT_I, payload, complex(p)
-    # REAL / RXLIKE / ANTIDIAG operators that could not be pivoted are rare; they share the GENERAL handler
-    return (K_SWAPX if base == K_SWAPX else K_GENERAL), plain, None
+    if base in (K_REAL, K_RXLIKE) and m[0, 0] == m[1, 1]:
+        # rotation [[c, -s], [s, c]] (real) or [[c, i s], [i s, c]]: three shears with a = off/(1+c), b = off
+        c = m[0, 0].real
+        o01, o10 = (m[0, 1].real, m[1, 0].real) if base == K_REAL else (m[0, 1].imag, m[1, 0].imag)
+        is_rot = (o01 == -o10) if base == K_REAL else (o01 == o10)
+        if is_rot and abs(c * c + o10 * o10 - 1.0) <= ROT_TOL:
+            sign = 1.0
+            if c < 0:                      # a half turn goes into the sign of the sweep scalar: keeps |a| <= 1
+                c, o01, o10, sign = -c, -o01, -o10, -1.0
+            return (K_ROT_R if base == K_REAL else K_ROT_I), np.array([o01 / (1.0 + c), o10]), \
+                (None if sign == 1.0 else complex(sign))
+    if base == K_REAL:
+        big = np.abs(m).max()
+        m00 = m[0, 0]
+        if m00 != 0 and abs(m00) >= PIVOT_RATIO * big:
+            p = m00.real
+            r, s, t = m[0, 1].real / p, m[1, 0].real / p, m[1, 1].real / p
+            if s == 1.0 and abs(r) == 1.0 and abs(t) == 1.0:
+                return K_SUMDIFF, np.array([r, t]), complex(p)
+    return K_GENERAL, plain, None
 
 
 def classify_op(mat: np.ndarray, bits: Sequence[int], gate_index: int = -1):
@@ -179,6 +188,90 @@ def classify_op(mat: np.ndarray, bits: Sequence[int], gate_index: int = -1):
     nnz = int(np.count_nonzero(reduced))
     return [POp('G', mix=tbits, ctrl=cbits, mat=reduced, cost=COST['G2'] * max(nnz, 4) / 16.0 + 0.3,
                 gate_index=gate_index)]
+
+
+_X = np.array([[0, 1], [1, 0]], dtype=np.complex128)
+
+
+def _g_cost(mix, ctrl, mat) -> float:
+    if len(mix) == 1:
+        return COST[encode_g1(mat, bool(ctrl))[0]]
+    return COST['G2'] * max(int(np.count_nonzero(mat)), 4) / 16.0 + 0.3
+
+
+def absorb_flips(ops: List[POp]) -> Tuple[List[POp], int]:
+    """Pauli-X gates of a sweep are not executed. Walking the sweep's operators in order, an uncontrolled X on
+    bit b toggles bit b of a pending flip mask F (the stored state is X_F applied to the logical one) and every
+    later operator U is replaced by X_F U X_F restricted to its bits:
+
+      phase term   phi^[all bits 1] with flipped bits expands into 2^|flipped| terms (phi or 1/phi by parity)
+      controls     a flipped control (control on 0) is rewritten  C0(W) = W . C1(W^-1)
+      1-bit G      either X G X (flip kept) or G X (flip absorbed), whichever is cheaper
+      2-bit G      rows and columns permuted
+
+    Returns the rewritten list and F; the kernel applies F as an XOR on the addresses of the sweep's final store.
+    Every flipped bit is a mixing bit of some operator of the sweep, hence a tile bit."""
+    flip = 0
+    out: List[POp] = []
+
+    def phase(bits, factor, gi):
+        fl = [b for b in bits if (flip >> b) & 1]
+        keep = [b for b in bits if not (flip >> b) & 1]
+        for sub in range(1 << len(fl)):
+            tb = [fl[i] for i in range(len(fl)) if (sub >> i) & 1]
+            f = complex(factor) if len(tb) % 2 == 0 else 1.0 / complex(factor)
+            if f != 1:
+                out.append(POp('P', dbits=keep + tb, mat=f, cost=COST['P'], gate_index=gi))
+
+    def gate(mix, ctrl, mat, flipped_ctrl, gi):
+        nonlocal flip
+        if flipped_ctrl:
+            a, rest = flipped_ctrl[0], flipped_ctrl[1:]
+            gate(mix, ctrl, np.linalg.inv(mat), rest, gi)                 # C_a(W^-1), control a now on 1
+            gate(mix, [c for c in ctrl if c != a], mat, rest, gi)         # W without control a
+            return
+        k = len(mix)
+        if k == 1:
+            b = mix[0]
+            fb = (flip >> b) & 1
+            if not ctrl:
+                if np.array_equal(mat, _X):
+                    flip ^= 1 << b
+                    return
+                if mat[0, 0] == 0 and mat[1, 1] == 0:
+                    # antidiagonal = diag(m01, m10) . X
+                    flip ^= 1 << b
+                    phase([], mat[0, 1], gi)
+                    phase([b], mat[1, 0] / mat[0, 1], gi)
+                    return
+                if fb:
+                    keep, absorb = _X @ mat @ _X, mat @ _X
+                    if _g_cost(mix, ctrl, absorb) < _g_cost(mix, ctrl, keep):
+                        flip ^= 1 << b
+                        mat = absorb
+                    else:
+                        mat = keep
+            elif fb:
+                mat = _X @ mat @ _X
+        else:
+            perm = [i ^ (2 * ((flip >> mix[0]) & 1)) ^ ((flip >> mix[1]) & 1) for i in range(4)]
+            mat = mat[np.ix_(perm, perm)]
+        mat = np.ascontiguousarray(mat)
+        if classify.is_identity(mat):
+            return
+        out.append(POp('G', mix=mix, ctrl=ctrl, mat=mat, cost=_g_cost(mix, ctrl, mat), gate_index=gi))
+
+    for op in ops:
+        if op.kind == 'P':
+            if any((flip >> b) & 1 for b in op.dbits):
+                phase(list(op.dbits), op.mat, op.gate_index)
+            else:
+                out.append(op)
+        else:
+            k = len(op.mix)
+            mat = np.asarray(op.mat, dtype=np.complex128).reshape(1 << k, 1 << k)
+            gate(list(op.mix), list(op.ctrl), mat, [c for c in op.ctrl if (flip >> c) & 1], op.gate_index)
+    return out, flip
 
 
 def merge_phase_terms(ops: List[POp]) -> List[POp]:
@@ -223,13 +316,14 @@ class Round:
 
 
 class SweepPlan:
-    __slots__ = ('tile', 'ops', 'rounds', 'cost')
+    __slots__ = ('tile', 'ops', 'rounds', 'cost', 'store_xor')
 
-    def __init__(self, tile: List[int], ops: List[POp]):
+    def __init__(self, tile: List[int], ops: List[POp], store_xor: int = 0):
         self.tile = tile      # index-bit positions, ascending, length M
         self.ops = ops
         self.rounds: List[Round] = []
         self.cost = sum(o.cost for o in ops)
+        self.store_xor = store_xor   # pending X flips, applied by the final store (absorb_flips)
 
 
 class Planner:
@@ -254,7 +348,7 @@ class Planner:
         def_any: set = set()
         def_mix: set = set()
         cost = 0.0
-        nbytes = 80 + 8 * ROUND_HEADER_BYTES
+        nbytes = SWEEP_HEADER_BYTES + 8 * ROUND_HEADER_BYTES
         full = False
         for op in ops:
             ok = not full and not _conflicts(op, def_any, def_mix)
@@ -267,7 +361,9 @@ class Planner:
                     ok = False
             if ok and cost + op.cost > self.max_cost and chosen:
                 ok = False
-            opbytes = 16 + (64 if (op.kind == 'G' and len(op.mix) == 1) else 272 if op.kind == 'G' else 16)
+            # a flipped control can split an operator in two, a flipped phase term of k bits into 2^k (absorb_flips)
+            opbytes = 2 * (16 + 64) if (op.kind == 'G' and len(op.mix) == 1) else 2 * (16 + 272) if op.kind == 'G' \
+                else 32 * (1 << len(op.dbits))
             if ok and nbytes + opbytes > MAX_SWEEP_BYTES - 4 * ROUND_HEADER_BYTES:
                 ok = False
                 full = True
@@ -446,7 +542,9 @@ class Planner:
             chosen, remaining, tile = self._form_sweep(remaining)
             if not chosen:
                 raise RuntimeError('planner made no progress')
-            sweep = SweepPlan(tile, merge_phase_terms(chosen))
+            ops, store_xor = absorb_flips(chosen)
+            assert all(b in tile for b in range(self.nbits) if (store_xor >> b) & 1)
+            sweep = SweepPlan(tile, merge_phase_terms(ops), store_xor)
             self._form_rounds(sweep)
             sweeps.append(sweep)
         return sweeps
@@ -464,7 +562,14 @@ class Planner:
             else:
                 reg_cmask |= 1 << ri
         factor = complex(factor)
-        handler = H_CPH_SCALAR if reg_cmask == 0 else (H_CPH_NEG if factor == -1 else H_CPH_REG)
+        regs = [i for i in range(REG_BITS) if (reg_cmask >> i) & 1]
+        if not regs:
+            handler = H_CPH_SCALAR
+        elif factor == -1:
+            handler = (H_CPH_NEG1 + regs[0]) if len(regs) == 1 else \
+                (H_CPH_NEG2 + G2_PAIRS.index((regs[1], regs[0]))) if len(regs) == 2 else H_CPH_NEGM
+        else:
+            handler = (H_CPH_REG1 + regs[0]) if len(regs) == 1 else H_CPH_REGM
         return _op_record(handler, reg_cmask, idx_cmask, struct.pack('<dd', factor.real, factor.imag))
 
     @staticmethod
@@ -485,10 +590,13 @@ class Planner:
             kind, payload, pivot = encode_g1(op.mat, bool(op.ctrl))
             j = reg_index(op.mix[0])
             if op.ctrl:
-                handler = (H_G1C_SWAPX if kind == K_SWAPX else H_G1C_GENERAL) + j
-            else:
-                handler = H_G1_OF_KIND[kind] + j
-            return _op_record(handler, reg_cmask, idx_cmask, payload.tobytes()), pivot
+                if kind == K_SWAPX:
+                    return _op_record(H_G1C_SWAPX + j, reg_cmask, idx_cmask), None
+                return _op_record(H_G1C_GENERAL + j, reg_cmask, idx_cmask, payload.tobytes()), None
+            if kind == K_SWAPX:
+                raise RuntimeError('uncontrolled X must have been absorbed into the flip mask')
+            handler = {K_GENERAL: H_G1_GENERAL, K_SUMDIFF: H_G1_SUMDIFF, K_ROT_R: H_G1_ROT_R, K_ROT_I: H_G1_ROT_I}[kind]
+            return _op_record(handler + j, reg_cmask, idx_cmask, payload.tobytes()), pivot
         j0, j1 = reg_index(op.mix[0]), reg_index(op.mix[1])
         mat = np.ascontiguousarray(op.mat, dtype=np.complex128).reshape(2, 2, 2, 2)
         if j0 < j1:   # kernel wants the operator's MSB qubit on the higher register bit
@@ -512,7 +620,7 @@ class Planner:
                 if t >= first and t < first + (4 if first == 0 else 8) and (value >> (t - first)) & 1:
                     tb |= 1 << p
                     tg |= 1 << sweep.tile[p]
-            return struct.pack('<IIQ', tb, 0, tg)
+            return struct.pack('<IIQ', swz(tb) << 4, tb, tg)
 
         return b''.join(entry(v, 0) for v in range(16)) + b''.join(entry(v, 4) for v in range(32))
 
@@ -544,22 +652,30 @@ class Planner:
                 encoded[target][1].append(self._emit_phase((), scalar, pos_of, {}))
             rounds_blob = b''
             nops = 0
+            any_g2 = False
             for rd, blobs in encoded:
                 ops_blob = b''.join(blobs) + _op_record(H_END, 0, 0)
                 nops += len(blobs)
                 has_scalar = int(any(is_scalar_term(b) for b in blobs))
-                has_g2 = int(any(H_G2 <= b[0] < H_G2 + 6 for b in blobs))
+                has_g2 = int(any(H_G2 <= struct.unpack_from('<I', b, 0)[0] < H_G2 + 6 for b in blobs))
+                any_g2 = any_g2 or bool(has_g2)
                 thrpad = list(rd.thr) + [0] * (12 - len(rd.thr))
-                rounds_blob += struct.pack('<II4B12BBB6x', len(blobs), ROUND_HEADER_BYTES + len(ops_blob), *rd.regs,
-                                           *thrpad, has_scalar, has_g2)
+                rgb = [16 << sweep.tile[p] for p in rd.regs]
+                rst = [-v if (sweep.store_xor >> sweep.tile[p]) & 1 else v for v, p in zip(rgb, rd.regs)]
+                rounds_blob += struct.pack('<II4B12BBB6x4I4q4q', len(blobs), ROUND_HEADER_BYTES + len(ops_blob),
+                                           *rd.regs, *thrpad, has_scalar, has_g2,
+                                           *[swz(1 << p) << 4 for p in rd.regs], *rgb, *rst)
                 rounds_blob += self._thread_luts(sweep, rd.thr) + ops_blob
             holes = [b for b in range(self.nbits) if b not in sweep.tile]
             gpos = list(sweep.tile) + [0] * (16 - len(sweep.tile))
             hole = holes + [0] * (MAX_HOLES - len(holes))
-            size = 80 + len(rounds_blob)
+            size = SWEEP_HEADER_BYTES + len(rounds_blob)
             if size > MAX_SWEEP_BYTES:
                 raise RuntimeError('sweep record too large ({} bytes)'.format(size))
-            body += struct.pack('<IIII16B48B', size, len(sweep.rounds), nops, 0, *gpos, *hole) + rounds_blob
+            flags = (SWEEP_FLAG_G2 if any_g2 else 0) | \
+                (SWEEP_FLAG_STORE_SYNC if (sweep.store_xor and len(sweep.rounds) == 1) else 0)
+            body += struct.pack('<IIII16B48BQ8x', size, len(sweep.rounds), nops, flags, *gpos, *hole,
+                                sweep.store_xor) + rounds_blob
         total = 32 + len(body)
         header = struct.pack('<IIIIIIQ', PLAN_MAGIC, PLAN_VERSION, self.nbits, self.M, REG_BITS, len(sweeps), total)
         return header + body

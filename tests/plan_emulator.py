@@ -18,24 +18,40 @@ def swz(idx):
     return idx ^ ((x ^ (x >> 3) ^ (x >> 6) ^ (x >> 9)) & 7)
 
 
+G2_PAIRS = [(1, 0), (2, 0), (2, 1), (3, 0), (3, 1), (3, 2)]
+(H_G1_GENERAL, H_G1_SUMDIFF, H_G1_ROT_R, H_G1_ROT_I, H_G1C_GENERAL, H_G1C_SWAPX, H_CPH_SCALAR, H_CPH_REG1,
+ H_CPH_NEG1, H_CPH_NEG2, H_CPH_REGM, H_CPH_NEGM, H_END, H_G2) = 0, 4, 8, 12, 16, 20, 24, 25, 29, 33, 39, 40, 41, 42
+SWEEP_HEADER, ROUND_HEADER = 96, 112 + 768
+
+
 def parse(blob: bytes):
     magic, version, nbits, M, rbits, nsweeps, total = struct.unpack_from('<IIIIIIQ', blob, 0)
-    assert magic == 0x50424651 and version == 6 and rbits == R and total == len(blob)
+    assert magic == 0x50424651 and version == 7 and rbits == R and total == len(blob)
     off = 32
     sweeps = []
     for _ in range(nsweeps):
-        size, nrounds, nops, _ = struct.unpack_from('<IIII', blob, off)
+        size, nrounds, nops, flags = struct.unpack_from('<IIII', blob, off)
         gpos = list(blob[off + 16: off + 16 + M])
         hole = list(blob[off + 32: off + 32 + (nbits - M)])
-        roff = off + 80
+        store_xor = struct.unpack_from('<Q', blob, off + 80)[0]
+        assert all((store_xor >> b) & 1 == 0 for b in hole), 'store_xor leaves the tile'
+        assert bool(flags & 2) == (store_xor != 0 and nrounds == 1)
+        roff = off + SWEEP_HEADER
         rounds = []
         for _r in range(nrounds):
             rn, rbytes = struct.unpack_from('<II', blob, roff)
             regpos = list(blob[roff + 8: roff + 12])
             thrpos = list(blob[roff + 12: roff + 12 + (M - R)])
             has_scalar, has_g2 = blob[roff + 24], blob[roff + 25]
+            ps_b = struct.unpack_from('<4I', blob, roff + 32)
+            rgb = struct.unpack_from('<4q', blob, roff + 48)
+            rst = struct.unpack_from('<4q', blob, roff + 80)
+            for i in range(R):
+                g = 16 << gpos[regpos[i]]
+                assert ps_b[i] == swz(1 << regpos[i]) << 4 and rgb[i] == g
+                assert rst[i] == (-g if (store_xor >> gpos[regpos[i]]) & 1 else g)
             # thread LUTs (16 + 32 entries of <IIQ): must reproduce the deposit of the thread bits
-            lut = [struct.unpack_from('<IIQ', blob, roff + 32 + 16 * i) for i in range(48)]
+            lut = [struct.unpack_from('<IIQ', blob, roff + 112 + 16 * i) for i in range(48)]
             for tid in range(1 << (M - R)):
                 tb = tg = 0
                 for t in range(M - R):
@@ -43,72 +59,86 @@ def parse(blob: bytes):
                         tb |= 1 << thrpos[t]
                         tg |= 1 << gpos[thrpos[t]]
                 lo, hi = lut[tid & 15], lut[16 + ((tid >> 4) & 31)]
-                assert (lo[0] | hi[0], lo[2] | hi[2]) == (tb, tg), 'bad thread LUT'
-            ooff = roff + 32 + 768
+                assert (lo[1] | hi[1], lo[2] | hi[2], lo[0] ^ hi[0]) == (tb, tg, swz(tb) << 4), 'bad thread LUT'
+            ooff = roff + ROUND_HEADER
             ops = []
             for _o in range(rn + 1):
-                handler, rcm, size16, _p0, _p1, icm = struct.unpack_from('<BBBBIQ', blob, ooff)
-                obytes = 16 * size16
+                handler, obytes, rcm, _p0, icm = struct.unpack_from('<IHBBQ', blob, ooff)
                 payload = blob[ooff + 16: ooff + obytes]
                 ooff += obytes
                 if _o == rn:
-                    assert handler == 37 and obytes == 16, 'round must end with an END record'
+                    assert handler == H_END and obytes == 16, 'round must end with an END record'
                     break
-                if handler < 20:
+                if handler < H_G1C_GENERAL:
                     assert rcm == 0 and icm == 0
-                    typ, kind, j0, j1 = 1, [0, 3, 5, 6, 7][handler // 4], handler % 4, 0
-                elif handler < 28:
-                    typ, kind, j0, j1 = 1, (0 if handler < 24 else 3), handler % 4, 0
-                elif handler in (28, 29, 30):
-                    typ, kind, j0, j1 = 3, int(handler == 30), 0, 0
-                    assert (handler == 28) == (rcm == 0)
+                    kind = ['general', 'sumdiff', 'rot_r', 'rot_i'][handler // 4]
+                    assert obytes == (80 if kind == 'general' else 32)
+                    typ, j0, j1 = 1, handler % 4, 0
+                elif handler < H_CPH_SCALAR:
+                    kind = 'general' if handler < H_G1C_SWAPX else 'swapx'
+                    assert obytes == (80 if kind == 'general' else 16)
+                    typ, j0, j1 = 1, handler % 4, 0
+                    assert not (rcm >> j0) & 1
+                elif handler < H_END:
+                    typ, j0, j1 = 3, 0, 0
+                    assert obytes == 32
+                    kind = 'neg' if handler in range(H_CPH_NEG1, H_CPH_REGM) or handler == H_CPH_NEGM else 'mul'
+                    if handler == H_CPH_SCALAR:
+                        assert rcm == 0
+                    elif handler < H_CPH_NEG1:
+                        assert rcm == 1 << (handler - H_CPH_REG1)
+                    elif handler < H_CPH_NEG2:
+                        assert rcm == 1 << (handler - H_CPH_NEG1)
+                    elif handler < H_CPH_REGM:
+                        q0, q1 = G2_PAIRS[handler - H_CPH_NEG2]
+                        assert rcm == (1 << q0) | (1 << q1)
+                    else:
+                        assert 0 < rcm < NE
                 else:
-                    assert 31 <= handler < 37
-                    typ, kind = 2, 0
-                    j0, j1 = [(1, 0), (2, 0), (2, 1), (3, 0), (3, 1), (3, 2)][handler - 31]
+                    assert H_G2 <= handler < H_G2 + 6 and obytes == 16 + 272
+                    typ, kind = 2, 'dense'
+                    j0, j1 = G2_PAIRS[handler - H_G2]
                 ops.append(dict(type=typ, kind=kind, j0=j0, j1=j1, reg_cmask=rcm, idx_cmask=icm, payload=payload))
             assert ooff == roff + rbytes
             assert has_g2 == int(any(o['type'] == 2 for o in ops))
             rounds.append(dict(regpos=regpos, thrpos=thrpos, ops=ops, has_scalar=has_scalar))
             roff += rbytes
         assert roff == off + size
-        sweeps.append(dict(gpos=gpos, hole=hole, rounds=rounds))
+        assert bool(flags & 1) == any(o['type'] == 2 for rd in rounds for o in rd['ops'])
+        sweeps.append(dict(gpos=gpos, hole=hole, rounds=rounds, store_xor=store_xor))
         off += size
     assert off == len(blob)
     return dict(nbits=nbits, M=M, sweeps=sweeps)
 
 
 def _apply_g1(a, op):
-    m = np.frombuffer(op['payload'], dtype=np.complex128, count=4).reshape(2, 2)
-    j, rc = op['j0'], op['reg_cmask']
+    j, rc, kind = op['j0'], op['reg_cmask'], op['kind']
+    if kind == 'general':
+        m = np.frombuffer(op['payload'], dtype=np.complex128, count=4).reshape(2, 2)
+    elif kind != 'swapx':
+        c0, c1 = struct.unpack_from('<dd', op['payload'], 0)
     for p in range(NE // 2):
         e0 = ((p >> j) << (j + 1)) | (p & ((1 << j) - 1))
         e1 = e0 | (1 << j)
         if (e0 & rc) != rc:
             continue
         x, y = a[e0], a[e1]
-        if op['kind'] == 3:      # SWAPX
+        if kind == 'swapx':
             a[e0], a[e1] = y, x
-        elif op['kind'] == 1:    # REAL
-            a[e0] = m[0, 0].real * x + m[0, 1].real * y
-            a[e1] = m[1, 0].real * x + m[1, 1].real * y
-        elif op['kind'] == 2:    # RXLIKE
-            a[e0] = m[0, 0].real * x + 1j * m[0, 1].imag * y
-            a[e1] = 1j * m[1, 0].imag * x + m[1, 1].real * y
-        elif op['kind'] == 4:    # ANTIDIAG
-            a[e0] = m[0, 1] * y
-            a[e1] = m[1, 0] * x
-        elif op['kind'] == 5:    # SUMDIFF (pivoted): x' = x + r0 y, y' = x + r1 y
-            r0, r1 = m[0, 0].real, m[0, 0].imag
-            assert abs(r0) == 1 and abs(r1) == 1
-            a[e0] = x + r0 * y
-            a[e1] = a[e0] + (r1 - r0) * y      # formed from x' like the kernel does
-        elif op['kind'] == 6:    # ROT_R (pivoted): x' = x + r y, y' = y + s x
-            a[e0] = x + m[0, 0].real * y
-            a[e1] = y + m[0, 0].imag * x
-        elif op['kind'] == 7:    # ROT_I (pivoted): x' = x + i a y, y' = y + i b x
-            a[e0] = x + 1j * m[0, 0].real * y
-            a[e1] = y + 1j * m[0, 0].imag * x
+        elif kind == 'sumdiff':     # pivoted: x' = x + r0 y, y' = x' + (r1 - r0) y
+            assert abs(c0) == 1 and abs(c1) == 1
+            a[e0] = x + c0 * y
+            a[e1] = a[e0] + (c1 - c0) * y      # formed from x' like the kernel does
+        elif kind == 'rot_r':       # three shears: x += a y; y += b x; x += a y
+            x = x + c0 * y
+            y = y + c1 * x
+            x = x + c0 * y
+            a[e0], a[e1] = x, y
+        elif kind == 'rot_i':       # x += i a y; y += i b x; x += i a y
+            x = x + 1j * c0 * y
+            y = y + 1j * c1 * x
+            x = x + 1j * c0 * y
+            a[e0], a[e1] = x, y
         else:
             a[e0] = m[0, 0] * x + m[0, 1] * y
             a[e1] = m[1, 0] * x + m[1, 1] * y
@@ -129,10 +159,8 @@ def _apply_g2(a, op):
         for r in range(4):
             acc = 0j
             for c in range(4):
-                if (nz >> (4 * r + c)) & 1:
-                    acc += m[r, c] * vin[c]
-                else:
-                    assert m[r, c] == 0
+                assert ((nz >> (4 * r + c)) & 1) == int(m[r, c] != 0)
+                acc += m[r, c] * vin[c]
             a[ids[r]] = acc
 
 
@@ -146,7 +174,7 @@ def _apply_cph(a, op, on, scalar):
         return scalar * factor
     for e in range(NE):
         if (e & rc) == rc:
-            if op['kind'] == 1:
+            if op['kind'] == 'neg':
                 assert factor == -1
                 a[e] = -a[e]
             else:
@@ -228,7 +256,6 @@ def execute(blob: bytes, state: np.ndarray, index_hi: int = 0, check_layout: boo
                             scalar = _apply_cph(a, op, on, scalar)
                         elif on:
                             if op['type'] == 1:
-                                assert op['reg_cmask'] == 0 or op['kind'] in (0, 3)
                                 _apply_g1(a, op)
                             else:
                                 _apply_g2(a, op)
@@ -238,6 +265,7 @@ def execute(blob: bytes, state: np.ndarray, index_hi: int = 0, check_layout: boo
                         assert scalar == 1
                     regs_all[tid] = a
                 # all threads have read the tile before anyone writes it (the kernel's barriers)
+                staged = []
                 for tid in range(T):
                     tb = tg = 0
                     for t in range(M - R):
@@ -253,5 +281,9 @@ def execute(blob: bytes, state: np.ndarray, index_hi: int = 0, check_layout: boo
                         if rnd + 1 < nrounds:
                             tile[swz(tb | toff)] = regs_all[tid, e]
                         else:
-                            state[gb | tg | goff] = regs_all[tid, e]
+                            staged.append(((gb | tg | goff) ^ sweep['store_xor'], regs_all[tid, e]))
+                if rnd + 1 == nrounds:
+                    # pending X flips: amplitude i lands at i ^ store_xor (all loads of the tile came first)
+                    for addr, val in staged:
+                        state[addr] = val
     return state

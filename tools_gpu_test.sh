@@ -1,0 +1,5 @@
+#!/bin/bash
+# GPU parity tests only
+mkdir -p gpurun_out
+timeout 1500 python -m pytest tests -m gpu -q --timeout 900 -p no:cacheprovider "$@" > gpurun_out/pytest.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest.log
+tail -n 30 gpurun_out/pytest.log

@@ -55,11 +55,11 @@ for k in (8, 16, 32, 64):
 time_plan('1 round, 32 RX', [(RX, [hi[i % 4]]) for i in range(32)])
 time_plan('1 round, 32 RY', [(RY, [hi[i % 4]]) for i in range(32)])
 time_plan('1 round, 32 general', [(GEN, [hi[i % 4]]) for i in range(32)])
-time_plan('1 round, 32 X (alternating with H to defeat cancellation)', [((X if i % 2 else H), [hi[i % 4]]) for i in range(64)])
+time_plan('1 round, 32 X + 32 H on the same bits (X = flip mask: should cost like 32 H)', [((X if i % 2 else H), [hi[(i // 2) % 4]]) for i in range(64)])
 time_plan('1 round, 32 CNOT reg-reg', [(CNOT, [hi[i % 4], hi[(i + 1) % 4]]) for i in range(32)])
 time_plan('1 round, 32 CNOT thread-ctrl (bit 26 -> reg)', [(CNOT, [26, hi[i % 4]]) for i in range(32)])
 time_plan('1 round, 32 CNOT lane-ctrl (bit 1 -> reg)', [(CNOT, [1, hi[i % 4]]) for i in range(32)])
-time_plan('1 round, 32 T on reg bits (+H between)', [((T if i % 2 else H), [hi[i % 4]]) for i in range(64)])
+time_plan('1 round, 32 T on reg bits (+H between, same bit)', [((T if i % 2 else H), [hi[(i // 2) % 4]]) for i in range(64)])
 time_plan('1 round, 32 CZ reg-reg (+H between)', [((CZ, [hi[i % 4], hi[(i + 1) % 4]]) if i % 2 else (H, [hi[i % 4]])) for i in range(64)])
 time_plan('32 scalar phases on distinct thread bits', [(O.gate_matrix('RZ', (0.1 * i,)), [4 + (i % 12)]) for i in range(32)])
 # rounds: H on 4r distinct bits
