@@ -285,7 +285,7 @@ def main():
         if runner is None:
             qf.Circuit._execute(segments, state)
         else:
-            state = runner.execute(state)     # remaps swap the shard with the runner's scratch buffer
+            state = runner.execute(state)     # in place (the remaps exchange blocks through staging chunks)
 
     def barrier():
         if world > 1:
@@ -345,7 +345,7 @@ def main():
     # end-to-end through the public API with host buffers (N=1: State from pinned host memory -> Circuit.run ->
     # result back in pinned host memory). At N>1 each rank does the same with its shard.
     e2e = None
-    if not args.no_e2e:
+    if not args.no_e2e and nlocal <= 31:     # 2 x 16 GiB of pinned host memory per rank at 30 qubits per GPU
         nbytes = 16 << nlocal
         host_in = torch.zeros(1 << nlocal, dtype=torch.complex128).pin_memory()
         if rank == 0:

@@ -57,7 +57,7 @@ class Emit:
 
 def emit_on_check(E):
     """Skip the op unless all idx_cmask bits are set in the thread's full index."""
-    E('ld.shared.u64 cm, [cur+8];', 'and.b64 tm, cm, %s;' % TFULL, 'setp.ne.b64 poff, tm, cm;', '@poff bra TAIL;')
+    E('and.b64 tm, cm, %s;' % TFULL, 'setp.ne.b64 poff, tm, cm;', '@poff bra TAIL;')
 
 
 def emit_rc(E):
@@ -79,7 +79,7 @@ def emit_general_pair(E, x, y):
 
 
 def emit_load_matrix(E):
-    for q in range(4):
+    for q in range(1, 4):          # c0, c1 come from the loop top
         E('ld.shared.v2.f64 {c%d, c%d}, [cur+%d];' % (2 * q, 2 * q + 1, 16 + 16 * q))
     E('neg.f64 n1, c1;', 'neg.f64 n3, c3;', 'neg.f64 n5, c5;', 'neg.f64 n7, c7;')
 
@@ -113,7 +113,7 @@ def gen(has_g2):
     for j in range(R):
         handler(H['G1_SUMDIFF'] + j, 'L_SD%d' % j)
         # x' = x + r0 y, y' = x' + (r1 - r0) y: sums only (exact zeros under destructive interference)
-        body('ld.shared.v2.f64 {c0, c1}, [cur+16];', 'sub.f64 c2, c1, c0;')
+        body('sub.f64 c2, c1, c0;')
         for x, y in pairs_of(j):
             body('fma.rn.f64 %s, c0, %s, %s;' % (re_(x), re_(y), re_(x)),
                  'fma.rn.f64 %s, c0, %s, %s;' % (im_(x), im_(y), im_(x)),
@@ -123,7 +123,6 @@ def gen(has_g2):
     for j in range(R):
         handler(H['G1_ROT_R'] + j, 'L_RR%d' % j)
         # three real shears: x += a y; y += b x; x += a y  (in place, no temporaries)
-        body('ld.shared.v2.f64 {c0, c1}, [cur+16];')
         for x, y in pairs_of(j):
             body('fma.rn.f64 %s, c0, %s, %s;' % (re_(x), re_(y), re_(x)),
                  'fma.rn.f64 %s, c0, %s, %s;' % (im_(x), im_(y), im_(x)),
@@ -135,7 +134,7 @@ def gen(has_g2):
     for j in range(R):
         handler(H['G1_ROT_I'] + j, 'L_RI%d' % j)
         # three imaginary shears: x += i a y; y += i b x; x += i a y
-        body('ld.shared.v2.f64 {c0, c1}, [cur+16];', 'neg.f64 n1, c0;', 'neg.f64 n3, c1;')
+        body('neg.f64 n1, c0;', 'neg.f64 n3, c1;')
         for x, y in pairs_of(j):
             body('fma.rn.f64 %s, n1, %s, %s;' % (re_(x), im_(y), re_(x)),
                  'fma.rn.f64 %s, c0, %s, %s;' % (im_(x), re_(y), im_(x)),
@@ -169,7 +168,7 @@ def gen(has_g2):
     # ---- phase terms ----
     handler(H['CPH_SCALAR'], 'L_PS')
     emit_on_check(body)
-    body('ld.shared.v2.f64 {c0, c1}, [cur+16];', 'neg.f64 n1, c1;',
+    body('neg.f64 n1, c1;',
          'mul.f64 t0, n1, %s;' % PHI, 'mul.f64 t1, c1, %s;' % PHR,
          'fma.rn.f64 %s, c0, %s, t0;' % (PHR, PHR), 'fma.rn.f64 %s, c0, %s, t1;' % (PHI, PHI), 'bra TAIL;')
 
@@ -184,7 +183,7 @@ def gen(has_g2):
     for j in range(R):
         handler(H['CPH_REG1'] + j, 'L_P1%d' % j)
         emit_on_check(body)
-        body('ld.shared.v2.f64 {c0, c1}, [cur+16];', 'neg.f64 n1, c1;')
+        body('neg.f64 n1, c1;')
         for e in range(NE):
             if (e >> j) & 1:
                 cmul(e)
@@ -209,7 +208,7 @@ def gen(has_g2):
         emit_on_check(body)
         emit_rc(body)
         if not is_neg:
-            body('ld.shared.v2.f64 {c0, c1}, [cur+16];', 'neg.f64 n1, c1;')
+            body('neg.f64 n1, c1;')
         for e in range(1, NE):
             skip = body.label('SKIPM')
             body('and.b32 t32, rc, %d;' % ((NE - 1) & ~e), 'setp.ne.u32 pe, t32, 0;', '@pe bra.uni %s;' % skip)
@@ -257,6 +256,10 @@ def gen(has_g2):
       'and.b32 t32, w, 0xffff;',
       'add.u32 %s, %s, t32;' % (OP, OP),
       'ld.shared.v2.u32 {hn, wn}, [%s];' % OP,     # the next header is in flight while the handler runs
+      # control mask and the first two payload doubles of THIS op: issued before the jump so that they land
+      # while the branch resolves (ops without them read the next record's bytes, harmlessly)
+      'ld.shared.u64 cm, [cur+8];',
+      'ld.shared.v2.f64 {c0, c1}, [cur+16];',
       'brx.idx h, ts;')
     E(*body.lines)
     E('TAIL:', 'mov.u32 h, hn;', 'mov.u32 w, wn;', 'bra LOOP;', 'L_END:', '}')

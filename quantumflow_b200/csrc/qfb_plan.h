@@ -50,7 +50,8 @@ typedef struct {
 } qfb_plan_header; /* 32 bytes */
 
 #define QFB_SWEEP_FLAG_G2 1u          /* some round holds G2 ops (selects the kernel variant) */
-#define QFB_SWEEP_FLAG_STORE_SYNC 2u  /* single-round sweep with store_xor != 0: barrier between loads and stores */
+#define QFB_SWEEP_FLAG_STORE_SYNC 2u  /* single-round sweep that permutes on store: barrier between loads and stores */
+#define QFB_SWEEP_FLAG_STORE_PERM 4u  /* spos != gpos: a header-only "store record" follows the last round */
 
 typedef struct {
     uint32_t bytes; /* whole sweep record including this header */
@@ -59,9 +60,14 @@ typedef struct {
     uint32_t flags;
     uint8_t gpos[16]; /* gpos[j] = index bit position of tile bit j (ascending) */
     uint8_t hole[QFB_PLAN_MAX_HOLES]; /* hole[i] = index bit position of tile-id bit i (ascending) */
-    uint64_t store_xor; /* pending X flips of the sweep (index-bit mask, subset of the tile bits) */
+    uint64_t store_xor; /* pending X flips of the sweep, in STORE bit positions (subset of the tile bits) */
     uint8_t pad[8];
-} qfb_sweep_header; /* 96 bytes */
+    uint8_t spos[16]; /* index bit position tile bit j is STORED to: a permutation of gpos[] (= gpos[] unless
+                         QFB_SWEEP_FLAG_STORE_PERM). The sweep then also performs the in-place bit permutation
+                         gpos[j] -> spos[j] of the state (qubit remap of a sharded state, no extra pass). The store
+                         record is a round header with nops = 0 and an END op whose regpos / thrpos equal the last
+                         round's and whose rst[] / thread LUT tg are the images under spos[]. */
+} qfb_sweep_header; /* 112 bytes */
 
 typedef struct {
     uint32_t stb; /* byte offset of the thread's first amplitude in the swizzled exchange buffer: swz(tb) << 4 */

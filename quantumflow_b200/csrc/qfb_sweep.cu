@@ -26,6 +26,12 @@
 
 namespace qfb {
 
+#ifndef QFB_MINB12
+#define QFB_MINB12 2
+#endif
+#ifndef QFB_MINB11
+#define QFB_MINB11 5
+#endif
 constexpr int R = QFB_PLAN_REG_BITS;
 constexpr int NE = 1 << R;  // amplitudes per thread
 
@@ -45,7 +51,7 @@ __device__ __forceinline__ void cmul_inplace(c128 &a, double fr, double fi) {
 template <int M>
 struct SweepCfg {
     static constexpr int T = 1 << (M - R);                 // threads per CTA
-    static constexpr int MINB = (M >= 13) ? 1 : ((M == 12) ? 2 : ((M == 11) ? 4 : 8));
+    static constexpr int MINB = (M >= 13) ? 1 : ((M == 12) ? QFB_MINB12 : ((M == 11) ? QFB_MINB11 : 8));
     static constexpr int TILE_BYTES = 16 << M;
 };
 
@@ -64,8 +70,6 @@ __device__ __forceinline__ void spread(T (&q)[NE], T base, const S (&step)[R], F
 }
 
 constexpr int HLUT_BITS = 6;                                  // tile-id bits per look-up
-constexpr int HLUT_MAX = (QFB_PLAN_MAX_HOLES + HLUT_BITS - 1) / HLUT_BITS;
-constexpr int HLUT_BYTES = HLUT_MAX * (1 << HLUT_BITS) * 8;   // 4 KiB
 
 template <int M, bool HAS_G2>
 __global__ void __launch_bounds__(SweepCfg<M>::T, SweepCfg<M>::MINB)
@@ -75,7 +79,8 @@ sweep_kernel(c128 *__restrict__ state, const uint8_t *__restrict__ rec_g, uint32
     extern __shared__ __align__(16) uint8_t smem[];
     uint8_t *tile = smem;
     uint64_t *hlut = reinterpret_cast<uint64_t *>(smem + SweepCfg<M>::TILE_BYTES);
-    uint8_t *rec = smem + SweepCfg<M>::TILE_BYTES + HLUT_BYTES;
+    const int nlut = (nholes + HLUT_BITS - 1) / HLUT_BITS;
+    uint8_t *rec = smem + SweepCfg<M>::TILE_BYTES + (nlut << (HLUT_BITS + 3));
     const int tid = threadIdx.x;
     {
         const uint4 *s4 = reinterpret_cast<const uint4 *>(rec_g);
@@ -88,8 +93,8 @@ sweep_kernel(c128 *__restrict__ state, const uint8_t *__restrict__ rec_g, uint32
     const uint64_t ntiles = 1ull << nholes;
     const uint64_t store_xor = sh->store_xor;
     const bool store_sync = (sh->flags & QFB_SWEEP_FLAG_STORE_SYNC) != 0;
+    const bool store_perm = (sh->flags & QFB_SWEEP_FLAG_STORE_PERM) != 0;
     // tile id -> index bits (deposit through hole[]): HLUT_BITS tile-id bits per table look-up
-    const int nlut = (nholes + HLUT_BITS - 1) / HLUT_BITS;
     for (int i = tid; i < nlut << HLUT_BITS; i += T) {
         const int k = i >> HLUT_BITS;
         uint64_t v = 0;
@@ -191,6 +196,14 @@ sweep_kernel(c128 *__restrict__ state, const uint8_t *__restrict__ rec_g, uint32
         // ---- last round: coalesced STG.128; amplitude i goes to address i ^ store_xor (pending X flips): the
         // base takes the XOR, the per-register-bit steps of a flipped bit are negative (rst[], set by the planner)
         if (store_sync) __syncthreads();   // single-round sweep: all loads of the tile precede the permuted stores
+        if (store_perm) {
+            // in-place permutation of the tile bits (qubit remap of a sharded state): a header-only record after
+            // the last round holds the images of the thread and register bits under the STORE bit positions
+            rh = reinterpret_cast<const qfb_round_header *>(rp + rh->bytes);
+            const uint4 l0 = *reinterpret_cast<const uint4 *>(&rh->lut_lo[tid & 15]);
+            const uint4 l1 = *reinterpret_cast<const uint4 *>(&rh->lut_hi[(tid >> 4) & 31]);
+            tg = (((uint64_t)l0.w << 32) | l0.z) | (((uint64_t)l1.w << 32) | l1.z);
+        }
         {
             int64_t step[R];
 #pragma unroll
@@ -259,26 +272,46 @@ static int validate_plan(const uint8_t *p, size_t nbytes, std::vector<SweepInfo>
             seen |= 1ull << sh.hole[i];
         }
         QFB_CHECK_ARG((sh.store_xor & ~tilemask) == 0, "plan: sweep %u store_xor leaves the tile", s);
-        const bool want_sync = sh.store_xor != 0 && sh.nrounds == 1;
+        bool perm = false;
+        {
+            uint64_t sseen = 0;
+            for (int j = 0; j < M; ++j) {
+                QFB_CHECK_ARG(sh.spos[j] < h.nbits && ((tilemask >> sh.spos[j]) & 1ull) && !((sseen >> sh.spos[j]) & 1ull),
+                              "plan: sweep %u spos is not a permutation of the tile bits", s);
+                sseen |= 1ull << sh.spos[j];
+                perm = perm || sh.spos[j] != sh.gpos[j];
+            }
+        }
+        QFB_CHECK_ARG(((sh.flags & QFB_SWEEP_FLAG_STORE_PERM) != 0) == perm, "plan: sweep %u bad store-perm flag", s);
+        const bool want_sync = (sh.store_xor != 0 || perm) && sh.nrounds == 1;
         QFB_CHECK_ARG(((sh.flags & QFB_SWEEP_FLAG_STORE_SYNC) != 0) == want_sync, "plan: sweep %u bad store-sync flag", s);
         size_t roff = off + sizeof(sh);
         const size_t send = off + sh.bytes;
         bool sweep_g2 = false;
-        for (uint32_t r = 0; r < sh.nrounds; ++r) {
+        qfb_round_header last_rh;
+        memset(&last_rh, 0, sizeof(last_rh));
+        // rounds, then (with a store permutation) the header-only store record, checked against spos[]
+        for (uint32_t r = 0; r < sh.nrounds + (perm ? 1u : 0u); ++r) {
             QFB_CHECK_ARG(roff + sizeof(qfb_round_header) <= send, "plan: sweep %u truncated round %u", s, r);
             qfb_round_header rh;
             memcpy(&rh, p + roff, sizeof(rh));
-            QFB_CHECK_ARG(rh.bytes % 16 == 0 && rh.bytes >= sizeof(rh) && roff + rh.bytes <= send,
-                          "plan: sweep %u round %u bad size", s, r);
+            const bool store_rec = r == sh.nrounds;
+            const uint8_t *ipos = store_rec ? sh.spos : sh.gpos;   // index-bit images used by this record
+            if (store_rec) {
+                QFB_CHECK_ARG(rh.nops == 0 && memcmp(rh.regpos, last_rh.regpos, 4) == 0 &&
+                                  memcmp(rh.thrpos, last_rh.thrpos, 12) == 0,
+                              "plan: sweep %u store record does not match the last round", s);
+            }
             sweep_g2 = sweep_g2 || rh.has_g2;
             uint32_t tseen = 0;
             for (int i = 0; i < R; ++i) {
                 QFB_CHECK_ARG(rh.regpos[i] < M && !((tseen >> rh.regpos[i]) & 1u), "plan: bad regpos");
                 tseen |= 1u << rh.regpos[i];
                 const int64_t gbytes = (int64_t)16 << sh.gpos[rh.regpos[i]];
-                const bool flipped = (sh.store_xor >> sh.gpos[rh.regpos[i]]) & 1ull;
+                const int64_t sbytes = (int64_t)16 << ipos[rh.regpos[i]];
+                const bool flipped = (sh.store_xor >> ipos[rh.regpos[i]]) & 1ull;
                 QFB_CHECK_ARG(rh.ps_b[i] == (swz_host(1u << rh.regpos[i]) << 4) && rh.rgb[i] == gbytes &&
-                                  rh.rst[i] == (flipped ? -gbytes : gbytes),
+                                  rh.rst[i] == (flipped ? -sbytes : sbytes),
                               "plan: sweep %u round %u bad register-bit images", s, r);
             }
             for (int t = 0; t < M - R; ++t) {
@@ -292,7 +325,7 @@ static int validate_plan(const uint8_t *p, size_t nbytes, std::vector<SweepInfo>
                 for (int b = 0; b < M - R; ++b) {
                     if ((t >> b) & 1) {
                         tb |= 1u << rh.thrpos[b];
-                        tg |= 1ull << sh.gpos[rh.thrpos[b]];
+                        tg |= 1ull << ipos[rh.thrpos[b]];
                     }
                 }
                 const qfb_thread_lut &lo = rh.lut_lo[t & 15], &hi = rh.lut_hi[(t >> 4) & 31];
@@ -345,6 +378,7 @@ static int validate_plan(const uint8_t *p, size_t nbytes, std::vector<SweepInfo>
             QFB_CHECK_ARG(ended, "plan: missing END record");
             QFB_CHECK_ARG(ooff == rend, "plan: round size mismatch");
             roff += rh.bytes;
+            last_rh = rh;
         }
         QFB_CHECK_ARG(roff == send, "plan: sweep size mismatch");
         QFB_CHECK_ARG(((sh.flags & QFB_SWEEP_FLAG_G2) != 0) == sweep_g2, "plan: sweep %u bad G2 flag", s);
@@ -359,8 +393,15 @@ template <int M, bool G2>
 static int launch_sweep(c128 *state, const uint8_t *rec_dev, uint32_t rec_bytes, int nbits, uint64_t index_hi,
                         cudaStream_t st) {
     constexpr int T = SweepCfg<M>::T;
-    // +16: the op loop prefetches one header past the END record of a round
-    const size_t smem = (size_t)SweepCfg<M>::TILE_BYTES + HLUT_BYTES + rec_bytes + 16;
+    // +32: the op loop reads one header + 16 payload bytes past the END record of a round
+    const int nholes = nbits - M;
+    const size_t hlut_bytes = (size_t)((nholes + HLUT_BITS - 1) / HLUT_BITS) << (HLUT_BITS + 3);
+    // QFB_SMEM_PAD (bytes): occupancy experiments only -- extra dynamic shared memory lowers the CTAs per SM
+    static const size_t smem_pad = [] {
+        const char *v = getenv("QFB_SMEM_PAD");
+        return v ? (size_t)atol(v) : (size_t)0;
+    }();
+    const size_t smem = (size_t)SweepCfg<M>::TILE_BYTES + hlut_bytes + rec_bytes + 32 + smem_pad;
     static thread_local size_t configured[64] = {0};
     int dev = 0;
     QFB_CUDA(cudaGetDevice(&dev));
@@ -375,7 +416,6 @@ static int launch_sweep(c128 *state, const uint8_t *rec_dev, uint32_t rec_bytes,
     int resident = 0;  // CTAs per SM for this launch's shared-memory footprint (host-side arithmetic)
     QFB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, sweep_kernel<M, G2>, T, smem));
     resident = std::max(1, resident);
-    const int nholes = nbits - M;
     const uint64_t ntiles = 1ull << nholes;
     const uint64_t cap = (uint64_t)sm_count_cached() * resident;
     const int grid = (int)std::min<uint64_t>(ntiles, cap);

@@ -42,7 +42,7 @@ MAX_DIAG_BITS = 5
 (H_G1_GENERAL, H_G1_SUMDIFF, H_G1_ROT_R, H_G1_ROT_I, H_G1C_GENERAL, H_G1C_SWAPX, H_CPH_SCALAR, H_CPH_REG1,
  H_CPH_NEG1, H_CPH_NEG2, H_CPH_REGM, H_CPH_NEGM, H_END, H_G2) = 0, 4, 8, 12, 16, 20, 24, 25, 29, 33, 39, 40, 41, 42
 G2_PAIRS = [(1, 0), (2, 0), (2, 1), (3, 0), (3, 1), (3, 2)]
-SWEEP_FLAG_G2, SWEEP_FLAG_STORE_SYNC = 1, 2
+SWEEP_FLAG_G2, SWEEP_FLAG_STORE_SYNC, SWEEP_FLAG_STORE_PERM = 1, 2, 4
 
 
 def _op_record(handler: int, reg_cmask: int, idx_cmask: int, payload: bytes = b'') -> bytes:
@@ -61,7 +61,7 @@ def swz(idx: int) -> int:
     return idx ^ ((x ^ (x >> 3) ^ (x >> 6) ^ (x >> 9)) & 7)
 
 
-SWEEP_HEADER_BYTES = 96
+SWEEP_HEADER_BYTES = 112
 ROUND_HEADER_BYTES = 112 + 16 * (16 + 32)
 
 # QFB_G1_* kinds (csrc/qfb_plan.h)
@@ -316,14 +316,15 @@ class Round:
 
 
 class SweepPlan:
-    __slots__ = ('tile', 'ops', 'rounds', 'cost', 'store_xor')
+    __slots__ = ('tile', 'ops', 'rounds', 'cost', 'store_xor', 'spos')
 
     def __init__(self, tile: List[int], ops: List[POp], store_xor: int = 0):
         self.tile = tile      # index-bit positions, ascending, length M
         self.ops = ops
         self.rounds: List[Round] = []
         self.cost = sum(o.cost for o in ops)
-        self.store_xor = store_xor   # pending X flips, applied by the final store (absorb_flips)
+        self.store_xor = store_xor   # pending X flips, applied by the final store (absorb_flips); STORE positions
+        self.spos = list(tile)       # index-bit position tile bit j is stored to (!= tile: in-place bit permutation)
 
 
 class Planner:
@@ -535,6 +536,74 @@ class Planner:
             rd.ops = ops
 
     # ---- driver -----------------------------------------------------------------------------------
+    def attach_permutation(self, sweeps: List[SweepPlan], perm: Sequence[int]) -> None:
+        """Make the plan end with the in-place bit permutation `perm` (destination bit j <- source bit perm[j],
+        the convention of qfb_permute_bits) at no extra pass when the moved bits are tile bits of the last sweep:
+        the sweep then stores tile bit b at position dst_of[b]. Otherwise bare sweeps are appended (one usually;
+        more when the moved bits do not fit into one tile)."""
+        nb = self.nbits
+        assert sorted(perm) == list(range(nb))
+        content = list(range(nb))               # content[pos] = source bit currently at position pos
+        want = list(perm)                       # position j must end up holding source bit perm[j]
+
+        def apply(sweep: SweepPlan, mapping: Dict[int, int]) -> None:
+            # mapping: position -> new position, for the tile bits of `sweep` (identity elsewhere)
+            sweep.spos = [mapping.get(b, b) for b in sweep.tile]
+            sweep.store_xor = sum(1 << mapping.get(b, b) for b in range(nb) if (sweep.store_xor >> b) & 1)
+            if not sweep.rounds:
+                # bare sweep: a load round (lanes on index bits 0.. under tile[]) before the store round
+                regs = [p for p in range(self.M - 1, -1, -1) if p >= self.L][:REG_BITS]
+                regs.sort()
+                sweep.rounds.append(Round(regs, self._thread_order(regs, True), []))
+            # store round: the lanes walk the tile positions that are stored to index bits 0, 1, 2 ...
+            lanes = [sweep.spos.index(t) for t in range(min(self.L, self.M - REG_BITS))]
+            regs = [p for p in range(self.M - 1, -1, -1) if p not in lanes][:REG_BITS]
+            regs.sort()
+            thr = lanes + [p for p in range(self.M) if p not in lanes and p not in regs]
+            sweep.rounds.append(Round(regs, thr, []))
+
+        first = True
+        while content != want:
+            # transpositions that each put one source bit into its final position, grouped while they fit a tile
+            moved: List[int] = []
+            mapping: Dict[int, int] = {}
+            trial = list(content)
+            last = sweeps[-1] if (first and sweeps) else None
+            cap = self.M - self.L
+            while trial != want:
+                j = next(q for q in range(nb) if trial[q] != want[q])
+                q = trial.index(want[j])
+                new_moved = sorted(set(moved) | {j, q})
+                if last is not None:
+                    fits = all(b in last.tile for b in new_moved)
+                else:
+                    fits = len([b for b in new_moved if b >= self.L]) <= cap
+                if not fits:
+                    break
+                moved = new_moved
+                trial[j], trial[q] = trial[q], trial[j]
+            if not moved:
+                if last is not None:
+                    first = False       # the last sweep cannot host it: start over with appended bare sweeps
+                    continue
+                raise RuntimeError('bit permutation does not fit a tile')
+            # composite position map of this group: where does the content of position b end up
+            for b in moved:
+                mapping[b] = trial.index(content[b])
+            if last is not None:
+                apply(last, mapping)
+            else:
+                tile = set(range(self.L)) | set(moved)
+                b = 0
+                while len(tile) < self.M:
+                    tile.add(b)
+                    b += 1
+                bare = SweepPlan(sorted(tile), [])
+                apply(bare, mapping)
+                sweeps.append(bare)
+            content = trial
+            first = False
+
     def plan(self, pops: List[POp]) -> List[SweepPlan]:
         sweeps: List[SweepPlan] = []
         remaining = list(pops)
@@ -612,14 +681,15 @@ class Planner:
                           mat.tobytes() + struct.pack('<I12x', nz)), None
 
     @staticmethod
-    def _thread_luts(sweep: SweepPlan, thr: Sequence[int]) -> bytes:
-        """lut_lo[v] deposits thread bits 0..3 of v, lut_hi[v] thread bits 4.. of (v << 4)."""
+    def _thread_luts(ipos: Sequence[int], thr: Sequence[int]) -> bytes:
+        """lut_lo[v] deposits thread bits 0..3 of v, lut_hi[v] thread bits 4.. of (v << 4); ipos[p] = index-bit
+        image of tile position p."""
         def entry(value: int, first: int) -> bytes:
             tb = tg = 0
             for t, p in enumerate(thr):
                 if t >= first and t < first + (4 if first == 0 else 8) and (value >> (t - first)) & 1:
                     tb |= 1 << p
-                    tg |= 1 << sweep.tile[p]
+                    tg |= 1 << ipos[p]
             return struct.pack('<IIQ', swz(tb) << 4, tb, tg)
 
         return b''.join(entry(v, 0) for v in range(16)) + b''.join(entry(v, 4) for v in range(32))
@@ -665,17 +735,28 @@ class Planner:
                 rounds_blob += struct.pack('<II4B12BBB6x4I4q4q', len(blobs), ROUND_HEADER_BYTES + len(ops_blob),
                                            *rd.regs, *thrpad, has_scalar, has_g2,
                                            *[swz(1 << p) << 4 for p in rd.regs], *rgb, *rst)
-                rounds_blob += self._thread_luts(sweep, rd.thr) + ops_blob
+                rounds_blob += self._thread_luts(sweep.tile, rd.thr) + ops_blob
+            perm = sweep.spos != list(sweep.tile)
+            if perm:
+                # header-only store record: the last round's bit assignment with the images under spos
+                rd = sweep.rounds[-1]
+                thrpad = list(rd.thr) + [0] * (12 - len(rd.thr))
+                rgb = [16 << sweep.tile[p] for p in rd.regs]
+                rst = [(-1 if (sweep.store_xor >> sweep.spos[p]) & 1 else 1) * (16 << sweep.spos[p]) for p in rd.regs]
+                rounds_blob += struct.pack('<II4B12BBB6x4I4q4q', 0, ROUND_HEADER_BYTES + 16, *rd.regs, *thrpad, 0, 0,
+                                           *[swz(1 << p) << 4 for p in rd.regs], *rgb, *rst)
+                rounds_blob += self._thread_luts(sweep.spos, rd.thr) + _op_record(H_END, 0, 0)
             holes = [b for b in range(self.nbits) if b not in sweep.tile]
             gpos = list(sweep.tile) + [0] * (16 - len(sweep.tile))
             hole = holes + [0] * (MAX_HOLES - len(holes))
             size = SWEEP_HEADER_BYTES + len(rounds_blob)
             if size > MAX_SWEEP_BYTES:
                 raise RuntimeError('sweep record too large ({} bytes)'.format(size))
-            flags = (SWEEP_FLAG_G2 if any_g2 else 0) | \
-                (SWEEP_FLAG_STORE_SYNC if (sweep.store_xor and len(sweep.rounds) == 1) else 0)
-            body += struct.pack('<IIII16B48BQ8x', size, len(sweep.rounds), nops, flags, *gpos, *hole,
-                                sweep.store_xor) + rounds_blob
+            flags = (SWEEP_FLAG_G2 if any_g2 else 0) | (SWEEP_FLAG_STORE_PERM if perm else 0) | \
+                (SWEEP_FLAG_STORE_SYNC if ((sweep.store_xor or perm) and len(sweep.rounds) == 1) else 0)
+            spos = list(sweep.spos) + [0] * (16 - len(sweep.spos))
+            body += struct.pack('<IIII16B48BQ8x16B', size, len(sweep.rounds), nops, flags, *gpos, *hole,
+                                sweep.store_xor, *spos) + rounds_blob
         total = 32 + len(body)
         header = struct.pack('<IIIIIIQ', PLAN_MAGIC, PLAN_VERSION, self.nbits, self.M, REG_BITS, len(sweeps), total)
         return header + body
@@ -697,15 +778,21 @@ class Segment:
 
 
 def build_segments(nbits: int, bitops: Sequence[Tuple[np.ndarray, Sequence[int]]], tile_bits: int = None,
-                   low_bits: int = None, max_cost: float = None) -> List[Segment]:
-    """Plan a list of (matrix, bits) operators for a state with `nbits` local index bits."""
+                   low_bits: int = None, max_cost: float = None, final_perm: Sequence[int] = None) -> List[Segment]:
+    """Plan a list of (matrix, bits) operators for a state with `nbits` local index bits. `final_perm` (destination
+    bit j <- source bit final_perm[j]) is an in-place bit permutation executed after the last operator, fused into
+    the last sweep when its tile holds the moved bits (the local half of a qubit remap, sharded.py)."""
     planner = Planner(nbits, tile_bits, low_bits, max_cost)
     segments: List[Segment] = []
     pending: List[POp] = []
+    if final_perm is not None and list(final_perm) == list(range(nbits)):
+        final_perm = None
 
-    def flush():
-        if pending:
-            sweeps = planner.plan(pending)
+    def flush(last: bool = False):
+        if pending or (last and final_perm is not None):
+            sweeps = planner.plan(pending) if pending else []
+            if last and final_perm is not None:
+                planner.attach_permutation(sweeps, final_perm)
             blob = planner.serialise(sweeps)
             segments.append(Segment('plan', blob=blob, nsweeps=len(sweeps),
                                     nops=len({op.gate_index for op in pending}),
@@ -721,7 +808,7 @@ def build_segments(nbits: int, bitops: Sequence[Tuple[np.ndarray, Sequence[int]]
             segments.append(Segment('op', mat=item.mat, bits=item.bits, nsweeps=1, nops=1))
         else:
             pending.extend(item)
-    flush()
+    flush(last=True)
     return segments
 
 

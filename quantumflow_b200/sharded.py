@@ -7,8 +7,13 @@ kept on the host, so "swapping back" is never needed.
 * diagonal operators and control qubits on rank bits cost no communication: the kernels resolve them from
   `index_hi` (= the rank), see qfb_apply_diag / qfb_run_plan;
 * an operator that MIXES a rank bit triggers a remap: k rank bits are exchanged with the k top local bits by a
-  pairwise block exchange (for k = p this is the all-to-all of SURVEY 8e) over NCCL / NVLink, after a local
-  bit-permutation sweep has moved the outgoing logical qubits to the top local positions;
+  pairwise block exchange (for k = p this is the all-to-all of SURVEY 8e) over NCCL / NVLink. The outgoing logical
+  qubits are first moved to the top local positions by an in-place bit permutation that rides on the final store
+  of the stage's last sweep (planner.attach_permutation: no extra pass over the shard);
+* the exchange is IN PLACE: block j of the shard is swapped with the matching block of peer (mine ^ s) in step s
+  (XOR pairing, so every pair agrees on the order), chunk by chunk through two small staging buffers - chunk
+  i+1 is on the wire while chunk i is copied out of its staging buffer. Memory: shard + 2 staging chunks, which
+  is what lets a 2^33-amplitude (128 GiB) shard live on a 180 GB GPU;
 * which qubits become global is decided Belady-style: the ones whose next mixing use is farthest away.
 
 `ShardedCircuit` only needs three callables for the local work (run segments, permute bits, allocate scratch),
@@ -42,21 +47,22 @@ def _mixing_and_diag_bits(mat: np.ndarray, bits: Sequence[int]) -> Tuple[frozens
 
 
 class Stage:
-    """Local work between two remaps: operators with PHYSICAL bit positions, planned for nl local bits."""
-    __slots__ = ('bitops', 'segments')
+    """Local work between two remaps: operators with PHYSICAL bit positions, planned for nl local bits, followed
+    by the in-place local bit permutation `final_perm` (dst local bit j <- src local bit final_perm[j]; None =
+    identity) that prepares the next remap."""
+    __slots__ = ('bitops', 'segments', 'final_perm')
 
-    def __init__(self, bitops: List[BitOp]):
+    def __init__(self, bitops: List[BitOp], final_perm: Optional[List[int]] = None):
         self.bitops = bitops
         self.segments = None
+        self.final_perm = final_perm
 
 
 class Remap:
-    """Exchange rank bits `rank_positions` (positions inside the rank index) with the top-k local bits, after the
-    local permutation `local_perm` (dst local bit j <- src local bit local_perm[j]; None = identity)."""
-    __slots__ = ('local_perm', 'rank_positions')
+    """Exchange rank bits `rank_positions` (positions inside the rank index) with the top-k local bits."""
+    __slots__ = ('rank_positions',)
 
-    def __init__(self, local_perm: Optional[List[int]], rank_positions: List[int]):
-        self.local_perm = local_perm
+    def __init__(self, rank_positions: List[int]):
         self.rank_positions = rank_positions
 
 
@@ -132,7 +138,11 @@ def schedule(nbits: int, p: int, bitops: Sequence[BitOp]) -> Tuple[List[object],
         for i, t in enumerate(rank_positions):
             b_local, b_rank = logical_at[top[i]], logical_at[nl + t]
             phys_of[b_local], phys_of[b_rank] = nl + t, top[i]
-        steps.append(Remap(local_perm, rank_positions))
+        if local_perm is not None:
+            if not steps or not isinstance(steps[-1], Stage):
+                steps.append(Stage([]))
+            steps[-1].final_perm = local_perm
+        steps.append(Remap(rank_positions))
     return steps, phys_of
 
 
@@ -142,7 +152,8 @@ class ShardedCircuit:
 
     def __init__(self, circuit, nqubits: int, world: int, rank: int, tile_bits: int = None, low_bits: int = None,
                  max_cost: float = None, bitops: Sequence[BitOp] = None,
-                 run_stage: Callable = None, permute: Callable = None, group=None):
+                 run_stage: Callable = None, permute: Callable = None, group=None,
+                 staging_bytes: int = 512 << 20):
         p = world.bit_length() - 1
         assert (1 << p) == world, 'world size must be a power of two'
         self.n, self.p, self.nl = nqubits, p, nqubits - p
@@ -154,16 +165,17 @@ class ShardedCircuit:
         self.steps, self.final_phys_of = schedule(nqubits, p, bitops)
         self._plan_args = dict(tile_bits=tile_bits, low_bits=low_bits, max_cost=max_cost)
         self._run_stage = run_stage or self._run_stage_gpu
-        self._permute = permute or self._permute_gpu
-        self._scratch = None
+        self._permute = permute            # test double only (out of place); the GPU path fuses it into the plan
+        self._staging_bytes = int(staging_bytes)
+        self._staging = None
         self._comm_seconds = 0.0
         self._comm_bytes = 0
         self._remaps = 0
         self._executions = 0
         for st in self.steps:
             if isinstance(st, Stage):
-                st.segments = planner.build_segments(self.nl, st.bitops, **self._plan_args) \
-                    if run_stage is None else None
+                st.segments = planner.build_segments(self.nl, st.bitops, final_perm=st.final_perm,
+                                                     **self._plan_args) if run_stage is None else None
 
     # ---- default (GPU) local work ------------------------------------------------------------------
     def _run_stage_gpu(self, stage: Stage, shard: torch.Tensor) -> None:
@@ -175,12 +187,6 @@ class ShardedCircuit:
                 seg.uploaded.launch(shard, index_hi=self.rank)
             else:
                 engine.apply_operator(shard, seg.mat, seg.bits, inplace=True, index_hi=self.rank)
-
-    def _permute_gpu(self, shard: torch.Tensor, perm: List[int], out: torch.Tensor) -> None:
-        from . import _lib
-        lib = _lib.load()
-        _lib.check(lib.qfb_permute_bits(out.data_ptr(), shard.data_ptr(), self.nl, _lib.int_array(perm), 0,
-                                        torch.cuda.current_stream().cuda_stream))
 
     # ---- bookkeeping ---------------------------------------------------------------------------------
     def local_segments(self) -> List[planner.Segment]:
@@ -197,57 +203,72 @@ class ShardedCircuit:
         ex = max(1, self._executions)
         return {'remaps_per_step': self._remaps / ex, 'bytes_sent_per_rank_per_step': self._comm_bytes / ex,
                 'ms_per_step': self.comm_ms_per_step(),
-                'note': 'pairwise block exchange (isend/irecv) of k rank bits with the top-k local bits; '
-                        'time includes the local bit-permutation sweep; not overlapped with compute yet'}
+                'note': 'in-place pairwise block exchange (isend/irecv, XOR pairing) of k rank bits with the top-k '
+                        'local bits, chunked through two staging buffers; the local bit permutation is fused '
+                        'into the last sweep of the preceding stage; not overlapped with compute yet'}
 
     def reset_comm_counters(self) -> None:
         self._comm_seconds, self._comm_bytes, self._remaps, self._executions = 0.0, 0, 0, 0
 
     # ---- execution ---------------------------------------------------------------------------------
-    def _exchange(self, shard: torch.Tensor, scratch: torch.Tensor, rank_positions: List[int]) -> None:
-        """Block j of this rank (top-k local bits = j) goes to the peer whose selected rank bits equal j and lands
-        there at block (my selected rank bits). Result is written to `scratch`."""
+    def _exchange(self, shard: torch.Tensor, rank_positions: List[int]) -> None:
+        """In place: block j of this rank (top-k local bits = j) is swapped with block `mine` of the peer whose
+        selected rank bits equal j. Step s pairs mine with mine ^ s on every rank, so both sides of a pair issue
+        their transfers in the same order; chunks go through two staging buffers (receive chunk i+1 while chunk
+        i is copied into place)."""
         k = len(rank_positions)
         nblocks = 1 << k
         blk = shard.numel() >> k
         mine = 0
         for i, t in enumerate(rank_positions):
             mine |= ((self.rank >> t) & 1) << i
-        ops = []
-        for j in range(nblocks):
-            src = shard[j * blk:(j + 1) * blk]
-            if j == mine:
-                scratch[j * blk:(j + 1) * blk].copy_(src)
-                continue
+        chunk = max(1, min(blk, self._staging_bytes // shard.element_size()))
+        if self._staging is None or self._staging.numel() < 2 * chunk or self._staging.device != shard.device \
+                or self._staging.dtype != shard.dtype:
+            self._staging = torch.empty(2 * chunk, dtype=shard.dtype, device=shard.device)
+        pending = None
+        nsent = 0
+        for s in range(1, nblocks):
+            j = mine ^ s
             peer = self.rank
             for i, t in enumerate(rank_positions):
                 peer = (peer & ~(1 << t)) | (((j >> i) & 1) << t)
-            dst = scratch[j * blk:(j + 1) * blk]
-            ops.append(dist.P2POp(dist.isend, src, peer, group=self.group))
-            ops.append(dist.P2POp(dist.irecv, dst, peer, group=self.group))
-            self._comm_bytes += src.numel() * src.element_size()
-        for req in dist.batch_isend_irecv(ops):
-            req.wait()
+            for off in range(0, blk, chunk):
+                n = min(chunk, blk - off)
+                mine_chunk = shard[j * blk + off: j * blk + off + n]
+                buf = self._staging[(nsent % 2) * chunk: (nsent % 2) * chunk + n]
+                reqs = dist.batch_isend_irecv([dist.P2POp(dist.isend, mine_chunk, peer, group=self.group),
+                                               dist.P2POp(dist.irecv, buf, peer, group=self.group)])
+                nsent += 1
+                self._comm_bytes += n * shard.element_size()
+                if pending is not None:
+                    for req in pending[0]:
+                        req.wait()
+                    pending[1].copy_(pending[2])
+                pending = (reqs, mine_chunk, buf)
+        if pending is not None:
+            for req in pending[0]:
+                req.wait()
+            pending[1].copy_(pending[2])
 
     def execute(self, shard: torch.Tensor) -> torch.Tensor:
+        """Runs the circuit in place on this rank's shard and returns it (the same tensor)."""
         assert shard.numel() == 1 << self.nl and shard.is_contiguous()
         timed = shard.is_cuda
         for st in self.steps:
             if isinstance(st, Stage):
                 self._run_stage(st, shard)
+                if st.final_perm is not None and self._permute is not None:
+                    out = torch.empty_like(shard)          # test double: small shards, out of place
+                    self._permute(shard, st.final_perm, out)
+                    shard.copy_(out)
                 continue
-            if self._scratch is None or self._scratch.shape != shard.shape or self._scratch.device != shard.device:
-                self._scratch = torch.empty_like(shard)
             if timed:
                 ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 ev0.record()
             else:
                 t0 = time.perf_counter()
-            if st.local_perm is not None:
-                self._permute(shard, st.local_perm, self._scratch)
-                shard, self._scratch = self._scratch, shard
-            self._exchange(shard, self._scratch, st.rank_positions)
-            shard, self._scratch = self._scratch, shard
+            self._exchange(shard, st.rank_positions)
             self._remaps += 1
             if timed:
                 ev1.record()

@@ -21,7 +21,7 @@ def swz(idx):
 G2_PAIRS = [(1, 0), (2, 0), (2, 1), (3, 0), (3, 1), (3, 2)]
 (H_G1_GENERAL, H_G1_SUMDIFF, H_G1_ROT_R, H_G1_ROT_I, H_G1C_GENERAL, H_G1C_SWAPX, H_CPH_SCALAR, H_CPH_REG1,
  H_CPH_NEG1, H_CPH_NEG2, H_CPH_REGM, H_CPH_NEGM, H_END, H_G2) = 0, 4, 8, 12, 16, 20, 24, 25, 29, 33, 39, 40, 41, 42
-SWEEP_HEADER, ROUND_HEADER = 96, 112 + 768
+SWEEP_HEADER, ROUND_HEADER = 112, 112 + 768
 
 
 def parse(blob: bytes):
@@ -34,11 +34,16 @@ def parse(blob: bytes):
         gpos = list(blob[off + 16: off + 16 + M])
         hole = list(blob[off + 32: off + 32 + (nbits - M)])
         store_xor = struct.unpack_from('<Q', blob, off + 80)[0]
+        spos = list(blob[off + 96: off + 96 + M])
+        assert sorted(spos) == sorted(gpos), 'spos must permute the tile bits'
+        perm = spos != gpos
         assert all((store_xor >> b) & 1 == 0 for b in hole), 'store_xor leaves the tile'
-        assert bool(flags & 2) == (store_xor != 0 and nrounds == 1)
+        assert bool(flags & 2) == ((store_xor != 0 or perm) and nrounds == 1)
+        assert bool(flags & 4) == perm
         roff = off + SWEEP_HEADER
         rounds = []
-        for _r in range(nrounds):
+        for _r in range(nrounds + int(perm)):
+            ipos = spos if _r == nrounds else gpos
             rn, rbytes = struct.unpack_from('<II', blob, roff)
             regpos = list(blob[roff + 8: roff + 12])
             thrpos = list(blob[roff + 12: roff + 12 + (M - R)])
@@ -47,9 +52,9 @@ def parse(blob: bytes):
             rgb = struct.unpack_from('<4q', blob, roff + 48)
             rst = struct.unpack_from('<4q', blob, roff + 80)
             for i in range(R):
-                g = 16 << gpos[regpos[i]]
+                g, sg = 16 << gpos[regpos[i]], 16 << ipos[regpos[i]]
                 assert ps_b[i] == swz(1 << regpos[i]) << 4 and rgb[i] == g
-                assert rst[i] == (-g if (store_xor >> gpos[regpos[i]]) & 1 else g)
+                assert rst[i] == (-sg if (store_xor >> ipos[regpos[i]]) & 1 else sg)
             # thread LUTs (16 + 32 entries of <IIQ): must reproduce the deposit of the thread bits
             lut = [struct.unpack_from('<IIQ', blob, roff + 112 + 16 * i) for i in range(48)]
             for tid in range(1 << (M - R)):
@@ -57,7 +62,7 @@ def parse(blob: bytes):
                 for t in range(M - R):
                     if (tid >> t) & 1:
                         tb |= 1 << thrpos[t]
-                        tg |= 1 << gpos[thrpos[t]]
+                        tg |= 1 << ipos[thrpos[t]]
                 lo, hi = lut[tid & 15], lut[16 + ((tid >> 4) & 31)]
                 assert (lo[1] | hi[1], lo[2] | hi[2], lo[0] ^ hi[0]) == (tb, tg, swz(tb) << 4), 'bad thread LUT'
             ooff = roff + ROUND_HEADER
@@ -101,11 +106,14 @@ def parse(blob: bytes):
                 ops.append(dict(type=typ, kind=kind, j0=j0, j1=j1, reg_cmask=rcm, idx_cmask=icm, payload=payload))
             assert ooff == roff + rbytes
             assert has_g2 == int(any(o['type'] == 2 for o in ops))
-            rounds.append(dict(regpos=regpos, thrpos=thrpos, ops=ops, has_scalar=has_scalar))
+            if _r == nrounds:
+                assert rn == 0 and (regpos, thrpos) == (rounds[-1]['regpos'], rounds[-1]['thrpos']), 'bad store record'
+            else:
+                rounds.append(dict(regpos=regpos, thrpos=thrpos, ops=ops, has_scalar=has_scalar))
             roff += rbytes
         assert roff == off + size
         assert bool(flags & 1) == any(o['type'] == 2 for rd in rounds for o in rd['ops'])
-        sweeps.append(dict(gpos=gpos, hole=hole, rounds=rounds, store_xor=store_xor))
+        sweeps.append(dict(gpos=gpos, spos=spos, hole=hole, rounds=rounds, store_xor=store_xor))
         off += size
     assert off == len(blob)
     return dict(nbits=nbits, M=M, sweeps=sweeps)
@@ -211,7 +219,7 @@ def execute(blob: bytes, state: np.ndarray, index_hi: int = 0, check_layout: boo
     state = np.array(state, dtype=np.complex128).reshape(-1)
     T = 1 << (M - R)
     for sweep in plan['sweeps']:
-        gpos, hole = sweep['gpos'], sweep['hole']
+        gpos, spos, hole = sweep['gpos'], sweep['spos'], sweep['hole']
         assert sorted(gpos + hole) == list(range(nbits))
         nrounds = len(sweep['rounds'])
         for tile_id in range(1 << (nbits - M)):
@@ -231,7 +239,10 @@ def execute(blob: bytes, state: np.ndarray, index_hi: int = 0, check_layout: boo
                 if check_layout and (rnd == 0 or rnd == nrounds - 1):
                     # edge rounds: lanes must walk the lowest index bits (coalesced 128-byte lines)
                     nlow = min(3, M - R)
-                    assert [gpos[thrpos[t]] for t in range(nlow)] == list(range(nlow)), 'uncoalesced edge round'
+                    if rnd == 0:
+                        assert [gpos[thrpos[t]] for t in range(nlow)] == list(range(nlow)), 'uncoalesced load round'
+                    if rnd == nrounds - 1:
+                        assert [spos[thrpos[t]] for t in range(nlow)] == list(range(nlow)), 'uncoalesced store round'
                 regs_all = np.zeros((T, NE), dtype=np.complex128)
                 for tid in range(T):
                     tb = tg = 0
@@ -271,13 +282,13 @@ def execute(blob: bytes, state: np.ndarray, index_hi: int = 0, check_layout: boo
                     for t in range(M - R):
                         bit = (tid >> t) & 1
                         tb |= bit << thrpos[t]
-                        tg |= bit << gpos[thrpos[t]]
+                        tg |= bit << spos[thrpos[t]]       # only used by the final store: STORE positions
                     for e in range(NE):
                         toff = goff = 0
                         for i in range(R):
                             if (e >> i) & 1:
                                 toff |= 1 << regpos[i]
-                                goff |= 1 << gpos[regpos[i]]
+                                goff |= 1 << spos[regpos[i]]
                         if rnd + 1 < nrounds:
                             tile[swz(tb | toff)] = regs_all[tid, e]
                         else:

@@ -29,7 +29,8 @@ def _worker(rank, world, port, n, depth, seed, out_dir):
         import quantumflow_b200 as qf
         from quantumflow_b200 import engine, sharded, workloads
         circ = workloads.wb_circuit(qf, n, depth, seed)
-        runner = sharded.ShardedCircuit(circ, n, world, rank)
+        # 256 KiB staging chunks: the in-place exchange runs its chunked, double-buffered path
+        runner = sharded.ShardedCircuit(circ, n, world, rank, staging_bytes=1 << 18)
         nl = runner.nl
         shard = torch.zeros(1 << nl, dtype=torch.complex128, device='cuda')
         if rank == 0:

@@ -203,3 +203,36 @@ def test_identity_and_global_phase_ops():
 def test_planner_rejects_tiny_states():
     with pytest.raises(ValueError):
         planner.build_segments(3, [(O.gate_matrix('H'), [0])])
+
+
+@pytest.mark.parametrize('nbits,tile,perm_seed', [(9, 7, 0), (10, 9, 1), (12, 12, 2), (8, 5, 3), (13, 12, 4)])
+def test_final_bit_permutation_is_fused_or_appended(nbits, tile, perm_seed):
+    """build_segments(final_perm=...) ends the plan with the in-place bit permutation of a qubit remap: fused into
+    the last sweep when the moved bits are tile bits, appended as bare sweeps otherwise."""
+    rnd = random.Random(perm_seed)
+    specs = workloads.wb_gate_list(nbits, 2, perm_seed)
+    ops = [(O.gate_matrix(name, params), [nbits - 1 - q for q in qubits]) for name, params, qubits in specs]
+    perm = list(range(nbits))
+    moved = rnd.sample(range(nbits), min(nbits, 2 + 2 * (perm_seed % 3)))     # includes low bits sometimes
+    shuffled = list(moved)
+    rnd.shuffle(shuffled)
+    for a, b in zip(moved, shuffled):
+        perm[a] = b
+    rng = np.random.RandomState(perm_seed)
+    vec = rng.normal(size=1 << nbits) + 1j * rng.normal(size=1 << nbits)
+    for with_ops in (True, False):
+        segs = planner.build_segments(nbits, ops if with_ops else [], tile_bits=tile, final_perm=perm)
+        got = vec.copy()
+        for seg in segs:
+            assert seg.kind == 'plan'
+            validate_with_library(seg.blob)
+            got = E.execute(seg.blob, got)
+        want = vec.copy()
+        if with_ops:
+            want = O.run_specs(specs, nbits, want.reshape([2] * nbits)).reshape(-1)
+        idx = np.arange(1 << nbits)
+        src = np.zeros_like(idx)
+        for j, pj in enumerate(perm):
+            src |= ((idx >> j) & 1) << pj
+        want = want[src]
+        assert np.abs(got - want).max() < AMP_TOL

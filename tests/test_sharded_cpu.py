@@ -33,13 +33,13 @@ def test_schedule_keeps_every_mixing_operator_local_and_tracks_the_map():
     for st in steps:
         if isinstance(st, sharded.Stage):
             nstage += 1
+            assert st.final_perm is None or sorted(st.final_perm) == list(range(nl))
             for mat, bits in st.bitops:
                 mix, _ = sharded._mixing_and_diag_bits(np.asarray(mat), list(bits))
                 assert all(b < nl for b in mix), 'mixing operator on a rank bit'
                 nops += 1
         else:
             assert 1 <= len(st.rank_positions) <= p
-            assert st.local_perm is None or sorted(st.local_perm) == list(range(nl))
     assert nops == len(specs)
     nremap = len(steps) - nstage
     assert 1 <= nremap <= 2 * 6 + 2          # about one remap per layer (SURVEY 8e estimate)
@@ -91,8 +91,9 @@ def _worker(rank, world, port, n, specs, full_in, out_dir):
                 src |= ((idx >> j) & 1) << pj
             out.numpy()[:] = shard.numpy()[src]
 
+        # a tiny staging buffer forces the chunked, double-buffered path of the in-place exchange
         runner = sharded.ShardedCircuit(None, n, world, rank, bitops=_bitops(specs, n), run_stage=run_stage,
-                                        permute=permute)
+                                        permute=permute, staging_bytes=16 * 24)
         shard = torch.from_numpy(np.ascontiguousarray(full_in[rank << nl:(rank + 1) << nl]))
         shard = runner.execute(shard)
         np.save(os.path.join(out_dir, 'shard{}.npy'.format(rank)), shard.numpy())
