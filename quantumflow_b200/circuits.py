@@ -25,7 +25,7 @@ __all__ = ['Circuit', 'count_operations', 'map_gate', 'qft_circuit', 'reversal_c
            'ccnot_circuit', 'zyz_circuit', 'phase_estimation_circuit', 'addition_circuit', 'ghz_circuit']
 
 # states smaller than this are latency-bound; they go through the one-gate kernels
-PLANNER_MIN_BITS = 5
+PLANNER_MIN_BITS = 6
 # a run of gates shorter than this is not worth a plan
 PLANNER_MIN_OPS = 2
 

@@ -9,18 +9,18 @@ update unrolled over register bit J / register mask, so they are emitted by the 
 typed 48 times. The output is committed next to this script; `python gen_oploop.py` regenerates it and
 tests/test_abi.py checks that the committed file is current.
 
-asm operands (see sweep_kernel): %0..%31 amplitude components (a[e].re = %(2e), a[e].im = %(2e+1)), %32/%33 the
-round's running scalar phase (re, im), %34 shared-memory address of the next op record (in/out), %35 the full
-index of the thread's first amplitude (tile base | thread bits | rank bits << nbits).
+asm operands (see sweep_kernel), NE = 2^R amplitudes per thread: %0..%(2NE-1) amplitude components (a[e].re =
+%(2e), a[e].im = %(2e+1)), then the round's running scalar phase (re, im), the shared-memory address of the next
+op record (in/out) and the full index of the thread's first amplitude (tile base | thread bits | rank bits << nbits).
 """
 import os
 import re
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-R = 4
+R = 5
 NE = 1 << R
-PAIRS = [(1, 0), (2, 0), (2, 1), (3, 0), (3, 1), (3, 2)]
-PHR, PHI, OP, TFULL = '%32', '%33', '%34', '%35'
+PAIRS = [(j0, j1) for j0 in range(R) for j1 in range(j0)]
+PHR, PHI, OP, TFULL = ['%%%d' % (2 * NE + i) for i in range(4)]
 
 
 def handler_ids():
@@ -222,8 +222,8 @@ def gen(has_g2):
             emit_on_check(body)
             emit_rc(body)
             others = [b for b in range(R) if b not in (j0, j1)]
-            for g in range(4):
-                eb = ((g & 1) << others[0]) | ((g >> 1) << others[1])
+            for g in range(1 << len(others)):
+                eb = sum(((g >> i) & 1) << b for i, b in enumerate(others))
                 skip = body.label('SKIPG')
                 free = (NE - 1) & ~(1 << j0) & ~(1 << j1) & ~eb
                 body('and.b32 t32, rc, %d;' % free, 'setp.ne.u32 pe, t32, 0;', '@pe bra.uni %s;' % skip)

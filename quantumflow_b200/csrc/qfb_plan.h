@@ -5,7 +5,9 @@
  * (32 B per amplitude). In a sweep every CTA owns tiles of 2^M amplitudes: the M "tile bits" are index bit
  * positions chosen by the planner (gpos[], ascending; the low bits are always included so that every global
  * access is a full 128-byte line). A tile is processed in ROUNDS. In a round each thread holds 2^R amplitudes
- * in registers: R "register bits" (regpos[], tile-bit positions) enumerate the amplitudes of one thread and
+ * in registers (R = 5: 32 amplitudes = 128 registers; the cost of an op is its arithmetic plus a fixed ~100-cycle
+ * dispatch bubble per SM sub-partition, profiles/README.md, so the more amplitudes an op updates per thread the
+ * better): R "register bits" (regpos[], tile-bit positions) enumerate the amplitudes of one thread and
  * the remaining M-R tile bits (thrpos[]) enumerate the threads. Ops of a round are
  *
  *   G1   dense 1-bit operator on a register bit, optionally controlled
@@ -32,10 +34,10 @@
 #include <stdint.h>
 
 #define QFB_PLAN_MAGIC 0x50424651u /* "QFBP" */
-#define QFB_PLAN_VERSION 7u
-#define QFB_PLAN_REG_BITS 4
+#define QFB_PLAN_VERSION 8u
+#define QFB_PLAN_REG_BITS 5
 #define QFB_PLAN_MAX_TILE_BITS 13
-#define QFB_PLAN_MIN_TILE_BITS 5
+#define QFB_PLAN_MIN_TILE_BITS 6
 #define QFB_PLAN_MAX_HOLES 48
 #define QFB_PLAN_MAX_SWEEP_BYTES (40 * 1024)
 
@@ -81,19 +83,19 @@ typedef struct {
 typedef struct {
     uint32_t nops;
     uint32_t bytes;     /* whole round record: header + thread LUTs + ops */
-    uint8_t regpos[4];  /* tile-bit position of register bit i */
+    uint8_t regpos[8];  /* tile-bit position of register bit i, i < R */
     uint8_t thrpos[12]; /* tile-bit position of thread bit t, t < M-R */
     uint8_t has_scalar; /* 1 when the round holds CPH terms without register bits */
     uint8_t has_g2;     /* 1 when the round holds G2 ops */
-    uint8_t pad[6];
-    uint32_t ps_b[4];   /* swz(1 << regpos[i]) << 4: byte offset of register bit i in the exchange buffer */
-    int64_t rgb[4];     /* 16 << gpos[regpos[i]]: byte distance in the state between register bit i = 0 and 1 */
-    int64_t rst[4];     /* the same for the final store: negative when store_xor flips that bit */
+    uint8_t pad[2];
+    uint32_t ps_b[8];   /* swz(1 << regpos[i]) << 4: byte offset of register bit i in the exchange buffer */
+    int64_t rgb[8];     /* 16 << gpos[regpos[i]]: byte distance in the state between register bit i = 0 and 1 */
+    int64_t rst[8];     /* the same for the final store: negative when store_xor flips that bit */
     /* thread id -> (stb, tb, tg) in two table look-ups instead of a per-bit deposit loop:
      * x = lut_lo[tid & 15].x ^ lut_hi[tid >> 4].x (the bit sets are disjoint and swz is linear over XOR) */
     qfb_thread_lut lut_lo[QFB_PLAN_LUT_LO];
     qfb_thread_lut lut_hi[QFB_PLAN_LUT_HI];
-} qfb_round_header; /* 112 + 768 bytes */
+} qfb_round_header; /* 192 + 768 bytes */
 
 /* kinds of dense 1-bit operators: structure of the 2x2 operator, chosen by the planner to save FP64 work and
  * register copies; (x, y) = the pair of amplitudes, every update is in place.
@@ -106,7 +108,8 @@ typedef struct {
  *            a = -tan(phi/2), b = sin(phi): exact determinant 1, |a| <= 1 (the planner folds a half turn into
  *            the sign of the sweep scalar), no pivot, no temporaries. 6 per pair.
  *   ROT_I    [[c, i s], [i s, c]] (RX) the same way with imaginary shears  x += i a y; y += i b x; x += i a y. */
-/* Handler ids: ONE DENSE switch in the kernel's op interpreter (a jump table, BRX).
+/* Handler ids: ONE jump table (brx.idx) in the kernel's op interpreter. j = register bit (0..R-1), pair = index
+ * of (j0 > j1) in (1,0) (2,0) (2,1) (3,0) (3,1) (3,2) (4,0) (4,1) (4,2) (4,3).
  *   QFB_H_G1_GENERAL + j  uncontrolled dense 1-bit operator on register bit j (16 FP64 per pair)
  *   QFB_H_G1_SUMDIFF + j  pivoted Hadamard-like
  *   QFB_H_G1_ROT_R + j    real rotation (RY), three shears
@@ -116,26 +119,26 @@ typedef struct {
  *   QFB_H_CPH_SCALAR      phase term without register bits: accumulates into the round's scalar
  *   QFB_H_CPH_REG1 + j    phase term on register bit j (and idx_cmask)
  *   QFB_H_CPH_NEG1 + j    the same with factor -1 (sign flip, no FP64 work)
- *   QFB_H_CPH_NEG2 + pair factor -1 on two register bits, pair as for G2 (CZ between register bits)
+ *   QFB_H_CPH_NEG2 + pair factor -1 on two register bits (CZ between register bits)
  *   QFB_H_CPH_REGM / NEGM any other register mask (reg_cmask)
- *   QFB_H_G2 + pair       dense 2-bit operator, (j0, j1) = (1,0) (2,0) (2,1) (3,0) (3,1) (3,2)
- *   QFB_H_END             terminates the round's op list */
+ *   QFB_H_END             terminates the round's op list
+ *   QFB_H_G2 + pair       dense 2-bit operator on register bits (j0, j1) */
 enum {
     QFB_H_G1_GENERAL = 0,
-    QFB_H_G1_SUMDIFF = 4,
-    QFB_H_G1_ROT_R = 8,
-    QFB_H_G1_ROT_I = 12,
-    QFB_H_G1C_GENERAL = 16,
-    QFB_H_G1C_SWAPX = 20,
-    QFB_H_CPH_SCALAR = 24,
-    QFB_H_CPH_REG1 = 25,
-    QFB_H_CPH_NEG1 = 29,
-    QFB_H_CPH_NEG2 = 33,
-    QFB_H_CPH_REGM = 39,
-    QFB_H_CPH_NEGM = 40,
-    QFB_H_END = 41,
-    QFB_H_G2 = 42,
-    QFB_H_COUNT = 48
+    QFB_H_G1_SUMDIFF = 5,
+    QFB_H_G1_ROT_R = 10,
+    QFB_H_G1_ROT_I = 15,
+    QFB_H_G1C_GENERAL = 20,
+    QFB_H_G1C_SWAPX = 25,
+    QFB_H_CPH_SCALAR = 30,
+    QFB_H_CPH_REG1 = 31,
+    QFB_H_CPH_NEG1 = 36,
+    QFB_H_CPH_NEG2 = 41,
+    QFB_H_CPH_REGM = 51,
+    QFB_H_CPH_NEGM = 52,
+    QFB_H_END = 53,
+    QFB_H_G2 = 54,
+    QFB_H_COUNT = 64
 };
 
 typedef struct {

@@ -26,12 +26,6 @@
 
 namespace qfb {
 
-#ifndef QFB_MINB12
-#define QFB_MINB12 2
-#endif
-#ifndef QFB_MINB11
-#define QFB_MINB11 5
-#endif
 constexpr int R = QFB_PLAN_REG_BITS;
 constexpr int NE = 1 << R;  // amplitudes per thread
 
@@ -51,7 +45,8 @@ __device__ __forceinline__ void cmul_inplace(c128 &a, double fr, double fi) {
 template <int M>
 struct SweepCfg {
     static constexpr int T = 1 << (M - R);                 // threads per CTA
-    static constexpr int MINB = (M >= 13) ? 1 : ((M == 12) ? QFB_MINB12 : ((M == 11) ? QFB_MINB11 : 8));
+    // 2^R amplitudes = 4 * 2^R registers per thread: 170 registers at 3 CTAs of 128 threads (M = 12)
+    static constexpr int MINB = (M >= 13) ? 1 : ((M == 12) ? 3 : ((M == 11) ? 6 : 8));
     static constexpr int TILE_BYTES = 16 << M;
 };
 
@@ -150,7 +145,9 @@ sweep_kernel(c128 *__restrict__ state, const uint8_t *__restrict__ rec_g, uint32
 #define QFB_AMP(e) "+d"(a[e].re), "+d"(a[e].im)
 #define QFB_OPLOOP_OPERANDS                                                                                   \
     QFB_AMP(0), QFB_AMP(1), QFB_AMP(2), QFB_AMP(3), QFB_AMP(4), QFB_AMP(5), QFB_AMP(6), QFB_AMP(7), QFB_AMP(8),    \
-        QFB_AMP(9), QFB_AMP(10), QFB_AMP(11), QFB_AMP(12), QFB_AMP(13), QFB_AMP(14), QFB_AMP(15), "+d"(phr),     \
+        QFB_AMP(9), QFB_AMP(10), QFB_AMP(11), QFB_AMP(12), QFB_AMP(13), QFB_AMP(14), QFB_AMP(15), QFB_AMP(16),    \
+        QFB_AMP(17), QFB_AMP(18), QFB_AMP(19), QFB_AMP(20), QFB_AMP(21), QFB_AMP(22), QFB_AMP(23), QFB_AMP(24),   \
+        QFB_AMP(25), QFB_AMP(26), QFB_AMP(27), QFB_AMP(28), QFB_AMP(29), QFB_AMP(30), QFB_AMP(31), "+d"(phr),     \
         "+d"(phi), "+r"(op)                                                                                   \
         : "l"(tfull)
             if constexpr (HAS_G2) {
@@ -231,6 +228,12 @@ struct PlanHandle {
     size_t dev_bytes;
 };
 
+// register-bit pairs (j0 > j1) in handler order
+static const int J0[10] = {1, 2, 2, 3, 3, 3, 4, 4, 4, 4}, J1[10] = {0, 0, 1, 0, 1, 2, 0, 1, 2, 3};
+constexpr int NPAIRS = R * (R - 1) / 2;
+static_assert(R == 5 && QFB_H_CPH_NEG2 + NPAIRS == QFB_H_CPH_REGM && QFB_H_G2 + NPAIRS == QFB_H_COUNT,
+              "handler ids in qfb_plan.h assume R = 5");
+
 static uint32_t swz_host(uint32_t idx) {
     const uint32_t x = idx >> 3;
     return idx ^ ((x ^ (x >> 3) ^ (x >> 6) ^ (x >> 9)) & 7u);
@@ -298,7 +301,7 @@ static int validate_plan(const uint8_t *p, size_t nbytes, std::vector<SweepInfo>
             const bool store_rec = r == sh.nrounds;
             const uint8_t *ipos = store_rec ? sh.spos : sh.gpos;   // index-bit images used by this record
             if (store_rec) {
-                QFB_CHECK_ARG(rh.nops == 0 && memcmp(rh.regpos, last_rh.regpos, 4) == 0 &&
+                QFB_CHECK_ARG(rh.nops == 0 && memcmp(rh.regpos, last_rh.regpos, R) == 0 &&
                                   memcmp(rh.thrpos, last_rh.thrpos, 12) == 0,
                               "plan: sweep %u store record does not match the last round", s);
             }
@@ -350,22 +353,20 @@ static int validate_plan(const uint8_t *p, size_t nbytes, std::vector<SweepInfo>
                     QFB_CHECK_ARG(bytes == 16 + 64 && rcm == 0 && oh.idx_cmask == 0, "plan: bad G1 op");
                 } else if (hd >= QFB_H_G1_SUMDIFF && hd < QFB_H_G1C_GENERAL) {
                     QFB_CHECK_ARG(bytes == 32 && rcm == 0 && oh.idx_cmask == 0, "plan: bad pivoted G1 op");
-                } else if (hd >= QFB_H_G1C_GENERAL && hd < QFB_H_G1C_SWAPX + 4) {
-                    const int j = (hd - QFB_H_G1C_GENERAL) & 3;
+                } else if (hd >= QFB_H_G1C_GENERAL && hd < QFB_H_G1C_SWAPX + R) {
+                    const int j = (hd - QFB_H_G1C_GENERAL) % R;
                     const uint32_t want = hd < QFB_H_G1C_SWAPX ? 16 + 64 : 16;   // controlled X carries no matrix
                     QFB_CHECK_ARG(bytes == want && !((rcm >> j) & 1) && rcm < NE, "plan: bad controlled G1 op");
                 } else if (hd == QFB_H_CPH_SCALAR) {
                     QFB_CHECK_ARG(bytes == 32 && rcm == 0 && rh.has_scalar == 1, "plan: bad scalar CPH op");
                 } else if (hd >= QFB_H_CPH_REG1 && hd < QFB_H_CPH_NEG2) {
-                    QFB_CHECK_ARG(bytes == 32 && rcm == (1 << ((hd - QFB_H_CPH_REG1) & 3)), "plan: bad 1-bit CPH op");
+                    QFB_CHECK_ARG(bytes == 32 && rcm == (1 << ((hd - QFB_H_CPH_REG1) % R)), "plan: bad 1-bit CPH op");
                 } else if (hd >= QFB_H_CPH_NEG2 && hd < QFB_H_CPH_REGM) {
-                    static const int J0[6] = {1, 2, 2, 3, 3, 3}, J1[6] = {0, 0, 1, 0, 1, 2};
                     const int pi = hd - QFB_H_CPH_NEG2;
                     QFB_CHECK_ARG(bytes == 32 && rcm == ((1 << J0[pi]) | (1 << J1[pi])), "plan: bad 2-bit CPH op");
                 } else if (hd == QFB_H_CPH_REGM || hd == QFB_H_CPH_NEGM) {
                     QFB_CHECK_ARG(bytes == 32 && rcm > 0 && rcm < NE, "plan: bad CPH op");
-                } else if (hd >= QFB_H_G2 && hd < QFB_H_G2 + 6) {
-                    static const int J0[6] = {1, 2, 2, 3, 3, 3}, J1[6] = {0, 0, 1, 0, 1, 2};
+                } else if (hd >= QFB_H_G2 && hd < QFB_H_G2 + NPAIRS) {
                     const int j0 = J0[hd - QFB_H_G2], j1 = J1[hd - QFB_H_G2];
                     QFB_CHECK_ARG(rh.has_g2 == 1 && bytes == 16 + 272 && !((rcm >> j0) & 1) && !((rcm >> j1) & 1) &&
                                       rcm < NE,
@@ -433,7 +434,6 @@ static int launch_sweep(c128 *state, const uint8_t *rec_dev, uint32_t rec_bytes,
 static int launch_sweep_dispatch(int M, bool g2, c128 *state, const uint8_t *rec_dev, uint32_t rec_bytes,
                                  int nbits, uint64_t index_hi, cudaStream_t st) {
     switch (M) {
-        QFB_SWEEP_CASE(5)
         QFB_SWEEP_CASE(6)
         QFB_SWEEP_CASE(7)
         QFB_SWEEP_CASE(8)

@@ -31,17 +31,17 @@ import numpy as np
 from . import classify
 
 PLAN_MAGIC = 0x50424651
-PLAN_VERSION = 7
-REG_BITS = 4
+PLAN_VERSION = 8
+REG_BITS = 5
 MAX_TILE_BITS = 13
-MIN_TILE_BITS = 5
+MIN_TILE_BITS = 6
 MAX_HOLES = 48
 MAX_SWEEP_BYTES = 40 * 1024
 MAX_DIAG_BITS = 5
 # handler ids (csrc/qfb_plan.h)
 (H_G1_GENERAL, H_G1_SUMDIFF, H_G1_ROT_R, H_G1_ROT_I, H_G1C_GENERAL, H_G1C_SWAPX, H_CPH_SCALAR, H_CPH_REG1,
- H_CPH_NEG1, H_CPH_NEG2, H_CPH_REGM, H_CPH_NEGM, H_END, H_G2) = 0, 4, 8, 12, 16, 20, 24, 25, 29, 33, 39, 40, 41, 42
-G2_PAIRS = [(1, 0), (2, 0), (2, 1), (3, 0), (3, 1), (3, 2)]
+ H_CPH_NEG1, H_CPH_NEG2, H_CPH_REGM, H_CPH_NEGM, H_END, H_G2) = 0, 5, 10, 15, 20, 25, 30, 31, 36, 41, 51, 52, 53, 54
+G2_PAIRS = [(j0, j1) for j0 in range(REG_BITS) for j1 in range(j0)]
 SWEEP_FLAG_G2, SWEEP_FLAG_STORE_SYNC, SWEEP_FLAG_STORE_PERM = 1, 2, 4
 
 
@@ -55,6 +55,13 @@ def is_scalar_term(record: bytes) -> bool:
     return struct.unpack_from('<I', record, 0)[0] == H_CPH_SCALAR
 
 
+def _round_header(nops, nbytes, regs, thrpad, has_scalar, has_g2, rgb, rst) -> bytes:
+    """qfb_round_header without the thread LUTs (192 bytes)."""
+    pad8 = [0] * (8 - REG_BITS)
+    return struct.pack('<II8B12BBB2x8I8q8q', nops, nbytes, *regs, *pad8, *thrpad, has_scalar, has_g2,
+                       *[swz(1 << p) << 4 for p in regs], *pad8, *rgb, *pad8, *rst, *pad8)
+
+
 def swz(idx: int) -> int:
     """XOR swizzle of the exchange buffer (16-byte granularity), see csrc/qfb_sweep.cu."""
     x = idx >> 3
@@ -62,7 +69,7 @@ def swz(idx: int) -> int:
 
 
 SWEEP_HEADER_BYTES = 112
-ROUND_HEADER_BYTES = 112 + 16 * (16 + 32)
+ROUND_HEADER_BYTES = 192 + 16 * (16 + 32)
 
 # QFB_G1_* kinds (csrc/qfb_plan.h)
 K_GENERAL, K_REAL, K_RXLIKE, K_SWAPX, K_ANTIDIAG, K_SUMDIFF, K_ROT_R, K_ROT_I = range(8)
@@ -514,7 +521,7 @@ class Planner:
                 if mask == 0:
                     cost = 0.05 if r in scalar_rounds else 1.05
                 else:
-                    touched = 16 >> bin(mask).count('1')
+                    touched = (1 << REG_BITS) >> bin(mask).count('1')
                     cost = (0.1 if op.mat == -1 else 0.5) * touched / 8.0
                 if best is None or cost < best[0]:
                     best = (cost, r, mask)
@@ -727,14 +734,13 @@ class Planner:
                 ops_blob = b''.join(blobs) + _op_record(H_END, 0, 0)
                 nops += len(blobs)
                 has_scalar = int(any(is_scalar_term(b) for b in blobs))
-                has_g2 = int(any(H_G2 <= struct.unpack_from('<I', b, 0)[0] < H_G2 + 6 for b in blobs))
+                has_g2 = int(any(H_G2 <= struct.unpack_from('<I', b, 0)[0] < H_G2 + len(G2_PAIRS) for b in blobs))
                 any_g2 = any_g2 or bool(has_g2)
                 thrpad = list(rd.thr) + [0] * (12 - len(rd.thr))
                 rgb = [16 << sweep.tile[p] for p in rd.regs]
                 rst = [-v if (sweep.store_xor >> sweep.tile[p]) & 1 else v for v, p in zip(rgb, rd.regs)]
-                rounds_blob += struct.pack('<II4B12BBB6x4I4q4q', len(blobs), ROUND_HEADER_BYTES + len(ops_blob),
-                                           *rd.regs, *thrpad, has_scalar, has_g2,
-                                           *[swz(1 << p) << 4 for p in rd.regs], *rgb, *rst)
+                rounds_blob += _round_header(len(blobs), ROUND_HEADER_BYTES + len(ops_blob), rd.regs, thrpad,
+                                             has_scalar, has_g2, rgb, rst)
                 rounds_blob += self._thread_luts(sweep.tile, rd.thr) + ops_blob
             perm = sweep.spos != list(sweep.tile)
             if perm:
@@ -743,8 +749,7 @@ class Planner:
                 thrpad = list(rd.thr) + [0] * (12 - len(rd.thr))
                 rgb = [16 << sweep.tile[p] for p in rd.regs]
                 rst = [(-1 if (sweep.store_xor >> sweep.spos[p]) & 1 else 1) * (16 << sweep.spos[p]) for p in rd.regs]
-                rounds_blob += struct.pack('<II4B12BBB6x4I4q4q', 0, ROUND_HEADER_BYTES + 16, *rd.regs, *thrpad, 0, 0,
-                                           *[swz(1 << p) << 4 for p in rd.regs], *rgb, *rst)
+                rounds_blob += _round_header(0, ROUND_HEADER_BYTES + 16, rd.regs, thrpad, 0, 0, rgb, rst)
                 rounds_blob += self._thread_luts(sweep.spos, rd.thr) + _op_record(H_END, 0, 0)
             holes = [b for b in range(self.nbits) if b not in sweep.tile]
             gpos = list(sweep.tile) + [0] * (16 - len(sweep.tile))

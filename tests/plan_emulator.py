@@ -9,7 +9,7 @@ import struct
 
 import numpy as np
 
-R = 4
+R = 5
 NE = 1 << R
 
 
@@ -18,15 +18,15 @@ def swz(idx):
     return idx ^ ((x ^ (x >> 3) ^ (x >> 6) ^ (x >> 9)) & 7)
 
 
-G2_PAIRS = [(1, 0), (2, 0), (2, 1), (3, 0), (3, 1), (3, 2)]
+G2_PAIRS = [(j0, j1) for j0 in range(R) for j1 in range(j0)]
 (H_G1_GENERAL, H_G1_SUMDIFF, H_G1_ROT_R, H_G1_ROT_I, H_G1C_GENERAL, H_G1C_SWAPX, H_CPH_SCALAR, H_CPH_REG1,
- H_CPH_NEG1, H_CPH_NEG2, H_CPH_REGM, H_CPH_NEGM, H_END, H_G2) = 0, 4, 8, 12, 16, 20, 24, 25, 29, 33, 39, 40, 41, 42
-SWEEP_HEADER, ROUND_HEADER = 112, 112 + 768
+ H_CPH_NEG1, H_CPH_NEG2, H_CPH_REGM, H_CPH_NEGM, H_END, H_G2) = 0, 5, 10, 15, 20, 25, 30, 31, 36, 41, 51, 52, 53, 54
+SWEEP_HEADER, ROUND_HEADER = 112, 192 + 768
 
 
 def parse(blob: bytes):
     magic, version, nbits, M, rbits, nsweeps, total = struct.unpack_from('<IIIIIIQ', blob, 0)
-    assert magic == 0x50424651 and version == 7 and rbits == R and total == len(blob)
+    assert magic == 0x50424651 and version == 8 and rbits == R and total == len(blob)
     off = 32
     sweeps = []
     for _ in range(nsweeps):
@@ -45,18 +45,18 @@ def parse(blob: bytes):
         for _r in range(nrounds + int(perm)):
             ipos = spos if _r == nrounds else gpos
             rn, rbytes = struct.unpack_from('<II', blob, roff)
-            regpos = list(blob[roff + 8: roff + 12])
-            thrpos = list(blob[roff + 12: roff + 12 + (M - R)])
-            has_scalar, has_g2 = blob[roff + 24], blob[roff + 25]
-            ps_b = struct.unpack_from('<4I', blob, roff + 32)
-            rgb = struct.unpack_from('<4q', blob, roff + 48)
-            rst = struct.unpack_from('<4q', blob, roff + 80)
+            regpos = list(blob[roff + 8: roff + 8 + R])
+            thrpos = list(blob[roff + 16: roff + 16 + (M - R)])
+            has_scalar, has_g2 = blob[roff + 28], blob[roff + 29]
+            ps_b = struct.unpack_from('<8I', blob, roff + 32)
+            rgb = struct.unpack_from('<8q', blob, roff + 64)
+            rst = struct.unpack_from('<8q', blob, roff + 128)
             for i in range(R):
                 g, sg = 16 << gpos[regpos[i]], 16 << ipos[regpos[i]]
                 assert ps_b[i] == swz(1 << regpos[i]) << 4 and rgb[i] == g
                 assert rst[i] == (-sg if (store_xor >> ipos[regpos[i]]) & 1 else sg)
             # thread LUTs (16 + 32 entries of <IIQ): must reproduce the deposit of the thread bits
-            lut = [struct.unpack_from('<IIQ', blob, roff + 112 + 16 * i) for i in range(48)]
+            lut = [struct.unpack_from('<IIQ', blob, roff + 192 + 16 * i) for i in range(48)]
             for tid in range(1 << (M - R)):
                 tb = tg = 0
                 for t in range(M - R):
@@ -76,13 +76,13 @@ def parse(blob: bytes):
                     break
                 if handler < H_G1C_GENERAL:
                     assert rcm == 0 and icm == 0
-                    kind = ['general', 'sumdiff', 'rot_r', 'rot_i'][handler // 4]
+                    kind = ['general', 'sumdiff', 'rot_r', 'rot_i'][handler // R]
                     assert obytes == (80 if kind == 'general' else 32)
-                    typ, j0, j1 = 1, handler % 4, 0
+                    typ, j0, j1 = 1, handler % R, 0
                 elif handler < H_CPH_SCALAR:
                     kind = 'general' if handler < H_G1C_SWAPX else 'swapx'
                     assert obytes == (80 if kind == 'general' else 16)
-                    typ, j0, j1 = 1, handler % 4, 0
+                    typ, j0, j1 = 1, handler % R, 0
                     assert not (rcm >> j0) & 1
                 elif handler < H_END:
                     typ, j0, j1 = 3, 0, 0
@@ -100,7 +100,7 @@ def parse(blob: bytes):
                     else:
                         assert 0 < rcm < NE
                 else:
-                    assert H_G2 <= handler < H_G2 + 6 and obytes == 16 + 272
+                    assert H_G2 <= handler < H_G2 + len(G2_PAIRS) and obytes == 16 + 272
                     typ, kind = 2, 'dense'
                     j0, j1 = G2_PAIRS[handler - H_G2]
                 ops.append(dict(type=typ, kind=kind, j0=j0, j1=j1, reg_cmask=rcm, idx_cmask=icm, payload=payload))
@@ -158,8 +158,8 @@ def _apply_g2(a, op):
     j0, j1, rc = op['j0'], op['j1'], op['reg_cmask']
     assert j0 > j1
     others = [b for b in range(R) if b not in (j0, j1)]
-    for g in range(4):
-        eb = ((g & 1) << others[0]) | ((g >> 1) << others[1])
+    for g in range(1 << len(others)):
+        eb = sum(((g >> i) & 1) << b for i, b in enumerate(others))
         if (eb & rc) != rc:
             continue
         ids = [eb, eb | (1 << j1), eb | (1 << j0), eb | (1 << j0) | (1 << j1)]

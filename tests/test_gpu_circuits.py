@@ -115,7 +115,7 @@ def test_mixed_arity_circuit_matches_reference(golden):
     assert np.abs(amps(nested.run()) - amps(ket)).max() < AMP_TOL
 
 
-@pytest.mark.parametrize('tile', [5, 6, 7, 8, 9, 10, 11, 12, 13])
+@pytest.mark.parametrize('tile', [6, 7, 8, 9, 10, 11, 12, 13])
 def test_every_tile_size_of_the_sweep_kernel(tile):
     n = 14
     specs = workloads.wb_gate_list(n, 6, tile)
