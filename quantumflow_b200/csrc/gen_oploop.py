@@ -121,27 +121,23 @@ def gen(has_g2):
                  'fma.rn.f64 %s, %s, c2, %s;' % (im_(y), im_(y), im_(x)))
         body('bra TAIL;')
     for j in range(R):
-        handler(H['G1_ROT_R'] + j, 'L_RR%d' % j)
-        # three real shears: x += a y; y += b x; x += a y  (in place, no temporaries)
+        handler(H['G1_LU_R'] + j, 'L_LR%d' % j)
+        # two real shears: x += a y; y += b x  (in place, no temporaries)
         for x, y in pairs_of(j):
             body('fma.rn.f64 %s, c0, %s, %s;' % (re_(x), re_(y), re_(x)),
                  'fma.rn.f64 %s, c0, %s, %s;' % (im_(x), im_(y), im_(x)),
                  'fma.rn.f64 %s, c1, %s, %s;' % (re_(y), re_(x), re_(y)),
-                 'fma.rn.f64 %s, c1, %s, %s;' % (im_(y), im_(x), im_(y)),
-                 'fma.rn.f64 %s, c0, %s, %s;' % (re_(x), re_(y), re_(x)),
-                 'fma.rn.f64 %s, c0, %s, %s;' % (im_(x), im_(y), im_(x)))
+                 'fma.rn.f64 %s, c1, %s, %s;' % (im_(y), im_(x), im_(y)))
         body('bra TAIL;')
     for j in range(R):
-        handler(H['G1_ROT_I'] + j, 'L_RI%d' % j)
-        # three imaginary shears: x += i a y; y += i b x; x += i a y
+        handler(H['G1_LU_I'] + j, 'L_LI%d' % j)
+        # two imaginary shears: x += i a y; y += i b x
         body('neg.f64 n1, c0;', 'neg.f64 n3, c1;')
         for x, y in pairs_of(j):
             body('fma.rn.f64 %s, n1, %s, %s;' % (re_(x), im_(y), re_(x)),
                  'fma.rn.f64 %s, c0, %s, %s;' % (im_(x), re_(y), im_(x)),
                  'fma.rn.f64 %s, n3, %s, %s;' % (re_(y), im_(x), re_(y)),
-                 'fma.rn.f64 %s, c1, %s, %s;' % (im_(y), re_(x), im_(y)),
-                 'fma.rn.f64 %s, n1, %s, %s;' % (re_(x), im_(y), re_(x)),
-                 'fma.rn.f64 %s, c0, %s, %s;' % (im_(x), re_(y), im_(x)))
+                 'fma.rn.f64 %s, c1, %s, %s;' % (im_(y), re_(x), im_(y)))
         body('bra TAIL;')
     # ---- controlled dense / X ----
     for j in range(R):
@@ -187,6 +183,13 @@ def gen(has_g2):
         for e in range(NE):
             if (e >> j) & 1:
                 cmul(e)
+        body('bra TAIL;')
+    for j in range(R):
+        handler(H['CPH_RSC1'] + j, 'L_R1%d' % j)
+        emit_on_check(body)
+        for e in range(NE):
+            if (e >> j) & 1:
+                body('mul.f64 %s, %s, c0;' % (re_(e), re_(e)), 'mul.f64 %s, %s, c0;' % (im_(e), im_(e)))
         body('bra TAIL;')
     for j in range(R):
         handler(H['CPH_NEG1'] + j, 'L_N1%d' % j)

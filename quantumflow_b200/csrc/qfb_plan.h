@@ -34,7 +34,7 @@
 #include <stdint.h>
 
 #define QFB_PLAN_MAGIC 0x50424651u /* "QFBP" */
-#define QFB_PLAN_VERSION 8u
+#define QFB_PLAN_VERSION 10u
 #define QFB_PLAN_REG_BITS 5
 #define QFB_PLAN_MAX_TILE_BITS 13
 #define QFB_PLAN_MIN_TILE_BITS 6
@@ -104,20 +104,22 @@ typedef struct {
  *   SUMDIFF  Hadamard-like divided by its (0,0) entry ("pivot"; the planner multiplies the pivots of a sweep into
  *            one uniform scalar that rides on a CPH term): x' = x + r0 y, y' = x' + (r1 - r0) y with r = +-1.
  *            Sums only, so destructive interference gives exact zeros like the reference's h*x + h*y. 4 per pair.
- *   ROT_R    real rotation [[c, -s], [s, c]] (RY) as three shears  x += a y; y += b x; x += a y  with
- *            a = -tan(phi/2), b = sin(phi): exact determinant 1, |a| <= 1 (the planner folds a half turn into
- *            the sign of the sweep scalar), no pivot, no temporaries. 6 per pair.
- *   ROT_I    [[c, i s], [i s, c]] (RX) the same way with imaginary shears  x += i a y; y += i b x; x += i a y. */
+ *   LU_R     any real 2x2 operator G (RY, X.H.X, ...) in LDU form  G = p . diag(1, s) . [[1,0],[b,1]] . [[1,a],[0,1]]:
+ *            the kernel runs the two shears  x += a y; y += b x  (4 per pair, in place, no temporaries), p joins
+ *            the sweep scalar, and the relative scale s stays PENDING on that bit: the planner multiplies it into
+ *            the next operator that mixes the bit (or emits it as a CPH term when it must).
+ *   LU_I     the same for real diagonal / imaginary off-diagonal operators (RX): x += i a y; y += i b x. */
 /* Handler ids: ONE jump table (brx.idx) in the kernel's op interpreter. j = register bit (0..R-1), pair = index
  * of (j0 > j1) in (1,0) (2,0) (2,1) (3,0) (3,1) (3,2) (4,0) (4,1) (4,2) (4,3).
  *   QFB_H_G1_GENERAL + j  uncontrolled dense 1-bit operator on register bit j (16 FP64 per pair)
  *   QFB_H_G1_SUMDIFF + j  pivoted Hadamard-like
- *   QFB_H_G1_ROT_R + j    real rotation (RY), three shears
- *   QFB_H_G1_ROT_I + j    RX-like rotation, three imaginary shears
+ *   QFB_H_G1_LU_R + j     two real shears (any real operator, see above)
+ *   QFB_H_G1_LU_I + j     two imaginary shears (RX-like operators)
  *   QFB_H_G1C_GENERAL + j controlled dense 1-bit operator   (reg_cmask / idx_cmask)
  *   QFB_H_G1C_SWAPX + j   controlled X (CNOT, CCNOT ...)
  *   QFB_H_CPH_SCALAR      phase term without register bits: accumulates into the round's scalar
  *   QFB_H_CPH_REG1 + j    phase term on register bit j (and idx_cmask)
+ *   QFB_H_CPH_RSC1 + j    the same with a real factor (a pending LDU scale that had to be emitted): 2 FP64 per amplitude
  *   QFB_H_CPH_NEG1 + j    the same with factor -1 (sign flip, no FP64 work)
  *   QFB_H_CPH_NEG2 + pair factor -1 on two register bits (CZ between register bits)
  *   QFB_H_CPH_REGM / NEGM any other register mask (reg_cmask)
@@ -126,19 +128,20 @@ typedef struct {
 enum {
     QFB_H_G1_GENERAL = 0,
     QFB_H_G1_SUMDIFF = 5,
-    QFB_H_G1_ROT_R = 10,
-    QFB_H_G1_ROT_I = 15,
+    QFB_H_G1_LU_R = 10,
+    QFB_H_G1_LU_I = 15,
     QFB_H_G1C_GENERAL = 20,
     QFB_H_G1C_SWAPX = 25,
     QFB_H_CPH_SCALAR = 30,
     QFB_H_CPH_REG1 = 31,
-    QFB_H_CPH_NEG1 = 36,
-    QFB_H_CPH_NEG2 = 41,
-    QFB_H_CPH_REGM = 51,
-    QFB_H_CPH_NEGM = 52,
-    QFB_H_END = 53,
-    QFB_H_G2 = 54,
-    QFB_H_COUNT = 64
+    QFB_H_CPH_RSC1 = 36,
+    QFB_H_CPH_NEG1 = 41,
+    QFB_H_CPH_NEG2 = 46,
+    QFB_H_CPH_REGM = 56,
+    QFB_H_CPH_NEGM = 57,
+    QFB_H_END = 58,
+    QFB_H_G2 = 59,
+    QFB_H_COUNT = 69
 };
 
 typedef struct {
@@ -151,7 +154,7 @@ typedef struct {
 
 /* payloads (follow the header)
  *   G1 GENERAL / G1C: double m[8]   row-major 2x2 complex (64 B)
- *   G1 SUMDIFF: double r[2] = (r0, r1); ROT_R / ROT_I: double (a, b)   (16 B)
+ *   G1 SUMDIFF: double r[2] = (r0, r1); LU_R / LU_I: double (a, b)   (16 B)
  *   G2 : double m[32]; uint32 nzmask; uint32 pad[3]   row-major 4x4 complex, bit (4r+c) of nzmask set when
  *                      entry (r,c) is non-zero (272 B)
  *   CPH: double factor[2]  (16 B)

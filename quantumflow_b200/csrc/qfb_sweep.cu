@@ -361,6 +361,11 @@ static int validate_plan(const uint8_t *p, size_t nbytes, std::vector<SweepInfo>
                     QFB_CHECK_ARG(bytes == 32 && rcm == 0 && rh.has_scalar == 1, "plan: bad scalar CPH op");
                 } else if (hd >= QFB_H_CPH_REG1 && hd < QFB_H_CPH_NEG2) {
                     QFB_CHECK_ARG(bytes == 32 && rcm == (1 << ((hd - QFB_H_CPH_REG1) % R)), "plan: bad 1-bit CPH op");
+                    if (hd >= QFB_H_CPH_RSC1 && hd < QFB_H_CPH_NEG1) {
+                        double im;
+                        memcpy(&im, p + ooff + 24, 8);
+                        QFB_CHECK_ARG(im == 0.0, "plan: real-scale CPH op with a complex factor");
+                    }
                 } else if (hd >= QFB_H_CPH_NEG2 && hd < QFB_H_CPH_REGM) {
                     const int pi = hd - QFB_H_CPH_NEG2;
                     QFB_CHECK_ARG(bytes == 32 && rcm == ((1 << J0[pi]) | (1 << J1[pi])), "plan: bad 2-bit CPH op");

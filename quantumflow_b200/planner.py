@@ -31,7 +31,7 @@ import numpy as np
 from . import classify
 
 PLAN_MAGIC = 0x50424651
-PLAN_VERSION = 8
+PLAN_VERSION = 10
 REG_BITS = 5
 MAX_TILE_BITS = 13
 MIN_TILE_BITS = 6
@@ -39,8 +39,9 @@ MAX_HOLES = 48
 MAX_SWEEP_BYTES = 40 * 1024
 MAX_DIAG_BITS = 5
 # handler ids (csrc/qfb_plan.h)
-(H_G1_GENERAL, H_G1_SUMDIFF, H_G1_ROT_R, H_G1_ROT_I, H_G1C_GENERAL, H_G1C_SWAPX, H_CPH_SCALAR, H_CPH_REG1,
- H_CPH_NEG1, H_CPH_NEG2, H_CPH_REGM, H_CPH_NEGM, H_END, H_G2) = 0, 5, 10, 15, 20, 25, 30, 31, 36, 41, 51, 52, 53, 54
+(H_G1_GENERAL, H_G1_SUMDIFF, H_G1_LU_R, H_G1_LU_I, H_G1C_GENERAL, H_G1C_SWAPX, H_CPH_SCALAR, H_CPH_REG1,
+ H_CPH_RSC1, H_CPH_NEG1, H_CPH_NEG2, H_CPH_REGM, H_CPH_NEGM, H_END, H_G2) = \
+    0, 5, 10, 15, 20, 25, 30, 31, 36, 41, 46, 56, 57, 58, 59
 G2_PAIRS = [(j0, j1) for j0 in range(REG_BITS) for j1 in range(j0)]
 SWEEP_FLAG_G2, SWEEP_FLAG_STORE_SYNC, SWEEP_FLAG_STORE_PERM = 1, 2, 4
 
@@ -72,13 +73,13 @@ SWEEP_HEADER_BYTES = 112
 ROUND_HEADER_BYTES = 192 + 16 * (16 + 32)
 
 # QFB_G1_* kinds (csrc/qfb_plan.h)
-K_GENERAL, K_REAL, K_RXLIKE, K_SWAPX, K_ANTIDIAG, K_SUMDIFF, K_ROT_R, K_ROT_I = range(8)
+K_GENERAL, K_REAL, K_RXLIKE, K_SWAPX, K_ANTIDIAG, K_SUMDIFF, K_LU_R, K_LU_I = range(8)
 
 DEFAULT_TILE_BITS = 12
 DEFAULT_LOW_BITS = 3
 # cost units ~ FP64 work per amplitude relative to a dense 1-bit operator (16 FP64 ops per amplitude pair)
-COST = {K_GENERAL: 1.0, K_REAL: 1.0, K_RXLIKE: 1.0, K_SWAPX: 0.3, K_ANTIDIAG: 1.0, K_SUMDIFF: 0.25, K_ROT_R: 0.375,
-        K_ROT_I: 0.375, 'G2': 2.5, 'P': 0.1}
+COST = {K_GENERAL: 1.0, K_REAL: 1.0, K_RXLIKE: 1.0, K_SWAPX: 0.3, K_ANTIDIAG: 1.0, K_SUMDIFF: 0.25, K_LU_R: 0.25,
+        K_LU_I: 0.25, 'G2': 2.5, 'P': 0.1}
 DEFAULT_MAX_COST = 28.0
 # pivot on the (0,0) entry unless it is this much smaller than the largest entry
 PIVOT_RATIO = 1e-3
@@ -86,9 +87,10 @@ PIVOT_RATIO = 1e-3
 
 class POp:
     """A classified operator: kind 'G' (mixing) or 'P' (phase term)."""
-    __slots__ = ('kind', 'mix', 'ctrl', 'dbits', 'mat', 'cost', 'mixset', 'diagset', 'anyset', 'gate_index')
+    __slots__ = ('kind', 'mix', 'ctrl', 'dbits', 'mat', 'cost', 'mixset', 'diagset', 'anyset', 'gate_index', 'enc')
 
-    def __init__(self, kind, mix=(), ctrl=(), dbits=(), mat=None, cost=1.0, gate_index=-1):
+    def __init__(self, kind, mix=(), ctrl=(), dbits=(), mat=None, cost=1.0, gate_index=-1, enc=None):
+        self.enc = enc          # (kind, payload, scalar) chosen by absorb_scales for an uncontrolled 1-bit operator
         self.kind = kind
         self.mix = tuple(int(b) for b in mix)
         self.ctrl = tuple(int(b) for b in ctrl)
@@ -127,40 +129,50 @@ def phase_polynomial(table: np.ndarray, k: int) -> Dict[int, complex]:
     return phi
 
 
-ROT_TOL = 8e-16
+# LDU pivots on the (0,0) entry; absorb_frame swaps the rows (a free X flip) when the (1,0) entry is larger
+LU_PIVOT = 0.05
+# pending scales outside [1 / SCALE_LIMIT, SCALE_LIMIT] are emitted as phase terms instead of being carried on
+SCALE_LIMIT = 65536.0
 
 
-def encode_g1(mat: np.ndarray, controlled: bool) -> Tuple[int, np.ndarray, Optional[complex]]:
-    """(kind, payload doubles, scalar) for a 2x2 operator. `scalar` is the uniform factor that has been divided
-    out (None when the operator is applied as is); payload: 8 doubles (row-major matrix) for GENERAL / SWAPX,
-    2 doubles for the structured kinds (csrc/qfb_plan.h)."""
+def encode_g1(mat: np.ndarray, controlled: bool) -> Tuple[int, np.ndarray, Optional[complex], complex]:
+    """(kind, payload doubles, scalar, pending) for a 2x2 operator: the kernel applies S (named by kind + payload)
+    and the operator equals  scalar . diag(1, pending) . S.  `scalar` (None = 1) is uniform and joins the sweep
+    scalar; `pending` (1 = none) is a relative scale of the bit's |1> half that absorb_frame carries forward.
+    Payload: 8 doubles (row-major matrix) for GENERAL / SWAPX, 2 doubles for the structured kinds."""
     m = np.array(mat, dtype=np.complex128).reshape(2, 2)
     plain = np.ascontiguousarray(m).view(np.float64).reshape(-1).copy()
+    if classify.g1_kind(m) == K_SWAPX:
+        return K_SWAPX, plain, None, 1.0
+    g00 = m[0, 0]
+    if controlled or g00 == 0 or abs(g00) < LU_PIVOT * abs(m[1, 0]):
+        return K_GENERAL, plain, None, 1.0
+    # the structure is judged with the phase of the pivot divided out (e.g. i . RX-like is RX-like)
+    unit = g00 / abs(g00)
+    if unit.imag == 0 or unit.real == 0:
+        m = m / unit                       # exact: a division by +-1 or +-i
+    else:
+        unit = 1.0
     base = classify.g1_kind(m)            # 0 general, 1 real, 2 rxlike, 3 swapx, 4 antidiag
-    if base == K_SWAPX:
-        return K_SWAPX, plain, None
-    if controlled or base == K_ANTIDIAG:
-        return K_GENERAL, plain, None
-    if base in (K_REAL, K_RXLIKE) and m[0, 0] == m[1, 1]:
-        # rotation [[c, -s], [s, c]] (real) or [[c, i s], [i s, c]]: three shears with a = off/(1+c), b = off
-        c = m[0, 0].real
-        o01, o10 = (m[0, 1].real, m[1, 0].real) if base == K_REAL else (m[0, 1].imag, m[1, 0].imag)
-        is_rot = (o01 == -o10) if base == K_REAL else (o01 == o10)
-        if is_rot and abs(c * c + o10 * o10 - 1.0) <= ROT_TOL:
-            sign = 1.0
-            if c < 0:                      # a half turn goes into the sign of the sweep scalar: keeps |a| <= 1
-                c, o01, o10, sign = -c, -o01, -o10, -1.0
-            return (K_ROT_R if base == K_REAL else K_ROT_I), np.array([o01 / (1.0 + c), o10]), \
-                (None if sign == 1.0 else complex(sign))
+    if base not in (K_REAL, K_RXLIKE):
+        return K_GENERAL, plain, None, 1.0
+    p = m[0, 0].real
+    if base == K_REAL and m[1, 0] == m[0, 0]:
+        # [[1, r0], [1, r1]] . p: sums and differences only (Hadamard: r = +-1 keeps exact zeros)
+        return K_SUMDIFF, np.array([m[0, 1].real / p, m[1, 1].real / p]), complex(p * unit), 1.0
+    # LDU: G = diag(p, q) . [[1, 0], [l, 1]] . [[1, u], [0, 1]],  p = g00, q = det / g00
     if base == K_REAL:
-        big = np.abs(m).max()
-        m00 = m[0, 0]
-        if m00 != 0 and abs(m00) >= PIVOT_RATIO * big:
-            p = m00.real
-            r, s, t = m[0, 1].real / p, m[1, 0].real / p, m[1, 1].real / p
-            if s == 1.0 and abs(r) == 1.0 and abs(t) == 1.0:
-                return K_SUMDIFF, np.array([r, t]), complex(p)
-    return K_GENERAL, plain, None
+        g01, g10, g11 = m[0, 1].real, m[1, 0].real, m[1, 1].real
+        cross = g10 * g01 / p
+        kind = K_LU_R
+    else:
+        g01, g10, g11 = m[0, 1].imag, m[1, 0].imag, m[1, 1].real      # off-diagonal entries are i g01, i g10
+        cross = -g10 * g01 / p                                        # (i g10)(i g01) = -g10 g01
+        kind = K_LU_I
+    q = g11 - cross
+    if abs(q) <= 1e-9 * (abs(g11) + abs(cross)):
+        return K_GENERAL, plain, None, 1.0                            # singular: projectors, full damping
+    return kind, np.array([g01 / p, g10 / q]), complex(p * unit), q / p
 
 
 def classify_op(mat: np.ndarray, bits: Sequence[int], gate_index: int = -1):
@@ -206,18 +218,25 @@ def _g_cost(mix, ctrl, mat) -> float:
     return COST['G2'] * max(int(np.count_nonzero(mat)), 4) / 16.0 + 0.3
 
 
-def absorb_flips(ops: List[POp]) -> Tuple[List[POp], int]:
-    """Pauli-X gates of a sweep are not executed. Walking the sweep's operators in order, an uncontrolled X on
-    bit b toggles bit b of a pending flip mask F (the stored state is X_F applied to the logical one) and every
-    later operator U is replaced by X_F U X_F restricted to its bits:
+def absorb_frame(ops: List[POp], scale: Dict[int, complex]) -> Tuple[List[POp], int]:
+    """Pauli-X gates and relative scales are not executed, they are tracked. While a sweep's operators are walked
+    in order, the stored state phi relates to the true one by  psi = X_F . D . phi :
 
-      phase term   phi^[all bits 1] with flipped bits expands into 2^|flipped| terms (phi or 1/phi by parity)
-      controls     a flipped control (control on 0) is rewritten  C0(W) = W . C1(W^-1)
-      1-bit G      either X G X (flip kept) or G X (flip absorbed), whichever is cheaper
-      2-bit G      rows and columns permuted
+      F   pending bit flips: an uncontrolled X on bit b toggles bit b of F and costs nothing; the kernel applies F
+          as an XOR on the addresses of the sweep's final store (every flipped bit is a mixing bit of some
+          operator of the sweep, hence a tile bit);
+      D   = prod_b diag(1, scale[b]): what LDU leaves behind. A real (or RX-like) 1-bit operator G is executed as
+          two shears; G = p . diag(1, s) . L . U, p joins the sweep scalar and s stays pending on the bit until
+          the next operator that mixes the bit absorbs it (G' = G . diag(1, s)) or it has to be emitted as a phase
+          term (before a controlled target, at the end of the plan). `scale` is carried from sweep to sweep.
 
-    Returns the rewritten list and F; the kernel applies F as an XOR on the addresses of the sweep's final store.
-    Every flipped bit is a mixing bit of some operator of the sweep, hence a tile bit."""
+    Every later operator U is replaced by what must act on phi:
+      phase term   commutes with D; flipped bits expand phi^[all bits 1] into 2^|flipped| terms (phi or 1/phi)
+      controls     commute with D; a flipped control (control on 0) is rewritten  C0(W) = W . C1(W^-1)
+      1-bit G      X^f' G X^f diag(1, s): f' = f or 1 - f (a free row swap), whichever gives the better pivot
+      2-bit G      rows and columns permuted by F, scales multiplied in
+
+    Returns the rewritten list and F."""
     flip = 0
     out: List[POp] = []
 
@@ -230,6 +249,11 @@ def absorb_flips(ops: List[POp]) -> Tuple[List[POp], int]:
             if f != 1:
                 out.append(POp('P', dbits=keep + tb, mat=f, cost=COST['P'], gate_index=gi))
 
+    def flush_scale(b, gi):
+        lam = scale.pop(b, 1.0)
+        if lam != 1:
+            out.append(POp('P', dbits=[b], mat=complex(lam), cost=COST['P'], gate_index=gi))   # physical frame
+
     def gate(mix, ctrl, mat, flipped_ctrl, gi):
         nonlocal flip
         if flipped_ctrl:
@@ -238,31 +262,54 @@ def absorb_flips(ops: List[POp]) -> Tuple[List[POp], int]:
             gate(mix, [c for c in ctrl if c != a], mat, rest, gi)         # W without control a
             return
         k = len(mix)
-        if k == 1:
+        if k == 1 and not ctrl:
             b = mix[0]
-            fb = (flip >> b) & 1
-            if not ctrl:
-                if np.array_equal(mat, _X):
+            if np.array_equal(mat, _X):
+                flip ^= 1 << b
+                return
+            if mat[0, 0] == 0 and mat[1, 1] == 0:
+                # antidiagonal = diag(m01, m10) . X
+                flip ^= 1 << b
+                phase([], mat[0, 1], gi)
+                phase([b], mat[1, 0] / mat[0, 1], gi)
+                return
+            if (flip >> b) & 1:
+                mat = _X @ mat @ _X
+            g = mat @ np.diag([1.0, scale.pop(b, 1.0)])
+            if classify.is_diagonal(g):
+                # the operator was the inverse of the pending scale up to a phase: back to a phase term
+                out.append(POp('P', dbits=[], mat=complex(g[0, 0]), cost=0.0, gate_index=gi))
+                if g[1, 1] != g[0, 0]:
+                    scale[b] = g[1, 1] / g[0, 0]
+                return
+            kind, payload, scalar, pending = encode_g1(g, False)
+            if kind != K_SUMDIFF and abs(g[0, 0]) < 0.6 * abs(g[1, 0]):
+                # swap the rows (toggle the flip): the pivot is the larger entry of the first column
+                swapped = encode_g1(_X @ g, False)
+                if COST[swapped[0]] <= COST[kind]:
                     flip ^= 1 << b
-                    return
-                if mat[0, 0] == 0 and mat[1, 1] == 0:
-                    # antidiagonal = diag(m01, m10) . X
-                    flip ^= 1 << b
-                    phase([], mat[0, 1], gi)
-                    phase([b], mat[1, 0] / mat[0, 1], gi)
-                    return
-                if fb:
-                    keep, absorb = _X @ mat @ _X, mat @ _X
-                    if _g_cost(mix, ctrl, absorb) < _g_cost(mix, ctrl, keep):
-                        flip ^= 1 << b
-                        mat = absorb
-                    else:
-                        mat = keep
-            elif fb:
+                    g = _X @ g
+                    kind, payload, scalar, pending = swapped
+            out.append(POp('G', mix=mix, mat=np.ascontiguousarray(g), cost=COST[kind], gate_index=gi,
+                           enc=(kind, payload, scalar)))
+            if pending != 1:
+                scale[b] = pending
+                if not 1.0 / SCALE_LIMIT < abs(pending) < SCALE_LIMIT:
+                    flush_scale(b, gi)          # keep the stored amplitudes within a sane dynamic range
+            return
+        if k == 1:
+            flush_scale(mix[0], gi)                 # a controlled target cannot absorb the scale
+            if (flip >> mix[0]) & 1:
                 mat = _X @ mat @ _X
         else:
             perm = [i ^ (2 * ((flip >> mix[0]) & 1)) ^ ((flip >> mix[1]) & 1) for i in range(4)]
             mat = mat[np.ix_(perm, perm)]
+            if ctrl:
+                flush_scale(mix[0], gi)
+                flush_scale(mix[1], gi)
+            else:
+                la, lb = scale.pop(mix[0], 1.0), scale.pop(mix[1], 1.0)
+                mat = mat @ np.diag([1.0, lb, la, la * lb])
         mat = np.ascontiguousarray(mat)
         if classify.is_identity(mat):
             return
@@ -614,12 +661,24 @@ class Planner:
     def plan(self, pops: List[POp]) -> List[SweepPlan]:
         sweeps: List[SweepPlan] = []
         remaining = list(pops)
+        scale: Dict[int, complex] = {}     # pending relative scales (absorb_scales), carried across sweeps
         while remaining:
             chosen, remaining, tile = self._form_sweep(remaining)
             if not chosen:
                 raise RuntimeError('planner made no progress')
-            ops, store_xor = absorb_flips(chosen)
+            ops, store_xor = absorb_frame(chosen, scale)
             assert all(b in tile for b in range(self.nbits) if (store_xor >> b) & 1)
+            if not remaining:
+                # end of the plan: the pending scales become phase terms (they act before the final store)
+                for b in sorted(scale):
+                    if scale[b] != 1:
+                        ops.append(POp('P', dbits=[b], mat=complex(scale[b]), cost=COST['P']))
+                scale.clear()
+            for b in list(scale):
+                if (store_xor >> b) & 1:
+                    # the final store swaps the two halves of bit b: diag(1, s) becomes diag(s, 1) = s diag(1, 1/s)
+                    ops.append(POp('P', dbits=[], mat=complex(scale[b]), cost=0.0))
+                    scale[b] = 1.0 / scale[b]
             sweep = SweepPlan(tile, merge_phase_terms(ops), store_xor)
             self._form_rounds(sweep)
             sweeps.append(sweep)
@@ -644,8 +703,10 @@ class Planner:
         elif factor == -1:
             handler = (H_CPH_NEG1 + regs[0]) if len(regs) == 1 else \
                 (H_CPH_NEG2 + G2_PAIRS.index((regs[1], regs[0]))) if len(regs) == 2 else H_CPH_NEGM
+        elif len(regs) == 1:
+            handler = (H_CPH_RSC1 if factor.imag == 0 else H_CPH_REG1) + regs[0]    # real scale: 2 FP64 per amplitude
         else:
-            handler = (H_CPH_REG1 + regs[0]) if len(regs) == 1 else H_CPH_REGM
+            handler = H_CPH_REGM
         return _op_record(handler, reg_cmask, idx_cmask, struct.pack('<dd', factor.real, factor.imag))
 
     @staticmethod
@@ -663,7 +724,12 @@ class Planner:
             else:
                 reg_cmask |= 1 << ri
         if len(op.mix) == 1:
-            kind, payload, pivot = encode_g1(op.mat, bool(op.ctrl))
+            if op.enc is not None:
+                kind, payload, pivot = op.enc
+            else:
+                kind, payload, pivot, pending = encode_g1(op.mat, bool(op.ctrl))
+                if pending != 1:
+                    raise RuntimeError('an operator with a pending scale must go through absorb_scales')
             j = reg_index(op.mix[0])
             if op.ctrl:
                 if kind == K_SWAPX:
@@ -671,7 +737,7 @@ class Planner:
                 return _op_record(H_G1C_GENERAL + j, reg_cmask, idx_cmask, payload.tobytes()), None
             if kind == K_SWAPX:
                 raise RuntimeError('uncontrolled X must have been absorbed into the flip mask')
-            handler = {K_GENERAL: H_G1_GENERAL, K_SUMDIFF: H_G1_SUMDIFF, K_ROT_R: H_G1_ROT_R, K_ROT_I: H_G1_ROT_I}[kind]
+            handler = {K_GENERAL: H_G1_GENERAL, K_SUMDIFF: H_G1_SUMDIFF, K_LU_R: H_G1_LU_R, K_LU_I: H_G1_LU_I}[kind]
             return _op_record(handler + j, reg_cmask, idx_cmask, payload.tobytes()), pivot
         j0, j1 = reg_index(op.mix[0]), reg_index(op.mix[1])
         mat = np.ascontiguousarray(op.mat, dtype=np.complex128).reshape(2, 2, 2, 2)

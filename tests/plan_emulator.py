@@ -20,13 +20,14 @@ def swz(idx):
 
 G2_PAIRS = [(j0, j1) for j0 in range(R) for j1 in range(j0)]
 (H_G1_GENERAL, H_G1_SUMDIFF, H_G1_ROT_R, H_G1_ROT_I, H_G1C_GENERAL, H_G1C_SWAPX, H_CPH_SCALAR, H_CPH_REG1,
- H_CPH_NEG1, H_CPH_NEG2, H_CPH_REGM, H_CPH_NEGM, H_END, H_G2) = 0, 5, 10, 15, 20, 25, 30, 31, 36, 41, 51, 52, 53, 54
+ H_CPH_RSC1, H_CPH_NEG1, H_CPH_NEG2, H_CPH_REGM, H_CPH_NEGM, H_END, H_G2) = \
+    0, 5, 10, 15, 20, 25, 30, 31, 36, 41, 46, 56, 57, 58, 59
 SWEEP_HEADER, ROUND_HEADER = 112, 192 + 768
 
 
 def parse(blob: bytes):
     magic, version, nbits, M, rbits, nsweeps, total = struct.unpack_from('<IIIIIIQ', blob, 0)
-    assert magic == 0x50424651 and version == 8 and rbits == R and total == len(blob)
+    assert magic == 0x50424651 and version == 10 and rbits == R and total == len(blob)
     off = 32
     sweeps = []
     for _ in range(nsweeps):
@@ -90,8 +91,11 @@ def parse(blob: bytes):
                     kind = 'neg' if handler in range(H_CPH_NEG1, H_CPH_REGM) or handler == H_CPH_NEGM else 'mul'
                     if handler == H_CPH_SCALAR:
                         assert rcm == 0
-                    elif handler < H_CPH_NEG1:
+                    elif handler < H_CPH_RSC1:
                         assert rcm == 1 << (handler - H_CPH_REG1)
+                    elif handler < H_CPH_NEG1:
+                        assert rcm == 1 << (handler - H_CPH_RSC1)
+                        assert struct.unpack_from('<dd', payload, 0)[1] == 0.0
                     elif handler < H_CPH_NEG2:
                         assert rcm == 1 << (handler - H_CPH_NEG1)
                     elif handler < H_CPH_REGM:
@@ -134,18 +138,15 @@ def _apply_g1(a, op):
         if kind == 'swapx':
             a[e0], a[e1] = y, x
         elif kind == 'sumdiff':     # pivoted: x' = x + r0 y, y' = x' + (r1 - r0) y
-            assert abs(c0) == 1 and abs(c1) == 1
             a[e0] = x + c0 * y
             a[e1] = a[e0] + (c1 - c0) * y      # formed from x' like the kernel does
-        elif kind == 'rot_r':       # three shears: x += a y; y += b x; x += a y
+        elif kind == 'rot_r':       # LU_R, two shears: x += a y; y += b x
             x = x + c0 * y
             y = y + c1 * x
-            x = x + c0 * y
             a[e0], a[e1] = x, y
-        elif kind == 'rot_i':       # x += i a y; y += i b x; x += i a y
+        elif kind == 'rot_i':       # LU_I: x += i a y; y += i b x
             x = x + 1j * c0 * y
             y = y + 1j * c1 * x
-            x = x + 1j * c0 * y
             a[e0], a[e1] = x, y
         else:
             a[e0] = m[0, 0] * x + m[0, 1] * y
