@@ -69,7 +69,7 @@ constexpr int HLUT_BITS = 6;                                  // tile-id bits pe
 template <int M, bool HAS_G2>
 __global__ void __launch_bounds__(SweepCfg<M>::T, SweepCfg<M>::MINB)
 sweep_kernel(c128 *__restrict__ state, const uint8_t *__restrict__ rec_g, uint32_t rec_bytes, int nholes,
-             uint64_t hi_shifted) {
+             uint64_t hi_shifted, int contiguous, int pf_mask) {
     constexpr int T = SweepCfg<M>::T;
     extern __shared__ __align__(16) uint8_t smem[];
     uint8_t *tile = smem;
@@ -106,7 +106,14 @@ sweep_kernel(c128 *__restrict__ state, const uint8_t *__restrict__ rec_g, uint32
     const auto add64 = [](const char *p, int64_t s) { return p + s; };
     const auto xor32 = [](uint32_t x, uint32_t s) { return x ^ s; };
 
-    for (uint64_t tile_id = blockIdx.x; tile_id < ntiles; tile_id += gridDim.x) {
+    // QFB_TILE_ORDER (experiment knob, default 1): 1 = every CTA walks a contiguous range of tile ids (consecutive
+    // tiles are neighbouring 128-byte lines, so a tile's loads and the prefetch of the next one fall into the
+    // same DRAM pages), 0 = tiles strided over the CTAs
+    const uint64_t per_cta = (ntiles + gridDim.x - 1) / gridDim.x;
+    const uint64_t tile_first = contiguous ? blockIdx.x * per_cta : blockIdx.x;
+    const uint64_t tile_step = contiguous ? 1 : gridDim.x;
+    const uint64_t tile_end = contiguous ? (tile_first + per_cta < ntiles ? tile_first + per_cta : ntiles) : ntiles;
+    for (uint64_t tile_id = tile_first; tile_id < tile_end; tile_id += tile_step) {
         const uint64_t gb = tile_base(tile_id);
         const uint8_t *rp = rec + sizeof(qfb_sweep_header);
         const qfb_round_header *rh = reinterpret_cast<const qfb_round_header *>(rp);
@@ -128,9 +135,11 @@ sweep_kernel(c128 *__restrict__ state, const uint8_t *__restrict__ rec_g, uint32
             spread(p, reinterpret_cast<const char *>(state + (gb | tg)), step, add64);
 #pragma unroll
             for (int e = 0; e < NE; ++e) a[e] = ldg_stream(reinterpret_cast<const c128 *>(p[e]));
-            if (tile_id + gridDim.x < ntiles && (tid & 7) == 0) {
-                // warm L2 with the next tile's lines (one request per 128-byte line)
-                const int64_t delta = (int64_t)(tile_base(tile_id + gridDim.x) - gb) * 16;
+            if (tile_id + tile_step < tile_end && (tid & pf_mask) == 0) {
+                // warm L2 with the next tile's lines. One request per 64 bytes: the L2 fetch granularity is 64 B,
+                // one prefetch per 128-byte line made only half of the tile's sectors hit (ncu: 49 % hit rate of
+                // the evict-first reads, profiles/r1_sweep_v8_summary.txt)
+                const int64_t delta = (int64_t)(tile_base(tile_id + tile_step) - gb) * 16;
 #pragma unroll
                 for (int e = 0; e < NE; ++e) asm volatile("prefetch.global.L2 [%0];" ::"l"(p[e] + delta));
             }
@@ -426,7 +435,15 @@ static int launch_sweep(c128 *state, const uint8_t *rec_dev, uint32_t rec_bytes,
     const uint64_t cap = (uint64_t)sm_count_cached() * resident;
     const int grid = (int)std::min<uint64_t>(ntiles, cap);
     const uint64_t hi_shifted = (nbits >= 64) ? 0ull : (index_hi << nbits);
-    sweep_kernel<M, G2><<<grid, T, smem, st>>>(state, rec_dev, rec_bytes, nholes, hi_shifted);
+    static const int tile_order = [] {
+        const char *v = getenv("QFB_TILE_ORDER");
+        return v ? atoi(v) : 1;
+    }();
+    static const int pf_mask = [] {     // QFB_PF_MASK: lanes whose (tid & mask) == 0 issue the L2 prefetches
+        const char *v = getenv("QFB_PF_MASK");
+        return v ? atoi(v) : 3;
+    }();
+    sweep_kernel<M, G2><<<grid, T, smem, st>>>(state, rec_dev, rec_bytes, nholes, hi_shifted, tile_order, pf_mask);
     QFB_LAUNCH_CHECK();
     return QFB_OK;
 }

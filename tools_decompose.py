@@ -58,7 +58,7 @@ def strip(sw, keep_rounds, kinds=()):
         # one round that both loads and stores: register bits must avoid the low tile positions
         rd = s2.rounds[0]
         if any(p < P.L for p in rd.regs):
-            regs = [p for p in range(P.M - 1, -1, -1) if p >= P.L][:4]
+            regs = [p for p in range(P.M - 1, -1, -1) if p >= P.L][:planner.REG_BITS]
             regs.sort()
             s2.rounds = [planner.Round(regs, P._thread_order(regs, True), [])]
         s2.store_xor = 0
@@ -74,7 +74,7 @@ run('same tiles, one empty round', [strip(s, False) for s in sweeps])
 contig = []
 for s in sweeps:
     c = planner.SweepPlan(list(range(P.M)), [], 0)
-    regs = list(range(P.M - 4, P.M))
+    regs = list(range(P.M - planner.REG_BITS, P.M))
     c.rounds = [planner.Round(regs, P._thread_order(regs, True), [])]
     contig.append(c)
 run('contiguous tiles, one empty round', contig)

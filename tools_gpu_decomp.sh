@@ -1,5 +1,3 @@
 #!/bin/bash
 mkdir -p gpurun_out
 python tools_decompose.py 30 12 3 2>&1 | tee gpurun_out/decompose_12_3.jsonl
-python tools_decompose.py 30 12 4 2>&1 | tee gpurun_out/decompose_12_4.jsonl
-python tools_decompose.py 30 11 3 2>&1 | tee gpurun_out/decompose_11_3.jsonl
