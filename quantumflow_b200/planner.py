@@ -23,6 +23,7 @@ Passes, all order preserving up to commutation:
               sums only; RX / RY: two fused multiply-adds per amplitude); the pivots of a sweep are multiplied
               into one uniform scalar that is applied once.
 """
+import random
 import struct
 from typing import Dict, List, Optional, Sequence, Tuple
 
@@ -81,6 +82,8 @@ DEFAULT_LOW_BITS = 3
 COST = {K_GENERAL: 1.0, K_REAL: 1.0, K_RXLIKE: 1.0, K_SWAPX: 0.3, K_ANTIDIAG: 1.0, K_SUMDIFF: 0.25, K_LU_R: 0.25,
         K_LU_I: 0.25, 'G2': 2.5, 'P': 0.1}
 DEFAULT_MAX_COST = 28.0
+# randomised variants of the greedy sweep split tried by Planner._partition (0 = plain greedy)
+DEFAULT_TRIES = 24
 # pivot on the (0,0) entry unless it is this much smaller than the largest entry
 PIVOT_RATIO = 1e-3
 
@@ -382,7 +385,8 @@ class SweepPlan:
 
 
 class Planner:
-    def __init__(self, nbits: int, tile_bits: int = None, low_bits: int = None, max_cost: float = None):
+    def __init__(self, nbits: int, tile_bits: int = None, low_bits: int = None, max_cost: float = None,
+                 tries: int = None):
         self.nbits = int(nbits)
         m = DEFAULT_TILE_BITS if tile_bits is None else int(tile_bits)
         m = min(m, self.nbits, MAX_TILE_BITS)
@@ -394,9 +398,13 @@ class Planner:
         low = DEFAULT_LOW_BITS if low_bits is None else int(low_bits)
         self.L = max(0, min(low, m - REG_BITS))
         self.max_cost = DEFAULT_MAX_COST if max_cost is None else float(max_cost)
+        self.tries = DEFAULT_TRIES if tries is None else int(tries)
 
     # ---- pass 2: sweeps ---------------------------------------------------------------------------
-    def _form_sweep(self, ops: List[POp]) -> Tuple[List[POp], List[POp], List[int]]:
+    def _form_sweep(self, ops: List[POp], rnd=None, p_new: float = 1.0) -> Tuple[List[POp], List[POp], List[int]]:
+        """One sweep: the operators that join it, the deferred rest, the tile bits. With `rnd`, an operator that
+        would bring a NEW bit into the tile is only admitted with probability p_new (randomised variants of the
+        greedy walk, see _partition)."""
         tile = set(range(self.L))
         chosen: List[POp] = []
         deferred: List[POp] = []
@@ -413,6 +421,8 @@ class Planner:
                         max(op.mix)))
                 need = op.mixset - tile
                 if len(tile) + len(need) > self.M:
+                    ok = False
+                elif need and rnd is not None and chosen and rnd.random() > p_new:
                     ok = False
             if ok and cost + op.cost > self.max_cost and chosen:
                 ok = False
@@ -658,14 +668,35 @@ class Planner:
             content = trial
             first = False
 
+    def _partition(self, pops: List[POp]) -> List[Tuple[List[POp], List[int]]]:
+        """Split the operator list into sweeps. Every sweep costs one pass over the state (the dominant cost), so
+        besides the plain greedy walk a few randomised variants are tried (fixed seeds: the plan is deterministic)
+        and the split with the fewest sweeps wins."""
+        best = None
+        for trial in range(1 + self.tries):
+            rnd = random.Random(trial) if trial else None
+            p_new = 1.0 if trial == 0 else (0.9 if trial % 3 else 0.8)
+            parts: List[Tuple[List[POp], List[int]]] = []
+            remaining = list(pops)
+            while remaining:
+                chosen, remaining, tile = self._form_sweep(remaining, rnd, p_new)
+                if not chosen:
+                    raise RuntimeError('planner made no progress')
+                parts.append((chosen, tile))
+                if best is not None and len(parts) >= len(best):
+                    break
+            else:
+                best = parts
+            if len(pops) < 64:
+                break
+        return best
+
     def plan(self, pops: List[POp]) -> List[SweepPlan]:
         sweeps: List[SweepPlan] = []
-        remaining = list(pops)
-        scale: Dict[int, complex] = {}     # pending relative scales (absorb_scales), carried across sweeps
-        while remaining:
-            chosen, remaining, tile = self._form_sweep(remaining)
-            if not chosen:
-                raise RuntimeError('planner made no progress')
+        scale: Dict[int, complex] = {}     # pending relative scales (absorb_frame), carried across sweeps
+        parts = self._partition(pops) if pops else []
+        for index, (chosen, tile) in enumerate(parts):
+            remaining = index + 1 < len(parts)
             ops, store_xor = absorb_frame(chosen, scale)
             assert all(b in tile for b in range(self.nbits) if (store_xor >> b) & 1)
             if not remaining:

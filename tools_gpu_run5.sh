@@ -9,7 +9,7 @@ for l in sys.stdin:
     try: d=json.loads(l)
     except Exception: print(l.strip()); continue
     print('%-62s %7.2f ms rounds %d' % (d['case'][:62], d['ms'], d['rounds']))"
-for cfg in "12 3 28" "12 3 40" "11 3 28" "13 3 28"; do
+for cfg in "12 3 28" "12 3 40"; do
   set -- $cfg
   timeout 600 python bench.py --steps 3 --warmup 3 --no-e2e --no-cpu-baseline --tile-bits $1 --low-bits $2 --max-cost $3 2>> gpurun_out/sweep_knobs.err | tee -a gpurun_out/bench_knobs.jsonl | python -c "
 import sys, json
