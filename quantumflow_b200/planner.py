@@ -464,7 +464,9 @@ class Planner:
         rest = [p for p in free if p not in head]
         return head + rest
 
-    def _form_rounds(self, sweep: SweepPlan) -> None:
+    def _split_rounds(self, sweep: SweepPlan, rnd=None, p_new: float = 1.0) -> List[Tuple[List[int], List[POp]]]:
+        """Greedy split of a sweep's operators into rounds of R register bits; with `rnd`, an operator that needs
+        a NEW register bit is only admitted with probability p_new (randomised variants, see _form_rounds)."""
         pos_of = {b: j for j, b in enumerate(sweep.tile)}
         remaining = list(sweep.ops)
         rounds: List[Tuple[List[int], List[POp]]] = []
@@ -482,6 +484,8 @@ class Planner:
                     if first and any(pos_of[b] < self.L for b in op.mix):
                         ok = False
                     elif len(regs) + len(need) > REG_BITS:
+                        ok = False
+                    elif need and regs and rnd is not None and rnd.random() > p_new:
                         ok = False
                     else:
                         regs += need
@@ -502,6 +506,18 @@ class Planner:
         # drop an empty first round when the sweep has another round that can serve as the load round
         if len(rounds) > 1 and not rounds[0][1] and not any(p < self.L for p in rounds[1][0]):
             rounds.pop(0)
+        return rounds
+
+    def _form_rounds(self, sweep: SweepPlan) -> None:
+        # every extra round is one more trip of the tile through shared memory: keep the split with the fewest
+        rounds = self._split_rounds(sweep)
+        if len(sweep.ops) >= 16:
+            for trial in range(1, 1 + self.tries):
+                if len(rounds) <= 2:
+                    break
+                cand = self._split_rounds(sweep, random.Random(trial), 0.85)
+                if len(cand) < len(rounds):
+                    rounds = cand
         final: List[Round] = []
         nr = len(rounds)
         for r, (regs, chosen) in enumerate(rounds):
