@@ -139,6 +139,65 @@ class Circuit(Operation):
                 i = max(j, i + 1)
         return ket
 
+    def run_pipelined(self, host_inputs, host_outputs, qubits: Qubits = None, depth: int = 3) -> None:
+        """Apply the circuit to a stream of states that live in HOST memory (engine API, no reference equivalent).
+
+        host_inputs / host_outputs: equally long sequences of pinned, contiguous complex128 host tensors with
+        2^n elements each (n = number of qubits; an input may appear several times). State i is copied to the
+        device, run through the circuit's plan and copied back to host_outputs[i]. Three streams and `depth`
+        device buffers form a pipeline: the upload of state i+1 and the download of state i-1 run under the
+        sweeps of state i, so the sustained cost per state is max(upload, sweeps, download) instead of their sum
+        (PCIe is full duplex). Only gate-only circuits (what the planner accepts) are supported."""
+        import torch
+        qubits = tuple(self.qubits if qubits is None else qubits)
+        count = len(qubits)
+        flat = self._flat_elements()
+        if count < PLANNER_MIN_BITS or not all(_plannable_gate(e) for e in flat):
+            raise ValueError('run_pipelined needs a gate-only circuit on at least {} qubits'.format(PLANNER_MIN_BITS))
+        if len(host_inputs) != len(host_outputs):
+            raise ValueError('host_inputs and host_outputs differ in length')
+        for t in list(host_inputs) + list(host_outputs):
+            if t.is_cuda or not t.is_pinned() or t.dtype != torch.complex128 or t.numel() != 1 << count \
+                    or not t.is_contiguous():
+                raise ValueError('run_pipelined needs pinned contiguous complex128 host tensors of 2^n elements')
+
+        def bitops(gates):
+            return [(g.matrix(), [count - 1 - qubits.index(q) for q in g.qubits]) for g in gates]
+
+        segments = self._segments(flat, ('run', qubits), count, bitops)
+        dev = torch.device('cuda', torch.cuda.current_device())
+        depth = max(1, min(int(depth), len(host_inputs)))
+        buffers = [torch.empty(1 << count, dtype=torch.complex128, device=dev) for _ in range(depth)]
+        up, work, down = torch.cuda.Stream(dev), torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+        start = torch.cuda.Event()
+        start.record(torch.cuda.current_stream(dev))
+        for st in (up, work, down):
+            st.wait_event(start)
+        downloaded = [None] * depth             # event: the buffer's previous result has left the device
+        last = None
+        for i, (src, dst) in enumerate(zip(host_inputs, host_outputs)):
+            buf = buffers[i % depth]
+            with torch.cuda.stream(up):
+                if downloaded[i % depth] is not None:
+                    up.wait_event(downloaded[i % depth])
+                buf.copy_(src.reshape(-1), non_blocking=True)
+                uploaded = torch.cuda.Event()
+                uploaded.record(up)
+            with torch.cuda.stream(work):
+                work.wait_event(uploaded)
+                self._execute(segments, buf)
+                computed = torch.cuda.Event()
+                computed.record(work)
+            with torch.cuda.stream(down):
+                down.wait_event(computed)
+                dst.reshape(-1).copy_(buf, non_blocking=True)
+                last = torch.cuda.Event()
+                last.record(down)
+                downloaded[i % depth] = last
+        if last is not None:
+            torch.cuda.current_stream(dev).wait_event(last)
+            last.synchronize()                   # the host buffers are valid when the call returns
+
     def evolve(self, rho: Density = None) -> Density:
         """Apply the circuit to a density matrix (default |0...0><0...0|)."""
         owned = rho is None

@@ -240,3 +240,27 @@ def test_full_size_round_trip(n, depth):
     vec = back.tensor.reshape(-1)
     assert abs(complex(vec[0].item()) - 1) < 1e-9
     assert abs(float(qf.asarray(back.norm())) - 1) < 1e-9
+
+
+def test_run_pipelined_matches_run_on_host_resident_states():
+    """Circuit.run_pipelined: states in pinned host memory stream through upload / sweeps / download."""
+    n = 14
+    circ = workloads.wb_circuit(qf, n, 6, 5)
+    rng = np.random.RandomState(7)
+    states = []
+    for _ in range(5):
+        v = rng.normal(size=1 << n) + 1j * rng.normal(size=1 << n)
+        states.append(v / np.linalg.norm(v))
+    ins = [torch.from_numpy(v.copy()).pin_memory() for v in states]
+    outs = [torch.empty(1 << n, dtype=torch.complex128).pin_memory() for _ in states]
+    circ.run_pipelined(ins, outs, depth=3)
+    for v, out in zip(states, outs):
+        want = amps(circ.run(qf.State(v.reshape([2] * n))))
+        assert np.abs(out.numpy() - want).max() < AMP_TOL
+    # the same input several times, two buffers
+    circ.run_pipelined([ins[0]] * 4, outs[:4], depth=2)
+    want = amps(circ.run(qf.State(states[0].reshape([2] * n))))
+    for out in outs[:4]:
+        assert np.abs(out.numpy() - want).max() < AMP_TOL
+    with pytest.raises(ValueError):
+        circ.run_pipelined([torch.zeros(1 << n, dtype=torch.complex128)], outs[:1])      # not pinned
