@@ -153,7 +153,7 @@ class ShardedCircuit:
     def __init__(self, circuit, nqubits: int, world: int, rank: int, tile_bits: int = None, low_bits: int = None,
                  max_cost: float = None, bitops: Sequence[BitOp] = None,
                  run_stage: Callable = None, permute: Callable = None, group=None,
-                 staging_bytes: int = 512 << 20):
+                 staging_bytes: int = 1 << 30):
         p = world.bit_length() - 1
         assert (1 << p) == world, 'world size must be a power of two'
         self.n, self.p, self.nl = nqubits, p, nqubits - p
