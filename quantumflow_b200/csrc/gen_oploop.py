@@ -156,9 +156,12 @@ def gen(has_g2):
         emit_rc(body)
         for x, y in pairs_of(j):
             skip = emit_pair_guard(body, x, j)
-            body('mov.f64 t0, %s;' % re_(x), 'mov.f64 t1, %s;' % im_(x),
-                 'mov.f64 %s, %s;' % (re_(x), re_(y)), 'mov.f64 %s, %s;' % (im_(x), im_(y)),
-                 'mov.f64 %s, t0;' % re_(y), 'mov.f64 %s, t1;' % im_(y))
+            # the swap as multiplications by the payload's 1.0 (exact copies): one FP64-pipe instruction per
+            # 64-bit move instead of two 32-bit register moves, i.e. half the issue slots; the FP64 pipe has
+            # room (28 % busy on the benchmark, profiles/r1_sweep_v8_summary.txt)
+            body('mul.f64 t0, %s, c0;' % re_(x), 'mul.f64 t1, %s, c0;' % im_(x),
+                 'mul.f64 %s, %s, c0;' % (re_(x), re_(y)), 'mul.f64 %s, %s, c0;' % (im_(x), im_(y)),
+                 'mul.f64 %s, t0, c0;' % re_(y), 'mul.f64 %s, t1, c0;' % im_(y))
             body(skip + ':')
         body('bra TAIL;')
     # ---- phase terms ----

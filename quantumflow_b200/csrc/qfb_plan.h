@@ -34,7 +34,7 @@
 #include <stdint.h>
 
 #define QFB_PLAN_MAGIC 0x50424651u /* "QFBP" */
-#define QFB_PLAN_VERSION 10u
+#define QFB_PLAN_VERSION 11u
 #define QFB_PLAN_REG_BITS 5
 #define QFB_PLAN_MAX_TILE_BITS 13
 #define QFB_PLAN_MIN_TILE_BITS 6
@@ -153,7 +153,7 @@ typedef struct {
 } qfb_op_header; /* 16 bytes */
 
 /* payloads (follow the header)
- *   G1 GENERAL / G1C: double m[8]   row-major 2x2 complex (64 B)
+ *   G1 GENERAL / G1C_GENERAL: double m[8]   row-major 2x2 complex (64 B); G1C_SWAPX: double (1.0, 0) (16 B)
  *   G1 SUMDIFF: double r[2] = (r0, r1); LU_R / LU_I: double (a, b)   (16 B)
  *   G2 : double m[32]; uint32 nzmask; uint32 pad[3]   row-major 4x4 complex, bit (4r+c) of nzmask set when
  *                      entry (r,c) is non-zero (272 B)

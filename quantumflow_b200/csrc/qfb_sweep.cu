@@ -364,7 +364,12 @@ static int validate_plan(const uint8_t *p, size_t nbytes, std::vector<SweepInfo>
                     QFB_CHECK_ARG(bytes == 32 && rcm == 0 && oh.idx_cmask == 0, "plan: bad pivoted G1 op");
                 } else if (hd >= QFB_H_G1C_GENERAL && hd < QFB_H_G1C_SWAPX + R) {
                     const int j = (hd - QFB_H_G1C_GENERAL) % R;
-                    const uint32_t want = hd < QFB_H_G1C_SWAPX ? 16 + 64 : 16;   // controlled X carries no matrix
+                    const uint32_t want = hd < QFB_H_G1C_SWAPX ? 16 + 64 : 32;   // controlled X: the constant 1.0
+                    if (hd >= QFB_H_G1C_SWAPX) {
+                        double one;
+                        memcpy(&one, p + ooff + 16, 8);
+                        QFB_CHECK_ARG(bytes == 32 && one == 1.0, "plan: controlled X needs the payload 1.0");
+                    }
                     QFB_CHECK_ARG(bytes == want && !((rcm >> j) & 1) && rcm < NE, "plan: bad controlled G1 op");
                 } else if (hd == QFB_H_CPH_SCALAR) {
                     QFB_CHECK_ARG(bytes == 32 && rcm == 0 && rh.has_scalar == 1, "plan: bad scalar CPH op");

@@ -32,7 +32,7 @@ import numpy as np
 from . import classify
 
 PLAN_MAGIC = 0x50424651
-PLAN_VERSION = 10
+PLAN_VERSION = 11
 REG_BITS = 5
 MAX_TILE_BITS = 13
 MIN_TILE_BITS = 6
@@ -780,7 +780,8 @@ class Planner:
             j = reg_index(op.mix[0])
             if op.ctrl:
                 if kind == K_SWAPX:
-                    return _op_record(H_G1C_SWAPX + j, reg_cmask, idx_cmask), None
+                    # payload (1.0, 0): the kernel swaps by multiplying with it (FP64-pipe moves)
+                    return _op_record(H_G1C_SWAPX + j, reg_cmask, idx_cmask, struct.pack('<dd', 1.0, 0.0)), None
                 return _op_record(H_G1C_GENERAL + j, reg_cmask, idx_cmask, payload.tobytes()), None
             if kind == K_SWAPX:
                 raise RuntimeError('uncontrolled X must have been absorbed into the flip mask')

@@ -27,7 +27,7 @@ SWEEP_HEADER, ROUND_HEADER = 112, 192 + 768
 
 def parse(blob: bytes):
     magic, version, nbits, M, rbits, nsweeps, total = struct.unpack_from('<IIIIIIQ', blob, 0)
-    assert magic == 0x50424651 and version == 10 and rbits == R and total == len(blob)
+    assert magic == 0x50424651 and version == 11 and rbits == R and total == len(blob)
     off = 32
     sweeps = []
     for _ in range(nsweeps):
@@ -82,7 +82,7 @@ def parse(blob: bytes):
                     typ, j0, j1 = 1, handler % R, 0
                 elif handler < H_CPH_SCALAR:
                     kind = 'general' if handler < H_G1C_SWAPX else 'swapx'
-                    assert obytes == (80 if kind == 'general' else 16)
+                    assert obytes == (80 if kind == 'general' else 32)
                     typ, j0, j1 = 1, handler % R, 0
                     assert not (rcm >> j0) & 1
                 elif handler < H_END:
