@@ -347,16 +347,29 @@ def main():
     e2e = None
     if not args.no_e2e and nlocal <= 31:     # 2 x 16 GiB of pinned host memory per rank at 30 qubits per GPU
         nbytes = 16 << nlocal
-        host_in = torch.zeros(1 << nlocal, dtype=torch.complex128).pin_memory()
-        if rank == 0:
-            host_in[0] = 1.0
-        host_out = torch.empty(1 << nlocal, dtype=torch.complex128).pin_memory()
         del state
         torch.cuda.empty_cache()
+        try:
+            host_in = torch.zeros(1 << nlocal, dtype=torch.complex128).pin_memory()
+            if rank == 0:
+                host_in[0] = 1.0
+            host_out = torch.empty(1 << nlocal, dtype=torch.complex128).pin_memory()
+            pinned_ok = 1
+        except (RuntimeError, MemoryError):
+            host_in = host_out = None
+            pinned_ok = 0
+        if world > 1:       # every rank must take the same branch: the e2e loop contains collectives
+            flag = torch.tensor([pinned_ok], dtype=torch.int32, device=dev)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+            pinned_ok = int(flag.item())
+    if not args.no_e2e and nlocal <= 31 and not pinned_ok:
+        e2e = {'value': None, 'unit': 'gates/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0,
+               'skipped': 'pinned host buffers (2 x {} GiB per rank) could not be allocated'.format(nbytes >> 30)}
+    elif not args.no_e2e and nlocal <= 31:
         # N=1: Circuit.run_pipelined streams the states through upload / sweeps / download on three streams
         # (every step's 16 GiB input and 16 GiB result cross PCIe inside the timed region; pipeline fill and
         # drain are inside it too). N>1: each rank uploads its shard, runs the sharded circuit, downloads it.
-        e2e_steps = max(args.steps, 8) if runner is None else max(1, min(args.steps, 3))
+        e2e_steps = max(args.steps, 16) if runner is None else max(1, min(args.steps, 3))
 
         def e2e_steps_run(count):
             if runner is None:
