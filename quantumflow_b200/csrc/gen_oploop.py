@@ -248,6 +248,30 @@ def gen(has_g2):
                     body('mov.f64 %s, o%d;' % (re_(ids[r]), 2 * r), 'mov.f64 %s, o%d;' % (im_(ids[r]), 2 * r + 1))
                 body(skip + ':')
             body('bra TAIL;')
+    if has_g2:
+        for pi, (j0, j1) in enumerate(PAIRS):
+            handler(H['G2X'] + pi, 'L_GX%d' % pi)
+            # real X-shaped operator: (a0, a3) and (a1, a2) mix as two real 2x2 blocks (operator index = bit(j0) << 1 |
+            # bit(j1)); c0..c7 = m00 m03 m30 m33 m11 m12 m21 m22
+            emit_on_check(body)
+            emit_rc(body)
+            for q in range(1, 4):
+                body('ld.shared.v2.f64 {c%d, c%d}, [cur+%d];' % (2 * q, 2 * q + 1, 16 + 16 * q))
+            others = [b for b in range(R) if b not in (j0, j1)]
+            for g in range(1 << len(others)):
+                eb = sum(((g >> i) & 1) << b for i, b in enumerate(others))
+                skip = body.label('SKIPX')
+                free = (NE - 1) & ~(1 << j0) & ~(1 << j1) & ~eb
+                body('and.b32 t32, rc, %d;' % free, 'setp.ne.u32 pe, t32, 0;', '@pe bra.uni %s;' % skip)
+                ids = [eb, eb | (1 << j1), eb | (1 << j0), eb | (1 << j0) | (1 << j1)]
+                for (p, q, base) in ((ids[0], ids[3], 0), (ids[1], ids[2], 4)):
+                    for comp in (re_, im_):
+                        body('mul.f64 t0, c%d, %s;' % (base + 2, comp(p)),                      # m_qp * a_p
+                             'mul.f64 %s, %s, c%d;' % (comp(p), comp(p), base),                 # a_p *= m_pp
+                             'fma.rn.f64 %s, c%d, %s, %s;' % (comp(p), base + 1, comp(q), comp(p)),   # += m_pq a_q
+                             'fma.rn.f64 %s, %s, c%d, t0;' % (comp(q), comp(q), base + 3))      # a_q = m_qq a_q + t0
+                body(skip + ':')
+            body('bra TAIL;')
     targets[H['END']] = 'L_END'
 
     E('{',

@@ -34,7 +34,7 @@
 #include <stdint.h>
 
 #define QFB_PLAN_MAGIC 0x50424651u /* "QFBP" */
-#define QFB_PLAN_VERSION 11u
+#define QFB_PLAN_VERSION 12u
 #define QFB_PLAN_REG_BITS 5
 #define QFB_PLAN_MAX_TILE_BITS 13
 #define QFB_PLAN_MIN_TILE_BITS 6
@@ -124,7 +124,10 @@ typedef struct {
  *   QFB_H_CPH_NEG2 + pair factor -1 on two register bits (CZ between register bits)
  *   QFB_H_CPH_REGM / NEGM any other register mask (reg_cmask)
  *   QFB_H_END             terminates the round's op list
- *   QFB_H_G2 + pair       dense 2-bit operator on register bits (j0, j1) */
+ *   QFB_H_G2 + pair       dense 2-bit operator on register bits (j0, j1)
+ *   QFB_H_G2X + pair      real "X-shaped" 2-bit operator: non-zeros only at (0,0) (0,3) (3,0) (3,3) and (1,1) (1,2)
+ *                         (2,1) (2,2) -- the superoperator of every Pauli channel and of amplitude damping on
+ *                         (ket bit, bra bit): 4 FP64 per amplitude instead of 16 */
 enum {
     QFB_H_G1_GENERAL = 0,
     QFB_H_G1_SUMDIFF = 5,
@@ -141,7 +144,8 @@ enum {
     QFB_H_CPH_NEGM = 57,
     QFB_H_END = 58,
     QFB_H_G2 = 59,
-    QFB_H_COUNT = 69
+    QFB_H_G2X = 69,
+    QFB_H_COUNT = 79
 };
 
 typedef struct {
@@ -155,6 +159,7 @@ typedef struct {
 /* payloads (follow the header)
  *   G1 GENERAL / G1C_GENERAL: double m[8]   row-major 2x2 complex (64 B); G1C_SWAPX: double (1.0, 0) (16 B)
  *   G1 SUMDIFF: double r[2] = (r0, r1); LU_R / LU_I: double (a, b)   (16 B)
+ *   G2X: double m[8] = m00 m03 m30 m33 m11 m12 m21 m22 (64 B)
  *   G2 : double m[32]; uint32 nzmask; uint32 pad[3]   row-major 4x4 complex, bit (4r+c) of nzmask set when
  *                      entry (r,c) is non-zero (272 B)
  *   CPH: double factor[2]  (16 B)

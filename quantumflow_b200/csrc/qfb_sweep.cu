@@ -240,7 +240,7 @@ struct PlanHandle {
 // register-bit pairs (j0 > j1) in handler order
 static const int J0[10] = {1, 2, 2, 3, 3, 3, 4, 4, 4, 4}, J1[10] = {0, 0, 1, 0, 1, 2, 0, 1, 2, 3};
 constexpr int NPAIRS = R * (R - 1) / 2;
-static_assert(R == 5 && QFB_H_CPH_NEG2 + NPAIRS == QFB_H_CPH_REGM && QFB_H_G2 + NPAIRS == QFB_H_COUNT,
+static_assert(R == 5 && QFB_H_CPH_NEG2 + NPAIRS == QFB_H_CPH_REGM && QFB_H_G2 + NPAIRS == QFB_H_G2X && QFB_H_G2X + NPAIRS == QFB_H_COUNT,
               "handler ids in qfb_plan.h assume R = 5");
 
 static uint32_t swz_host(uint32_t idx) {
@@ -390,6 +390,11 @@ static int validate_plan(const uint8_t *p, size_t nbytes, std::vector<SweepInfo>
                     QFB_CHECK_ARG(rh.has_g2 == 1 && bytes == 16 + 272 && !((rcm >> j0) & 1) && !((rcm >> j1) & 1) &&
                                       rcm < NE,
                                   "plan: bad G2 op");
+                } else if (hd >= QFB_H_G2X && hd < QFB_H_G2X + NPAIRS) {
+                    const int j0 = J0[hd - QFB_H_G2X], j1 = J1[hd - QFB_H_G2X];
+                    QFB_CHECK_ARG(rh.has_g2 == 1 && bytes == 16 + 64 && !((rcm >> j0) & 1) && !((rcm >> j1) & 1) &&
+                                      rcm < NE,
+                                  "plan: bad X-shaped G2 op");
                 } else {
                     QFB_CHECK_ARG(false, "plan: unknown handler %d", hd);
                 }

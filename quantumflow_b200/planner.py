@@ -32,7 +32,7 @@ import numpy as np
 from . import classify
 
 PLAN_MAGIC = 0x50424651
-PLAN_VERSION = 11
+PLAN_VERSION = 12
 REG_BITS = 5
 MAX_TILE_BITS = 13
 MIN_TILE_BITS = 6
@@ -41,8 +41,8 @@ MAX_SWEEP_BYTES = 40 * 1024
 MAX_DIAG_BITS = 5
 # handler ids (csrc/qfb_plan.h)
 (H_G1_GENERAL, H_G1_SUMDIFF, H_G1_LU_R, H_G1_LU_I, H_G1C_GENERAL, H_G1C_SWAPX, H_CPH_SCALAR, H_CPH_REG1,
- H_CPH_RSC1, H_CPH_NEG1, H_CPH_NEG2, H_CPH_REGM, H_CPH_NEGM, H_END, H_G2) = \
-    0, 5, 10, 15, 20, 25, 30, 31, 36, 41, 46, 56, 57, 58, 59
+ H_CPH_RSC1, H_CPH_NEG1, H_CPH_NEG2, H_CPH_REGM, H_CPH_NEGM, H_END, H_G2, H_G2X) = \
+    0, 5, 10, 15, 20, 25, 30, 31, 36, 41, 46, 56, 57, 58, 59, 69
 G2_PAIRS = [(j0, j1) for j0 in range(REG_BITS) for j1 in range(j0)]
 SWEEP_FLAG_G2, SWEEP_FLAG_STORE_SYNC, SWEEP_FLAG_STORE_PERM = 1, 2, 4
 
@@ -207,17 +207,27 @@ def classify_op(mat: np.ndarray, bits: Sequence[int], gate_index: int = -1):
     if len(targets) == 1:
         kind = encode_g1(reduced, bool(cbits))[0]
         return [POp('G', mix=tbits, ctrl=cbits, mat=reduced, cost=COST[kind], gate_index=gate_index)]
-    nnz = int(np.count_nonzero(reduced))
-    return [POp('G', mix=tbits, ctrl=cbits, mat=reduced, cost=COST['G2'] * max(nnz, 4) / 16.0 + 0.3,
-                gate_index=gate_index)]
+    return [POp('G', mix=tbits, ctrl=cbits, mat=reduced, cost=_g_cost(tbits, cbits, reduced), gate_index=gate_index)]
 
 
 _X = np.array([[0, 1], [1, 0]], dtype=np.complex128)
 
 
+X_SHAPE = np.array([[1, 0, 0, 1], [0, 1, 1, 0], [0, 1, 1, 0], [1, 0, 0, 1]], dtype=bool)
+
+
+def is_real_x_shaped(mat: np.ndarray) -> bool:
+    """Non-zeros only on the two diagonals of the 4x4 operator, all real: every Pauli channel and amplitude damping
+    as a superoperator on (ket bit, bra bit); invariant under the frame pass (index XOR, real column scales)."""
+    m = np.asarray(mat).reshape(4, 4)
+    return not np.any(m[~X_SHAPE]) and not np.any(m.imag)
+
+
 def _g_cost(mix, ctrl, mat) -> float:
     if len(mix) == 1:
         return COST[encode_g1(mat, bool(ctrl))[0]]
+    if is_real_x_shaped(mat):
+        return 1.0 + (0.3 if ctrl else 0.0)
     return COST['G2'] * max(int(np.count_nonzero(mat)), 4) / 16.0 + 0.3
 
 
@@ -793,6 +803,10 @@ class Planner:
             mat = mat.transpose(1, 0, 3, 2)
             j0, j1 = j1, j0
         mat = np.ascontiguousarray(mat).reshape(4, 4)
+        if is_real_x_shaped(mat):
+            m = mat.real
+            payload = struct.pack('<8d', m[0, 0], m[0, 3], m[3, 0], m[3, 3], m[1, 1], m[1, 2], m[2, 1], m[2, 2])
+            return _op_record(H_G2X + G2_PAIRS.index((j0, j1)), reg_cmask, idx_cmask, payload), None
         nz = 0
         for r in range(4):
             for c in range(4):
@@ -848,7 +862,7 @@ class Planner:
                 ops_blob = b''.join(blobs) + _op_record(H_END, 0, 0)
                 nops += len(blobs)
                 has_scalar = int(any(is_scalar_term(b) for b in blobs))
-                has_g2 = int(any(H_G2 <= struct.unpack_from('<I', b, 0)[0] < H_G2 + len(G2_PAIRS) for b in blobs))
+                has_g2 = int(any(H_G2 <= struct.unpack_from('<I', b, 0)[0] < H_G2X + len(G2_PAIRS) for b in blobs))
                 any_g2 = any_g2 or bool(has_g2)
                 thrpad = list(rd.thr) + [0] * (12 - len(rd.thr))
                 rgb = [16 << sweep.tile[p] for p in rd.regs]

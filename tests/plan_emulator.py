@@ -20,14 +20,14 @@ def swz(idx):
 
 G2_PAIRS = [(j0, j1) for j0 in range(R) for j1 in range(j0)]
 (H_G1_GENERAL, H_G1_SUMDIFF, H_G1_ROT_R, H_G1_ROT_I, H_G1C_GENERAL, H_G1C_SWAPX, H_CPH_SCALAR, H_CPH_REG1,
- H_CPH_RSC1, H_CPH_NEG1, H_CPH_NEG2, H_CPH_REGM, H_CPH_NEGM, H_END, H_G2) = \
-    0, 5, 10, 15, 20, 25, 30, 31, 36, 41, 46, 56, 57, 58, 59
+ H_CPH_RSC1, H_CPH_NEG1, H_CPH_NEG2, H_CPH_REGM, H_CPH_NEGM, H_END, H_G2, H_G2X) = \
+    0, 5, 10, 15, 20, 25, 30, 31, 36, 41, 46, 56, 57, 58, 59, 69
 SWEEP_HEADER, ROUND_HEADER = 112, 192 + 768
 
 
 def parse(blob: bytes):
     magic, version, nbits, M, rbits, nsweeps, total = struct.unpack_from('<IIIIIIQ', blob, 0)
-    assert magic == 0x50424651 and version == 11 and rbits == R and total == len(blob)
+    assert magic == 0x50424651 and version == 12 and rbits == R and total == len(blob)
     off = 32
     sweeps = []
     for _ in range(nsweeps):
@@ -103,6 +103,15 @@ def parse(blob: bytes):
                         assert rcm == (1 << q0) | (1 << q1)
                     else:
                         assert 0 < rcm < NE
+                elif handler >= H_G2X:
+                    assert handler < H_G2X + len(G2_PAIRS) and obytes == 16 + 64
+                    typ, kind = 2, 'xshape'
+                    j0, j1 = G2_PAIRS[handler - H_G2X]
+                    v = struct.unpack_from('<8d', payload, 0)
+                    m = np.zeros((4, 4), dtype=np.complex128)
+                    m[0, 0], m[0, 3], m[3, 0], m[3, 3], m[1, 1], m[1, 2], m[2, 1], m[2, 2] = v
+                    nzm = sum(1 << (4 * r + c) for r in range(4) for c in range(4) if m[r, c] != 0)
+                    payload = m.tobytes() + struct.pack('<I12x', nzm)      # what _apply_g2 reads
                 else:
                     assert H_G2 <= handler < H_G2 + len(G2_PAIRS) and obytes == 16 + 272
                     typ, kind = 2, 'dense'
