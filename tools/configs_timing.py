@@ -2,12 +2,13 @@
 """Wall-clock of the BASELINE.json configurations that are parity cases rather than bench lines (C1 20-qubit random
 circuit, C3 14-qubit density evolution with depolarizing channels), through the public API on one GPU."""
 import json
+import os
 import sys
 import time
 
 import torch
 
-sys.path.insert(0, '.')
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import quantumflow_b200 as qf                      # noqa: E402
 from quantumflow_b200 import engine, workloads     # noqa: E402
 

@@ -2,21 +2,22 @@
 """Where does the time of the 30-qubit benchmark plan go? Times the real plan and stripped variants of it
 (same tiles and rounds without ops; same tiles with one empty round; contiguous tiles) on the GPU."""
 import json
+import os
 import sys
 
 import numpy as np
 import torch
 
-sys.path.insert(0, '.')
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import quantumflow_b200 as qf                               # noqa: E402
 from quantumflow_b200 import engine, planner, workloads     # noqa: E402
-from oracle import qf_oracle as O                           # noqa: E402  (gate matrices only)
 
 N = int(sys.argv[1]) if len(sys.argv) > 1 else 30
 TILE = int(sys.argv[2]) if len(sys.argv) > 2 else 12
 LOW = int(sys.argv[3]) if len(sys.argv) > 3 else 3
 
 specs = workloads.wb_gate_list(N, 20, 0)
-bitops = [(O.gate_matrix(name, params), [N - 1 - q for q in qs]) for name, params, qs in specs]
+bitops = [(g.matrix(), [N - 1 - q for q in g.qubits]) for g in workloads.circuit_from_specs(qf, specs).elements]
 P = planner.Planner(N, tile_bits=TILE, low_bits=LOW)
 pops = []
 for gi, (m, b) in enumerate(bitops):

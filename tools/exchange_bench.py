@@ -8,7 +8,7 @@ import time
 import torch
 import torch.distributed as dist
 
-sys.path.insert(0, '.')
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from quantumflow_b200 import sharded      # noqa: E402
 
 nl = int(sys.argv[1]) if len(sys.argv) > 1 else 30

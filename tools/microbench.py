@@ -2,14 +2,15 @@
 """Micro-benchmarks of the sweep kernel on synthetic plans (GPU): the cost of a bare sweep (load + store), of a
 round transition, and of each op kind, from differences between plans. Prints one JSON line per case."""
 import json
+import os
 import sys
 
 import numpy as np
 import torch
 
-sys.path.insert(0, '.')
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import quantumflow_b200 as qf                          # noqa: E402
 from quantumflow_b200 import engine, planner           # noqa: E402
-from oracle import qf_oracle as O                      # noqa: E402  (gate matrices only)
 
 N = int(sys.argv[1]) if len(sys.argv) > 1 else 30
 TILE = int(sys.argv[2]) if len(sys.argv) > 2 else 12
@@ -38,14 +39,14 @@ def time_plan(name, bitops, reps=5, **kw):
     return ms
 
 
-H = O.gate_matrix('H')
-X = O.gate_matrix('X')
-T = O.gate_matrix('T')
-RX = O.gate_matrix('RX', (0.7,))
-RY = O.gate_matrix('RY', (0.9,))
-CNOT = O.gate_matrix('CNOT')
-CZ = O.gate_matrix('CZ')
-GEN = O.gate_matrix('TX', (0.37,))
+H = qf.H(0).matrix()
+X = qf.X(0).matrix()
+T = qf.T(0).matrix()
+RX = qf.RX(0.7, 0).matrix()
+RY = qf.RY(0.9, 0).matrix()
+CNOT = qf.CNOT(0, 1).matrix()
+CZ = qf.CZ(0, 1).matrix()
+GEN = qf.TX(0.37, 0).matrix()
 
 hi = [20, 21, 22, 23]          # four high bits -> one round
 base = time_plan('1 round, 1 scalar phase (bare sweep)', [(T, [25])])
@@ -61,7 +62,7 @@ time_plan('1 round, 32 CNOT thread-ctrl (bit 26 -> reg)', [(CNOT, [26, hi[i % 4]
 time_plan('1 round, 32 CNOT lane-ctrl (bit 1 -> reg)', [(CNOT, [1, hi[i % 4]]) for i in range(32)])
 time_plan('1 round, 32 T on reg bits (+H between, same bit)', [((T if i % 2 else H), [hi[(i // 2) % 4]]) for i in range(64)])
 time_plan('1 round, 32 CZ reg-reg (+H between)', [((CZ, [hi[i % 4], hi[(i + 1) % 4]]) if i % 2 else (H, [hi[i % 4]])) for i in range(64)])
-time_plan('32 scalar phases on distinct thread bits', [(O.gate_matrix('RZ', (0.1 * i,)), [4 + (i % 12)]) for i in range(32)])
+time_plan('32 scalar phases on distinct thread bits', [(qf.RZ(0.1 * i, 0).matrix(), [4 + (i % 12)]) for i in range(32)])
 # rounds: H on 4r distinct bits
 for r in (2, 3, 4, 6):
     bits = list(range(3, 3 + 4 * r)) if 3 + 4 * r <= 3 + 9 else None
