@@ -55,13 +55,19 @@ class Emit:
         return '%s_%d' % (stem, self.nlabel)
 
 
-def emit_on_check(E):
-    """Skip the op unless all idx_cmask bits are set in the thread's full index."""
-    E('and.b64 tm, cm, %s;' % TFULL, 'setp.ne.b64 poff, tm, cm;', '@poff bra TAIL;')
+def emit_on_check(E, off='TAIL'):
+    """Skip the op (branch to `off`) unless all idx_cmask bits are set in the thread's full index."""
+    E('and.b64 tm, cm, %s;' % TFULL, 'setp.ne.b64 poff, tm, cm;', '@poff bra %s;' % off)
 
 
 def emit_rc(E):
-    E('bfe.u32 rc, w, 16, 8;')
+    E('ld.shared.u8 rc, [cur+6];')          # reg_cmask byte of the op header
+
+
+def emit_long_tail(E, nbytes):
+    """End of a handler whose record is longer than the 32-byte stride the loop assumes: step to the real next
+    record and fetch its handler id again."""
+    E('add.u32 %s, cur, %d;' % (OP, nbytes), 'ld.shared.u32 hn, [%s];' % OP, 'bra TAIL;')
 
 
 def emit_general_pair(E, x, y):
@@ -108,7 +114,7 @@ def gen(has_g2):
         emit_load_matrix(body)
         for x, y in pairs_of(j):
             emit_general_pair(body, x, y)
-        body('bra TAIL;')
+        emit_long_tail(body, 80)
     # ---- pivoted kinds ----
     for j in range(R):
         handler(H['G1_SUMDIFF'] + j, 'L_SD%d' % j)
@@ -142,14 +148,15 @@ def gen(has_g2):
     # ---- controlled dense / X ----
     for j in range(R):
         handler(H['G1C_GENERAL'] + j, 'L_CG%d' % j)
-        emit_on_check(body)
+        emit_on_check(body, 'L_CGT%d' % j)
         emit_rc(body)
         emit_load_matrix(body)
         for x, y in pairs_of(j):
             skip = emit_pair_guard(body, x, j)
             emit_general_pair(body, x, y)
             body(skip + ':')
-        body('bra TAIL;')
+        body('L_CGT%d:' % j)
+        emit_long_tail(body, 80)
     for j in range(R):
         handler(H['G1C_SWAPX'] + j, 'L_CX%d' % j)
         emit_on_check(body)
@@ -225,7 +232,7 @@ def gen(has_g2):
     if has_g2:
         for pi, (j0, j1) in enumerate(PAIRS):
             handler(H['G2'] + pi, 'L_G2%d' % pi)
-            emit_on_check(body)
+            emit_on_check(body, 'L_G2T%d' % pi)
             emit_rc(body)
             others = [b for b in range(R) if b not in (j0, j1)]
             for g in range(1 << len(others)):
@@ -247,13 +254,14 @@ def gen(has_g2):
                 for r in range(4):
                     body('mov.f64 %s, o%d;' % (re_(ids[r]), 2 * r), 'mov.f64 %s, o%d;' % (im_(ids[r]), 2 * r + 1))
                 body(skip + ':')
-            body('bra TAIL;')
+            body('L_G2T%d:' % pi)
+            emit_long_tail(body, 288)
     if has_g2:
         for pi, (j0, j1) in enumerate(PAIRS):
             handler(H['G2X'] + pi, 'L_GX%d' % pi)
             # real X-shaped operator: (a0, a3) and (a1, a2) mix as two real 2x2 blocks (operator index = bit(j0) << 1 |
             # bit(j1)); c0..c7 = m00 m03 m30 m33 m11 m12 m21 m22
-            emit_on_check(body)
+            emit_on_check(body, 'L_GXT%d' % pi)
             emit_rc(body)
             for q in range(1, 4):
                 body('ld.shared.v2.f64 {c%d, c%d}, [cur+%d];' % (2 * q, 2 * q + 1, 16 + 16 * q))
@@ -271,28 +279,30 @@ def gen(has_g2):
                              'fma.rn.f64 %s, c%d, %s, %s;' % (comp(p), base + 1, comp(q), comp(p)),   # += m_pq a_q
                              'fma.rn.f64 %s, %s, c%d, t0;' % (comp(q), comp(q), base + 3))      # a_q = m_qq a_q + t0
                 body(skip + ':')
-            body('bra TAIL;')
+            body('L_GXT%d:' % pi)
+            emit_long_tail(body, 80)
     targets[H['END']] = 'L_END'
 
     E('{',
-      '.reg .b32 h, hn, w, wn, cur, rc, t32;',
+      '.reg .b32 h, hn, cur, rc, t32;',
       '.reg .b64 cm, tm;',
       '.reg .pred poff, pe;',
       '.reg .f64 c<8>, n<8>, t<6>, o<8>;',
       'ts: .branchtargets %s;' % ', '.join(targets),
-      'ld.shared.v2.u32 {h, w}, [%s];' % OP,
+      'ld.shared.u32 h, [%s];' % OP,
       'LOOP:',
+      # every op record the common handlers use is 32 bytes (header + two doubles); the few long ones (dense
+      # matrices) correct the pointer themselves (emit_long_tail), so the loop needs no size decode
       'mov.u32 cur, %s;' % OP,
-      'and.b32 t32, w, 0xffff;',
-      'add.u32 %s, %s, t32;' % (OP, OP),
-      'ld.shared.v2.u32 {hn, wn}, [%s];' % OP,     # the next header is in flight while the handler runs
+      'add.u32 %s, %s, 32;' % (OP, OP),
+      'ld.shared.u32 hn, [%s];' % OP,              # the next handler id is in flight while the handler runs
       # control mask and the first two payload doubles of THIS op: issued before the jump so that they land
       # while the branch resolves (ops without them read the next record's bytes, harmlessly)
       'ld.shared.u64 cm, [cur+8];',
       'ld.shared.v2.f64 {c0, c1}, [cur+16];',
       'brx.idx h, ts;')
     E(*body.lines)
-    E('TAIL:', 'mov.u32 h, hn;', 'mov.u32 w, wn;', 'bra LOOP;', 'L_END:', '}')
+    E('TAIL:', 'mov.u32 h, hn;', 'bra LOOP;', 'L_END:', '}')
     return E.lines
 
 
