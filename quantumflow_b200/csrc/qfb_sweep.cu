@@ -106,14 +106,19 @@ sweep_kernel(c128 *__restrict__ state, const uint8_t *__restrict__ rec_g, uint32
     const auto add64 = [](const char *p, int64_t s) { return p + s; };
     const auto xor32 = [](uint32_t x, uint32_t s) { return x ^ s; };
 
-    // QFB_TILE_ORDER (experiment knob, default 1): 1 = every CTA walks a contiguous range of tile ids (consecutive
-    // tiles are neighbouring 128-byte lines, so a tile's loads and the prefetch of the next one fall into the
-    // same DRAM pages), 0 = tiles strided over the CTAs
+    // Order in which a CTA walks the tiles (QFB_TILE_ORDER, default 0): 0 = strided over the CTAs (the CTAs
+    // that run together touch neighbouring 128-byte lines), 1 = a contiguous range per CTA, 2 = strided pairs of
+    // neighbouring tiles (a tile and the prefetch of the next one fall into the same DRAM page).
     const uint64_t per_cta = (ntiles + gridDim.x - 1) / gridDim.x;
-    const uint64_t tile_first = contiguous ? blockIdx.x * per_cta : blockIdx.x;
-    const uint64_t tile_step = contiguous ? 1 : gridDim.x;
-    const uint64_t tile_end = contiguous ? (tile_first + per_cta < ntiles ? tile_first + per_cta : ntiles) : ntiles;
-    for (uint64_t tile_id = tile_first; tile_id < tile_end; tile_id += tile_step) {
+    auto tile_of = [&](uint64_t i) -> uint64_t {
+        if (contiguous == 1) return i < per_cta ? blockIdx.x * per_cta + i : ntiles;
+        if (contiguous == 2) return ((i >> 1) * gridDim.x + blockIdx.x) * 2 + (i & 1);
+        return blockIdx.x + i * gridDim.x;
+    };
+    for (uint64_t it = 0;; ++it) {
+        const uint64_t tile_id = tile_of(it);
+        if (tile_id >= ntiles) break;
+        const uint64_t tile_next = tile_of(it + 1);
         const uint64_t gb = tile_base(tile_id);
         const uint8_t *rp = rec + sizeof(qfb_sweep_header);
         const qfb_round_header *rh = reinterpret_cast<const qfb_round_header *>(rp);
@@ -135,11 +140,11 @@ sweep_kernel(c128 *__restrict__ state, const uint8_t *__restrict__ rec_g, uint32
             spread(p, reinterpret_cast<const char *>(state + (gb | tg)), step, add64);
 #pragma unroll
             for (int e = 0; e < NE; ++e) a[e] = ldg_stream(reinterpret_cast<const c128 *>(p[e]));
-            if (tile_id + tile_step < tile_end && (tid & pf_mask) == 0) {
+            if (tile_next < ntiles && (tid & pf_mask) == 0) {
                 // warm L2 with the next tile's lines. One request per 64 bytes: the L2 fetch granularity is 64 B,
                 // one prefetch per 128-byte line made only half of the tile's sectors hit (ncu: 49 % hit rate of
                 // the evict-first reads, profiles/r1_sweep_v8_summary.txt)
-                const int64_t delta = (int64_t)(tile_base(tile_id + tile_step) - gb) * 16;
+                const int64_t delta = (int64_t)(tile_base(tile_next) - gb) * 16;
 #pragma unroll
                 for (int e = 0; e < NE; ++e) asm volatile("prefetch.global.L2 [%0];" ::"l"(p[e] + delta));
             }
@@ -447,7 +452,7 @@ static int launch_sweep(c128 *state, const uint8_t *rec_dev, uint32_t rec_bytes,
     const uint64_t hi_shifted = (nbits >= 64) ? 0ull : (index_hi << nbits);
     static const int tile_order = [] {
         const char *v = getenv("QFB_TILE_ORDER");
-        return v ? atoi(v) : 1;
+        return v ? atoi(v) : 0;
     }();
     static const int pf_mask = [] {     // QFB_PF_MASK: lanes whose (tid & mask) == 0 issue the L2 prefetches
         const char *v = getenv("QFB_PF_MASK");

@@ -1,6 +1,7 @@
 #!/bin/bash
+# tile-order / prefetch-granularity knobs of the sweep kernel on the benchmark
 mkdir -p gpurun_out
-for cfg in "0 7" "0 3" "1 7" "1 3" "1 1"; do
+for cfg in "0 3" "1 3" "2 3" "2 7"; do
   set -- $cfg
   QFB_TILE_ORDER=$1 QFB_PF_MASK=$2 timeout 600 python bench.py --steps 3 --warmup 3 --no-e2e --no-cpu-baseline 2>> gpurun_out/knobs.err | python -c "
 import sys, json
