@@ -103,6 +103,12 @@ sweep_kernel(c128 *__restrict__ state, const uint8_t *__restrict__ rec_g, uint32
         for (int k = 0; k < nlut; ++k) gb |= hlut[(k << HLUT_BITS) | ((tile_id >> (k * HLUT_BITS)) & ((1 << HLUT_BITS) - 1))];
         return gb;
     };
+    // do the lanes of the load round walk index bits 0, 1, 2 (one 128-byte line per 8 lanes)?
+    bool lane_lines = false;
+    if (R >= 3 && M - R >= 3) {
+        const qfb_round_header *r0 = reinterpret_cast<const qfb_round_header *>(rec + sizeof(qfb_sweep_header));
+        lane_lines = sh->gpos[r0->thrpos[0]] == 0 && sh->gpos[r0->thrpos[1]] == 1 && sh->gpos[r0->thrpos[2]] == 2;
+    }
     const auto add64 = [](const char *p, int64_t s) { return p + s; };
     const auto xor32 = [](uint32_t x, uint32_t s) { return x ^ s; };
 
@@ -140,13 +146,32 @@ sweep_kernel(c128 *__restrict__ state, const uint8_t *__restrict__ rec_g, uint32
             spread(p, reinterpret_cast<const char *>(state + (gb | tg)), step, add64);
 #pragma unroll
             for (int e = 0; e < NE; ++e) a[e] = ldg_stream(reinterpret_cast<const c128 *>(p[e]));
-            if (tile_next < ntiles && (tid & pf_mask) == 0) {
-                // warm L2 with the next tile's lines. One request per 64 bytes: the L2 fetch granularity is 64 B,
-                // one prefetch per 128-byte line made only half of the tile's sectors hit (ncu: 49 % hit rate of
-                // the evict-first reads, profiles/r1_sweep_v8_summary.txt)
+            if (tile_next < ntiles) {
+                // Warm L2 with the next tile's lines, one request per 64 bytes (the L2 fetch granularity: one
+                // request per 128-byte line left half of the sectors to miss, ncu 49 % hit rate).
                 const int64_t delta = (int64_t)(tile_base(tile_next) - gb) * 16;
+                if (lane_lines) {
+                    // The 8 lanes that share the thread's 128-byte lines split the 2^R lines among themselves:
+                    // lane k takes the register indices whose top three bits are k (2 requests per line).
+                    constexpr int LOWB = R - 3;
+                    const int k = tid & 7;
+                    const char *base = p[0] + delta - (k << 4);
 #pragma unroll
-                for (int e = 0; e < NE; ++e) asm volatile("prefetch.global.L2 [%0];" ::"l"(p[e] + delta));
+                    for (int i = 0; i < 3; ++i)
+                        if ((k >> i) & 1) base += step[LOWB + i];
+#pragma unroll
+                    for (int j = 0; j < (1 << LOWB); ++j) {
+                        const char *q = base;
+#pragma unroll
+                        for (int i = 0; i < LOWB; ++i)
+                            if ((j >> i) & 1) q += step[i];
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(q));
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(q + 64));
+                    }
+                } else if ((tid & pf_mask) == 0) {
+#pragma unroll
+                    for (int e = 0; e < NE; ++e) asm volatile("prefetch.global.L2 [%0];" ::"l"(p[e] + delta));
+                }
             }
         }
 
