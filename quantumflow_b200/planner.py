@@ -411,10 +411,12 @@ class Planner:
         self.tries = DEFAULT_TRIES if tries is None else int(tries)
 
     # ---- pass 2: sweeps ---------------------------------------------------------------------------
-    def _form_sweep(self, ops: List[POp], rnd=None, p_new: float = 1.0) -> Tuple[List[POp], List[POp], List[int]]:
+    def _form_sweep(self, ops: List[POp], rnd=None, p_new: float = 1.0,
+                    forbidden: frozenset = frozenset()) -> Tuple[List[POp], List[POp], List[int]]:
         """One sweep: the operators that join it, the deferred rest, the tile bits. With `rnd`, an operator that
         would bring a NEW bit into the tile is only admitted with probability p_new (randomised variants of the
-        greedy walk, see _partition)."""
+        greedy walk, see _partition). Operators that mix a bit of `forbidden` (the global qubits of a sharded
+        state, sharded.schedule) are deferred."""
         tile = set(range(self.L))
         chosen: List[POp] = []
         deferred: List[POp] = []
@@ -425,6 +427,8 @@ class Planner:
         full = False
         for op in ops:
             ok = not full and not _conflicts(op, def_any, def_mix)
+            if ok and op.kind == 'G' and (op.mixset & forbidden):
+                ok = False
             if ok and op.kind == 'G':
                 if any(b >= self.nbits for b in op.mix):
                     raise ValueError('operator mixes bit {} outside the local index; remap first'.format(
@@ -910,11 +914,54 @@ class Segment:
         self.uploaded = None
 
 
+def classify_all(bitops: Sequence[Tuple[np.ndarray, Sequence[int]]]) -> List[object]:
+    """(matrix, bits) operators -> POp / Fallback items in program order (identities dropped)."""
+    items: List[object] = []
+    for gi, (mat, bits) in enumerate(bitops):
+        item = classify_op(np.asarray(mat), list(bits), gi)
+        if item is None:
+            continue
+        if isinstance(item, Fallback):
+            items.append(item)
+        else:
+            items.extend(item)
+    return items
+
+
+def remap_item(item, phys_of: Sequence[int]):
+    """The same POp / Fallback with every bit b replaced by phys_of[b]."""
+    if isinstance(item, Fallback):
+        return Fallback(item.mat, [phys_of[b] for b in item.bits])
+    return POp(item.kind, mix=[phys_of[b] for b in item.mix], ctrl=[phys_of[b] for b in item.ctrl],
+               dbits=[phys_of[b] for b in item.dbits], mat=item.mat, cost=item.cost, gate_index=item.gate_index)
+
+
+def item_bitop(item) -> Tuple[np.ndarray, List[int]]:
+    """(matrix, bits) of a POp / Fallback: what a reference executor (tests) applies."""
+    if isinstance(item, Fallback):
+        return item.mat, list(item.bits)
+    if item.kind == 'P':
+        k = len(item.dbits)
+        diag = np.ones(1 << k, dtype=np.complex128)
+        diag[-1] = item.mat
+        return np.diag(diag), list(item.dbits)
+    k, c = len(item.mix), len(item.ctrl)
+    full = np.eye(1 << (k + c), dtype=np.complex128)
+    full[-(1 << k):, -(1 << k):] = np.asarray(item.mat, dtype=np.complex128).reshape(1 << k, 1 << k)
+    return full, list(item.ctrl) + list(item.mix)
+
+
 def build_segments(nbits: int, bitops: Sequence[Tuple[np.ndarray, Sequence[int]]], tile_bits: int = None,
                    low_bits: int = None, max_cost: float = None, final_perm: Sequence[int] = None) -> List[Segment]:
     """Plan a list of (matrix, bits) operators for a state with `nbits` local index bits. `final_perm` (destination
     bit j <- source bit final_perm[j]) is an in-place bit permutation executed after the last operator, fused into
     the last sweep when its tile holds the moved bits (the local half of a qubit remap, sharded.py)."""
+    return build_segments_from_items(nbits, classify_all(bitops), tile_bits, low_bits, max_cost, final_perm)
+
+
+def build_segments_from_items(nbits: int, items: Sequence[object], tile_bits: int = None, low_bits: int = None,
+                              max_cost: float = None, final_perm: Sequence[int] = None) -> List[Segment]:
+    """build_segments for operators that are already classified (POp / Fallback, see classify_all)."""
     planner = Planner(nbits, tile_bits, low_bits, max_cost)
     segments: List[Segment] = []
     pending: List[POp] = []
@@ -932,15 +979,12 @@ def build_segments(nbits: int, bitops: Sequence[Tuple[np.ndarray, Sequence[int]]
                                     nrounds=sum(len(s.rounds) for s in sweeps)))
             pending.clear()
 
-    for gi, (mat, bits) in enumerate(bitops):
-        item = classify_op(np.asarray(mat), list(bits), gi)
-        if item is None:
-            continue
+    for item in items:
         if isinstance(item, Fallback):
             flush()
             segments.append(Segment('op', mat=item.mat, bits=item.bits, nsweeps=1, nops=1))
         else:
-            pending.extend(item)
+            pending.append(item)
     flush(last=True)
     return segments
 

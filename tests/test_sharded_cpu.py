@@ -29,18 +29,19 @@ def test_schedule_keeps_every_mixing_operator_local_and_tracks_the_map():
     assert sorted(phys_of) == list(range(n))
     nl = n - p
     nstage = 0
-    nops = 0
+    gates = set()
     for st in steps:
         if isinstance(st, sharded.Stage):
             nstage += 1
             assert st.final_perm is None or sorted(st.final_perm) == list(range(nl))
-            for mat, bits in st.bitops:
+            assert len(st.bitops) == len(st.items)
+            for item, (mat, bits) in zip(st.items, st.bitops):
                 mix, _ = sharded._mixing_and_diag_bits(np.asarray(mat), list(bits))
                 assert all(b < nl for b in mix), 'mixing operator on a rank bit'
-                nops += 1
+                gates.add(item.gate_index)          # a gate may contribute several phase terms
         else:
             assert 1 <= len(st.rank_positions) <= p
-    assert nops == len(specs)
+    assert gates == set(range(len(specs)))
     nremap = len(steps) - nstage
     assert 1 <= nremap <= 2 * 6 + 2          # about one remap per layer (SURVEY 8e estimate)
     # p = 0 degenerates to a single stage
