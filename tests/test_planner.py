@@ -1,6 +1,7 @@
 """Planner + binary plan format, verified on the CPU with the plan emulator (tests/plan_emulator.py walks a
 plan the way sweep_kernel does) against the oracle. The GPU tests then only have to establish that the kernel
 implements the same walk."""
+import math
 import random
 
 import numpy as np
@@ -236,3 +237,75 @@ def test_final_bit_permutation_is_fused_or_appended(nbits, tile, perm_seed):
             src |= ((idx >> j) & 1) << pj
         want = want[src]
         assert np.abs(got - want).max() < AMP_TOL
+
+
+def _controlled(mat, nctrl=1):
+    k = int(np.log2(mat.shape[0]))
+    full = np.eye(1 << (k + nctrl), dtype=np.complex128)
+    full[-(1 << k):, -(1 << k):] = mat
+    return full
+
+
+@pytest.mark.parametrize('seed,tile', [(0, 9), (1, 7), (2, 6), (3, 9)])
+def test_frame_pass_flips_scales_and_controls(seed, tile):
+    """absorb_frame under stress: X / Y flips, rotations close to a half turn (large LDU scales, the scale limit),
+    controlled rotations with flipped controls, real X-shaped 2-bit operators, dense 1-bit and 2-bit operators,
+    diagonal gates - all interleaved on 9 bits, executed by the plan emulator, against the plain oracle."""
+    rnd = random.Random(seed)
+    rng = np.random.RandomState(seed)
+    n = 9
+    ops = []
+    for _ in range(140):
+        kind = rnd.randrange(12)
+        a, b, c = rnd.sample(range(n), 3)
+        if kind == 0:
+            ops.append((O.gate_matrix('X'), [a]))
+        elif kind == 1:
+            ops.append((O.gate_matrix('Y'), [a]))
+        elif kind == 2:
+            ops.append((O.gate_matrix('H'), [a]))
+        elif kind == 3:       # rotations near pi: tiny cos(theta / 2), huge pending scales
+            ops.append((O.gate_matrix(rnd.choice(['RX', 'RY']), (math.pi + rnd.uniform(-1e-3, 1e-3),)), [a]))
+        elif kind == 4:
+            ops.append((O.gate_matrix(rnd.choice(['RX', 'RY', 'RZ']), (rnd.uniform(0, 2 * math.pi),)), [a]))
+        elif kind == 5:
+            ops.append((O.gate_matrix('T'), [a]))
+        elif kind == 6:
+            ops.append((O.gate_matrix(rnd.choice(['CNOT', 'CZ'])), [a, b]))
+        elif kind == 7:       # controlled rotation: the frame pass rewrites flipped controls
+            ops.append((_controlled(O.gate_matrix('RY', (rnd.uniform(0, 6),))), [a, b]))
+        elif kind == 8:
+            ops.append((O.gate_matrix('CCNOT'), [a, b, c]))
+        elif kind == 9:       # real X-shaped 2-bit operator (a Pauli-channel superoperator looks like this)
+            m = np.zeros((4, 4))
+            m[0, 0], m[0, 3], m[3, 0], m[3, 3], m[1, 1], m[1, 2], m[2, 1], m[2, 2] = rng.normal(size=8)
+            ops.append((m.astype(np.complex128), [a, b]))
+        elif kind == 10:      # dense 1-bit and 2-bit operators
+            q = np.linalg.qr(rng.normal(size=(2, 2)) + 1j * rng.normal(size=(2, 2)))[0]
+            ops.append((q, [a]))
+        else:
+            q = np.linalg.qr(rng.normal(size=(4, 4)) + 1j * rng.normal(size=(4, 4)))[0]
+            ops.append((q, [a, b]))
+    vec = rng.normal(size=1 << n) + 1j * rng.normal(size=1 << n)
+    vec /= np.linalg.norm(vec)
+    want = vec.copy()
+    for m, bits in ops:
+        want = O.tensormul_flat(m, want, bits)
+    got = run_segments(planner.build_segments(n, ops, tile_bits=tile), vec)
+    assert np.abs(got - want).max() < AMP_TOL * max(1.0, np.abs(want).max())
+
+
+def test_classified_items_round_trip_to_operators():
+    """planner.item_bitop (what reference executors of sharded stages apply) reproduces the classified operator."""
+    n = 6
+    specs = workloads.wb_gate_list(n, 4, 7) + [('CCNOT', (), (0, 3, 5)), ('CPHASE', (0.3,), (1, 4))]
+    ops = bitops_of(specs, n)
+    vec = np.random.RandomState(0).normal(size=1 << n) + 0j
+    want = vec.copy()
+    for m, bits in ops:
+        want = O.tensormul_flat(m, want, bits)
+    got = vec.copy()
+    for item in planner.classify_all(ops):
+        m, bits = planner.item_bitop(item)
+        got = O.tensormul_flat(m, got, bits)
+    assert np.abs(got - want).max() < AMP_TOL
