@@ -147,7 +147,8 @@ def _schedule_once(nbits: int, p: int, bitops: Sequence[BitOp], tile_bits: int, 
                 return [], remaining, True
             return [it], remaining[1:], False
         best = None
-        for trial in range(1 + (min(pl.tries, 8) if len(head) >= 64 else 0)):
+        # randomised variants only without tile refinement (a refined sweep is already the result of a search)
+        for trial in range(1 + (min(pl.tries, 8) if len(head) >= 64 and not pl.refine else 0)):
             rnd = random.Random(trial) if trial else None
             chosen, rest, _tile = pl._form_sweep(head, rnd, 1.0 if trial == 0 else 0.9, forbidden=glob)
             if best is None or sum(o.cost for o in chosen) > sum(o.cost for o in best[0]):
