@@ -106,6 +106,13 @@ int qfb_conj(void *dst, const void *src, uint64_t n, void *stream);
 /* rho is a [2^nq, 2^nq] row-major matrix */
 int qfb_density_diag(const void *rho, int nq, void *out_dev_c128, void *stream);
 int qfb_density_trace(const void *rho, int nq, double *out_dev2, void *stream);
+/* Partial trace of a [2]*nbits tensor (replaces the np.einsum with repeated subscripts of
+ * quantumflow/qubits.py:201-227): dst has 2^nkeep elements, dst index bit b <- src index bit keep_pos[b];
+ * trace_masks[t] = OR of the src index bits that hold traced qubit t in every rank block (ket bit | bra bit
+ * of a density); dst[j] = sum over the 2^ntr settings in which all copies of each traced qubit agree.
+ * keep_pos and trace_masks are host arrays and together cover every src index bit exactly once. */
+int qfb_partial_trace(void *dst, const void *src, int nbits, int nkeep, const int *keep_pos, int ntr,
+                      const uint64_t *trace_masks, void *stream);
 /* dst index bit j <- src index bit perm[j]  (generalised transpose of a [2]*nbits tensor) */
 int qfb_permute_bits(void *dst, const void *src, int nbits, const int *perm, int conj, void *stream);
 /* cumulative search used by sampling: for each u[j] in [0,total) find smallest i with cdf(i) > u[j];

@@ -41,6 +41,7 @@ PROTOTYPES = {
     'qfb_conj': (c_int, [c_void_p, c_void_p, c_uint64, c_void_p]),
     'qfb_density_diag': (c_int, [c_void_p, c_int, c_void_p, c_void_p]),
     'qfb_density_trace': (c_int, [c_void_p, c_int, c_void_p, c_void_p]),
+    'qfb_partial_trace': (c_int, [c_void_p, c_void_p, c_int, c_int, _c_int_p, c_int, POINTER(c_uint64), c_void_p]),
     'qfb_permute_bits': (c_int, [c_void_p, c_void_p, c_int, _c_int_p, c_int, c_void_p]),
     'qfb_sample_search': (c_int, [c_void_p, c_uint64, _c_double_p, c_int, POINTER(c_uint64), c_void_p]),
     'qfb_gate_grad': (c_int, [c_void_p, c_void_p, c_int, c_int, _c_int_p, c_void_p, c_void_p]),

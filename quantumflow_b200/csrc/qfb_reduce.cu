@@ -176,6 +176,64 @@ __global__ void __launch_bounds__(256) density_diag_kernel(const c128 *__restric
         stg128(out + i, ldg128(rho + i * (dim + 1)));
 }
 
+// ---- partial trace (reference: quantumflow/qubits.py:201-227, an np.einsum with repeated subscripts) ----
+// out[j] = sum over s in {0,1}^ntr of in[deposit(j, keep_pos) | spread(s, tmask)]: keep_pos[b] is the input index
+// bit of output bit b, tmask[t] the OR of the index bits of traced qubit t in all rank blocks of the tensor
+// (ket and bra bit of a density), so only the "all copies equal" elements are summed.
+struct PTraceParams {
+    int keep_pos[62];
+    uint64_t tmask[31];
+};
+
+__device__ __forceinline__ uint64_t ptrace_deposit(uint64_t j, int nkeep, const PTraceParams &pp) {
+    uint64_t base = 0;
+    for (int b = 0; b < nkeep; ++b) base |= ((j >> b) & 1ull) << pp.keep_pos[b];
+    return base;
+}
+
+// many outputs: one thread per output element walks the traced combinations in Gray-code order (one XOR per
+// term; the order is fixed, so the sum is deterministic)
+__global__ void __launch_bounds__(256) ptrace_thread_kernel(const c128 *__restrict__ in, c128 *__restrict__ out,
+                                                            uint64_t nout, int nkeep, int ntr,
+                                                            const __grid_constant__ PTraceParams pp) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    const uint64_t terms = 1ull << ntr;
+    for (uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; j < nout; j += stride) {
+        uint64_t idx = ptrace_deposit(j, nkeep, pp);
+        c128 acc = ldg128(in + idx);
+        for (uint64_t s = 1; s < terms; ++s) {
+            idx ^= pp.tmask[__ffsll((long long)s) - 1];
+            const c128 v = ldg128(in + idx);
+            acc.re += v.re;
+            acc.im += v.im;
+        }
+        stg128(out + j, acc);
+    }
+}
+
+// few outputs: one CTA per output element, the threads stride over the traced combinations, fixed-order block sum
+__global__ void __launch_bounds__(256) ptrace_block_kernel(const c128 *__restrict__ in, c128 *__restrict__ out,
+                                                           uint64_t nout, int nkeep, int ntr,
+                                                           const __grid_constant__ PTraceParams pp) {
+    __shared__ double scratch[8];
+    const uint64_t terms = 1ull << ntr;
+    for (uint64_t j = blockIdx.x; j < nout; j += gridDim.x) {
+        const uint64_t base = ptrace_deposit(j, nkeep, pp);
+        double re = 0.0, im = 0.0;
+        for (uint64_t s = threadIdx.x; s < terms; s += 256) {
+            uint64_t idx = base;
+            for (int t = 0; t < ntr; ++t)
+                if ((s >> t) & 1ull) idx |= pp.tmask[t];
+            const c128 v = ldg128(in + idx);
+            re += v.re;
+            im += v.im;
+        }
+        re = block_sum<256>(re, scratch);
+        im = block_sum<256>(im, scratch);
+        if (threadIdx.x == 0) stg128(out + j, cmake(re, im));
+    }
+}
+
 struct PermParams {
     c128 *dst;
     const c128 *src;
@@ -323,6 +381,41 @@ int qfb_density_diag(const void *rho, int nq, void *out_dev_c128, void *stream) 
     const uint64_t dim = 1ull << nq;
     density_diag_kernel<<<grid1d(dim), 256, 0, (cudaStream_t)stream>>>((const c128 *)rho, dim,
                                                                        (c128 *)out_dev_c128);
+    QFB_LAUNCH_CHECK();
+    return QFB_OK;
+}
+
+int qfb_partial_trace(void *dst, const void *src, int nbits, int nkeep, const int *keep_pos, int ntr,
+                      const uint64_t *trace_masks, void *stream) {
+    QFB_CHECK_ARG(dst && src && dst != src, "qfb_partial_trace: null or aliased pointer");
+    QFB_CHECK_ARG(nbits >= 1 && nbits <= 62 && nkeep >= 0 && ntr >= 0 && ntr <= 31 && nkeep + ntr <= nbits,
+                  "qfb_partial_trace: nbits=%d nkeep=%d ntr=%d out of range", nbits, nkeep, ntr);
+    QFB_CHECK_ARG((nkeep == 0 || keep_pos) && (ntr == 0 || trace_masks), "qfb_partial_trace: null bit list");
+    PTraceParams pp;
+    memset(&pp, 0, sizeof(pp));
+    uint64_t seen = 0;
+    for (int b = 0; b < nkeep; ++b) {
+        QFB_CHECK_ARG(keep_pos[b] >= 0 && keep_pos[b] < nbits && !((seen >> keep_pos[b]) & 1ull),
+                      "qfb_partial_trace: bad kept bit %d", keep_pos[b]);
+        seen |= 1ull << keep_pos[b];
+        pp.keep_pos[b] = keep_pos[b];
+    }
+    for (int t = 0; t < ntr; ++t) {
+        QFB_CHECK_ARG(trace_masks[t] != 0 && (trace_masks[t] >> nbits) == 0 && !(trace_masks[t] & seen),
+                      "qfb_partial_trace: bad trace mask %d", t);
+        seen |= trace_masks[t];
+        pp.tmask[t] = trace_masks[t];
+    }
+    QFB_CHECK_ARG(seen == ((nbits == 64) ? ~0ull : ((1ull << nbits) - 1ull)),
+                  "qfb_partial_trace: kept and traced bits do not cover the %d index bits", nbits);
+    const uint64_t nout = 1ull << nkeep;
+    if (nout >= 4096) {
+        ptrace_thread_kernel<<<grid1d(nout), 256, 0, (cudaStream_t)stream>>>((const c128 *)src, (c128 *)dst, nout,
+                                                                             nkeep, ntr, pp);
+    } else {
+        ptrace_block_kernel<<<(int)nout, 256, 0, (cudaStream_t)stream>>>((const c128 *)src, (c128 *)dst, nout, nkeep,
+                                                                         ntr, pp);
+    }
     QFB_LAUNCH_CHECK();
     return QFB_OK;
 }

@@ -231,6 +231,20 @@ def density_trace(tensor: torch.Tensor, nq: int) -> torch.Tensor:
     return torch.view_as_complex(out).reshape(())
 
 
+def partial_trace(tensor: torch.Tensor, keep_bits: Sequence[int], trace_masks: Sequence[int]) -> torch.Tensor:
+    """Sum over the settings in which all copies of each traced qubit agree (qfb_partial_trace): the result has
+    len(keep_bits) index bits, output bit b <- input bit keep_bits[b]; trace_masks[t] = OR of the input bits of
+    traced qubit t. Returns a flat tensor of 2^len(keep_bits) amplitudes."""
+    lib = _lib.load()
+    src = _require_amplitudes(tensor)
+    nb = nbits_of(src)
+    out = torch.empty(1 << len(keep_bits), dtype=CTYPE, device=src.device)
+    masks = (ctypes.c_uint64 * max(1, len(trace_masks)))(*[int(m) for m in trace_masks])
+    _lib.check(lib.qfb_partial_trace(out.data_ptr(), src.data_ptr(), nb, len(keep_bits), _lib.int_array(keep_bits),
+                                     len(trace_masks), masks, _stream()))
+    return out
+
+
 def sample_search(probs: torch.Tensor, uniforms: np.ndarray) -> np.ndarray:
     """Indices i with cdf(i-1) <= u*total < cdf(i) for each u (device block sums + host chunk search)."""
     lib = _lib.load()

@@ -116,14 +116,38 @@ class QubitVector:
         if not keep:
             raise ValueError('Cannot remove all qubits with partial_trace.')
         count, rank = self.qubit_nb, self.rank
-        letters = list(bk.EINSUM_SUBSCRIPTS[:count * rank])
-        for q in qubits:
-            ax = self.qubits.index(q)
-            for block in range(1, rank):
-                letters[block * count + ax] = letters[ax]
-        # repeated-subscript einsum on the host copy; read-out only (SURVEY 8f item 3 tracks the device version)
-        reduced = np.einsum(''.join(letters), self.asarray())
-        return QubitVector(reduced, keep, resident=self.resident)
+        traced = [self.qubits.index(q) for q in qubits]
+        letters = bk.EINSUM_SUBSCRIPTS[:count * rank]
+        keep_bits, masks = partial_trace_layout(count, rank, traced)
+        nkeep = len(keep_bits)
+        if not self.resident:
+            # operator domain (gates / channels: host tensors of a few thousand elements, b200bk docstring):
+            # the reference's own einsum call
+            sub = list(letters)
+            for ax in traced:
+                for block in range(1, rank):
+                    sub[block * count + ax] = sub[ax]
+            return QubitVector(np.einsum(''.join(sub), self.asarray()), keep, resident=False)
+        from . import engine
+        reduced = engine.partial_trace(self.tensor, keep_bits, masks).reshape([2] * nkeep)
+        return QubitVector(reduced, keep, resident=True)
+
+
+def partial_trace_layout(count: int, rank: int, traced: List[int]) -> Tuple[List[int], List[int]]:
+    """Index-bit description of a partial trace for qfb_partial_trace: (keep_bits, masks) for a [2]*(count*rank)
+    tensor whose qubit axes `traced` are summed over. keep_bits[b] = input index bit of output index bit b,
+    masks[t] = OR of the input index bits of traced axis t in every rank block.
+
+    The reference sums with np.einsum over repeated subscripts in implicit mode (qubits.py:216-225): the surviving
+    axes come out sorted by their subscript letter, and in ASCII the upper-case letters that label axes >= 26
+    sort before the lower-case ones. The same order is produced here."""
+    total = count * rank
+    letters = bk.EINSUM_SUBSCRIPTS[:total]
+    kept_axes = sorted((a for a in range(total) if a % count not in traced), key=lambda a: ord(letters[a]))
+    nkeep = len(kept_axes)
+    keep_bits = [total - 1 - kept_axes[nkeep - 1 - b] for b in range(nkeep)]
+    masks = [sum(1 << (total - 1 - (block * count + ax)) for block in range(rank)) for ax in traced]
+    return keep_bits, masks
 
 
 def _check_compatible(vec0: QubitVector, vec1: QubitVector) -> None:

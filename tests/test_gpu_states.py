@@ -216,3 +216,24 @@ def test_reference_channel_golden_values():
         acc += np.outer(out, out.conj()) / reps
     exact = qf.asarray(kraus.evolve(ket0.asdensity()).asoperator())
     assert np.abs(acc - exact).max() < 0.07
+
+
+@pytest.mark.parametrize('n,traced', [(3, [1, 2]), (4, [2]), (8, [5]), (8, [6, 0]), (8, [0, 1, 2, 3, 4, 6, 7]),
+                                      (9, [3, 8, 1])])
+def test_partial_trace_on_device_matches_reference_einsum(n, traced):
+    # reference qubits.py:201-227 (np.einsum with repeated subscripts on the host copy); here qfb_partial_trace:
+    # one CTA per output element for small results, one thread per output element from 4096 outputs on
+    np.random.seed(n)
+    rho = qf.random_density(n)
+    host = qf.asarray(rho.tensor)
+    letters = list('abcdefghijklmnopqrstuvwxyz'[:2 * n])
+    for q in traced:
+        letters[n + q] = letters[q]
+    want = np.einsum(''.join(letters), host)
+    before = qf.engine.launch_count()
+    red = rho.partial_trace(traced)
+    assert red.tensor.is_cuda and red.qubits == tuple(q for q in range(n) if q not in traced)
+    got = qf.asarray(red.tensor)
+    assert got.shape == want.shape and np.abs(got - want).max() < AMP_TOL
+    assert abs(complex(qf.asarray(red.trace())) - 1) < 1e-12
+    assert qf.engine.launch_count() > before

@@ -149,3 +149,37 @@ def test_classification():
     kinds = {name: classify.g1_kind(qf.STDGATES[name](*PARAMS[name]).matrix())
              for name in ('X', 'Y', 'H', 'RY', 'RX', 'TX')}
     assert kinds == {'X': 3, 'Y': 4, 'H': 1, 'RY': 1, 'RX': 2, 'TX': 0}
+
+
+def _emulate_partial_trace(flat, keep_bits, masks):
+    """What qfb_partial_trace computes, in numpy: out[j] = sum_s in[deposit(j, keep_bits) | spread(s, masks)]."""
+    nkeep, ntr = len(keep_bits), len(masks)
+    j = np.arange(1 << nkeep, dtype=np.int64)
+    base = np.zeros_like(j)
+    for b, pos in enumerate(keep_bits):
+        base |= ((j >> b) & 1) << pos
+    out = np.zeros(1 << nkeep, dtype=flat.dtype)
+    for s in range(1 << ntr):
+        off = sum(m for t, m in enumerate(masks) if (s >> t) & 1)
+        out = out + flat[base | off]
+    return out
+
+
+@pytest.mark.parametrize('count,rank,traced', [(3, 2, [1]), (4, 2, [0, 3]), (2, 4, [1]), (5, 2, [4, 0, 2]),
+                                               (9, 3, [0, 2, 3, 5, 6, 8])])
+def test_partial_trace_layout_matches_reference_einsum(count, rank, traced):
+    # reference qubits.py:216-225: implicit-mode np.einsum with the traced axis letter repeated in every block;
+    # (9, 3, ...) has 27 axes, so the last one is labelled 'A' and sorts FIRST in the reference's output
+    from quantumflow_b200.qubits import partial_trace_layout
+    from quantumflow_b200 import backend as bk
+    total = count * rank
+    rng = np.random.RandomState(count * 10 + rank)
+    data = rng.randint(-3, 4, size=[2] * total).astype(np.int64 if total < 20 else np.int8)
+    sub = list(bk.EINSUM_SUBSCRIPTS[:total])
+    for ax in traced:
+        for block in range(1, rank):
+            sub[block * count + ax] = sub[ax]
+    want = np.einsum(''.join(sub), data)
+    keep_bits, masks = partial_trace_layout(count, rank, traced)
+    got = _emulate_partial_trace(data.reshape(-1), keep_bits, masks).reshape(want.shape)
+    assert np.array_equal(got, want)
