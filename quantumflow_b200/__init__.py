@@ -1,7 +1,7 @@
 """quantumflow_b200 -- a B200-native gate-application engine behind the QuantumFlow API.
 
 `import quantumflow_b200 as qf` gives the hot-path subset of the reference's flat namespace
-(quantumflow/__init__.py:5-23): states, gates, channels, circuits, QAOA helpers and the closeness predicates,
+(quantumflow/__init__.py:5-23): states, gates, channels, circuits, programs, QAOA helpers and the closeness predicates,
 with `qf.backend` being the b200 tensor backend. Optional-dependency modules of the reference (forest,
 visualization, datasets, cvxpy-based measures) are out of scope and are not imported.
 """
@@ -17,8 +17,17 @@ from .channels import *                     # noqa: F401,F403
 from .stdops import *                       # noqa: F401,F403
 from .circuits import *                     # noqa: F401,F403
 from .dagcircuit import *                   # noqa: F401,F403
+from .programs import *                     # noqa: F401,F403
 from .measures import *                     # noqa: F401,F403
 from .qaoa import *                         # noqa: F401,F403
 from . import utils, workloads, planner, engine, classify   # noqa: F401
 
 from .config import version as __version__  # noqa: F401
+
+
+def __getattr__(name: str):
+    # qf.Parameter is sympy's Symbol in the reference; sympy is only imported when somebody asks for it
+    if name == 'Parameter':
+        from .programs import __getattr__ as _lazy
+        return _lazy(name)
+    raise AttributeError("module 'quantumflow_b200' has no attribute {!r}".format(name))

@@ -106,9 +106,11 @@ class Circuit(Operation):
             else:
                 engine.apply_operator(tensor, seg.mat, seg.bits, inplace=True)
 
-    def run(self, ket: State = None) -> State:
-        """Apply the circuit to a state (default |0...0> on the circuit's qubits)."""
-        owned = ket is None          # an engine-created buffer may be updated in place
+    def run(self, ket: State = None, _owned: bool = False) -> State:
+        """Apply the circuit to a state (default |0...0> on the circuit's qubits). `_owned` (engine-internal
+        callers such as Program.run): the buffer of `ket` belongs to the caller's own intermediate state and may
+        be updated in place."""
+        owned = ket is None or _owned          # an engine-created buffer may be updated in place
         if ket is None:
             ket = zero_state(qubits=self.qubits)
         flat = self._flat_elements()
@@ -198,9 +200,9 @@ class Circuit(Operation):
             torch.cuda.current_stream(dev).wait_event(last)
             last.synchronize()                   # the host buffers are valid when the call returns
 
-    def evolve(self, rho: Density = None) -> Density:
-        """Apply the circuit to a density matrix (default |0...0><0...0|)."""
-        owned = rho is None
+    def evolve(self, rho: Density = None, _owned: bool = False) -> Density:
+        """Apply the circuit to a density matrix (default |0...0><0...0|); `_owned` as in run()."""
+        owned = rho is None or _owned
         if rho is None:
             rho = zero_state(qubits=self.qubits).asdensity()
         flat = self._flat_elements()

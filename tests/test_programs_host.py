@@ -1,0 +1,131 @@
+"""Host logic of the program interpreter (quantumflow_b200/programs.py) and of the classical-memory operations
+(stdops.py) on a stand-in state: control flow never touches the amplitudes, so it is checked without a GPU.
+The cases follow the reference's tests/test_programs.py:40-104 and tests/test_stdops.py (classical ops)."""
+from collections import defaultdict
+
+import pytest
+
+import quantumflow_b200 as qf
+from quantumflow_b200.programs import HALTED, PC, TARGETS
+
+
+class _Tensor:
+    def data_ptr(self):
+        return 1234
+
+
+class FakeState:
+    """memory / update / tensor / qubits: what classical instructions and the interpreter loop use."""
+
+    def __init__(self, memory=None):
+        self._memory = dict(memory or {})
+        self.tensor = _Tensor()
+        self.qubits = ()
+
+    @property
+    def memory(self):
+        return defaultdict(int, self._memory)
+
+    def update(self, memory):
+        merged = self.memory
+        merged.update(memory)
+        return FakeState(merged)
+
+
+def run(prog, state=None):
+    return prog._interpret(state or FakeState(), None, lambda instr, st: instr.run(st),
+                           lambda circuit, st, owned: pytest.fail('no gate blocks expected'))
+
+
+def test_labels_are_compiled_into_targets():
+    prog = qf.Program([qf.Label('Here'), qf.Nop(), qf.Label('There')])
+    ket = run(prog)
+    assert ket.memory[TARGETS] == {'Here': 0, 'There': 2}
+    assert ket.memory[PC] == 3
+
+
+def test_jump_jumpwhen_jumpunless():
+    ro = qf.Register()
+    prog = qf.Program()
+    prog += qf.Move(ro[0], 0)
+    prog += qf.Jump('There')
+    prog += qf.Not(ro[0])
+    prog += qf.Label('There')
+    prog += qf.Not(ro[0])
+    assert run(prog).memory[ro[0]] == 1
+    prog += qf.JumpWhen('There', ro[0])
+    assert run(prog).memory[ro[0]] == 0
+    prog += qf.Not(ro[0])
+    prog += qf.JumpUnless('There', ro[0])
+    assert run(prog).memory[ro[0]] == 1
+
+
+def test_wait_and_halt():
+    ro = qf.Register()
+    prog = qf.Program([qf.Move(ro[0], 0), qf.Wait(), qf.Not(ro[0]), qf.Wait(), qf.Not(ro[0]), qf.Wait(),
+                       qf.Not(ro[0])])
+    assert run(prog).memory[ro[0]] == 1
+    prog = qf.Program([qf.Move(ro[0], 0), qf.Halt(), qf.Not(ro[0])])
+    ket = run(prog)
+    assert ket.memory[PC] == HALTED and ket.memory[ro[0]] == 0
+
+
+def test_declare_and_tuple_addresses():
+    prog = qf.Program([qf.Declare('ro', 'BIT', 3), qf.Move(('a', 0), 7)])
+    ket = run(prog)
+    ro = qf.Register('ro', 'BIT')
+    assert all(ro[i] in ket._memory and ket.memory[ro[i]] == 0 for i in range(3))
+    assert ket.memory[('a', 0)] == 7
+
+
+def test_classical_operations():
+    ro = qf.Register()
+    mem = {ro[0]: 1, ro[1]: 0, ro[2]: 6, ro[3]: 4}
+    cases = [(qf.Neg(ro[2]), ro[2], -6), (qf.Not(ro[0]), ro[0], 0), (qf.Not(ro[1]), ro[1], 1),
+             (qf.And(ro[0], ro[1]), ro[0], 0), (qf.Ior(ro[0], ro[1]), ro[0], 1), (qf.Or(ro[1], 1), ro[1], 1),
+             (qf.Xor(ro[0], 1), ro[0], 0), (qf.Add(ro[2], ro[3]), ro[2], 10), (qf.Sub(ro[2], 1), ro[2], 5),
+             (qf.Mul(ro[2], ro[3]), ro[2], 24), (qf.Div(ro[2], ro[3]), ro[2], 1.5), (qf.Move(ro[1], ro[2]), ro[1], 6),
+             (qf.EQ(ro[1], ro[2], ro[3]), ro[1], False), (qf.GT(ro[1], ro[2], ro[3]), ro[1], True),
+             (qf.GE(ro[1], ro[2], ro[2]), ro[1], True), (qf.LT(ro[1], ro[2], ro[3]), ro[1], False),
+             (qf.LE(ro[1], ro[3], ro[2]), ro[1], True), (qf.NE(ro[1], ro[2], ro[3]), ro[1], True)]
+    for op, addr, want in cases:
+        assert op.run(FakeState(mem)).memory[addr] == want, op.quil()
+        assert op.evolve(FakeState(mem)).memory[addr] == want
+    swapped = qf.Exchange(ro[2], ro[3]).run(FakeState(mem)).memory
+    assert swapped[ro[2]] == 4 and swapped[ro[3]] == 6
+
+
+def test_quil_text():
+    ro = qf.Register()
+    assert qf.Move(ro[0], 1).quil() == 'MOVE ro[0] 1' and qf.Not(ro[1]).quil() == 'NOT ro[1]'
+    assert qf.EQ(ro[0], ro[1], ro[2]).quil() == 'EQ ro[0] ro[1] ro[2]'
+    assert str(qf.Program([qf.Call('BELL', params=[], qubits=[])])) == 'BELL\n'
+    assert qf.Call('RX', [0.5], [3]).quil() == 'RX(0.5) 3' and qf.Call('CNOT', [], [0, 1]).quil() == 'CNOT 0 1'
+    assert qf.Include('somefile.quil', qf.Program()).quil() == 'INCLUDE "somefile.quil"'
+    assert qf.Label('x').quil() == 'LABEL @x' and qf.Jump('x').quil() == 'JUMP @x'
+    assert qf.JumpWhen('x', ro[0]).quil() == 'JUMP-WHEN @x ro[0]'
+    assert qf.JumpUnless('x', ro[0]).quil() == 'JUMP-UNLESS @x ro[0]'
+    assert qf.Pragma('gate_time', ['H', 1.5], 'freeform').quil() == 'PRAGMA gate_time H 1.5 "freeform"'
+    assert qf.Declare('ro', 'BIT', 4).quil() == 'DECLARE ro BIT [4]' and qf.Declare('x', 'REAL', 1).quil() == 'DECLARE x REAL'
+    assert qf.Declare('x', 'OCTET', 2, 'ro').quil() == 'DECLARE x OCTET [2] SHARING ro'
+    assert qf.Halt().quil() == 'HALT' and qf.Nop().qubits == () and qf.Nop().qubit_nb == 0
+    circ = qf.DefCircuit('bell', {}, instructions=[qf.Call('H', [], [0]), qf.Call('CNOT', [], [0, 1])])
+    assert circ.quil() == 'DEFCIRCUIT bell:\n    H 0\n    CNOT 0 1\n'
+    assert qf.DefCircuit('rot', {'%theta': 0.5}).quil() == 'DEFCIRCUIT rot(%theta):\n'
+
+
+def test_basic_blocks_split_at_control_flow_and_unknown_gates():
+    ro = qf.Register()
+    prog = qf.Program([qf.Call('H', [], [0]), qf.Call('CNOT', [], [0, 1]), qf.X(1),          # block 0..3
+                       qf.Label('loop'), qf.Call('RX', [0.3], [0]),                           # single call: no block
+                       qf.Measure(0, ro[0]), qf.Call('Y', [], [1]), qf.Call('NOSUCH', [], [0]), qf.Call('Z', [], [1]),
+                       qf.Call('T', [], [0]), qf.Call('S', [], [1]), qf.JumpUnless('loop', ro[0])])
+    blocks = prog._basic_blocks()
+    assert sorted((start, end) for start, (end, _c) in blocks.items()) == [(0, 3), (8, 11)]
+    assert [type(g).__name__ for g in blocks[0][1].elements] == ['H', 'CNOT', 'X']
+    assert prog._basic_blocks() is blocks                      # cached
+    prog += qf.Nop()
+    assert prog._basic_blocks() is not blocks                  # a changed program is analysed again
+    assert prog.qubits == [0, 1]
+    with pytest.raises(RuntimeError):
+        qf.Call('NOSUCH', [], [0]).gate({})
