@@ -1,6 +1,11 @@
 """Closeness predicates used as parity checks by every test (quantumflow/measures.py:32-53,118-129,183-210):
-Fubini-Study angle <= tolerance, i.e. insensitive to global phase. cvxpy-based measures are out of scope."""
+Fubini-Study angle <= tolerance, i.e. insensitive to global phase; and the spectral read-outs of a density
+(measures.py:76-181: fidelity, Bures distance / angle, entropy, mutual information). The reference itself notes
+that the spectral ones "cannot be calculated within the tensor backend": they are host eigendecompositions of the
+2^N x 2^N operator, a read-out for small N, while their inputs (partial traces, `asoperator`) are produced on the
+device. The cvxpy-based diamond norm is out of scope."""
 import numpy as np
+import scipy.stats
 
 from . import backend as bk
 from .config import TOLERANCE
@@ -8,7 +13,8 @@ from .ops import Channel, Gate
 from .qubits import asarray, fubini_study_angle, vectors_close
 from .states import Density, State
 
-__all__ = ['state_fidelity', 'state_angle', 'states_close', 'purity', 'density_angle', 'densities_close',
+__all__ = ['state_fidelity', 'state_angle', 'states_close', 'purity', 'fidelity', 'bures_distance', 'bures_angle',
+           'density_angle', 'densities_close', 'entropy', 'mutual_info',
            'gate_angle', 'gates_close', 'channel_angle', 'channels_close']
 
 
@@ -30,6 +36,56 @@ def states_close(state0: State, state1: State, tolerance: float = TOLERANCE) -> 
 def purity(rho: Density) -> bk.BKTensor:
     """tr(rho^2) = sum |rho_ij|^2 for Hermitian rho: one squared-norm reduction on the device."""
     return rho.vec.norm()
+
+
+def _operator(rho: Density) -> np.ndarray:
+    return np.asarray(asarray(rho.asoperator()))
+
+
+def _psd_sqrt(op: np.ndarray) -> np.ndarray:
+    """Square root of a Hermitian positive semi-definite matrix from its eigendecomposition (negative rounding
+    residue of the spectrum clipped)."""
+    vals, vecs = np.linalg.eigh((op + op.conj().T) / 2)
+    return (vecs * np.sqrt(np.maximum(vals, 0.0))) @ vecs.conj().T
+
+
+def fidelity(rho0: Density, rho1: Density) -> float:
+    """F(rho0, rho1) = (tr sqrt(sqrt(rho0) rho1 sqrt(rho0)))^2, clipped to [0, 1] (measures.py:76-91)."""
+    assert rho0.qubit_nb == rho1.qubit_nb
+    rho1 = rho1.permute(rho0.qubits)
+    root0 = _psd_sqrt(_operator(rho0))
+    inner = root0 @ _operator(rho1) @ root0
+    spectrum = np.maximum(np.linalg.eigvalsh((inner + inner.conj().T) / 2), 0.0)
+    return float(min(max(np.sum(np.sqrt(spectrum)) ** 2, 0.0), 1.0))
+
+
+def bures_distance(rho0: Density, rho1: Density) -> float:
+    """sqrt(tr rho0 + tr rho1 - 2 sqrt(F)) (measures.py:95-106)."""
+    fid = fidelity(rho0, rho1)
+    tr0 = np.real(np.trace(_operator(rho0)))
+    tr1 = np.real(np.trace(_operator(rho1)))
+    return float(np.sqrt(max(tr0 + tr1 - 2.0 * np.sqrt(fid), 0.0)))
+
+
+def bures_angle(rho0: Density, rho1: Density) -> float:
+    """arccos sqrt(F) (measures.py:110-115)."""
+    return float(np.arccos(np.sqrt(fidelity(rho0, rho1))))
+
+
+def entropy(rho: Density, base: float = None) -> float:
+    """Von Neumann entropy, in nats unless `base` is given (measures.py:133-148)."""
+    probs = np.maximum(np.linalg.eigvalsh(_operator(rho)), 0.0)
+    return float(scipy.stats.entropy(probs, base=base))
+
+
+def mutual_info(rho: Density, qubits0, qubits1=None, base: float = None) -> float:
+    """Bipartite von Neumann mutual information S(0) + S(1) - S(01); the reduced densities come from the device
+    partial trace (measures.py:152-180)."""
+    if qubits1 is None:
+        qubits1 = tuple(set(rho.qubits) - set(qubits0))
+    rho0 = rho.partial_trace(qubits1)
+    rho1 = rho.partial_trace(qubits0)
+    return entropy(rho0, base) + entropy(rho1, base) - entropy(rho, base)
 
 
 def density_angle(rho0: Density, rho1: Density) -> bk.BKTensor:

@@ -237,3 +237,32 @@ def test_partial_trace_on_device_matches_reference_einsum(n, traced):
     assert got.shape == want.shape and np.abs(got - want).max() < AMP_TOL
     assert abs(complex(qf.asarray(red.trace())) - 1) < 1e-12
     assert qf.engine.launch_count() > before
+
+
+def test_spectral_density_measures():
+    # reference tests/test_measures.py:59-84, 131-156
+    np.random.seed(11)
+    rho0, rho1 = qf.random_density(4), qf.random_density(4)
+    assert 0.0 <= qf.fidelity(rho0, rho1) <= 1.0
+    assert 0.0 <= qf.fidelity(rho0, qf.random_density([3, 2, 1, 0])) <= 1.0
+    assert abs(qf.fidelity(rho0, rho0) - 1) < 1e-9
+    ket0, ket1 = qf.random_state(3), qf.random_state(3)
+    want = float(qf.asarray(qf.state_fidelity(ket0, ket1)))
+    assert abs(qf.fidelity(ket0.asdensity(), ket1.asdensity()) - want) < 1e-7
+    # against the reference's own formula (scipy sqrtm), measures.py:86
+    from scipy.linalg import sqrtm
+    op0, op1 = qf.asarray(rho0.asoperator()), qf.asarray(rho1.asoperator())
+    ref = np.real(np.trace(sqrtm(sqrtm(op0) @ op1 @ sqrtm(op0))) ** 2)
+    assert abs(qf.fidelity(rho0, rho1) - ref) < 1e-9
+    assert abs(qf.bures_angle(rho0, rho1) - np.arccos(np.sqrt(ref))) < 1e-8
+    assert abs(qf.bures_distance(rho0, rho1) - np.sqrt(2 - 2 * np.sqrt(ref))) < 1e-8
+    mixed = qf.mixed_density(4)
+    assert np.isclose(qf.entropy(mixed, base=2), 4)
+    assert np.isclose(qf.entropy(qf.random_gate(4).aschannel().evolve(mixed), base=2), 4)
+    assert np.isclose(qf.entropy(ket0.asdensity()), 0, atol=1e-9)
+    info0 = qf.mutual_info(mixed, qubits0=[0, 1], qubits1=[2, 3])
+    local = qf.random_gate(2).aschannel().evolve(mixed)
+    assert np.isclose(info0, qf.mutual_info(local, qubits0=[0, 1], qubits1=[2, 3]))
+    assert np.isclose(info0, qf.mutual_info(local, qubits0=[0, 1]))
+    bell = qf.Circuit([qf.H(0), qf.CNOT(0, 1)]).run(qf.zero_state(2)).asdensity()
+    assert np.isclose(qf.mutual_info(bell, [0], [1], base=2), 2.0)
