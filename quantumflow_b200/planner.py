@@ -425,8 +425,8 @@ class Planner:
         self.refine = True if refine is None else bool(refine)
 
     # ---- pass 2: sweeps ---------------------------------------------------------------------------
-    def _form_sweep(self, ops: List[POp], rnd=None, p_new: float = 1.0,
-                    forbidden: frozenset = frozenset()) -> Tuple[List[POp], List[POp], List[int]]:
+    def _form_sweep(self, ops: List[POp], rnd=None, p_new: float = 1.0, forbidden: frozenset = frozenset(),
+                    required: frozenset = frozenset()) -> Tuple[List[POp], List[POp], List[int]]:
         """One sweep: the operators that join it, the deferred rest, the tile bits.
 
         A greedy walk in program order picks the tile (an operator joins while its mixing bits fit; with `rnd`, an
@@ -434,8 +434,12 @@ class Planner:
         variants, see _partition). The walk lets the first operators it meets claim the tile, so the tile is then
         refined by local search (_refine_tile): single-bit exchanges are kept while they raise the number of
         operators the sweep executes. Operators that mix a bit of `forbidden` (the global qubits of a sharded
-        state, sharded.schedule) are deferred."""
-        tile = set(range(self.L))
+        state, sharded.schedule) are deferred and such bits never pad the tile. The bits of `required` are tile
+        bits whatever the operators need (the bit positions a qubit remap moves: the sweep that holds them all
+        can store the permutation, attach_permutation)."""
+        tile = set(range(self.L)) | set(required)
+        if len(tile) > self.M:
+            raise ValueError('required bits do not fit a tile')
         cost = 0.0
         nbytes = SWEEP_HEADER_BYTES + 8 * ROUND_HEADER_BYTES
         def_any: set = set()
@@ -470,13 +474,13 @@ class Planner:
         # pad the tile with the lowest free bits (locality of the strided tile accesses)
         b = 0
         while len(tile) < self.M:
-            if b not in tile:
+            if b not in tile and b not in forbidden:
                 tile.add(b)
             b += 1
         tmask = sum(1 << b for b in tile)
         fmask = sum(1 << b for b in forbidden)
         if self.refine and len(ops) >= REFINE_MIN_OPS:
-            tmask = self._refine_tile(ops, tmask, fmask)
+            tmask = self._refine_tile(ops, tmask, fmask, sum(1 << b for b in required))
         chosen, deferred = self._closure(ops, tmask, fmask)
         return chosen, deferred, [b for b in range(self.nbits) if (tmask >> b) & 1]
 
@@ -561,12 +565,12 @@ class Planner:
                 count += 1
         return count
 
-    def _refine_tile(self, ops: List[POp], tmask: int, fmask: int) -> int:
+    def _refine_tile(self, ops: List[POp], tmask: int, fmask: int, keep: int = 0) -> int:
         """Local search over the tile of one sweep: exchange one tile bit (never the low bits, which every sweep
         needs for whole 128-byte lines) for one outside bit while that raises the number of executed operators;
         the best exchange of a pass is taken, up to REFINE_PASSES passes. On the 30-qubit benchmark this takes
         the plan from 20 sweeps (randomised greedy walks alone) to 15."""
-        low = (1 << self.L) - 1
+        low = ((1 << self.L) - 1) | keep        # bits that never leave the tile
         every = (1 << self.nbits) - 1
         recs = [(op.mixmask & every, op.diagmask & every, op.cost, op.plan_bytes) for op in ops[:REFINE_WINDOW]]
         best = self._count(recs, tmask, fmask)
@@ -844,10 +848,22 @@ class Planner:
                 break
         return best
 
-    def plan(self, pops: List[POp]) -> List[SweepPlan]:
+    def plan(self, pops: List[POp], parts: List[Tuple[List[POp], List[int]]] = None) -> List[SweepPlan]:
+        """Sweeps for the operator list. `parts` is a split made elsewhere -- (operators, tile bits) per sweep in
+        order, covering `pops` (sharded.schedule forms the sweeps itself, and knows which tile must hold the bits
+        of the next remap's permutation); without it the list is partitioned here."""
         sweeps: List[SweepPlan] = []
         scale: Dict[int, complex] = {}     # pending relative scales (absorb_frame), carried across sweeps
-        parts = self._partition(pops) if pops else []
+        if parts is None:
+            parts = self._partition(pops) if pops else []
+        else:
+            parts = [(list(chosen), sorted(tile)) for chosen, tile in parts]
+            if sum(len(chosen) for chosen, _ in parts) != len(pops):
+                raise ValueError('preset sweeps do not cover the operator list')
+            for chosen, tile in parts:
+                if len(set(tile)) != self.M or tile[:self.L] != list(range(self.L)) or tile[-1] >= self.nbits or \
+                        any(not op.mixset <= set(tile) for op in chosen):
+                    raise ValueError('preset sweep does not fit its tile')
         for index, (chosen, tile) in enumerate(parts):
             remaining = index + 1 < len(parts)
             ops, store_xor = absorb_frame(chosen, scale)
@@ -1083,17 +1099,37 @@ def build_segments(nbits: int, bitops: Sequence[Tuple[np.ndarray, Sequence[int]]
 
 
 def build_segments_from_items(nbits: int, items: Sequence[object], tile_bits: int = None, low_bits: int = None,
-                              max_cost: float = None, final_perm: Sequence[int] = None) -> List[Segment]:
-    """build_segments for operators that are already classified (POp / Fallback, see classify_all)."""
+                              max_cost: float = None, final_perm: Sequence[int] = None,
+                              preset: Sequence[Tuple[int, Optional[Sequence[int]]]] = None) -> List[Segment]:
+    """build_segments for operators that are already classified (POp / Fallback, see classify_all). `preset`
+    fixes the split into sweeps: (number of items, tile bits) per sweep in order, (1, None) for a Fallback."""
     planner = Planner(nbits, tile_bits, low_bits, max_cost)
     segments: List[Segment] = []
     pending: List[POp] = []
+    groups: List[Tuple[List[POp], List[int]]] = []      # preset sweeps, consumed from the end as items stream by
     if final_perm is not None and list(final_perm) == list(range(nbits)):
         final_perm = None
+    if preset is not None:
+        if sum(count for count, _ in preset) != len(items):
+            raise ValueError('preset sweeps do not cover the items')
+        at = 0
+        for count, tile in preset:
+            if tile is not None:
+                groups.append((list(items[at:at + count]), list(tile)))
+            at += count
+        groups.reverse()
 
     def flush(last: bool = False):
         if pending or (last and final_perm is not None):
-            sweeps = planner.plan(pending) if pending else []
+            parts = None
+            if preset is not None:
+                parts, need = [], len(pending)
+                while need > 0:
+                    parts.append(groups.pop())
+                    need -= len(parts[-1][0])
+                if need != 0:
+                    raise ValueError('preset sweeps do not line up with the Fallback operators')
+            sweeps = planner.plan(pending, parts) if pending else []
             if last and final_perm is not None:
                 planner.attach_permutation(sweeps, final_perm)
             blob = planner.serialise(sweeps)

@@ -50,12 +50,16 @@ class Stage:
     """Local work between two remaps: classified operators (planner.POp / planner.Fallback) with PHYSICAL bit
     positions, planned for nl local bits, followed by the in-place local bit permutation `final_perm` (dst local
     bit j <- src local bit final_perm[j]; None = identity) that prepares the next remap."""
-    __slots__ = ('items', 'segments', 'final_perm')
+    __slots__ = ('items', 'segments', 'final_perm', 'parts')
 
-    def __init__(self, items: List[object], final_perm: Optional[List[int]] = None):
+    def __init__(self, items: List[object], final_perm: Optional[List[int]] = None,
+                 parts: Optional[List[Tuple[int, Optional[List[int]]]]] = None):
         self.items = items
         self.segments = None
         self.final_perm = final_perm
+        # the sweeps the scheduler formed: (number of items, physical tile bits | None for a Fallback) in order;
+        # the stage planner keeps this split (planner.build_segments_from_items, preset=)
+        self.parts = parts
 
     @property
     def bitops(self) -> List[BitOp]:
@@ -79,6 +83,9 @@ THIN_CANDIDATES = (0.0, 0.25, 0.4)
 # (its memory pass, ~7 ms at 30 qubits per GPU; the operators' own time moves to other sweeps): the remap moves
 # the fraction 1 - 2^-k of the shard each way at ~0.5 TB/s = 15 / 24 / 28 ms for k = 1 / 2 / 3
 REMAP_COST_PER_FRACTION = 4.5
+# a stage's last sweep is re-formed around the bits the remap moves (saving the bare permutation sweep) when the new
+# sweep does at least this fraction of the old one's work; what it leaves behind runs in the next stage
+REFORM_MIN_WORK = 0.5
 
 
 def schedule(nbits: int, p: int, bitops: Sequence[BitOp], tile_bits: int = None, low_bits: int = None,
@@ -118,7 +125,9 @@ def _schedule_once(nbits: int, p: int, bitops: Sequence[BitOp], tile_bits: int, 
     nl = nbits - p
     phys_of = list(range(nbits))                       # identity: the top p qubits' bits are global
     remaining = planner.classify_all(bitops)
-    pl = planner.Planner(nbits, tile_bits, low_bits, max_cost) if nbits >= planner.MIN_TILE_BITS else None
+    # tiles are formed here in logical bits and handed to the stage planner (nl local bits): same tile size
+    tb = min(planner.DEFAULT_TILE_BITS if tile_bits is None else int(tile_bits), nl)
+    pl = planner.Planner(nbits, tb, low_bits, max_cost) if nl >= planner.MIN_TILE_BITS else None
     pinned = set(range(pl.L)) if pl is not None else set()
 
     def mixset(it) -> frozenset:
@@ -130,44 +139,54 @@ def _schedule_once(nbits: int, p: int, bitops: Sequence[BitOp], tile_bits: int, 
     def diagset(it) -> frozenset:
         return frozenset() if isinstance(it, planner.Fallback) else it.diagset
 
-    def next_sweep(glob: frozenset):
-        """(chosen, rest, waiting) - the best of a few randomised greedy sweeps over the executable operators;
-        waiting = some operator is held back by a global qubit."""
+    def next_sweep(glob: frozenset, remaining: List[object], required: frozenset = frozenset()):
+        """(chosen, rest, waiting, tile) - one sweep over the executable operators of `remaining` (tile in logical
+        bits, None for a single operator run by the one-gate kernels); waiting = some operator is held back by a
+        global qubit. `required`: bits the tile must hold (the positions a remap's local permutation moves)."""
         # a Fallback (dense > 2-bit operator) is a pass of its own: cut the list there
         cut = next((i for i, it in enumerate(remaining) if isinstance(it, planner.Fallback)), len(remaining))
         if cut == 0:
             it = remaining[0]
             if mixset(it) & glob:
-                return [], remaining, True
-            return [it], remaining[1:], False
+                return [], remaining, True, None
+            return [it], remaining[1:], False, None
         head, tail = remaining[:cut], remaining[cut:]
         if pl is None:
             it = head[0]
             if mixset(it) & glob:
-                return [], remaining, True
-            return [it], remaining[1:], False
+                return [], remaining, True, None
+            return [it], remaining[1:], False, None
         best = None
         # randomised variants only without tile refinement (a refined sweep is already the result of a search)
         for trial in range(1 + (min(pl.tries, 8) if len(head) >= 64 and not pl.refine else 0)):
             rnd = random.Random(trial) if trial else None
-            chosen, rest, _tile = pl._form_sweep(head, rnd, 1.0 if trial == 0 else 0.9, forbidden=glob)
+            chosen, rest, tile = pl._form_sweep(head, rnd, 1.0 if trial == 0 else 0.9, forbidden=glob,
+                                                required=required)
             if best is None or sum(o.cost for o in chosen) > sum(o.cost for o in best[0]):
-                best = (chosen, rest)
+                best = (chosen, rest, tile)
         waiting = any(op.kind == 'G' and (op.mixset & glob) for op in best[1]) or \
             (bool(tail) and bool(mixset(tail[0]) & glob))
-        return best[0], best[1] + tail, waiting
+        return best[0], best[1] + tail, waiting, best[2]
+
+    def take(chosen, tile):
+        stage_items.extend(planner.remap_item(op, phys_of) for op in chosen)
+        stage_parts.append((len(chosen), None if tile is None else sorted(phys_of[b] for b in tile)))
 
     steps: List[object] = []
     stage_items: List[object] = []
+    stage_parts: List[Tuple[int, Optional[List[int]]]] = []
     costs: List[float] = []              # work of the sweeps scheduled so far (thin-sweep threshold)
+    nbare = 0                            # remaps whose local permutation needs a bare sweep of its own
+    before_last: Optional[List[object]] = None    # the operator list the stage's last sweep was formed from
     fresh = True                         # no sweep yet since the last remap: take the next one whatever its size
     while remaining:
         glob = frozenset(b for b in range(nbits) if phys_of[b] >= nl)
-        chosen, rest, waiting = next_sweep(glob)
+        chosen, rest, waiting, tile = next_sweep(glob, remaining)
         work = sum(getattr(o, 'cost', 1.0) for o in chosen)
         thin = bool(costs) and work < thin_fraction * (sum(costs) / len(costs))
         if chosen and not (waiting and thin and not fresh):
-            stage_items.extend(planner.remap_item(op, phys_of) for op in chosen)
+            before_last = remaining
+            take(chosen, tile)
             costs.append(work)
             remaining = rest
             fresh = False
@@ -204,6 +223,26 @@ def _schedule_once(nbits: int, p: int, bitops: Sequence[BitOp], tile_bits: int, 
             perm[dst] = src
         local_perm = None if perm == list(range(nl)) else perm
         if local_perm is not None:
+            # The permutation is free when the stage's last sweep stores it, i.e. when that sweep's tile holds the
+            # moved positions; otherwise it costs a bare pass over the shard (planner.attach_permutation). The
+            # sweep was formed before the remap was known, so form it again from the same operator list with the
+            # moved bits as required tile bits, and keep the new one if it does at least the same work.
+            moved = frozenset(logical_at[j] for j in range(nl) if perm[j] != j)
+            last = stage_parts[-1] if stage_parts else None
+            hosted = last is not None and last[1] is not None and all(phys_of[b] in last[1] for b in moved)
+            if not hosted and last is not None and last[1] is not None and before_last is not None \
+                    and pl is not None and len(moved | pinned) <= pl.M:
+                old_items = stage_items[len(stage_items) - last[0]:]
+                chosen2, rest2, _waiting2, tile2 = next_sweep(glob, before_last, required=moved)
+                old_work = sum(getattr(o, 'cost', 1.0) for o in old_items)
+                if tile2 is not None and sum(o.cost for o in chosen2) >= REFORM_MIN_WORK * old_work - 1e-9:
+                    del stage_items[len(stage_items) - last[0]:]
+                    stage_parts.pop()
+                    take(chosen2, tile2)
+                    remaining = rest2
+                    hosted = True
+            if not hosted:
+                nbare += 1
             new_logical_at = {j: logical_at[perm[j]] for j in range(nl)}
             for j, b in new_logical_at.items():
                 phys_of[b] = j
@@ -214,13 +253,14 @@ def _schedule_once(nbits: int, p: int, bitops: Sequence[BitOp], tile_bits: int, 
             b_local, b_rank = logical_at[top[i]], logical_at[nl + t]
             phys_of[b_local], phys_of[b_rank] = nl + t, top[i]
         if stage_items or local_perm is not None:
-            steps.append(Stage(stage_items, local_perm))
-            stage_items = []
+            steps.append(Stage(stage_items, local_perm, stage_parts))
+            stage_items, stage_parts = [], []
         steps.append(Remap(rank_positions))
+        before_last = None
         fresh = True
     if stage_items:
-        steps.append(Stage(stage_items))
-    return steps, phys_of, len(costs)
+        steps.append(Stage(stage_items, None, stage_parts))
+    return steps, phys_of, len(costs) + nbare
 
 
 class ShardedCircuit:
@@ -252,6 +292,7 @@ class ShardedCircuit:
         for st in self.steps:
             if isinstance(st, Stage):
                 st.segments = planner.build_segments_from_items(self.nl, st.items, final_perm=st.final_perm,
+                                                                preset=st.parts,
                                                                 **self._plan_args) if run_stage is None else None
 
     # ---- default (GPU) local work ------------------------------------------------------------------

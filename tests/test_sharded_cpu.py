@@ -12,7 +12,7 @@ import torch.distributed as dist
 import torch.multiprocessing as mp
 
 from oracle import qf_oracle as O
-from quantumflow_b200 import sharded, workloads
+from quantumflow_b200 import planner, sharded, workloads
 
 from conftest import AMP_TOL
 
@@ -120,3 +120,55 @@ def test_sharded_execution_matches_oracle(tmp_path, world, n, depth, seed):
     want = O.run_specs(specs, n, full.reshape([2] * n)).reshape(-1)
     assert np.abs(got - want).max() < AMP_TOL
     assert int(np.load(os.path.join(str(tmp_path), 'remaps.npy'))[0]) >= 1
+
+
+def _swap_index_bits(vec, pairs):
+    idx = np.arange(vec.size, dtype=np.int64)
+    src = idx.copy()
+    for a, b in pairs:
+        diff = ((idx >> a) ^ (idx >> b)) & 1
+        src ^= (diff << a) | (diff << b)
+    return vec[src]
+
+
+@pytest.mark.parametrize('n,p,tile,depth,seed', [(12, 2, 7, 6, 0), (11, 1, 8, 8, 1), (13, 3, 8, 5, 2), (12, 2, 9, 7, 3)])
+def test_sharded_plans_run_on_the_plan_emulator(n, p, tile, depth, seed):
+    """The GPU path of a sharded circuit, minus the GPU: every stage is planned exactly as ShardedCircuit plans it
+    (the scheduler's own sweep split, preset=, with the remap's local permutation fused into the last sweep's
+    store or appended as a bare sweep), the plan blobs are validated by the library and executed by the plan
+    emulator on every rank's shard with index_hi = rank, and a remap exchanges index bits of the concatenated
+    shards as ShardedCircuit._exchange does."""
+    import plan_emulator as E
+    from test_planner import validate_with_library
+    specs = workloads.wb_gate_list(n, depth, seed)
+    nl = n - p
+    steps, phys_of = sharded.schedule(n, p, _bitops(specs, n), tile_bits=tile)
+    rng = np.random.RandomState(seed)
+    full = rng.normal(size=1 << n) + 1j * rng.normal(size=1 << n)
+    full /= np.linalg.norm(full)
+    phys = full.copy()                                  # identity map at the start: physical = logical
+    fused = bare = 0
+    for st in steps:
+        if isinstance(st, sharded.Stage):
+            assert sum(count for count, _ in st.parts) == len(st.items)
+            segs = planner.build_segments_from_items(nl, st.items, tile_bits=tile, final_perm=st.final_perm,
+                                                     preset=st.parts)
+            nsweeps = sum(s.nsweeps for s in segs)
+            if st.final_perm is not None:
+                fused += nsweeps == len(st.parts)
+                bare += nsweeps > len(st.parts)
+            for rank in range(1 << p):
+                shard = phys[rank << nl:(rank + 1) << nl].copy()
+                for seg in segs:
+                    assert seg.kind == 'plan'
+                    validate_with_library(seg.blob)
+                    shard = E.execute(seg.blob, shard, rank)
+                phys[rank << nl:(rank + 1) << nl] = shard
+        else:
+            k = len(st.rank_positions)
+            phys = _swap_index_bits(phys, [(nl + t, nl - k + i) for i, t in enumerate(st.rank_positions)])
+    shards = [phys[r << nl:(r + 1) << nl] for r in range(1 << p)]
+    got = sharded.gather_logical(shards, n, p, phys_of)
+    want = O.run_specs(specs, n, full.reshape([2] * n)).reshape(-1)
+    assert np.abs(got - want).max() < AMP_TOL
+    print('local permutations: fused into a stage sweep', fused, '/ bare sweep', bare)
