@@ -172,3 +172,24 @@ def test_sharded_plans_run_on_the_plan_emulator(n, p, tile, depth, seed):
     want = O.run_specs(specs, n, full.reshape([2] * n)).reshape(-1)
     assert np.abs(got - want).max() < AMP_TOL
     print('local permutations: fused into a stage sweep', fused, '/ bare sweep', bare)
+
+
+@pytest.mark.parametrize('n,p', [(31, 1), (32, 2), (33, 3)])
+def test_benchmark_size_sharded_plans_pass_the_library_validation(n, p):
+    """The plans bench.py launches at 2 / 4 / 8 GPUs (30 qubits per GPU), built as ShardedCircuit builds them and
+    checked by the library's plan validation (the host half of qfb_plan_upload); too large to emulate."""
+    from test_planner import validate_with_library
+    specs = workloads.wb_gate_list(n, 20, 0)
+    steps, phys_of = sharded.schedule(n, p, _bitops(specs, n))
+    assert sorted(phys_of) == list(range(n))
+    nsweeps = nremaps = 0
+    for st in steps:
+        if isinstance(st, sharded.Stage):
+            segs = planner.build_segments_from_items(n - p, st.items, final_perm=st.final_perm, preset=st.parts)
+            for seg in segs:
+                assert seg.kind == 'plan'
+                validate_with_library(seg.blob)
+            nsweeps += sum(s.nsweeps for s in segs)
+        else:
+            nremaps += 1
+    assert nsweeps <= 24 and 1 <= nremaps <= 6, (nsweeps, nremaps)
