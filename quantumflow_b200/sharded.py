@@ -406,3 +406,122 @@ def gather_logical(shards: Sequence[np.ndarray], nbits: int, p: int, phys_of: Se
     for logical, physical in enumerate(phys_of):
         src |= ((idx >> logical) & 1) << physical
     return phys[src]
+
+
+# ---------------------------------------------------------------------------------------------------------
+# read-out of a sharded state (SURVEY 8e "Reductions / readout"): every rank reduces its own shard with the
+# single-GPU kernels (engine.norm2 / marginal / expectation_diag / sample_search) and the partial results -- a
+# few doubles -- are combined with one small collective. All functions return the same value on every rank.
+# `local=` replaces the device reduction in the CPU tests (gloo, numpy shards).
+# ---------------------------------------------------------------------------------------------------------
+
+def _all_sum(values: Sequence[float], like: torch.Tensor, group=None) -> List[float]:
+    buf = torch.tensor([float(v) for v in values], dtype=torch.float64, device=like.device)
+    dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=group)
+    return [float(v) for v in buf.cpu()]
+
+
+def scatter_physical(full_logical: np.ndarray, nbits: int, phys_of: Sequence[int]) -> np.ndarray:
+    """Test helper, inverse of gather_logical: the physical (rank-major) vector of a logical flat vector."""
+    idx = np.arange(1 << nbits, dtype=np.int64)
+    dst = np.zeros_like(idx)
+    for logical, physical in enumerate(phys_of):
+        dst |= ((idx >> logical) & 1) << physical
+    phys = np.zeros_like(np.asarray(full_logical).reshape(-1))
+    phys[dst] = np.asarray(full_logical).reshape(-1)
+    return phys
+
+
+def norm2(shard: torch.Tensor, group=None, local: Callable = None) -> float:
+    """<psi|psi> of the sharded state: local squared norms, one all-reduce of a double."""
+    if local is None:
+        from . import engine
+        mine = float(engine.norm2(shard))
+    else:
+        mine = float(local(shard))
+    return _all_sum([mine], shard, group)[0]
+
+
+def marginal(shard: torch.Tensor, logical_bit: int, phys_of: Sequence[int], nl: int, rank: int, group=None,
+             local: Callable = None, local_norm2: Callable = None) -> Tuple[float, float]:
+    """(P(bit = 0), P(bit = 1)), unnormalised, of logical index bit `logical_bit` (qubit axis i of an N-qubit state
+    is bit N-1-i). A local bit is a marginal reduction of every shard; a rank bit splits the ranks: each rank
+    contributes its whole squared norm to the side its rank bit selects."""
+    pos = phys_of[logical_bit]
+    if pos < nl:
+        if local is None:
+            from . import engine
+            p0, p1 = (float(v) for v in engine.marginal(shard, pos).cpu())
+        else:
+            p0, p1 = (float(v) for v in local(shard, pos))
+    else:
+        if local_norm2 is None:
+            from . import engine
+            n2 = float(engine.norm2(shard))
+        else:
+            n2 = float(local_norm2(shard))
+        p0, p1 = (0.0, n2) if (rank >> (pos - nl)) & 1 else (n2, 0.0)
+    total = _all_sum([p0, p1], shard, group)
+    return total[0], total[1]
+
+
+def expectation_diag(shard: torch.Tensor, local_diag: torch.Tensor, group=None, local: Callable = None) -> float:
+    """sum_i d_i |psi_i|^2 for a real diagonal observable; `local_diag` is this rank's slice of the diagonal in
+    the PHYSICAL layout of the shard (physical_diagonal)."""
+    if local is None:
+        from . import engine
+        mine = float(engine.expectation_diag(shard, local_diag))
+    else:
+        mine = float(local(shard, local_diag))
+    return _all_sum([mine], shard, group)[0]
+
+
+def physical_diagonal(diag_logical: np.ndarray, phys_of: Sequence[int], nl: int, rank: int) -> np.ndarray:
+    """This rank's slice of a diagonal given in logical flat order (index bit b = logical bit b), laid out like
+    the shard: local physical index -> logical index through phys_of. For test-sized states (the whole diagonal
+    is materialised); production observables are built per shard the same way."""
+    nbits = len(phys_of)
+    flat = np.asarray(diag_logical).reshape(-1)
+    local = np.arange(1 << nl, dtype=np.int64) | (np.int64(rank) << nl)
+    logical = np.zeros_like(local)
+    for b, pos in enumerate(phys_of):
+        logical |= ((local >> pos) & 1) << b
+    assert flat.size == 1 << nbits
+    return flat[logical]
+
+
+def sample_indices(shard: torch.Tensor, uniforms: Sequence[float], phys_of: Sequence[int], nl: int, rank: int,
+                   world: int, group=None, local_norm2: Callable = None, local_search: Callable = None) -> np.ndarray:
+    """Basis-state indices (LOGICAL flat indices) drawn from |psi|^2 by inverting the cumulative distribution in
+    physical order: the ranks' squared norms are gathered (P doubles), each uniform picks the rank whose span of
+    the cumulative sum it falls into, that rank searches its own shard (engine.sample_search) and the indices are
+    combined with one all-reduce. `uniforms` in [0, 1) must be the same on every rank (shared seed)."""
+    if local_norm2 is None:
+        from . import engine
+        mine = float(engine.norm2(shard))
+    else:
+        mine = float(local_norm2(shard))
+    totals = torch.zeros(world, dtype=torch.float64, device=shard.device)
+    totals[rank] = mine
+    dist.all_reduce(totals, op=dist.ReduceOp.SUM, group=group)
+    totals = totals.cpu().numpy()
+    edges = np.concatenate([[0.0], np.cumsum(totals)])
+    u = np.asarray(uniforms, dtype=np.float64) * edges[-1]
+    owner = np.minimum(np.searchsorted(edges, u, side='right') - 1, world - 1)
+    out = torch.zeros(len(u), dtype=torch.int64, device=shard.device)
+    sel = np.nonzero(owner == rank)[0]
+    if sel.size:
+        # position inside this rank's span, rescaled to [0, 1) of the shard's own total
+        inner = np.clip((u[sel] - edges[rank]) / totals[rank], 0.0, np.nextafter(1.0, 0.0))
+        if local_search is None:
+            from . import engine
+            local_idx = np.asarray(engine.sample_search(engine.probabilities(shard).reshape(-1), inner), dtype=np.int64)
+        else:
+            local_idx = np.asarray(local_search(shard, inner), dtype=np.int64)
+        physical = local_idx | (np.int64(rank) << nl)
+        logical = np.zeros_like(physical)
+        for b, pos in enumerate(phys_of):
+            logical |= ((physical >> pos) & 1) << b
+        out[torch.as_tensor(sel, device=out.device)] = torch.as_tensor(logical, device=out.device)
+    dist.all_reduce(out, op=dist.ReduceOp.SUM, group=group)
+    return out.cpu().numpy()

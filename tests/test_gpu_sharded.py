@@ -63,3 +63,63 @@ def test_sharded_matches_single_gpu_and_oracle(tmp_path, world, n, depth, seed):
     assert np.abs(got - want).max() < AMP_TOL
     assert abs(float(np.load(os.path.join(str(tmp_path), 'norm.npy'))[0]) - 1) < 1e-10
     assert int(meta[n]) >= 1
+
+
+def _readout_worker(rank, world, port, n, phys_of, phys, diag, uniforms, out_dir):
+    import torch.distributed as dist
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group('nccl', rank=rank, world_size=world, device_id=torch.device('cuda', rank))
+    try:
+        from quantumflow_b200 import engine, sharded
+        nl = n - (world.bit_length() - 1)
+        shard = torch.from_numpy(np.ascontiguousarray(phys[rank << nl:(rank + 1) << nl])).cuda()
+        before = engine.launch_count()
+        vals = [sharded.norm2(shard)]
+        for b in range(n):
+            vals.extend(sharded.marginal(shard, b, phys_of, nl, rank))
+        local_diag = torch.from_numpy(sharded.physical_diagonal(diag, phys_of, nl, rank)).cuda()
+        vals.append(sharded.expectation_diag(shard, local_diag))
+        samples = sharded.sample_indices(shard, uniforms, phys_of, nl, rank, world)
+        assert engine.launch_count() > before
+        np.save(os.path.join(out_dir, 'readout{}.npy'.format(rank)), np.concatenate([vals, samples]))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize('world,n,seed', [(1, 12, 0), (2, 13, 1), (4, 14, 2)])
+def test_sharded_readout_on_device(tmp_path, world, n, seed):
+    """SURVEY 8e 'Reductions / readout' with the device kernels as the per-rank reductions and NCCL for the few
+    doubles that are combined (the CPU twin with numpy shards and gloo: tests/test_sharded_cpu.py)."""
+    if torch.cuda.device_count() < world:
+        pytest.skip('needs {} GPUs'.format(world))
+    import torch.multiprocessing as mp
+    from quantumflow_b200 import sharded
+    rng = np.random.RandomState(seed)
+    full = rng.normal(size=1 << n) + 1j * rng.normal(size=1 << n)
+    full *= 0.7 / np.linalg.norm(full)
+    phys_of = [int(v) for v in rng.permutation(n)]
+    phys = sharded.scatter_physical(full, n, phys_of)
+    diag = rng.normal(size=1 << n)
+    uniforms = rng.random_sample(64)
+    mp.spawn(_readout_worker, args=(world, _free_port(), n, phys_of, phys, diag, uniforms, str(tmp_path)),
+             nprocs=world, join=True)
+    outs = [np.load(os.path.join(str(tmp_path), 'readout{}.npy'.format(r))) for r in range(world)]
+    for o in outs[1:]:
+        assert np.array_equal(o, outs[0])
+    got = outs[0]
+    probs = np.abs(full) ** 2
+    assert abs(got[0] - probs.sum()) < 1e-13
+    for b in range(n):
+        one = ((np.arange(1 << n) >> b) & 1).astype(bool)
+        assert abs(got[1 + 2 * b] - probs[~one].sum()) < 1e-13 and abs(got[2 + 2 * b] - probs[one].sum()) < 1e-13
+    assert abs(got[1 + 2 * n] - (probs * diag).sum()) < 1e-12
+    samples = got[2 + 2 * n:].astype(np.int64)
+    cdf = np.cumsum(np.abs(phys) ** 2)
+    physical = np.minimum(np.searchsorted(cdf, uniforms * cdf[-1], side='right'), cdf.size - 1)
+    logical = np.zeros_like(physical)
+    for b, pos in enumerate(phys_of):
+        logical |= ((physical >> pos) & 1) << b
+    assert (samples == logical).mean() > 0.9
+    assert np.all(probs[samples] > 0)

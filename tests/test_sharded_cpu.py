@@ -193,3 +193,76 @@ def test_benchmark_size_sharded_plans_pass_the_library_validation(n, p):
         else:
             nremaps += 1
     assert nsweeps <= 24 and 1 <= nremaps <= 6, (nsweeps, nremaps)
+
+
+def _readout_worker(rank, world, port, n, phys_of, phys, diag, uniforms, out_dir):
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        p = world.bit_length() - 1
+        nl = n - p
+        shard = torch.from_numpy(np.ascontiguousarray(phys[rank << nl:(rank + 1) << nl]))
+
+        def np_norm2(t):
+            return float(np.vdot(t.numpy(), t.numpy()).real)
+
+        def np_marginal(t, pos):
+            pr = np.abs(t.numpy()) ** 2
+            one = ((np.arange(pr.size) >> pos) & 1).astype(bool)
+            return pr[~one].sum(), pr[one].sum()
+
+        def np_expect(t, d):
+            return float((np.abs(t.numpy()) ** 2 * d.numpy()).sum())
+
+        def np_search(t, inner):
+            cdf = np.cumsum(np.abs(t.numpy()) ** 2)
+            return np.minimum(np.searchsorted(cdf, np.asarray(inner) * cdf[-1], side='right'), cdf.size - 1)
+
+        res = {'norm2': sharded.norm2(shard, local=np_norm2)}
+        res['marginals'] = [sharded.marginal(shard, b, phys_of, nl, rank, local=np_marginal, local_norm2=np_norm2)
+                            for b in range(n)]
+        local_diag = torch.from_numpy(sharded.physical_diagonal(diag, phys_of, nl, rank))
+        res['expect'] = sharded.expectation_diag(shard, local_diag, local=np_expect)
+        res['samples'] = sharded.sample_indices(shard, uniforms, phys_of, nl, rank, world, local_norm2=np_norm2,
+                                                local_search=np_search)
+        np.save(os.path.join(out_dir, 'readout{}.npy'.format(rank)),
+                np.concatenate([[res['norm2']], np.ravel(res['marginals']), [res['expect']], res['samples']]))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize('world,n,seed', [(2, 8, 0), (4, 9, 1)])
+def test_sharded_readout_reductions(tmp_path, world, n, seed):
+    """SURVEY 8e 'Reductions / readout': norm, marginals (local and rank bits), a diagonal expectation and CDF
+    sampling of a sharded state agree with the unsharded numpy computation, identically on every rank."""
+    rng = np.random.RandomState(seed)
+    p = world.bit_length() - 1
+    full = rng.normal(size=1 << n) + 1j * rng.normal(size=1 << n)
+    full *= 0.7 / np.linalg.norm(full)                  # unnormalised on purpose
+    phys_of = [int(v) for v in rng.permutation(n)]      # some logical bits live in the rank bits
+    phys = sharded.scatter_physical(full, n, phys_of)
+    diag = rng.normal(size=1 << n)
+    uniforms = rng.random_sample(64)
+    mp.spawn(_readout_worker, args=(world, _free_port(), n, phys_of, phys, diag, uniforms, str(tmp_path)),
+             nprocs=world, join=True)
+    outs = [np.load(os.path.join(str(tmp_path), 'readout{}.npy'.format(r))) for r in range(world)]
+    for o in outs[1:]:
+        assert np.array_equal(o, outs[0])
+    got = outs[0]
+    probs = np.abs(full) ** 2
+    assert abs(got[0] - probs.sum()) < 1e-14
+    for b in range(n):
+        one = ((np.arange(1 << n) >> b) & 1).astype(bool)
+        assert abs(got[1 + 2 * b] - probs[~one].sum()) < 1e-14 and abs(got[2 + 2 * b] - probs[one].sum()) < 1e-14
+    assert abs(got[1 + 2 * n] - (probs * diag).sum()) < 1e-13
+    samples = got[2 + 2 * n:].astype(np.int64)
+    # the sampler inverts the CDF in PHYSICAL order: same construction on the gathered physical vector
+    cdf = np.cumsum(np.abs(phys) ** 2)
+    physical = np.minimum(np.searchsorted(cdf, uniforms * cdf[-1], side='right'), cdf.size - 1)
+    logical = np.zeros_like(physical)
+    for b, pos in enumerate(phys_of):
+        logical |= ((physical >> pos) & 1) << b
+    agree = samples == logical
+    assert agree.mean() > 0.9                           # rounding at span edges may move a draw to a neighbour
+    assert np.all(probs[samples] > 0)
