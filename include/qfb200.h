@@ -121,6 +121,19 @@ int qfb_permute_bits(void *dst, const void *src, int nbits, const int *perm, int
 int qfb_sample_search(const double *probs_dev, uint64_t n, const double *u_host, int nu, uint64_t *out_idx_host,
                       void *stream);
 
+/* ---- host-side planner support (no GPU work; quantumflow_b200/planner.py) ---- */
+/* Operators of a circuit in program order as parallel arrays: mix[i] / diag[i] = masks of the index bits operator
+ * i mixes / only reads, cost[i] = planner work units, bytes[i] = upper bound of its records in a sweep.
+ * count_executed: how many operators that touch a bit a sweep over the tile `tmask` executes (fmask = bits no
+ * operator may mix: the rank bits of a sharded state; max_cost / room = work and size caps of one sweep).
+ * refine_tile: local search over the tile -- exchange one tile bit outside `keep` for one bit outside the tile and
+ * `fmask` while that raises the count (best exchange of a pass, up to `passes` passes). */
+int qfb_plan_count_executed(const uint64_t *mix, const uint64_t *diag, const double *cost, const uint32_t *bytes,
+                            int nops, uint64_t tmask, uint64_t fmask, double max_cost, int64_t room, int *count_out);
+int qfb_plan_refine_tile(const uint64_t *mix, const uint64_t *diag, const double *cost, const uint32_t *bytes,
+                         int nops, int nbits, uint64_t tmask, uint64_t fmask, uint64_t keep, double max_cost,
+                         int64_t room, int passes, uint64_t *tmask_out, int *count_out);
+
 /* ---- autograd bridge ---- */
 /* grad_mat[r][c] = sum_groups g[base|off[r]] * conj(psi[base|off[c]])   (k <= 3), written to out_dev (4^k c128) */
 int qfb_gate_grad(const void *g, const void *psi, int nbits, int k, const int *bits, void *out_dev, void *stream);

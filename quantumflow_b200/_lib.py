@@ -5,7 +5,7 @@ if the library cannot be loaded, or a call fails, an exception is raised (no CPU
 """
 import ctypes
 import os
-from ctypes import c_char_p, c_double, c_int, c_size_t, c_uint64, c_void_p, POINTER
+from ctypes import c_char_p, c_double, c_int, c_int64, c_size_t, c_uint64, c_void_p, POINTER
 
 from . import _build
 
@@ -44,6 +44,10 @@ PROTOTYPES = {
     'qfb_partial_trace': (c_int, [c_void_p, c_void_p, c_int, c_int, _c_int_p, c_int, POINTER(c_uint64), c_void_p]),
     'qfb_permute_bits': (c_int, [c_void_p, c_void_p, c_int, _c_int_p, c_int, c_void_p]),
     'qfb_sample_search': (c_int, [c_void_p, c_uint64, _c_double_p, c_int, POINTER(c_uint64), c_void_p]),
+    'qfb_plan_count_executed': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_uint64, c_uint64, c_double,
+                                        c_int64, _c_int_p]),
+    'qfb_plan_refine_tile': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_uint64, c_uint64,
+                                     c_uint64, c_double, c_int64, c_int, POINTER(c_uint64), _c_int_p]),
     'qfb_gate_grad': (c_int, [c_void_p, c_void_p, c_int, c_int, _c_int_p, c_void_p, c_void_p]),
 }
 

@@ -87,7 +87,7 @@ DEFAULT_TRIES = 24
 # tile refinement (Planner._refine_tile): operator lists shorter than this are not worth the search
 REFINE_MIN_OPS = 24
 REFINE_PASSES = 6
-REFINE_TRIES = 8
+REFINE_TRIES = 24
 REFINE_WINDOW = 512      # operators of the list that the search scores (a sweep rarely executes more)
 # pivot on the (0,0) entry unless it is this much smaller than the largest entry
 PIVOT_RATIO = 1e-3
@@ -540,54 +540,30 @@ class Planner:
                 chosen.append(op)
         return chosen, deferred
 
-    def _count(self, recs, tmask: int, fmask: int) -> int:
-        """_closure(...) reduced to its score, on (mixmask, diagmask, cost, bytes) records: the number of executed
-        operators that touch a bit."""
-        allow = tmask & ~fmask
-        every = (1 << self.nbits) - 1
-        max_cost = self.max_cost
-        room = MAX_SWEEP_BYTES - 4 * ROUND_HEADER_BYTES - (SWEEP_HEADER_BYTES + 8 * ROUND_HEADER_BYTES)
-        da = dm = 0
-        cost = 0.0
-        count = 0
-        for mm, dd, c, nb in recs:
-            if (mm & da) or (dd & dm) or (mm & ~allow) or (count and cost + c > max_cost):
-                da |= mm | dd
-                dm |= mm
-                if not (allow & ~da):
-                    break          # no tile bit is open for mixing any more (what follows is phase terms at best)
-                continue
-            room -= nb
-            if room < 0:
-                break
-            cost += c
-            if mm | dd:
-                count += 1
-        return count
-
     def _refine_tile(self, ops: List[POp], tmask: int, fmask: int, keep: int = 0) -> int:
         """Local search over the tile of one sweep: exchange one tile bit (never the low bits, which every sweep
-        needs for whole 128-byte lines) for one outside bit while that raises the number of executed operators;
-        the best exchange of a pass is taken, up to REFINE_PASSES passes. On the 30-qubit benchmark this takes
-        the plan from 20 sweeps (randomised greedy walks alone) to 15."""
-        low = ((1 << self.L) - 1) | keep        # bits that never leave the tile
+        needs for whole 128-byte lines, nor the bits of `keep`) for one outside bit while that raises the number
+        of operators the sweep executes; the best exchange of a pass is taken, up to REFINE_PASSES passes. The
+        score is a bit-mask scan over the next REFINE_WINDOW operators, a few thousand scans per sweep: it runs
+        natively (qfb_plan_refine_tile, csrc/qfb_planhost.cu; the same scan in Python, which a test compares it
+        with: tests/plan_emulator.py::count_executed). On the 30-qubit benchmark the search takes the plan from
+        20 sweeps (randomised greedy walks alone) to 15."""
+        import ctypes
+        from . import _lib
+        lib = _lib.load()
+        window = ops[:REFINE_WINDOW]
+        n = len(window)
         every = (1 << self.nbits) - 1
-        recs = [(op.mixmask & every, op.diagmask & every, op.cost, op.plan_bytes) for op in ops[:REFINE_WINDOW]]
-        best = self._count(recs, tmask, fmask)
-        for _ in range(REFINE_PASSES):
-            base = tmask
-            ins = [b for b in range(self.nbits) if (base >> b) & 1 and not (low >> b) & 1]
-            outs = [b for b in range(self.nbits) if not (base >> b) & 1 and not (fmask >> b) & 1]
-            improved = False
-            for bi in ins:
-                without = base & ~(1 << bi)
-                for bo in outs:
-                    n = self._count(recs, without | (1 << bo), fmask)
-                    if n > best:
-                        best, tmask, improved = n, without | (1 << bo), True
-            if not improved:
-                break
-        return tmask
+        mix = np.fromiter((op.mixmask & every for op in window), dtype=np.uint64, count=n)
+        diag = np.fromiter((op.diagmask & every for op in window), dtype=np.uint64, count=n)
+        cost = np.fromiter((op.cost for op in window), dtype=np.float64, count=n)
+        nbytes = np.fromiter((op.plan_bytes for op in window), dtype=np.uint32, count=n)
+        room = MAX_SWEEP_BYTES - 4 * ROUND_HEADER_BYTES - (SWEEP_HEADER_BYTES + 8 * ROUND_HEADER_BYTES)
+        out = ctypes.c_uint64(0)
+        _lib.check(lib.qfb_plan_refine_tile(mix.ctypes.data, diag.ctypes.data, cost.ctypes.data, nbytes.ctypes.data, n,
+                                            self.nbits, tmask, fmask, ((1 << self.L) - 1) | keep,
+                                            float(self.max_cost), room, REFINE_PASSES, ctypes.byref(out), None))
+        return int(out.value)
 
     # ---- pass 3: rounds ---------------------------------------------------------------------------
     def _thread_order(self, regs: Sequence[int], coalesced: bool) -> List[int]:

@@ -86,7 +86,8 @@ REMAP_COST_PER_FRACTION = 4.5
 # a stage's last sweep is re-formed around the bits the remap moves (saving the bare permutation sweep) when the new
 # sweep does at least this fraction of the old one's work; what it leaves behind runs in the next stage
 REFORM_MIN_WORK = 0.5
-SWEEP_TRIES_REFINED = 3
+# randomised variants of each sweep's greedy start (fixed seeds): both counts are scheduled, the cost model decides
+SWEEP_TRIES_CANDIDATES = (3, 8)
 
 
 def schedule(nbits: int, p: int, bitops: Sequence[BitOp], tile_bits: int = None, low_bits: int = None,
@@ -95,20 +96,22 @@ def schedule(nbits: int, p: int, bitops: Sequence[BitOp], tile_bits: int = None,
     THIN_CANDIDATES are scheduled and the one with the lowest modelled cost (sweeps + remaps in sweep units) is
     returned; the choice is deterministic, so every rank takes the same one."""
     if thin is not None or p == 0:
-        steps, phys_of, _ = _schedule_once(nbits, p, bitops, tile_bits, low_bits, max_cost, thin or 0.0)
+        steps, phys_of, _ = _schedule_once(nbits, p, bitops, tile_bits, low_bits, max_cost, thin or 0.0,
+                                           SWEEP_TRIES_CANDIDATES[0])
         return steps, phys_of
     best = None
-    for cand in THIN_CANDIDATES:
-        steps, phys_of, nsweeps = _schedule_once(nbits, p, bitops, tile_bits, low_bits, max_cost, cand)
-        cost = nsweeps + sum(REMAP_COST_PER_FRACTION * (1.0 - 0.5 ** len(st.rank_positions))
-                             for st in steps if isinstance(st, Remap))
-        if best is None or cost < best[0] - 1e-9:
-            best = (cost, steps, phys_of)
+    for tries in SWEEP_TRIES_CANDIDATES:
+        for cand in THIN_CANDIDATES:
+            steps, phys_of, nsweeps = _schedule_once(nbits, p, bitops, tile_bits, low_bits, max_cost, cand, tries)
+            cost = nsweeps + sum(REMAP_COST_PER_FRACTION * (1.0 - 0.5 ** len(st.rank_positions))
+                                 for st in steps if isinstance(st, Remap))
+            if best is None or cost < best[0] - 1e-9:
+                best = (cost, steps, phys_of)
     return best[1], best[2]
 
 
 def _schedule_once(nbits: int, p: int, bitops: Sequence[BitOp], tile_bits: int, low_bits: int, max_cost: float,
-                   thin_fraction: float) -> Tuple[List[object], List[int], int]:
+                   thin_fraction: float, sweep_tries: int = 3) -> Tuple[List[object], List[int], int]:
     """Split `bitops` (logical bit positions, program order) into Stage / Remap steps.
 
     Sweeps (passes over the shard) are formed one at a time from the operators that are executable under the
@@ -159,8 +162,8 @@ def _schedule_once(nbits: int, p: int, bitops: Sequence[BitOp], tile_bits: int, 
             return [it], remaining[1:], False, None
         best = None
         # a few randomised variants of the greedy start (fixed seeds; with tile refinement each one is a local
-        # search of its own, so fewer of them): 8 GPUs 21 -> 19 sweeps, 2 GPUs 18 -> 17 on the benchmark
-        for trial in range(1 + (min(pl.tries, SWEEP_TRIES_REFINED if pl.refine else 8) if len(head) >= 64 else 0)):
+        # search of its own): 8 GPUs 21 -> 19 sweeps, 4 GPUs 20 -> 19, 2 GPUs 18 -> 17 on the benchmark
+        for trial in range(1 + (min(pl.tries, sweep_tries if pl.refine else 8) if len(head) >= 64 else 0)):
             rnd = random.Random(trial) if trial else None
             chosen, rest, tile = pl._form_sweep(head, rnd, 1.0 if trial == 0 else 0.9, forbidden=glob,
                                                 required=required)

@@ -308,3 +308,52 @@ def execute(blob: bytes, state: np.ndarray, index_hi: int = 0, check_layout: boo
                     for addr, val in staged:
                         state[addr] = val
     return state
+
+
+# ---------------------------------------------------------------------------------------------------------
+# The planner's tile score and tile search in plain Python: the statement that csrc/qfb_planhost.cu
+# (qfb_plan_count_executed / qfb_plan_refine_tile) is checked against (tests/test_planner.py).
+# ---------------------------------------------------------------------------------------------------------
+
+def count_executed(recs, tmask, fmask, max_cost, room):
+    """recs: (mixmask, diagmask, cost, bytes) per operator in program order. Number of operators that touch a bit
+    and that a sweep over the tile `tmask` executes."""
+    allow = tmask & ~fmask
+    da = dm = 0
+    work = 0.0
+    count = 0
+    for mm, dd, c, nb in recs:
+        if (mm & da) or (dd & dm) or (mm & ~allow) or (count and work + c > max_cost):
+            da |= mm | dd
+            dm |= mm
+            if not (allow & ~da):
+                break
+            continue
+        room -= nb
+        if room < 0:
+            break
+        work += c
+        if mm | dd:
+            count += 1
+    return count
+
+
+def refine_tile(recs, nbits, tmask, fmask, keep, max_cost, room, passes):
+    """Best single-bit exchange per pass while the count rises; returns (tile mask, count)."""
+    best = count_executed(recs, tmask, fmask, max_cost, room)
+    for _ in range(passes):
+        base = tmask
+        improved = False
+        for bi in range(nbits):
+            if not (base >> bi) & 1 or (keep >> bi) & 1:
+                continue
+            without = base & ~(1 << bi)
+            for bo in range(nbits):
+                if (base >> bo) & 1 or (fmask >> bo) & 1:
+                    continue
+                n = count_executed(recs, without | (1 << bo), fmask, max_cost, room)
+                if n > best:
+                    best, tmask, improved = n, without | (1 << bo), True
+        if not improved:
+            break
+    return tmask, best

@@ -309,3 +309,50 @@ def test_classified_items_round_trip_to_operators():
         m, bits = planner.item_bitop(item)
         got = O.tensormul_flat(m, got, bits)
     assert np.abs(got - want).max() < AMP_TOL
+
+
+@pytest.mark.parametrize('seed', range(6))
+def test_native_tile_search_matches_its_python_statement(seed):
+    """qfb_plan_count_executed / qfb_plan_refine_tile (csrc/qfb_planhost.cu) against tests/plan_emulator.py on
+    operator lists of benchmark circuits and on random masks, with and without forbidden / kept bits and caps."""
+    import ctypes
+    from quantumflow_b200 import _lib
+    lib = _lib.load()
+    rnd = random.Random(seed)
+    nbits = rnd.choice([10, 14, 20, 33])
+    if seed % 2 == 0:
+        specs = workloads.wb_gate_list(nbits, 6, seed)
+        items = planner.classify_all(bitops_of(specs, nbits))
+        recs = [(op.mixmask, op.diagmask, float(op.cost), int(op.plan_bytes)) for op in items]
+    else:
+        recs = []
+        for _ in range(300):
+            mm = sum(1 << b for b in rnd.sample(range(nbits), rnd.choice([0, 1, 1, 2])))
+            dd = sum(1 << b for b in rnd.sample(range(nbits), rnd.choice([0, 0, 1, 2]))) & ~mm
+            recs.append((mm, dd, rnd.choice([0.0, 0.25, 1.0]), rnd.choice([32, 160, 576])))
+    n = len(recs)
+    mix = np.array([r[0] for r in recs], dtype=np.uint64)
+    diag = np.array([r[1] for r in recs], dtype=np.uint64)
+    cost = np.array([r[2] for r in recs], dtype=np.float64)
+    nbytes = np.array([r[3] for r in recs], dtype=np.uint32)
+    for trial in range(8):
+        low = 7
+        fmask = sum(1 << b for b in rnd.sample(range(3, nbits), rnd.choice([0, 0, 2]))) if nbits > 6 else 0
+        free = [b for b in range(3, nbits) if not (fmask >> b) & 1]
+        tile_bits = rnd.sample(free, min(len(free), rnd.choice([3, 5, 9])))
+        tmask = low | sum(1 << b for b in tile_bits)
+        keep = low | (sum(1 << b for b in tile_bits[:2]) if trial % 3 == 0 else 0)
+        max_cost = rnd.choice([6.0, 28.0, 1e9])
+        room = rnd.choice([2000, 40000])
+        got = ctypes.c_int(-1)
+        assert lib.qfb_plan_count_executed(mix.ctypes.data, diag.ctypes.data, cost.ctypes.data, nbytes.ctypes.data, n,
+                                           tmask, fmask, max_cost, room, ctypes.byref(got)) == 0
+        assert got.value == E.count_executed(recs, tmask, fmask, max_cost, room)
+        out, cnt = ctypes.c_uint64(0), ctypes.c_int(-1)
+        assert lib.qfb_plan_refine_tile(mix.ctypes.data, diag.ctypes.data, cost.ctypes.data, nbytes.ctypes.data, n,
+                                        nbits, tmask, fmask, keep, max_cost, room, 6, ctypes.byref(out),
+                                        ctypes.byref(cnt)) == 0
+        want_mask, want_cnt = E.refine_tile(recs, nbits, tmask, fmask, keep, max_cost, room, 6)
+        assert (out.value, cnt.value) == (want_mask, want_cnt)
+        assert bin(out.value).count('1') == bin(tmask).count('1') and out.value & keep == keep
+        assert not out.value & fmask
