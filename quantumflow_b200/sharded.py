@@ -78,7 +78,7 @@ class Remap:
 # A sweep with less than this fraction of the work of the plan's average sweep so far is "thin": when operators
 # are waiting for a remap, the stage ends instead of spending a whole pass over the shard on it. schedule() tries
 # these thresholds and keeps the cheapest schedule under the cost model below.
-THIN_CANDIDATES = (0.0, 0.25, 0.4)
+THIN_CANDIDATES = (0.0, 0.25, 0.4, 0.6)
 # cost of a remap that exchanges k rank bits, in units of the part of a sweep that a saved sweep actually saves
 # (its memory pass, ~7 ms at 30 qubits per GPU; the operators' own time moves to other sweeps): the remap moves
 # the fraction 1 - 2^-k of the shard each way at ~0.5 TB/s = 15 / 24 / 28 ms for k = 1 / 2 / 3
