@@ -129,3 +129,39 @@ def test_basic_blocks_split_at_control_flow_and_unknown_gates():
     assert prog.qubits == [0, 1]
     with pytest.raises(RuntimeError):
         qf.Call('NOSUCH', [], [0]).gate({})
+
+
+def test_classical_operations_inside_a_circuit():
+    # reference tests/test_stdops.py:71-108 (test_logics), :111-130, :155-187; the circuit runs on a stand-in
+    # state: classical elements never touch the amplitudes
+    FakeState.qubit_nb = 0
+    c = qf.Register('c')
+    circ = qf.Circuit([qf.Move(c[0], 0), qf.Move(c[1], 1), qf.And(c[0], c[1])])
+    ket = circ.run(FakeState())
+    assert ket.memory == {c[0]: 0, c[1]: 1}
+    circ += qf.Not(c[1])
+    circ += qf.And(c[0], c[1])
+    ket = circ.run(ket)
+    assert ket.memory == {c[0]: 0, c[1]: 0}
+    ket = qf.Circuit([qf.Move(c[0], 0), qf.Move(c[1], 1), qf.Ior(c[0], c[1])]).run(FakeState())
+    assert ket.memory == {c[0]: 1, c[1]: 1}
+    circ = qf.Circuit([qf.Move(c[0], 1), qf.Move(c[1], 1), qf.Xor(c[0], c[1])])
+    ket = circ.run(FakeState())
+    assert ket.memory == {c[0]: 0, c[1]: 1}
+    circ += qf.Exchange(c[0], c[1])
+    ket = circ.run(ket)
+    assert ket.memory == {c[0]: 1, c[1]: 0}
+    circ += qf.Move(c[0], c[1])
+    ket = circ.run(ket)
+    assert ket.memory == {c[0]: 0, c[1]: 0}
+    assert str(qf.Neg(c[10])) == 'NEG c[10]'
+    ro = qf.Register()
+    assert run(qf.Program([qf.Move(ro[0], 1), qf.Move(ro[1], 2), qf.Add(ro[0], ro[1]), qf.Add(ro[0], 4)])).memory[ro[0]] == 7
+    assert run(qf.Program([qf.Move(ro[0], 1), qf.Move(ro[1], 2), qf.Mul(ro[0], ro[1]), qf.Mul(ro[0], 4)])).memory[ro[0]] == 8
+    assert run(qf.Program([qf.Move(ro[0], 4), qf.Move(ro[1], 1), qf.Div(ro[0], ro[1]), qf.Div(ro[0], 2)])).memory[ro[0]] == 2
+    assert run(qf.Program([qf.Move(ro[0], 1), qf.Move(ro[1], 2), qf.Sub(ro[0], ro[1]), qf.Sub(ro[0], 4),
+                           qf.Neg(ro[0])])).memory[ro[0]] == 5
+    ket = run(qf.Program([qf.Move(ro[0], 1), qf.Move(ro[1], 2), qf.EQ(('eq', 0), ro[0], ro[1]),
+                          qf.GT(('gt', 0), ro[0], ro[1]), qf.GE(('ge', 0), ro[0], ro[1]),
+                          qf.LT(('lt', 0), ro[0], ro[1]), qf.LE(('le', 0), ro[0], ro[1])]))
+    assert [ket.memory[(k, 0)] for k in ('eq', 'gt', 'ge', 'lt', 'le')] == [0, 0, 0, 1, 1]
