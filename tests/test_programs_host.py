@@ -165,3 +165,21 @@ def test_classical_operations_inside_a_circuit():
                           qf.GT(('gt', 0), ro[0], ro[1]), qf.GE(('ge', 0), ro[0], ro[1]),
                           qf.LT(('lt', 0), ro[0], ro[1]), qf.LE(('le', 0), ro[0], ro[1])]))
     assert [ket.memory[(k, 0)] for k in ('eq', 'gt', 'ge', 'lt', 'le')] == [0, 0, 0, 1, 1]
+
+
+def test_registers_and_addresses():
+    # reference tests/test_cbits.py:12-53
+    ro = qf.Register()
+    assert ro.name == 'ro' and str(ro) == "Register('ro', 'BIT')"
+    assert qf.Register() == qf.Register('ro') and qf.Register('a') < qf.Register('b')
+    assert qf.Register('a') != qf.Register('b') and qf.Register('c') != 'foobar'
+    with pytest.raises(TypeError):
+        qf.Register('c') < 'foobar'
+    c0 = qf.Register('c')[0]
+    assert c0.register.name == 'c' and c0.key == 0 and c0.register.dtype == 'BIT'
+    assert str(c0) == 'c[0]' and repr(c0) == "Register('c', 'BIT')[0]"
+    assert {c0: '1234'}[qf.Register('c')[0]] == '1234'
+    assert qf.Register('c')[0] != qf.Register('c')[1] and qf.Register('d')[0] != qf.Register('c')[0]
+    assert qf.Register('c')[0] != 'foobar' and qf.Register('c')[0] < qf.Register('c')[1]
+    with pytest.raises(TypeError):
+        qf.Register('c')[0] < 'foobar'
