@@ -133,6 +133,13 @@ int qfb_plan_count_executed(const uint64_t *mix, const uint64_t *diag, const dou
 int qfb_plan_refine_tile(const uint64_t *mix, const uint64_t *diag, const double *cost, const uint32_t *bytes,
                          int nops, int nbits, uint64_t tmask, uint64_t fmask, uint64_t keep, double max_cost,
                          int64_t room, int passes, uint64_t *tmask_out, int *count_out);
+/* refine_tile_lookahead: the same exchanges scored by the operators this sweep executes PLUS the operators the
+ * best next sweep (greedy tile of low_bits + first-come bits up to tile_bits, then refine_tile) executes on
+ * what is left; up to `lookahead_passes` passes, inner searches with `passes`. */
+int qfb_plan_refine_tile_lookahead(const uint64_t *mix, const uint64_t *diag, const double *cost,
+                                   const uint32_t *bytes, int nops, int nbits, int low_bits, int tile_bits,
+                                   uint64_t tmask, uint64_t fmask, uint64_t keep, double max_cost, int64_t room,
+                                   int passes, int lookahead_passes, uint64_t *tmask_out, int *score_out);
 
 /* ---- autograd bridge ---- */
 /* grad_mat[r][c] = sum_groups g[base|off[r]] * conj(psi[base|off[c]])   (k <= 3), written to out_dev (4^k c128) */

@@ -88,6 +88,8 @@ DEFAULT_TRIES = 24
 REFINE_MIN_OPS = 24
 REFINE_PASSES = 6
 REFINE_TRIES = 24
+LOOKAHEAD_PASSES = 3
+LOOKAHEAD_TRIES = 1        # partitions formed with the two-sweep look-ahead (kept only when they need fewer sweeps)
 REFINE_WINDOW = 512      # operators of the list that the search scores (a sweep rarely executes more)
 # pivot on the (0,0) entry unless it is this much smaller than the largest entry
 PIVOT_RATIO = 1e-3
@@ -426,7 +428,8 @@ class Planner:
 
     # ---- pass 2: sweeps ---------------------------------------------------------------------------
     def _form_sweep(self, ops: List[POp], rnd=None, p_new: float = 1.0, forbidden: frozenset = frozenset(),
-                    required: frozenset = frozenset()) -> Tuple[List[POp], List[POp], List[int]]:
+                    required: frozenset = frozenset(), lookahead: bool = False
+                    ) -> Tuple[List[POp], List[POp], List[int]]:
         """One sweep: the operators that join it, the deferred rest, the tile bits.
 
         A greedy walk in program order picks the tile (an operator joins while its mixing bits fit; with `rnd`, an
@@ -480,7 +483,7 @@ class Planner:
         tmask = sum(1 << b for b in tile)
         fmask = sum(1 << b for b in forbidden)
         if self.refine and len(ops) >= REFINE_MIN_OPS:
-            tmask = self._refine_tile(ops, tmask, fmask, sum(1 << b for b in required))
+            tmask = self._refine_tile(ops, tmask, fmask, sum(1 << b for b in required), lookahead)
         chosen, deferred = self._closure(ops, tmask, fmask)
         return chosen, deferred, [b for b in range(self.nbits) if (tmask >> b) & 1]
 
@@ -540,7 +543,7 @@ class Planner:
                 chosen.append(op)
         return chosen, deferred
 
-    def _refine_tile(self, ops: List[POp], tmask: int, fmask: int, keep: int = 0) -> int:
+    def _refine_tile(self, ops: List[POp], tmask: int, fmask: int, keep: int = 0, lookahead: bool = False) -> int:
         """Local search over the tile of one sweep: exchange one tile bit (never the low bits, which every sweep
         needs for whole 128-byte lines, nor the bits of `keep`) for one outside bit while that raises the number
         of operators the sweep executes; the best exchange of a pass is taken, up to REFINE_PASSES passes. The
@@ -563,6 +566,13 @@ class Planner:
         _lib.check(lib.qfb_plan_refine_tile(mix.ctypes.data, diag.ctypes.data, cost.ctypes.data, nbytes.ctypes.data, n,
                                             self.nbits, tmask, fmask, ((1 << self.L) - 1) | keep,
                                             float(self.max_cost), room, REFINE_PASSES, ctypes.byref(out), None))
+        if lookahead:
+            # second search, from the tile found above: score = operators of this sweep + operators of the best
+            # sweep that can follow it (what a tile leaves behind matters as much as what it takes)
+            _lib.check(lib.qfb_plan_refine_tile_lookahead(
+                mix.ctypes.data, diag.ctypes.data, cost.ctypes.data, nbytes.ctypes.data, n, self.nbits, self.L,
+                self.M, int(out.value), fmask, ((1 << self.L) - 1) | keep, float(self.max_cost), room,
+                REFINE_PASSES, LOOKAHEAD_PASSES, ctypes.byref(out), None))
         return int(out.value)
 
     # ---- pass 3: rounds ---------------------------------------------------------------------------
@@ -822,6 +832,19 @@ class Planner:
                 best = parts
             if len(pops) < 64:
                 break
+        if self.refine and len(pops) >= 64:
+            # the two-sweep look-ahead costs ~100x the plain search: a few partitions only, and only a partition
+            # with FEWER sweeps replaces the one found above
+            for trial in range(LOOKAHEAD_TRIES):
+                rnd = random.Random(1000 + trial) if trial else None
+                parts = []
+                remaining = list(pops)
+                while remaining and len(parts) < len(best) - 1:
+                    chosen, remaining, tile = self._form_sweep(remaining, rnd, 1.0 if trial == 0 else 0.9,
+                                                               lookahead=True)
+                    parts.append((chosen, tile))
+                if not remaining:
+                    best = parts
         return best
 
     def plan(self, pops: List[POp], parts: List[Tuple[List[POp], List[int]]] = None) -> List[SweepPlan]:

@@ -100,9 +100,12 @@ def schedule(nbits: int, p: int, bitops: Sequence[BitOp], tile_bits: int = None,
                                            SWEEP_TRIES_CANDIDATES[0])
         return steps, phys_of
     best = None
-    for tries in SWEEP_TRIES_CANDIDATES:
-        for cand in THIN_CANDIDATES:
-            steps, phys_of, nsweeps = _schedule_once(nbits, p, bitops, tile_bits, low_bits, max_cost, cand, tries)
+    # (randomised variants per sweep, two-sweep look-ahead of the tile search): the look-ahead runs without
+    # variants - picking the variant that does most work NOW is exactly what it is there to avoid
+    for tries, lookahead in [(t, False) for t in SWEEP_TRIES_CANDIDATES] + [(0, True)]:
+        for cand in (THIN_CANDIDATES[1:3] if lookahead else THIN_CANDIDATES):     # the look-ahead is the slow one
+            steps, phys_of, nsweeps = _schedule_once(nbits, p, bitops, tile_bits, low_bits, max_cost, cand, tries,
+                                                     lookahead)
             cost = nsweeps + sum(REMAP_COST_PER_FRACTION * (1.0 - 0.5 ** len(st.rank_positions))
                                  for st in steps if isinstance(st, Remap))
             if best is None or cost < best[0] - 1e-9:
@@ -111,7 +114,8 @@ def schedule(nbits: int, p: int, bitops: Sequence[BitOp], tile_bits: int = None,
 
 
 def _schedule_once(nbits: int, p: int, bitops: Sequence[BitOp], tile_bits: int, low_bits: int, max_cost: float,
-                   thin_fraction: float, sweep_tries: int = 3) -> Tuple[List[object], List[int], int]:
+                   thin_fraction: float, sweep_tries: int = 3, lookahead: bool = False
+                   ) -> Tuple[List[object], List[int], int]:
     """Split `bitops` (logical bit positions, program order) into Stage / Remap steps.
 
     Sweeps (passes over the shard) are formed one at a time from the operators that are executable under the
@@ -166,7 +170,7 @@ def _schedule_once(nbits: int, p: int, bitops: Sequence[BitOp], tile_bits: int, 
         for trial in range(1 + (min(pl.tries, sweep_tries if pl.refine else 8) if len(head) >= 64 else 0)):
             rnd = random.Random(trial) if trial else None
             chosen, rest, tile = pl._form_sweep(head, rnd, 1.0 if trial == 0 else 0.9, forbidden=glob,
-                                                required=required)
+                                                required=required, lookahead=lookahead and trial == 0)
             if best is None or sum(o.cost for o in chosen) > sum(o.cost for o in best[0]):
                 best = (chosen, rest, tile)
         waiting = any(op.kind == 'G' and (op.mixset & glob) for op in best[1]) or \

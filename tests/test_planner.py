@@ -356,3 +356,17 @@ def test_native_tile_search_matches_its_python_statement(seed):
         assert (out.value, cnt.value) == (want_mask, want_cnt)
         assert bin(out.value).count('1') == bin(tmask).count('1') and out.value & keep == keep
         assert not out.value & fmask
+        # two-sweep look-ahead: whatever it scores, the result is a tile of the same size that keeps `keep`, avoids
+        # `fmask`, and does not score worse than its start; same answer when asked twice
+        m = bin(tmask).count('1')
+        la, sc0, sc1 = ctypes.c_uint64(0), ctypes.c_int(-1), ctypes.c_int(-1)
+        args = (mix.ctypes.data, diag.ctypes.data, cost.ctypes.data, nbytes.ctypes.data, n, nbits, 3, m)
+        assert lib.qfb_plan_refine_tile_lookahead(*args, tmask, fmask, keep, max_cost, room, 6, 0, ctypes.byref(la),
+                                                  ctypes.byref(sc0)) == 0 and la.value == tmask
+        assert lib.qfb_plan_refine_tile_lookahead(*args, tmask, fmask, keep, max_cost, room, 6, 3, ctypes.byref(la),
+                                                  ctypes.byref(sc1)) == 0
+        assert bin(la.value).count('1') == m and la.value & keep == keep and not la.value & fmask
+        assert sc1.value >= sc0.value >= E.count_executed(recs, tmask, fmask, max_cost, room)
+        again = ctypes.c_uint64(0)
+        assert lib.qfb_plan_refine_tile_lookahead(*args, tmask, fmask, keep, max_cost, room, 6, 3,
+                                                  ctypes.byref(again), None) == 0 and again.value == la.value
