@@ -86,6 +86,7 @@ DEFAULT_MAX_COST = 28.0
 DEFAULT_TRIES = 24
 # tile refinement (Planner._refine_tile): operator lists shorter than this are not worth the search
 REFINE_MIN_OPS = 24
+SWEEP_WINDOW = 4096         # operators of the list that one sweep may draw from
 REFINE_PASSES = 6
 REFINE_TRIES = 24
 LOOKAHEAD_PASSES = 3
@@ -443,6 +444,11 @@ class Planner:
         tile = set(range(self.L)) | set(required)
         if len(tile) > self.M:
             raise ValueError('required bits do not fit a tile')
+        # Only the next SWEEP_WINDOW operators are candidates (everything behind them is deferred as it stands:
+        # deferring is always legal, and a sweep holds a few hundred operators at most). Keeps the planner linear
+        # in the length of the circuit instead of quadratic.
+        beyond = ops[SWEEP_WINDOW:]
+        ops = ops[:SWEEP_WINDOW] if beyond else ops
         cost = 0.0
         nbytes = SWEEP_HEADER_BYTES + 8 * ROUND_HEADER_BYTES
         def_any: set = set()
@@ -485,7 +491,7 @@ class Planner:
         if self.refine and len(ops) >= REFINE_MIN_OPS:
             tmask = self._refine_tile(ops, tmask, fmask, sum(1 << b for b in required), lookahead)
         chosen, deferred = self._closure(ops, tmask, fmask)
-        return chosen, deferred, [b for b in range(self.nbits) if (tmask >> b) & 1]
+        return chosen, deferred + beyond, [b for b in range(self.nbits) if (tmask >> b) & 1]
 
     def _closure(self, ops: List[POp], tmask: int, fmask: int, count_only: bool = False):
         """The operators a sweep over the tile `tmask` executes, in program order: an operator joins when it mixes
