@@ -493,10 +493,10 @@ class Planner:
         chosen, deferred = self._closure(ops, tmask, fmask)
         return chosen, deferred + beyond, [b for b in range(self.nbits) if (tmask >> b) & 1]
 
-    def _closure(self, ops: List[POp], tmask: int, fmask: int, count_only: bool = False):
-        """The operators a sweep over the tile `tmask` executes, in program order: an operator joins when it mixes
-        tile bits only, commutes with everything deferred before it and fits the sweep's work and size caps.
-        Returns (chosen, deferred), or with count_only the number of chosen operators that touch a bit."""
+    def _closure(self, ops: List[POp], tmask: int, fmask: int) -> Tuple[List[POp], List[POp]]:
+        """(chosen, deferred): the operators a sweep over the tile `tmask` executes, in program order, and the rest.
+        An operator joins when it mixes tile bits only (never a bit of `fmask`), commutes with everything deferred
+        before it and fits the sweep's work and size caps."""
         allow = tmask & ~fmask
         every = (1 << self.nbits) - 1
         max_cost = self.max_cost
@@ -506,15 +506,13 @@ class Planner:
         da = dm = 0                    # bits touched / mixed by the deferred operators so far
         cost = 0.0
         nbytes = SWEEP_HEADER_BYTES + 8 * ROUND_HEADER_BYTES
-        count = 0
         started = False
         blocked = len(ops)             # from here on every bit is blocked: only bit-free scalar factors still pass
         for i, op in enumerate(ops):
             mm = op.mixmask
             dd = op.diagmask
             if (mm & da) or (dd & dm) or (mm & ~allow) or (started and cost + op.cost > max_cost):
-                if not count_only:
-                    deferred.append(op)
+                deferred.append(op)
                 da |= mm | dd
                 dm |= mm
                 if dm & every == every:
@@ -523,18 +521,12 @@ class Planner:
                 continue
             if nbytes + op.plan_bytes > cap:
                 # the sweep record is full: everything from here on waits for the next sweep
-                if not count_only:
-                    deferred.extend(ops[i:])
+                deferred.extend(ops[i:])
                 break
             started = True
             cost += op.cost
             nbytes += op.plan_bytes
-            if mm | dd:
-                count += 1
-            if not count_only:
-                chosen.append(op)
-        if count_only:
-            return count
+            chosen.append(op)
         for i in range(blocked, len(ops)):
             op = ops[i]
             if (op.mixmask | op.diagmask) or (started and cost + op.cost > max_cost):
