@@ -274,6 +274,9 @@ def main():
         segments = runner.local_segments()
     plan_seconds = time.perf_counter() - t_plan0
     stats = planner.plan_stats(segments)
+    # fingerprint of the executed plan (all sweep records): lets a reader check which plan a number belongs to
+    import hashlib
+    stats['plan_sha256'] = hashlib.sha256(b''.join(s.blob for s in segments if s.blob)).hexdigest()[:16]
 
     dev = torch.device('cuda', local_rank)
     state = torch.zeros(1 << nlocal, dtype=torch.complex128, device=dev)
