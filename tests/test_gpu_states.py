@@ -266,3 +266,24 @@ def test_spectral_density_measures():
     assert np.isclose(info0, qf.mutual_info(local, qubits0=[0, 1]))
     bell = qf.Circuit([qf.H(0), qf.CNOT(0, 1)]).run(qf.zero_state(2)).asdensity()
     assert np.isclose(qf.mutual_info(bell, [0], [1], base=2), 2.0)
+
+
+def test_state_dump_round_trip(tmp_path):
+    # chunked on-disk dump of device-resident states (host-side layout tests: test_stateio_host.py)
+    from quantumflow_b200 import stateio
+    np.random.seed(21)
+    ket = qf.random_state(12)
+    path = str(tmp_path / 'ket.qfb')
+    stateio.save_state(ket, path, chunk_bytes=16 * 1000)            # 5 chunks through the pinned staging buffer
+    assert stateio.read_header(path) == (12, 1, 1 << 12)
+    assert np.array_equal(np.fromfile(path, dtype=np.complex128, offset=stateio.HEADER_BYTES),
+                          qf.asarray(ket.tensor).reshape(-1))
+    back = stateio.load_state(path, chunk_bytes=16 * 700)
+    assert back.tensor.is_cuda and back.qubits == ket.qubits
+    assert np.array_equal(qf.asarray(back.tensor), qf.asarray(ket.tensor))
+    rho = qf.random_density(4)
+    path = str(tmp_path / 'rho.qfb')
+    stateio.save_state(rho, path)
+    back = stateio.load_state(path, qubits=rho.qubits)
+    assert isinstance(back, qf.Density) and back.qubit_nb == 4
+    assert np.array_equal(qf.asarray(back.tensor), qf.asarray(rho.tensor))
