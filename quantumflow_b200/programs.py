@@ -216,78 +216,79 @@ class DefCircuit(Program):
         return '\n'.join(lines) + '\n'
 
 
-class Wait(Instruction):
+class _NoEffect(Instruction):
+    """Instructions the interpreter records but does not act upon."""
+
+    def run(self, ket: State) -> State:
+        return ket
+
+
+class Wait(_NoEffect):
     """Hand control back to the caller (recorded, no effect)."""
 
-    def run(self, ket: State) -> State:
-        return ket
 
-
-class Nop(Instruction):
-    def run(self, ket: State) -> State:
-        return ket
+class Nop(_NoEffect):
+    """No operation."""
 
 
 class Halt(Instruction):
+    """Stop the program: the program counter becomes HALTED."""
+
     def run(self, ket: State) -> State:
         return ket.update({PC: HALTED})
 
 
-class Load(Instruction):
-    def __init__(self, target: Addr, left: str, right: Addr) -> None:
+class _MemoryTransfer(Instruction):
+    """LOAD / STORE between classical memory regions: printable, not executable (as in the reference)."""
+
+    def __init__(self, target, left, right) -> None:
         self.target, self.left, self.right = target, left, right
 
     def quil(self) -> str:
-        return '{} {} {} {}'.format(self.name, self.target, self.left, self.right)
+        return ' '.join(str(part) for part in (self.name, self.target, self.left, self.right))
 
     def run(self, ket: State) -> State:
         raise NotImplementedError()
 
 
-class Store(Instruction):
-    def __init__(self, target: str, left: Addr, right: Union[int, Addr]) -> None:
-        self.target, self.left, self.right = target, left, right
+class Load(_MemoryTransfer):
+    """LOAD target left right"""
+
+
+class Store(_MemoryTransfer):
+    """STORE target left right"""
+
+
+class _Targeted(Instruction):
+    """Instructions that name a label."""
+
+    def __init__(self, target: str) -> None:
+        self.target = target
 
     def quil(self) -> str:
-        return '{} {} {} {}'.format(self.name, self.target, self.left, self.right)
-
-    def run(self, ket: State) -> State:
-        raise NotImplementedError()
+        return '{} @{}'.format(self.name, self.target)
 
 
-class Label(Instruction):
+class Label(_Targeted, _NoEffect):
     """A jump target."""
 
-    def __init__(self, target: str) -> None:
-        self.target = target
 
-    def quil(self) -> str:
-        return '{} @{}'.format(self.name, self.target)
-
-    def run(self, ket: State) -> State:
-        return ket
-
-
-class Jump(Instruction):
-    def __init__(self, target: str) -> None:
-        self.target = target
-
-    def quil(self) -> str:
-        return '{} @{}'.format(self.name, self.target)
+class Jump(_Targeted):
+    """Unconditional jump."""
 
     def run(self, ket: State) -> State:
         return ket.update({PC: ket.memory[TARGETS][self.target]})
 
 
-class _ConditionalJump(Instruction):
+class _ConditionalJump(_Targeted):
     _jump_when: bool = True
 
     def __init__(self, target: str, condition: Addr) -> None:
-        self.target = target
+        super().__init__(target)
         self.condition = condition
 
     def quil(self) -> str:
-        return '{} @{} {}'.format(self.name, self.target, self.condition)
+        return '{} {}'.format(super().quil(), self.condition)
 
     def run(self, ket: State) -> State:
         memory = ket.memory
@@ -314,7 +315,7 @@ class JumpUnless(_ConditionalJump):
         return 'JUMP-UNLESS'
 
 
-class Pragma(Instruction):
+class Pragma(_NoEffect):
     """PRAGMA <command> <arg>* "<freeform>"? -- recorded, no effect."""
 
     def __init__(self, command: str, args: List[float] = None, freeform: str = None) -> None:
@@ -327,9 +328,6 @@ class Pragma(Instruction):
         if self.freeform:
             parts.append('"{}"'.format(self.freeform))
         return ' '.join(parts)
-
-    def run(self, ket: State) -> State:
-        return ket
 
 
 class Include(Instruction):
