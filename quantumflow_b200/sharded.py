@@ -235,7 +235,8 @@ def _schedule_once(nbits: int, p: int, bitops: Sequence[BitOp], tile_bits: int, 
             # The permutation is free when the stage's last sweep stores it, i.e. when that sweep's tile holds the
             # moved positions; otherwise it costs a bare pass over the shard (planner.attach_permutation). The
             # sweep was formed before the remap was known, so form it again from the same operator list with the
-            # moved bits as required tile bits, and keep the new one if it does at least the same work.
+            # moved bits as required tile bits, and keep the new one if it does at least REFORM_MIN_WORK of the old
+            # one's work (the operators it drops stay in the list and run in the next stage).
             moved = frozenset(logical_at[j] for j in range(nl) if perm[j] != j)
             last = stage_parts[-1] if stage_parts else None
             hosted = last is not None and last[1] is not None and all(phys_of[b] in last[1] for b in moved)
