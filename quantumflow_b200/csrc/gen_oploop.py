@@ -228,6 +228,20 @@ def gen(has_g2):
             neg(e) if is_neg else cmul(e)
             body(skip + ':')
         body('bra TAIL;')
+    # ---- diagonal table over the register index: a[e] *= table[e] where e & reg_cmask != 0 (flag: every e) ----
+    handler(H['CPH_TABLE'], 'L_TB')
+    emit_rc(body)
+    body('ld.shared.u8 t32, [cur+7];', 'setp.ne.u32 poff, t32, 0;', 'selp.u32 rc, %d, rc, poff;' % (NE - 1))
+    for e in range(NE):
+        skip = body.label('SKIPT')
+        if e == 0:
+            body('@!poff bra.uni %s;' % skip)
+        else:
+            body('and.b32 t32, rc, %d;' % e, 'setp.eq.u32 pe, t32, 0;', '@pe bra.uni %s;' % skip)
+        body('ld.shared.v2.f64 {c0, c1}, [cur+%d];' % (16 + 16 * e), 'neg.f64 n1, c1;')
+        cmul(e)
+        body(skip + ':')
+    emit_long_tail(body, 16 + 16 * NE)
     # ---- dense 2-bit operator on register bits j0 > j1 (operator index = bit(j0) << 1 | bit(j1)) ----
     if has_g2:
         for pi, (j0, j1) in enumerate(PAIRS):

@@ -34,7 +34,7 @@
 #include <stdint.h>
 
 #define QFB_PLAN_MAGIC 0x50424651u /* "QFBP" */
-#define QFB_PLAN_VERSION 12u
+#define QFB_PLAN_VERSION 13u
 #define QFB_PLAN_REG_BITS 5
 #define QFB_PLAN_MAX_TILE_BITS 13
 #define QFB_PLAN_MIN_TILE_BITS 6
@@ -123,6 +123,11 @@ typedef struct {
  *   QFB_H_CPH_NEG1 + j    the same with factor -1 (sign flip, no FP64 work)
  *   QFB_H_CPH_NEG2 + pair factor -1 on two register bits (CZ between register bits)
  *   QFB_H_CPH_REGM / NEGM any other register mask (reg_cmask)
+ *   QFB_H_CPH_TABLE       diagonal table over the register index (reg_cmask = the register bits it depends on):
+ *                         amplitude e is multiplied by table[e] where e & reg_cmask != 0 -- all phase terms of a
+ *                         round whose bits are register bits, multiplied together by the planner (4 FP64 per
+ *                         touched amplitude for the whole group). With flag = 1 the table also carries the plan's
+ *                         uniform factor and acts on every amplitude, entry 0 included.
  *   QFB_H_END             terminates the round's op list
  *   QFB_H_G2 + pair       dense 2-bit operator on register bits (j0, j1)
  *   QFB_H_G2X + pair      real "X-shaped" 2-bit operator: non-zeros only at (0,0) (0,3) (3,0) (3,3) and (1,1) (1,2)
@@ -145,14 +150,15 @@ enum {
     QFB_H_END = 58,
     QFB_H_G2 = 59,
     QFB_H_G2X = 69,
-    QFB_H_COUNT = 79
+    QFB_H_CPH_TABLE = 79,
+    QFB_H_COUNT = 80
 };
 
 typedef struct {
     uint32_t handler;
     uint16_t bytes;    /* whole op record including this header (multiple of 16) */
     uint8_t reg_cmask; /* control / phase mask over the register index */
-    uint8_t pad;
+    uint8_t flag;      /* QFB_H_CPH_TABLE: 1 = acts on every amplitude; 0 elsewhere */
     uint64_t idx_cmask; /* control / phase mask over thread-level bits of the FULL index (incl. rank bits) */
 } qfb_op_header; /* 16 bytes */
 
@@ -162,7 +168,7 @@ typedef struct {
  *   G2X: double m[8] = m00 m03 m30 m33 m11 m12 m21 m22 (64 B)
  *   G2 : double m[32]; uint32 nzmask; uint32 pad[3]   row-major 4x4 complex, bit (4r+c) of nzmask set when
  *                      entry (r,c) is non-zero (272 B)
- *   CPH: double factor[2]  (16 B)
+ *   CPH: double factor[2]  (16 B); CPH_TABLE: double table[2^R][2]  (512 B)
  *   END: none
  */
 #endif

@@ -270,7 +270,7 @@ struct PlanHandle {
 // register-bit pairs (j0 > j1) in handler order
 static const int J0[10] = {1, 2, 2, 3, 3, 3, 4, 4, 4, 4}, J1[10] = {0, 0, 1, 0, 1, 2, 0, 1, 2, 3};
 constexpr int NPAIRS = R * (R - 1) / 2;
-static_assert(R == 5 && QFB_H_CPH_NEG2 + NPAIRS == QFB_H_CPH_REGM && QFB_H_G2 + NPAIRS == QFB_H_G2X && QFB_H_G2X + NPAIRS == QFB_H_COUNT,
+static_assert(R == 5 && QFB_H_CPH_NEG2 + NPAIRS == QFB_H_CPH_REGM && QFB_H_G2 + NPAIRS == QFB_H_G2X && QFB_H_G2X + NPAIRS == QFB_H_CPH_TABLE,
               "handler ids in qfb_plan.h assume R = 5");
 
 static uint32_t swz_host(uint32_t idx) {
@@ -415,6 +415,10 @@ static int validate_plan(const uint8_t *p, size_t nbytes, std::vector<SweepInfo>
                     QFB_CHECK_ARG(bytes == 32 && rcm == ((1 << J0[pi]) | (1 << J1[pi])), "plan: bad 2-bit CPH op");
                 } else if (hd == QFB_H_CPH_REGM || hd == QFB_H_CPH_NEGM) {
                     QFB_CHECK_ARG(bytes == 32 && rcm > 0 && rcm < NE, "plan: bad CPH op");
+                } else if (hd == QFB_H_CPH_TABLE) {
+                    QFB_CHECK_ARG(bytes == 16 + 16 * NE && oh.idx_cmask == 0 && rcm < NE && oh.flag <= 1 &&
+                                      (rcm != 0 || oh.flag == 1),
+                                  "plan: bad diagonal table op");
                 } else if (hd >= QFB_H_G2 && hd < QFB_H_G2 + NPAIRS) {
                     const int j0 = J0[hd - QFB_H_G2], j1 = J1[hd - QFB_H_G2];
                     QFB_CHECK_ARG(rh.has_g2 == 1 && bytes == 16 + 272 && !((rcm >> j0) & 1) && !((rcm >> j1) & 1) &&

@@ -32,7 +32,7 @@ import numpy as np
 from . import classify
 
 PLAN_MAGIC = 0x50424651
-PLAN_VERSION = 12
+PLAN_VERSION = 13
 REG_BITS = 5
 MAX_TILE_BITS = 13
 MIN_TILE_BITS = 6
@@ -41,16 +41,16 @@ MAX_SWEEP_BYTES = 40 * 1024
 MAX_DIAG_BITS = 5
 # handler ids (csrc/qfb_plan.h)
 (H_G1_GENERAL, H_G1_SUMDIFF, H_G1_LU_R, H_G1_LU_I, H_G1C_GENERAL, H_G1C_SWAPX, H_CPH_SCALAR, H_CPH_REG1,
- H_CPH_RSC1, H_CPH_NEG1, H_CPH_NEG2, H_CPH_REGM, H_CPH_NEGM, H_END, H_G2, H_G2X) = \
-    0, 5, 10, 15, 20, 25, 30, 31, 36, 41, 46, 56, 57, 58, 59, 69
+ H_CPH_RSC1, H_CPH_NEG1, H_CPH_NEG2, H_CPH_REGM, H_CPH_NEGM, H_END, H_G2, H_G2X, H_CPH_TABLE) = \
+    0, 5, 10, 15, 20, 25, 30, 31, 36, 41, 46, 56, 57, 58, 59, 69, 79
 G2_PAIRS = [(j0, j1) for j0 in range(REG_BITS) for j1 in range(j0)]
 SWEEP_FLAG_G2, SWEEP_FLAG_STORE_SYNC, SWEEP_FLAG_STORE_PERM = 1, 2, 4
 
 
-def _op_record(handler: int, reg_cmask: int, idx_cmask: int, payload: bytes = b'') -> bytes:
+def _op_record(handler: int, reg_cmask: int, idx_cmask: int, payload: bytes = b'', flag: int = 0) -> bytes:
     size = 16 + len(payload)
     assert size % 16 == 0 and size < 65536
-    return struct.pack('<IHBBQ', handler, size, reg_cmask, 0, idx_cmask) + payload
+    return struct.pack('<IHBBQ', handler, size, reg_cmask, flag, idx_cmask) + payload
 
 
 def is_scalar_term(record: bytes) -> bool:
@@ -99,10 +99,11 @@ PIVOT_RATIO = 1e-3
 class POp:
     """A classified operator: kind 'G' (mixing) or 'P' (phase term)."""
     __slots__ = ('kind', 'mix', 'ctrl', 'dbits', 'mat', 'cost', 'mixset', 'diagset', 'anyset', 'gate_index', 'enc',
-                 'mixmask', 'diagmask', 'plan_bytes')
+                 'mixmask', 'diagmask', 'plan_bytes', 'terms')
 
-    def __init__(self, kind, mix=(), ctrl=(), dbits=(), mat=None, cost=1.0, gate_index=-1, enc=None):
+    def __init__(self, kind, mix=(), ctrl=(), dbits=(), mat=None, cost=1.0, gate_index=-1, enc=None, terms=None):
         self.enc = enc          # (kind, payload, scalar) chosen by absorb_scales for an uncontrolled 1-bit operator
+        self.terms = terms      # kind 'T' (diagonal table over register bits): [(bits, factor)], see _form_tables
         self.kind = kind
         self.mix = tuple(int(b) for b in mix)
         self.ctrl = tuple(int(b) for b in ctrl)
@@ -119,7 +120,7 @@ class POp:
         # upper bound of the operator's records in a sweep: a flipped control can split an operator in two, a
         # flipped phase term of k bits into 2^k (absorb_frame)
         self.plan_bytes = 2 * (16 + 64) if (kind == 'G' and len(self.mix) == 1) else 2 * (16 + 272) if kind == 'G' \
-            else 32 * (1 << len(self.dbits))
+            else (16 + 512) if kind == 'T' else 32 * (1 << len(self.dbits))
 
 
 class Fallback:
@@ -378,6 +379,51 @@ def merge_phase_terms(ops: List[POp]) -> List[POp]:
                 del open_terms[key]
             out.append(op)
     return [op for op in out if not (op.kind == 'P' and op.mat == 1)]
+
+
+def sink_phase_terms(parts: List[Tuple[List[POp], List[int]]]) -> List[Tuple[List[POp], List[int]]]:
+    """Move every phase term forward, across sweeps, to just before the next operator that mixes one of its bits
+    (its anchor). Legal: a phase term commutes with everything that does not mix its bits, and the execution
+    order keeps the program order of operators that share a mixed bit. Why: the anchor's target is a REGISTER bit
+    in the anchor's round, so the term arrives where it costs least -- as an entry of the round's diagonal table
+    (_form_tables) instead of a per-thread scalar pass over all amplitudes (128 FP64 instructions per thread and
+    round) or a phase pass of its own in an earlier sweep. Terms without an anchor (nothing mixes their bits any
+    more) and global phases stay where they are. A sweep whose record would outgrow MAX_SWEEP_BYTES takes no
+    more terms."""
+    flat: List[Tuple[int, POp]] = [(si, op) for si, (chosen, _) in enumerate(parts) for op in chosen]
+    next_mix: Dict[int, int] = {}           # bit -> flat position of the next operator that mixes it
+    anchor_of: Dict[int, int] = {}          # flat position of a phase term -> flat position of its anchor
+    for pos in range(len(flat) - 1, -1, -1):
+        op = flat[pos][1]
+        if op.kind == 'P':
+            hits = [next_mix[b] for b in op.dbits if b in next_mix]
+            if hits:
+                anchor_of[pos] = min(hits)
+        else:
+            for b in op.mix:
+                next_mix[b] = pos
+    room = [MAX_SWEEP_BYTES - 4 * ROUND_HEADER_BYTES - (SWEEP_HEADER_BYTES + 8 * ROUND_HEADER_BYTES) -
+            sum(op.plan_bytes for op in chosen) for chosen, _ in parts]
+    before: Dict[int, List[POp]] = {}       # flat position of an anchor -> the terms that now precede it
+    moved = set()
+    for pos, apos in anchor_of.items():
+        si, op = flat[pos]
+        sa = flat[apos][0]
+        if sa == si or room[sa] < op.plan_bytes:
+            continue
+        room[sa] -= op.plan_bytes
+        room[si] += op.plan_bytes
+        before.setdefault(apos, []).append(op)
+        moved.add(pos)
+    if not moved:
+        return parts
+    out: List[Tuple[List[POp], List[int]]] = [([], tile) for _, tile in parts]
+    for pos, (si, op) in enumerate(flat):
+        if pos in moved:
+            continue
+        out[si][0].extend(before.get(pos, ()))
+        out[si][0].append(op)
+    return out
 
 
 def _conflicts(op: POp, def_any: set, def_mix: set) -> bool:
@@ -657,6 +703,7 @@ class Planner:
             final.append(Round(regs, self._thread_order(regs, edge), chosen))
         sweep.rounds = final
         self._relocate_phase_terms(sweep)
+        self._form_tables(sweep)
 
     def _relocate_phase_terms(self, sweep: SweepPlan) -> None:
         """Move every phase term, inside its commutation window, to the round where it is cheapest."""
@@ -710,12 +757,21 @@ class Planner:
         scalar_rounds = {max(range(nr), key=lambda r: (votes[r], -r))} if terms else set()
         # after[r][i]: terms that run right after G op i of round r (i = -1: at the start of the round)
         after: List[Dict[int, List[POp]]] = [dict() for _ in range(nr)]
+        # a term whose bits are ALL register bits of a round joins that round's diagonal table (_form_tables):
+        # almost free, and the more terms a table collects the better
+        allin = [0] * nr
+        for op, lo, hi in terms:
+            for r in legal_rounds(lo, hi):
+                if op.dbits and bin(reg_mask(op, r)).count('1') == len(op.dbits):
+                    allin[r] += 1
         for op, lo, hi in terms:
             best = None
             for r in legal_rounds(lo, hi):
                 mask = reg_mask(op, r)
                 if mask == 0:
                     cost = 0.05 if r in scalar_rounds else 1.05
+                elif bin(mask).count('1') == len(op.dbits) and allin[r] >= 2:
+                    cost = 0.04 - 0.001 * min(allin[r], 20)
                 else:
                     touched = (1 << REG_BITS) >> bin(mask).count('1')
                     cost = (0.1 if op.mat == -1 else 0.5) * touched / 8.0
@@ -737,6 +793,74 @@ class Planner:
                 ops.append(g)
                 ops.extend(after[r].get(i, []))
             rd.ops = ops
+
+    def _form_tables(self, sweep: SweepPlan) -> None:
+        """Phase terms whose bits are all register bits of their round are multiplied into diagonal TABLES: one
+        complex multiplication per touched amplitude for the whole group (4 FP64 instructions) instead of one
+        pass per term (a 1-bit term alone touches half the amplitudes). A term may sit anywhere between the last
+        operator before it and the first one after it that mix one of its bits; the fewest table positions that
+        serve all terms of a round are found by stabbing these intervals (latest legal position first). A
+        position that serves a single term keeps the term as it is."""
+        for rd in sweep.rounds:
+            regbits = {sweep.tile[p] for p in rd.regs}
+            ops = rd.ops
+            gidx = [i for i, op in enumerate(ops) if op.kind == 'G']
+            ng = len(gidx)
+            cands = []                 # (hi, lo, position in ops): complex factors
+            signs = []                 # the same for factor -1 terms: sign flips cost no FP64 work on their own
+            seen_g = 0
+            for i, op in enumerate(ops):
+                if op.kind == 'G':
+                    seen_g += 1
+                    continue
+                if op.kind != 'P' or not op.dbits or not all(b in regbits for b in op.dbits):
+                    continue
+                lo = seen_g
+                while lo > 0 and not (ops[gidx[lo - 1]].mixset & op.diagset):
+                    lo -= 1
+                hi = seen_g
+                while hi < ng and not (ops[gidx[hi]].mixset & op.diagset):
+                    hi += 1
+                (signs if op.mat == -1 else cands).append((hi, lo, i))
+            if len(cands) < 2:
+                continue
+            cands.sort()
+            groups: Dict[int, List[int]] = {}      # gap (index of the G operator the table precedes) -> terms
+            covered = set()
+            for hi, lo, i in cands:
+                if i in covered:
+                    continue
+                members = [j for (h2, l2, j) in cands if j not in covered and l2 <= hi <= h2]
+                covered.update(members)
+                groups[hi] = members
+            tables = {gap: members for gap, members in groups.items() if len(members) >= 2}
+            if not tables:
+                continue
+            # a sign flip whose bits the table touches anyway rides along for free
+            for hi, lo, i in signs:
+                for gap, members in tables.items():
+                    if lo <= gap <= hi and set(ops[i].dbits) <= {b for j in members for b in ops[j].dbits}:
+                        members.append(i)
+                        break
+            drop = {i for members in tables.values() for i in members}
+            new_ops: List[POp] = []
+            g = 0
+
+            def emit(gap: int) -> None:
+                members = tables.get(gap)
+                if members:
+                    bits = sorted({b for i in members for b in ops[i].dbits})
+                    new_ops.append(POp('T', dbits=bits, cost=COST['P'], gate_index=ops[members[0]].gate_index,
+                                       terms=[(ops[i].dbits, complex(ops[i].mat)) for i in members]))
+
+            for i, op in enumerate(ops):
+                if op.kind == 'G':
+                    emit(g)
+                    g += 1
+                if i not in drop:
+                    new_ops.append(op)
+            emit(ng)
+            rd.ops = new_ops
 
     # ---- driver -----------------------------------------------------------------------------------
     def attach_permutation(self, sweeps: List[SweepPlan], perm: Sequence[int]) -> None:
@@ -861,6 +985,7 @@ class Planner:
                 if len(set(tile)) != self.M or tile[:self.L] != list(range(self.L)) or tile[-1] >= self.nbits or \
                         any(not op.mixset <= set(tile) for op in chosen):
                     raise ValueError('preset sweep does not fit its tile')
+        parts = [(chosen, tile) for chosen, tile in sink_phase_terms(parts) if chosen]
         for index, (chosen, tile) in enumerate(parts):
             remaining = index + 1 < len(parts)
             ops, store_xor = absorb_frame(chosen, scale)
@@ -969,17 +1094,44 @@ class Planner:
 
         return b''.join(entry(v, 0) for v in range(16)) + b''.join(entry(v, 4) for v in range(32))
 
+    @staticmethod
+    def _emit_table(op: POp, pos_of, reg_of, scalar: complex = 1.0) -> bytes:
+        """Diagonal table over the register index: entry e = product of the factors of the terms whose bits are
+        all set in e. With `scalar` (the plan's uniform factor) every entry is multiplied by it and the record
+        is flagged to act on ALL amplitudes (entry 0 included)."""
+        masks = []
+        for bits, factor in op.terms:
+            mask = 0
+            for b in bits:
+                mask |= 1 << reg_of[pos_of[b]]
+            masks.append((mask, complex(factor)))
+        union = 0
+        for mask, _ in masks:
+            union |= mask
+        entries = np.ones(1 << REG_BITS, dtype=np.complex128)
+        for e in range(1 << REG_BITS):
+            for mask, factor in masks:
+                if (e & mask) == mask:
+                    entries[e] *= factor
+        whole = scalar != 1
+        if whole:
+            entries *= complex(scalar)
+        return _op_record(H_CPH_TABLE, union, 0, entries.tobytes(), flag=int(whole))
+
     def serialise(self, sweeps: List[SweepPlan]) -> bytes:
         body = b''
-        for sweep in sweeps:
+        carry = 1.0 + 0j       # uniform factor (pivots, global phases) of the sweeps so far, applied once
+        for si, sweep in enumerate(sweeps):
             pos_of = {b: j for j, b in enumerate(sweep.tile)}
-            encoded: List[Tuple[Round, List[bytes]]] = []
+            encoded: List[Tuple[Round, List[object]]] = []
             scalar = 1.0 + 0j
             for rd in sweep.rounds:
                 reg_of = {p: i for i, p in enumerate(rd.regs)}
-                blobs: List[bytes] = []
+                blobs: List[object] = []
                 for op in rd.ops:
-                    if op.kind == 'P':
+                    if op.kind == 'T':
+                        blobs.append((op, reg_of))      # encoded below, once the sweep's uniform factor is known
+                    elif op.kind == 'P':
                         if not op.dbits:          # global phase: joins the sweep scalar
                             scalar *= complex(op.mat)
                             continue
@@ -990,11 +1142,28 @@ class Planner:
                             scalar *= pivot
                         blobs.append(blob)
                 encoded.append((rd, blobs))
-            if scalar != 1:
-                # one unconditional per-thread scalar term; put it where a scalar is applied anyway
-                target = next((i for i, (_, bl) in enumerate(encoded) if any(is_scalar_term(b) for b in bl)),
-                              len(encoded) - 1)
-                encoded[target][1].append(self._emit_phase((), scalar, pos_of, {}))
+            # The uniform factor commutes with everything: it rides along from sweep to sweep and is applied once,
+            # by the plan's last sweep (or earlier, when it leaves a range that is safe for the stored amplitudes'
+            # exponents), inside a diagonal table if the sweep has one -- otherwise as a per-thread scalar term.
+            carry *= scalar
+            last = si + 1 == len(sweeps)
+            due = carry != 1 and (last or not 2.0 ** -200 < abs(carry) < 2.0 ** 200)
+            if due:
+                host = next(((i, k) for i, (_, bl) in enumerate(encoded) for k, b in enumerate(bl)
+                             if isinstance(b, tuple)), None)
+                if host is not None:
+                    i, k = host
+                    op, reg_of = encoded[i][1][k]
+                    encoded[i][1][k] = self._emit_table(op, pos_of, reg_of, carry)
+                else:
+                    target = next((i for i, (_, bl) in enumerate(encoded)
+                                   if any(isinstance(b, bytes) and is_scalar_term(b) for b in bl)), len(encoded) - 1)
+                    encoded[target][1].append(self._emit_phase((), carry, pos_of, {}))
+                carry = 1.0 + 0j
+            for _, bl in encoded:
+                for k, b in enumerate(bl):
+                    if isinstance(b, tuple):
+                        bl[k] = self._emit_table(b[0], pos_of, b[1])
             rounds_blob = b''
             nops = 0
             any_g2 = False

@@ -20,14 +20,14 @@ def swz(idx):
 
 G2_PAIRS = [(j0, j1) for j0 in range(R) for j1 in range(j0)]
 (H_G1_GENERAL, H_G1_SUMDIFF, H_G1_ROT_R, H_G1_ROT_I, H_G1C_GENERAL, H_G1C_SWAPX, H_CPH_SCALAR, H_CPH_REG1,
- H_CPH_RSC1, H_CPH_NEG1, H_CPH_NEG2, H_CPH_REGM, H_CPH_NEGM, H_END, H_G2, H_G2X) = \
-    0, 5, 10, 15, 20, 25, 30, 31, 36, 41, 46, 56, 57, 58, 59, 69
+ H_CPH_RSC1, H_CPH_NEG1, H_CPH_NEG2, H_CPH_REGM, H_CPH_NEGM, H_END, H_G2, H_G2X, H_CPH_TABLE) = \
+    0, 5, 10, 15, 20, 25, 30, 31, 36, 41, 46, 56, 57, 58, 59, 69, 79
 SWEEP_HEADER, ROUND_HEADER = 112, 192 + 768
 
 
 def parse(blob: bytes):
     magic, version, nbits, M, rbits, nsweeps, total = struct.unpack_from('<IIIIIIQ', blob, 0)
-    assert magic == 0x50424651 and version == 12 and rbits == R and total == len(blob)
+    assert magic == 0x50424651 and version == 13 and rbits == R and total == len(blob)
     off = 32
     sweeps = []
     for _ in range(nsweeps):
@@ -69,13 +69,20 @@ def parse(blob: bytes):
             ooff = roff + ROUND_HEADER
             ops = []
             for _o in range(rn + 1):
-                handler, obytes, rcm, _p0, icm = struct.unpack_from('<IHBBQ', blob, ooff)
+                handler, obytes, rcm, flag, icm = struct.unpack_from('<IHBBQ', blob, ooff)
                 payload = blob[ooff + 16: ooff + obytes]
                 ooff += obytes
                 if _o == rn:
                     assert handler == H_END and obytes == 16, 'round must end with an END record'
                     break
-                if handler < H_G1C_GENERAL:
+                if handler == H_CPH_TABLE:
+                    # diagonal table over the register index; flag 1 = acts on every amplitude (entry 0 included)
+                    assert obytes == 16 + 16 * NE and icm == 0 and flag in (0, 1) and (rcm != 0 or flag == 1)
+                    typ, kind, j0, j1 = 4, 'table', 0, 0
+                    tbl = np.frombuffer(payload, dtype=np.complex128, count=NE)
+                    if not flag:
+                        assert all(tbl[e] == tbl[e & rcm] for e in range(NE)) and tbl[0] == 1
+                elif handler < H_G1C_GENERAL:
                     assert rcm == 0 and icm == 0
                     kind = ['general', 'sumdiff', 'rot_r', 'rot_i'][handler // R]
                     assert obytes == (80 if kind == 'general' else 32)
@@ -116,7 +123,8 @@ def parse(blob: bytes):
                     assert H_G2 <= handler < H_G2 + len(G2_PAIRS) and obytes == 16 + 272
                     typ, kind = 2, 'dense'
                     j0, j1 = G2_PAIRS[handler - H_G2]
-                ops.append(dict(type=typ, kind=kind, j0=j0, j1=j1, reg_cmask=rcm, idx_cmask=icm, payload=payload))
+                ops.append(dict(type=typ, kind=kind, j0=j0, j1=j1, reg_cmask=rcm, idx_cmask=icm, payload=payload,
+                                flag=flag))
             assert ooff == roff + rbytes
             assert has_g2 == int(any(o['type'] == 2 for o in ops))
             if _r == nrounds:
@@ -272,7 +280,12 @@ def execute(blob: bytes, state: np.ndarray, index_hi: int = 0, check_layout: boo
                     scalar = 1.0 + 0j
                     for op in rd['ops']:
                         on = (tfull & op['idx_cmask']) == op['idx_cmask']
-                        if op['type'] == 3:
+                        if op['type'] == 4:
+                            tbl = np.frombuffer(op['payload'], dtype=np.complex128, count=NE)
+                            for e in range(NE):
+                                if op['flag'] or (e & op['reg_cmask']):
+                                    a[e] = tbl[e] * a[e]
+                        elif op['type'] == 3:
                             assert op['reg_cmask'] != 0 or rd['has_scalar'] == 1
                             scalar = _apply_cph(a, op, on, scalar)
                         elif on:
