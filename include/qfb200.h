@@ -80,6 +80,14 @@ int qfb_plan_validate(const void *plan_host, size_t plan_bytes);
 int qfb_plan_upload(const void *plan_host, size_t plan_bytes, void **handle_out, void *stream);
 int qfb_plan_launch(void *handle, void *state, int nbits, uint64_t index_hi, void *stream);
 int qfb_plan_destroy(void *handle);
+/* Sweep-specialised kernels (csrc/qfb_jit.cu): qfb_plan_upload emits every sweep of the plan as straight-line PTX,
+ * compiles it in-process for sm_100a and loads it (environment: QFB_JIT=0/1, QFB_JIT_MIN_BITS). The two entry
+ * points below are pure host code (no GPU, no driver): the PTX text of one sweep (`needed` = bytes incl. the
+ * terminator, `ncoef` = coefficients in the constant bank), and a compile check of every sweep of a plan
+ * (`log` receives the PTX compiler's register / spill report). */
+int qfb_jit_ptx(const void *plan_host, size_t plan_bytes, int sweep, char *buf, size_t cap, size_t *needed,
+                size_t *ncoef);
+int qfb_jit_check(const void *plan_host, size_t plan_bytes, char *log, size_t cap);
 /* number of kernel launches performed by this library in this process (bench.py's gpu_launches) */
 uint64_t qfb_launch_count(void);
 

@@ -11,8 +11,8 @@ import subprocess
 CSRC = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'csrc')
 LIB_PATH = os.path.join(CSRC, 'libqfb200.so')
 STAMP_PATH = os.path.join(CSRC, '.libqfb200.stamp')
-SOURCES = ['qfb_api.cu', 'qfb_apply.cu', 'qfb_reduce.cu', 'qfb_sweep.cu', 'qfb_planhost.cu']
-HEADERS = ['qfb_common.cuh', 'qfb_plan.h', 'qfb_oploop.inc', os.path.join('..', '..', 'include', 'qfb200.h')]
+SOURCES = ['qfb_api.cu', 'qfb_apply.cu', 'qfb_reduce.cu', 'qfb_sweep.cu', 'qfb_planhost.cu', 'qfb_jit.cu']
+HEADERS = ['qfb_common.cuh', 'qfb_plan.h', 'qfb_jit.h', 'qfb_oploop.inc', os.path.join('..', '..', 'include', 'qfb200.h')]
 
 NVCC_FLAGS = ['-O3', '-std=c++17', '-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo',
               '-Xcompiler', '-fPIC', '-shared']
@@ -46,7 +46,10 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
     if not force and library_is_current():
         return LIB_PATH
     nvcc = _find_nvcc()
-    cmd = [nvcc] + NVCC_FLAGS + (['-Xptxas', '-v'] if verbose else []) + ['-o', LIB_PATH] + SOURCES
+    # the PTX compiler (sweep-specialised kernels, qfb_jit.cu) is linked statically; the driver API is resolved
+    # with dlopen at run time so that the library still loads where libcuda is absent
+    cmd = [nvcc] + NVCC_FLAGS + (['-Xptxas', '-v'] if verbose else []) + ['-o', LIB_PATH] + SOURCES + \
+        ['-lnvptxcompiler_static', '-lpthread', '-ldl']
     proc = subprocess.run(cmd, cwd=CSRC, capture_output=True, text=True)
     if proc.returncode != 0:
         raise RuntimeError('nvcc failed:\n' + proc.stdout + proc.stderr)

@@ -25,6 +25,8 @@ PROTOTYPES = {
     'qfb_plan_upload': (c_int, [c_void_p, c_size_t, POINTER(c_void_p), c_void_p]),
     'qfb_plan_launch': (c_int, [c_void_p, c_void_p, c_int, c_uint64, c_void_p]),
     'qfb_plan_destroy': (c_int, [c_void_p]),
+    'qfb_jit_ptx': (c_int, [c_void_p, c_size_t, c_int, c_char_p, c_size_t, POINTER(c_size_t), POINTER(c_size_t)]),
+    'qfb_jit_check': (c_int, [c_void_p, c_size_t, c_char_p, c_size_t]),
     'qfb_launch_count': (c_uint64, []),
     'qfb_vdot': (c_int, [c_void_p, c_void_p, c_uint64, c_void_p, c_void_p]),
     'qfb_norm2': (c_int, [c_void_p, c_uint64, c_void_p, c_void_p]),

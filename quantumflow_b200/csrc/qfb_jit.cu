@@ -1,0 +1,1009 @@
+// qfb_jit.cu -- sweep-specialised kernels: every sweep of a plan (qfb_plan.h) is emitted as straight-line PTX,
+// compiled in-process for sm_100a (nvPTXCompiler, statically linked) and loaded through the driver API.
+//
+// Why: the interpreter of qfb_sweep.cu pays a dispatch per operator, reads payloads from
+// shared memory and executes every register move; the plan of a sweep is known before the launch, so
+//   * operators become straight-line code that ptxas schedules ACROSS operators (no dispatch, no op headers),
+//   * coefficients are operands from the constant bank (the module's `qfb_coef`, written once per plan) --
+//     the code depends on the STRUCTURE of the sweep only, so one compiled image serves every plan with the
+//     same structure (a parametrised circuit in an optimisation loop compiles once),
+//   * a controlled X between register bits is a renaming of registers at code-generation time: no instruction
+//     (the FP64 pipe is the scarce resource: 1.83 warp instructions per clock and SM, profiles/r2_fp64_peaks.jsonl),
+//   * bit positions are immediates: tile-id deposit, thread-bit deposit and exchange offsets need no tables.
+// The data movement is the interpreter's: coalesced LDG.128 of round 0 (next tile prefetched into L2), XOR-swizzled
+// exchange through shared memory between rounds, coalesced STG.128 (with the pending X flips / bit permutation).
+//
+// Entry points: jit_generate (PTX text + coefficient values of one sweep), jit_compile (PTX -> cubin, no GPU
+// needed: the CPU test-suite compiles every benchmark sweep), JitSweep (loaded module) used by qfb_plan_upload.
+#include <dlfcn.h>
+#include <stdarg.h>
+#include <stdlib.h>
+#include <map>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <vector>
+#include <cuda.h>
+#include <nvPTXCompiler.h>
+#include "qfb_common.cuh"
+#include "qfb_jit.h"
+#include "qfb_plan.h"
+
+namespace qfb {
+
+namespace {
+
+constexpr int R = QFB_PLAN_REG_BITS;
+constexpr int NE = 1 << R;
+const int J0[10] = {1, 2, 2, 3, 3, 3, 4, 4, 4, 4}, J1[10] = {0, 0, 1, 0, 1, 2, 0, 1, 2, 3};
+
+uint32_t swz(uint32_t idx) {
+    const uint32_t x = idx >> 3;
+    return idx ^ ((x ^ (x >> 3) ^ (x >> 6) ^ (x >> 9)) & 7u);
+}
+
+struct Amp {
+    int re, im;   // %fd register numbers
+};
+
+// PTX text builder with virtual-register counters. Registers are single-assignment except inside predicated
+// regions (see Gen::op_*), which update the current registers in place so that both paths meet in one name.
+struct Gen {
+    std::string body;
+    std::vector<double> coef;
+    int nfd = 0, nrd = 0, nr = 0, np = 0, nlabel = 0;
+    int M = 0, nbits = 0, T = 0;
+
+    void e(const char *fmt, ...) {
+        char buf[512];
+        va_list ap;
+        va_start(ap, fmt);
+        vsnprintf(buf, sizeof(buf), fmt, ap);
+        va_end(ap);
+        body += buf;
+        body += '\n';
+    }
+    int fd() { return nfd++; }
+    int rd() { return nrd++; }
+    int r32() { return nr++; }
+    int pr() { return np++; }
+    int label() { return nlabel++; }
+    // a coefficient of the plan: an operand from the module's constant bank (value-independent code)
+    int cst(double v) {
+        const int reg = fd();
+        e("ld.const.f64 %%fd%d, [qfb_coef+%zu];", reg, coef.size() * 8);
+        coef.push_back(v);
+        return reg;
+    }
+};
+
+struct RoundInfo {
+    const qfb_round_header *rh;
+    const uint8_t *ops;       // first op record
+};
+
+// deposit the low bits of the 32-bit register `src` (bit t -> bit pos[t]) into a fresh 64-bit register
+int deposit64(Gen &g, int src32, const int *pos, int n) {
+    const int acc = g.rd();
+    g.e("mov.u64 %%rd%d, 0;", acc);
+    const int wide = g.rd();
+    g.e("cvt.u64.u32 %%rd%d, %%r%d;", wide, src32);
+    int t = 0;
+    while (t < n) {
+        int len = 1;
+        while (t + len < n && pos[t + len] == pos[t] + len) ++len;       // a run of consecutive positions
+        const int tmp = g.rd();
+        g.e("shr.u64 %%rd%d, %%rd%d, %d;", tmp, wide, t);
+        g.e("and.b64 %%rd%d, %%rd%d, %llu;", tmp, tmp, (unsigned long long)((1ull << len) - 1));
+        g.e("shl.b64 %%rd%d, %%rd%d, %d;", tmp, tmp, pos[t]);
+        g.e("or.b64 %%rd%d, %%rd%d, %%rd%d;", acc, acc, tmp);
+        t += len;
+    }
+    return acc;
+}
+
+// the same from a 64-bit source (tile id through the holes)
+int deposit64_from64(Gen &g, int src64, const int *pos, int n) {
+    const int acc = g.rd();
+    g.e("mov.u64 %%rd%d, 0;", acc);
+    int t = 0;
+    while (t < n) {
+        int len = 1;
+        while (t + len < n && pos[t + len] == pos[t] + len) ++len;
+        const int tmp = g.rd();
+        g.e("shr.u64 %%rd%d, %%rd%d, %d;", tmp, src64, t);
+        g.e("and.b64 %%rd%d, %%rd%d, %llu;", tmp, tmp, (unsigned long long)((1ull << len) - 1));
+        g.e("shl.b64 %%rd%d, %%rd%d, %d;", tmp, tmp, pos[t]);
+        g.e("or.b64 %%rd%d, %%rd%d, %%rd%d;", acc, acc, tmp);
+        t += len;
+    }
+    return acc;
+}
+
+// swizzled byte offset of the thread's first amplitude in the exchange buffer: swz(tb) << 4 (32-bit register)
+int thread_stb(Gen &g, int tid32, const uint8_t *thrpos, int nthr) {
+    const int tb = g.r32();
+    g.e("mov.u32 %%r%d, 0;", tb);
+    for (int t = 0; t < nthr; ++t) {
+        const int tmp = g.r32();
+        g.e("shr.u32 %%r%d, %%r%d, %d;", tmp, tid32, t);
+        g.e("and.b32 %%r%d, %%r%d, 1;", tmp, tmp);
+        g.e("shl.b32 %%r%d, %%r%d, %d;", tmp, tmp, (int)thrpos[t]);
+        g.e("or.b32 %%r%d, %%r%d, %%r%d;", tb, tb, tmp);
+    }
+    // f = (x ^ x>>3 ^ x>>6 ^ x>>9) & 7 with x = tb >> 3
+    const int x = g.r32(), f = g.r32(), t1 = g.r32();
+    g.e("shr.u32 %%r%d, %%r%d, 3;", x, tb);
+    g.e("shr.u32 %%r%d, %%r%d, 3;", t1, x);
+    g.e("xor.b32 %%r%d, %%r%d, %%r%d;", f, x, t1);
+    g.e("shr.u32 %%r%d, %%r%d, 6;", t1, x);
+    g.e("xor.b32 %%r%d, %%r%d, %%r%d;", f, f, t1);
+    g.e("shr.u32 %%r%d, %%r%d, 9;", t1, x);
+    g.e("xor.b32 %%r%d, %%r%d, %%r%d;", f, f, t1);
+    g.e("and.b32 %%r%d, %%r%d, 7;", f, f);
+    const int stb = g.r32();
+    g.e("xor.b32 %%r%d, %%r%d, %%r%d;", stb, tb, f);
+    g.e("shl.b32 %%r%d, %%r%d, 4;", stb, stb);
+    return stb;
+}
+
+// exchange-buffer address of register index e for a round: (stb ^ low(e) << 4) + high(e) -- the thread bits and
+// the register bits occupy different tile positions, so only the three swizzled low index bits need an XOR
+struct XchgAddr {
+    int base[8];      // 32-bit registers: smem + (stb ^ (k << 4)), -1 when unused
+    uint32_t low[NE], high[NE];
+};
+
+XchgAddr exchange_addresses(Gen &g, int smem32, int stb32, const uint8_t *regpos) {
+    XchgAddr x;
+    for (int k = 0; k < 8; ++k) x.base[k] = -1;
+    for (int e = 0; e < NE; ++e) {
+        uint32_t rb = 0;
+        for (int i = 0; i < R; ++i)
+            if ((e >> i) & 1) rb |= 1u << regpos[i];
+        const uint32_t s = swz(rb);
+        x.low[e] = s & 7u;
+        x.high[e] = (s & ~7u) << 4;
+    }
+    const int sum = g.r32();
+    g.e("add.u32 %%r%d, %%r%d, %%r%d;", sum, smem32, stb32);      // smem is 128-byte aligned: + == | here
+    for (int e = 0; e < NE; ++e) {
+        const int k = (int)x.low[e];
+        if (x.base[k] < 0) {
+            if (k == 0) {
+                x.base[k] = sum;
+            } else {
+                x.base[k] = g.r32();
+                g.e("xor.b32 %%r%d, %%r%d, %d;", x.base[k], sum, k << 4);
+            }
+        }
+    }
+    return x;
+}
+
+struct OpView {
+    qfb_op_header h;
+    const uint8_t *payload;
+};
+
+double payload_f64(const OpView &op, int i) {
+    double v;
+    memcpy(&v, op.payload + 8 * i, 8);
+    return v;
+}
+
+// ---- operators -------------------------------------------------------------------------------------------
+
+void pairs_of(int j, int p, int &e0, int &e1) {
+    e0 = ((p >> j) << (j + 1)) | (p & ((1 << j) - 1));
+    e1 = e0 | (1 << j);
+}
+
+// predicate "all idx_cmask bits are 1 in the thread's full index"; -1 when the mask is empty
+int thread_predicate(Gen &g, uint64_t cm, int tfull64) {
+    if (cm == 0) return -1;
+    const int t = g.rd(), p = g.pr();
+    g.e("and.b64 %%rd%d, %%rd%d, %llu;", t, tfull64, (unsigned long long)cm);
+    g.e("setp.eq.u64 %%p%d, %%rd%d, %llu;", p, t, (unsigned long long)cm);
+    return p;
+}
+
+// a *= (c + i s) into fresh registers; nc = -s
+void cmul_fresh(Gen &g, Amp &a, int c, int s, int ns) {
+    const int t0 = g.fd(), t1 = g.fd(), re = g.fd(), im = g.fd();
+    g.e("mul.f64 %%fd%d, %%fd%d, %%fd%d;", t0, ns, a.im);
+    g.e("mul.f64 %%fd%d, %%fd%d, %%fd%d;", t1, s, a.re);
+    g.e("fma.rn.f64 %%fd%d, %%fd%d, %%fd%d, %%fd%d;", re, a.re, c, t0);
+    g.e("fma.rn.f64 %%fd%d, %%fd%d, %%fd%d, %%fd%d;", im, a.im, c, t1);
+    a.re = re;
+    a.im = im;
+}
+
+// the same in place (inside a predicated region)
+void cmul_inplace(Gen &g, const Amp &a, int c, int s, int ns) {
+    const int t0 = g.fd(), t1 = g.fd();
+    g.e("mul.f64 %%fd%d, %%fd%d, %%fd%d;", t0, ns, a.im);
+    g.e("mul.f64 %%fd%d, %%fd%d, %%fd%d;", t1, s, a.re);
+    g.e("fma.rn.f64 %%fd%d, %%fd%d, %%fd%d, %%fd%d;", a.re, a.re, c, t0);
+    g.e("fma.rn.f64 %%fd%d, %%fd%d, %%fd%d, %%fd%d;", a.im, a.im, c, t1);
+}
+
+// dense 2x2 on (x, y): the interpreter's arithmetic (16 FP64), results in place when `inplace`
+void general_pair(Gen &g, Amp &x, Amp &y, const int *c, const int *n, bool inplace) {
+    const int t0 = g.fd(), t1 = g.fd(), t2 = g.fd(), t3 = g.fd(), t4 = g.fd(), t5 = g.fd();
+    g.e("mul.f64 %%fd%d, %%fd%d, %%fd%d;", t0, n[3], y.im);
+    g.e("fma.rn.f64 %%fd%d, %%fd%d, %%fd%d, %%fd%d;", t0, c[2], y.re, t0);
+    g.e("mul.f64 %%fd%d, %%fd%d, %%fd%d;", t1, c[3], y.re);
+    g.e("fma.rn.f64 %%fd%d, %%fd%d, %%fd%d, %%fd%d;", t1, c[2], y.im, t1);
+    g.e("mul.f64 %%fd%d, %%fd%d, %%fd%d;", t2, n[5], x.im);
+    g.e("fma.rn.f64 %%fd%d, %%fd%d, %%fd%d, %%fd%d;", t2, c[4], x.re, t2);
+    g.e("mul.f64 %%fd%d, %%fd%d, %%fd%d;", t3, c[5], x.re);
+    g.e("fma.rn.f64 %%fd%d, %%fd%d, %%fd%d, %%fd%d;", t3, c[4], x.im, t3);
+    g.e("fma.rn.f64 %%fd%d, %%fd%d, %%fd%d, %%fd%d;", t4, c[1], x.re, t1);
+    g.e("fma.rn.f64 %%fd%d, %%fd%d, %%fd%d, %%fd%d;", t5, c[7], y.re, t3);
+    Amp nx = x, ny = y;
+    if (!inplace) {
+        nx.re = g.fd();
+        nx.im = g.fd();
+        ny.re = g.fd();
+        ny.im = g.fd();
+    }
+    // order matters for the in-place form: x.re is rewritten before x.im reads the OLD x.re? No: x.im' needs old
+    // x.im and t4 (which already holds m00i * old x.re); x.re' needs old x.re and old x.im -> write x.re' to a
+    // temporary first
+    const int xr = g.fd(), yr = g.fd();
+    g.e("fma.rn.f64 %%fd%d, %%fd%d, %%fd%d, %%fd%d;", xr, x.re, c[0], t0);
+    g.e("fma.rn.f64 %%fd%d, %%fd%d, %%fd%d, %%fd%d;", xr, n[1], x.im, xr);
+    g.e("fma.rn.f64 %%fd%d, %%fd%d, %%fd%d, %%fd%d;", nx.im, x.im, c[0], t4);
+    g.e("fma.rn.f64 %%fd%d, %%fd%d, %%fd%d, %%fd%d;", yr, y.re, c[6], t2);
+    g.e("fma.rn.f64 %%fd%d, %%fd%d, %%fd%d, %%fd%d;", yr, n[7], y.im, yr);
+    g.e("fma.rn.f64 %%fd%d, %%fd%d, %%fd%d, %%fd%d;", ny.im, y.im, c[6], t5);
+    g.e("mov.f64 %%fd%d, %%fd%d;", nx.re, xr);
+    g.e("mov.f64 %%fd%d, %%fd%d;", ny.re, yr);
+    x = nx;
+    y = ny;
+}
+
+struct RoundState {
+    Amp a[NE];
+    int tfull;       // 64-bit register: rank bits | tile bits | thread bits of the first amplitude
+    int phr, phi;    // running per-thread scalar (has_scalar rounds)
+    bool scalar_live;
+};
+
+void load_matrix(Gen &g, const OpView &op, int *c, int *n) {
+    for (int i = 0; i < 8; ++i) c[i] = g.cst(payload_f64(op, i));
+    for (int i = 1; i < 8; i += 2) n[i] = g.cst(-payload_f64(op, i));
+}
+
+int emit_op(Gen &g, RoundState &st, const OpView &op, std::string &err) {
+    const int hd = (int)op.h.handler;
+    const int rcm = op.h.reg_cmask;
+    const uint64_t icm = op.h.idx_cmask;
+    if (hd >= QFB_H_G1_GENERAL && hd < QFB_H_G1C_GENERAL) {
+        const int kind = hd / R, j = hd % R;
+        if (kind == 0) {
+            int c[8], n[8];
+            load_matrix(g, op, c, n);
+            for (int p = 0; p < NE / 2; ++p) {
+                int e0, e1;
+                pairs_of(j, p, e0, e1);
+                general_pair(g, st.a[e0], st.a[e1], c, n, false);
+            }
+        } else if (kind == 1) {          // SUMDIFF: x' = x + r0 y ; y' = x' + (r1 - r0) y
+            const double r0 = payload_f64(op, 0), r1 = payload_f64(op, 1);
+            const int c0 = g.cst(r0), c2 = g.cst(r1 - r0);
+            for (int p = 0; p < NE / 2; ++p) {
+                int e0, e1;
+                pairs_of(j, p, e0, e1);
+                Amp &x = st.a[e0], &y = st.a[e1];
+                const int xr = g.fd(), xi = g.fd(), yr = g.fd(), yi = g.fd();
+                g.e("fma.rn.f64 %%fd%d, %%fd%d, %%fd%d, %%fd%d;", xr, c0, y.re, x.re);
+                g.e("fma.rn.f64 %%fd%d, %%fd%d, %%fd%d, %%fd%d;", xi, c0, y.im, x.im);
+                g.e("fma.rn.f64 %%fd%d, %%fd%d, %%fd%d, %%fd%d;", yr, y.re, c2, xr);
+                g.e("fma.rn.f64 %%fd%d, %%fd%d, %%fd%d, %%fd%d;", yi, y.im, c2, xi);
+                x.re = xr; x.im = xi; y.re = yr; y.im = yi;
+            }
+        } else if (kind == 2) {          // LU_R: x += a y ; y += b x
+            const int ca = g.cst(payload_f64(op, 0)), cb = g.cst(payload_f64(op, 1));
+            for (int p = 0; p < NE / 2; ++p) {
+                int e0, e1;
+                pairs_of(j, p, e0, e1);
+                Amp &x = st.a[e0], &y = st.a[e1];
+                const int xr = g.fd(), xi = g.fd(), yr = g.fd(), yi = g.fd();
+                g.e("fma.rn.f64 %%fd%d, %%fd%d, %%fd%d, %%fd%d;", xr, ca, y.re, x.re);
+                g.e("fma.rn.f64 %%fd%d, %%fd%d, %%fd%d, %%fd%d;", xi, ca, y.im, x.im);
+                g.e("fma.rn.f64 %%fd%d, %%fd%d, %%fd%d, %%fd%d;", yr, cb, xr, y.re);
+                g.e("fma.rn.f64 %%fd%d, %%fd%d, %%fd%d, %%fd%d;", yi, cb, xi, y.im);
+                x.re = xr; x.im = xi; y.re = yr; y.im = yi;
+            }
+        } else {                         // LU_I: x += i a y ; y += i b x
+            const double a = payload_f64(op, 0), b = payload_f64(op, 1);
+            const int ca = g.cst(a), cb = g.cst(b), na = g.cst(-a), nb = g.cst(-b);
+            for (int p = 0; p < NE / 2; ++p) {
+                int e0, e1;
+                pairs_of(j, p, e0, e1);
+                Amp &x = st.a[e0], &y = st.a[e1];
+                const int xr = g.fd(), xi = g.fd(), yr = g.fd(), yi = g.fd();
+                g.e("fma.rn.f64 %%fd%d, %%fd%d, %%fd%d, %%fd%d;", xr, na, y.im, x.re);
+                g.e("fma.rn.f64 %%fd%d, %%fd%d, %%fd%d, %%fd%d;", xi, ca, y.re, x.im);
+                g.e("fma.rn.f64 %%fd%d, %%fd%d, %%fd%d, %%fd%d;", yr, nb, xi, y.re);
+                g.e("fma.rn.f64 %%fd%d, %%fd%d, %%fd%d, %%fd%d;", yi, cb, xr, y.im);
+                x.re = xr; x.im = xi; y.re = yr; y.im = yi;
+            }
+        }
+        return QFB_OK;
+    }
+    if (hd >= QFB_H_G1C_GENERAL && hd < QFB_H_G1C_SWAPX) {
+        const int j = hd - QFB_H_G1C_GENERAL;
+        const int p = thread_predicate(g, icm, st.tfull);
+        int c[8], n[8];
+        load_matrix(g, op, c, n);
+        const int skip = g.label();
+        if (p >= 0) g.e("@!%%p%d bra L%d;", p, skip);
+        for (int q = 0; q < NE / 2; ++q) {
+            int e0, e1;
+            pairs_of(j, q, e0, e1);
+            if ((e0 & rcm) != rcm) continue;
+            general_pair(g, st.a[e0], st.a[e1], c, n, p >= 0);
+        }
+        if (p >= 0) g.e("L%d:", skip);
+        return QFB_OK;
+    }
+    if (hd >= QFB_H_G1C_SWAPX && hd < QFB_H_G1C_SWAPX + R) {
+        const int j = hd - QFB_H_G1C_SWAPX;
+        const int p = thread_predicate(g, icm, st.tfull);
+        for (int q = 0; q < NE / 2; ++q) {
+            int e0, e1;
+            pairs_of(j, q, e0, e1);
+            if ((e0 & rcm) != rcm) continue;
+            if (p < 0) {
+                std::swap(st.a[e0], st.a[e1]);            // controls in registers only: a renaming, no instruction
+            } else {
+                Amp &x = st.a[e0], &y = st.a[e1];
+                const int xr = g.fd(), xi = g.fd(), yr = g.fd(), yi = g.fd();
+                g.e("selp.f64 %%fd%d, %%fd%d, %%fd%d, %%p%d;", xr, y.re, x.re, p);
+                g.e("selp.f64 %%fd%d, %%fd%d, %%fd%d, %%p%d;", xi, y.im, x.im, p);
+                g.e("selp.f64 %%fd%d, %%fd%d, %%fd%d, %%p%d;", yr, x.re, y.re, p);
+                g.e("selp.f64 %%fd%d, %%fd%d, %%fd%d, %%p%d;", yi, x.im, y.im, p);
+                x.re = xr; x.im = xi; y.re = yr; y.im = yi;
+            }
+        }
+        return QFB_OK;
+    }
+    if (hd == QFB_H_CPH_SCALAR) {
+        // ph *= (p ? factor : 1)
+        const int fr = g.cst(payload_f64(op, 0)), fi = g.cst(payload_f64(op, 1));
+        int sr = fr, si = fi;
+        const int p = thread_predicate(g, icm, st.tfull);
+        if (p >= 0) {
+            sr = g.fd();
+            si = g.fd();
+            g.e("selp.f64 %%fd%d, %%fd%d, 0d3FF0000000000000, %%p%d;", sr, fr, p);
+            g.e("selp.f64 %%fd%d, %%fd%d, 0d0000000000000000, %%p%d;", si, fi, p);
+        }
+        if (!st.scalar_live) {
+            st.phr = sr;
+            st.phi = si;
+            st.scalar_live = true;
+        } else {
+            const int t0 = g.fd(), t1 = g.fd(), nr = g.fd(), ni = g.fd(), nsi = g.fd();
+            g.e("neg.f64 %%fd%d, %%fd%d;", nsi, si);
+            g.e("mul.f64 %%fd%d, %%fd%d, %%fd%d;", t0, nsi, st.phi);
+            g.e("mul.f64 %%fd%d, %%fd%d, %%fd%d;", t1, si, st.phr);
+            g.e("fma.rn.f64 %%fd%d, %%fd%d, %%fd%d, %%fd%d;", nr, sr, st.phr, t0);
+            g.e("fma.rn.f64 %%fd%d, %%fd%d, %%fd%d, %%fd%d;", ni, sr, st.phi, t1);
+            st.phr = nr;
+            st.phi = ni;
+        }
+        return QFB_OK;
+    }
+    if ((hd >= QFB_H_CPH_REG1 && hd < QFB_H_CPH_NEG1) || hd == QFB_H_CPH_REGM) {
+        const bool real_scale = hd >= QFB_H_CPH_RSC1 && hd < QFB_H_CPH_NEG1;
+        const double fr = payload_f64(op, 0), fi = payload_f64(op, 1);
+        const int c = g.cst(fr);
+        const int s = real_scale ? -1 : g.cst(fi), ns = real_scale ? -1 : g.cst(-fi);
+        const int p = thread_predicate(g, icm, st.tfull);
+        const int skip = g.label();
+        if (p >= 0) g.e("@!%%p%d bra L%d;", p, skip);
+        for (int e = 0; e < NE; ++e) {
+            if ((e & rcm) != rcm) continue;
+            if (real_scale) {
+                if (p >= 0) {
+                    g.e("mul.f64 %%fd%d, %%fd%d, %%fd%d;", st.a[e].re, st.a[e].re, c);
+                    g.e("mul.f64 %%fd%d, %%fd%d, %%fd%d;", st.a[e].im, st.a[e].im, c);
+                } else {
+                    const int re = g.fd(), im = g.fd();
+                    g.e("mul.f64 %%fd%d, %%fd%d, %%fd%d;", re, st.a[e].re, c);
+                    g.e("mul.f64 %%fd%d, %%fd%d, %%fd%d;", im, st.a[e].im, c);
+                    st.a[e].re = re;
+                    st.a[e].im = im;
+                }
+            } else if (p >= 0) {
+                cmul_inplace(g, st.a[e], c, s, ns);
+            } else {
+                cmul_fresh(g, st.a[e], c, s, ns);
+            }
+        }
+        if (p >= 0) g.e("L%d:", skip);
+        return QFB_OK;
+    }
+    if ((hd >= QFB_H_CPH_NEG1 && hd < QFB_H_CPH_REGM) || hd == QFB_H_CPH_NEGM) {
+        const int p = thread_predicate(g, icm, st.tfull);
+        for (int e = 0; e < NE; ++e) {
+            if ((e & rcm) != rcm) continue;
+            if (p >= 0) {
+                // sign bit of the high word, predicated: one integer-pipe instruction per component
+                g.e("@%%p%d xor.b64 %%fd%d, %%fd%d, 0x8000000000000000;", p, st.a[e].re, st.a[e].re);
+                g.e("@%%p%d xor.b64 %%fd%d, %%fd%d, 0x8000000000000000;", p, st.a[e].im, st.a[e].im);
+            } else {
+                const int re = g.fd(), im = g.fd();
+                g.e("neg.f64 %%fd%d, %%fd%d;", re, st.a[e].re);        // folds into the consumer's operand
+                g.e("neg.f64 %%fd%d, %%fd%d;", im, st.a[e].im);
+                st.a[e].re = re;
+                st.a[e].im = im;
+            }
+        }
+        return QFB_OK;
+    }
+    if (hd == QFB_H_CPH_TABLE) {
+        const bool whole = op.h.flag != 0;
+        for (int e = 0; e < NE; ++e) {
+            if (!whole && (e & rcm) == 0) continue;
+            const double fr = payload_f64(op, 2 * e), fi = payload_f64(op, 2 * e + 1);
+            const int c = g.cst(fr), s = g.cst(fi), ns = g.cst(-fi);
+            cmul_fresh(g, st.a[e], c, s, ns);
+        }
+        return QFB_OK;
+    }
+    if (hd >= QFB_H_G2 && hd < QFB_H_G2 + 10) {
+        const int j0 = J0[hd - QFB_H_G2], j1 = J1[hd - QFB_H_G2];
+        uint32_t nz;
+        memcpy(&nz, op.payload + 256, 4);
+        const int p = thread_predicate(g, icm, st.tfull);
+        int c[32], n[32];
+        for (int i = 0; i < 16; ++i) {
+            c[2 * i] = c[2 * i + 1] = n[2 * i + 1] = -1;
+            if (!((nz >> i) & 1)) continue;
+            c[2 * i] = g.cst(payload_f64(op, 2 * i));
+            c[2 * i + 1] = g.cst(payload_f64(op, 2 * i + 1));
+            n[2 * i + 1] = g.cst(-payload_f64(op, 2 * i + 1));
+        }
+        const int skip = g.label();
+        if (p >= 0) g.e("@!%%p%d bra L%d;", p, skip);
+        int others[R], no = 0;
+        for (int b = 0; b < R; ++b)
+            if (b != j0 && b != j1) others[no++] = b;
+        for (int q = 0; q < (1 << no); ++q) {
+            int eb = 0;
+            for (int i = 0; i < no; ++i) eb |= ((q >> i) & 1) << others[i];
+            if ((eb & rcm) != rcm) continue;
+            const int ids[4] = {eb, eb | (1 << j1), eb | (1 << j0), eb | (1 << j0) | (1 << j1)};
+            int ore[4], oim[4];
+            for (int r = 0; r < 4; ++r) {
+                ore[r] = g.fd();
+                oim[r] = g.fd();
+                bool first = true;
+                for (int cc = 0; cc < 4; ++cc) {
+                    const int i = 4 * r + cc;
+                    if (!((nz >> i) & 1)) continue;
+                    const Amp &in = st.a[ids[cc]];
+                    if (first) {
+                        g.e("mul.f64 %%fd%d, %%fd%d, %%fd%d;", ore[r], c[2 * i], in.re);
+                        g.e("mul.f64 %%fd%d, %%fd%d, %%fd%d;", oim[r], c[2 * i], in.im);
+                        first = false;
+                    } else {
+                        g.e("fma.rn.f64 %%fd%d, %%fd%d, %%fd%d, %%fd%d;", ore[r], c[2 * i], in.re, ore[r]);
+                        g.e("fma.rn.f64 %%fd%d, %%fd%d, %%fd%d, %%fd%d;", oim[r], c[2 * i], in.im, oim[r]);
+                    }
+                    g.e("fma.rn.f64 %%fd%d, %%fd%d, %%fd%d, %%fd%d;", ore[r], n[2 * i + 1], in.im, ore[r]);
+                    g.e("fma.rn.f64 %%fd%d, %%fd%d, %%fd%d, %%fd%d;", oim[r], c[2 * i + 1], in.re, oim[r]);
+                }
+                if (first) {
+                    g.e("mov.f64 %%fd%d, 0d0000000000000000;", ore[r]);
+                    g.e("mov.f64 %%fd%d, 0d0000000000000000;", oim[r]);
+                }
+            }
+            for (int r = 0; r < 4; ++r) {
+                if (p >= 0) {
+                    g.e("mov.f64 %%fd%d, %%fd%d;", st.a[ids[r]].re, ore[r]);
+                    g.e("mov.f64 %%fd%d, %%fd%d;", st.a[ids[r]].im, oim[r]);
+                } else {
+                    st.a[ids[r]].re = ore[r];
+                    st.a[ids[r]].im = oim[r];
+                }
+            }
+        }
+        if (p >= 0) g.e("L%d:", skip);
+        return QFB_OK;
+    }
+    if (hd >= QFB_H_G2X && hd < QFB_H_G2X + 10) {
+        const int j0 = J0[hd - QFB_H_G2X], j1 = J1[hd - QFB_H_G2X];
+        const int p = thread_predicate(g, icm, st.tfull);
+        int c[8];
+        for (int i = 0; i < 8; ++i) c[i] = g.cst(payload_f64(op, i));
+        const int skip = g.label();
+        if (p >= 0) g.e("@!%%p%d bra L%d;", p, skip);
+        int others[R], no = 0;
+        for (int b = 0; b < R; ++b)
+            if (b != j0 && b != j1) others[no++] = b;
+        for (int q = 0; q < (1 << no); ++q) {
+            int eb = 0;
+            for (int i = 0; i < no; ++i) eb |= ((q >> i) & 1) << others[i];
+            if ((eb & rcm) != rcm) continue;
+            const int ids[4] = {eb, eb | (1 << j1), eb | (1 << j0), eb | (1 << j0) | (1 << j1)};
+            const int pq[2][3] = {{ids[0], ids[3], 0}, {ids[1], ids[2], 4}};
+            for (int w = 0; w < 2; ++w) {
+                Amp &ap = st.a[pq[w][0]], &aq = st.a[pq[w][1]];
+                const int base = pq[w][2];
+                int *comp_p[2] = {&ap.re, &ap.im}, *comp_q[2] = {&aq.re, &aq.im};
+                for (int k = 0; k < 2; ++k) {
+                    const int t0 = g.fd(), t1 = g.fd(), np_ = g.fd(), nq_ = g.fd();
+                    g.e("mul.f64 %%fd%d, %%fd%d, %%fd%d;", t0, c[base + 2], *comp_p[k]);
+                    g.e("mul.f64 %%fd%d, %%fd%d, %%fd%d;", t1, *comp_p[k], c[base]);
+                    g.e("fma.rn.f64 %%fd%d, %%fd%d, %%fd%d, %%fd%d;", np_, c[base + 1], *comp_q[k], t1);
+                    g.e("fma.rn.f64 %%fd%d, %%fd%d, %%fd%d, %%fd%d;", nq_, *comp_q[k], c[base + 3], t0);
+                    if (p >= 0) {
+                        g.e("mov.f64 %%fd%d, %%fd%d;", *comp_p[k], np_);
+                        g.e("mov.f64 %%fd%d, %%fd%d;", *comp_q[k], nq_);
+                    } else {
+                        *comp_p[k] = np_;
+                        *comp_q[k] = nq_;
+                    }
+                }
+            }
+        }
+        if (p >= 0) g.e("L%d:", skip);
+        return QFB_OK;
+    }
+    err = "jit: unknown handler " + std::to_string(hd);
+    return QFB_ERR_UNSUPPORTED;
+}
+
+}  // namespace
+
+// ---- one sweep -> PTX --------------------------------------------------------------------------------------
+
+int jit_generate(const uint8_t *rec, int nbits, int M, JitSource &out, std::string &err) {
+    qfb_sweep_header sh;
+    memcpy(&sh, rec, sizeof(sh));
+    const int nholes = nbits - M, nthr = M - R, T = 1 << nthr;
+    if (nthr < 3 || M > QFB_PLAN_MAX_TILE_BITS) {
+        err = "jit: tile too small";
+        return QFB_ERR_UNSUPPORTED;
+    }
+    const bool store_perm = (sh.flags & QFB_SWEEP_FLAG_STORE_PERM) != 0;
+    const bool store_sync = (sh.flags & QFB_SWEEP_FLAG_STORE_SYNC) != 0;
+    std::vector<RoundInfo> rounds;
+    const uint8_t *rp = rec + sizeof(qfb_sweep_header);
+    for (uint32_t r = 0; r < sh.nrounds + (store_perm ? 1u : 0u); ++r) {
+        const qfb_round_header *rh = reinterpret_cast<const qfb_round_header *>(rp);
+        rounds.push_back(RoundInfo{rh, rp + sizeof(qfb_round_header)});
+        rp += rh->bytes;
+    }
+    const int nrounds = (int)sh.nrounds;
+    const qfb_round_header *store_rh = rounds.back().rh;      // the store record when permuting, else the last round
+    const uint8_t *store_ipos = store_perm ? sh.spos : sh.gpos;
+
+    Gen g;
+    g.M = M;
+    g.nbits = nbits;
+    g.T = T;
+    // ---- prologue (tile independent) ----
+    const int tid = g.r32(), cta = g.r32(), ncta = g.r32(), smem = g.r32();
+    g.e("mov.u32 %%r%d, %%tid.x;", tid);
+    g.e("mov.u32 %%r%d, %%ctaid.x;", cta);
+    g.e("mov.u32 %%r%d, %%nctaid.x;", ncta);
+    g.e("mov.u32 %%r%d, qfb_smem;", smem);
+    const int state = g.rd(), hi = g.rd();
+    g.e("ld.param.u64 %%rd%d, [p_state];", state);
+    g.e("cvta.to.global.u64 %%rd%d, %%rd%d;", state, state);
+    g.e("ld.param.u64 %%rd%d, [p_hi];", hi);
+    // thread-bit images per round: index-bit image (64-bit) and exchange offset (32-bit)
+    std::vector<int> tg(nrounds), stb(nrounds);
+    for (int r = 0; r < nrounds; ++r) {
+        int pos[16];
+        for (int t = 0; t < nthr; ++t) pos[t] = sh.gpos[rounds[r].rh->thrpos[t]];
+        tg[r] = deposit64(g, tid, pos, nthr);
+        stb[r] = thread_stb(g, tid, rounds[r].rh->thrpos, nthr);
+    }
+    int tg_store;
+    {
+        int pos[16];
+        for (int t = 0; t < nthr; ++t) pos[t] = store_ipos[store_rh->thrpos[t]];
+        tg_store = deposit64(g, tid, pos, nthr);
+    }
+    // L2 prefetch of the next tile: the 8 lanes that share the thread's 128-byte lines split its 2^R lines
+    // (lane k takes the register indices whose top three bits are k); koff = byte offset of lane k's first line
+    const qfb_round_header *r0 = rounds[0].rh;
+    const bool lane_lines = sh.gpos[r0->thrpos[0]] == 0 && sh.gpos[r0->thrpos[1]] == 1 && sh.gpos[r0->thrpos[2]] == 2;
+    int64_t step0[R];
+    for (int i = 0; i < R; ++i) step0[i] = (int64_t)16 << sh.gpos[r0->regpos[i]];
+    int koff = -1;
+    if (lane_lines) {
+        const int k = g.r32();
+        g.e("and.b32 %%r%d, %%r%d, 7;", k, tid);
+        koff = g.rd();
+        const int t = g.rd();
+        g.e("mul.wide.u32 %%rd%d, %%r%d, 16;", t, k);
+        g.e("neg.s64 %%rd%d, %%rd%d;", koff, t);
+        for (int i = 0; i < 3; ++i) {
+            const int b = g.r32(), p = g.pr(), sel = g.rd();
+            g.e("and.b32 %%r%d, %%r%d, %d;", b, k, 1 << i);
+            g.e("setp.ne.u32 %%p%d, %%r%d, 0;", p, b);
+            g.e("selp.b64 %%rd%d, %lld, 0, %%p%d;", sel, (long long)step0[R - 3 + i], p);
+            g.e("add.s64 %%rd%d, %%rd%d, %%rd%d;", koff, koff, sel);
+        }
+    }
+    int hole[QFB_PLAN_MAX_HOLES];
+    for (int i = 0; i < nholes; ++i) hole[i] = sh.hole[i];
+    // ---- tile loop: tile = ctaid, ctaid + nctaid, ... ----
+    const int tile = g.rd(), stride = g.rd(), gb = g.rd();
+    g.e("cvt.u64.u32 %%rd%d, %%r%d;", tile, cta);
+    g.e("cvt.u64.u32 %%rd%d, %%r%d;", stride, ncta);
+    const unsigned long long ntiles = 1ull << nholes;
+    {
+        const int p = g.pr();
+        g.e("setp.ge.u64 %%p%d, %%rd%d, %llu;", p, tile, ntiles);
+        g.e("@%%p%d bra L_EXIT;", p);
+    }
+    {
+        const int first = deposit64_from64(g, tile, hole, nholes);
+        g.e("mov.u64 %%rd%d, %%rd%d;", gb, first);
+    }
+    g.e("L_TILE:");
+    // next tile (for the prefetch and for the next iteration)
+    const int tile_next = g.rd(), has_next = g.pr();
+    g.e("add.u64 %%rd%d, %%rd%d, %%rd%d;", tile_next, tile, stride);
+    g.e("setp.lt.u64 %%p%d, %%rd%d, %llu;", has_next, tile_next, ntiles);
+    const int gb_next = deposit64_from64(g, tile_next, hole, nholes);
+    const int higb = g.rd();
+    g.e("or.b64 %%rd%d, %%rd%d, %%rd%d;", higb, hi, gb);
+
+    RoundState st;
+    st.scalar_live = false;
+    st.phr = st.phi = -1;
+    // ---- round 0: coalesced loads straight into registers ----
+    const int base0 = g.rd();
+    {
+        const int idx = g.rd();
+        g.e("or.b64 %%rd%d, %%rd%d, %%rd%d;", idx, gb, tg[0]);
+        g.e("shl.b64 %%rd%d, %%rd%d, 4;", idx, idx);
+        g.e("add.u64 %%rd%d, %%rd%d, %%rd%d;", base0, state, idx);
+    }
+    for (int e = 0; e < NE; ++e) {
+        int64_t off = 0;
+        for (int i = 0; i < R; ++i)
+            if ((e >> i) & 1) off += step0[i];
+        st.a[e].re = g.fd();
+        st.a[e].im = g.fd();
+        const int addr = g.rd();
+        g.e("add.s64 %%rd%d, %%rd%d, %lld;", addr, base0, (long long)off);
+        g.e("ld.global.cs.v2.f64 {%%fd%d, %%fd%d}, [%%rd%d];", st.a[e].re, st.a[e].im, addr);
+    }
+    {
+        // prefetch: delta = 16 * (gb_next - gb)
+        const int skip = g.label();
+        g.e("@!%%p%d bra L%d;", has_next, skip);
+        const int delta = g.rd(), pbase = g.rd();
+        g.e("sub.s64 %%rd%d, %%rd%d, %%rd%d;", delta, gb_next, gb);
+        g.e("shl.b64 %%rd%d, %%rd%d, 4;", delta, delta);
+        g.e("add.s64 %%rd%d, %%rd%d, %%rd%d;", pbase, base0, delta);
+        if (lane_lines) {
+            g.e("add.s64 %%rd%d, %%rd%d, %%rd%d;", pbase, pbase, koff);
+            for (int j = 0; j < (1 << (R - 3)); ++j) {
+                int64_t off = 0;
+                for (int i = 0; i < R - 3; ++i)
+                    if ((j >> i) & 1) off += step0[i];
+                const int q = g.rd();
+                g.e("add.s64 %%rd%d, %%rd%d, %lld;", q, pbase, (long long)off);
+                g.e("prefetch.global.L2 [%%rd%d];", q);
+                g.e("prefetch.global.L2 [%%rd%d+64];", q);
+            }
+        } else {
+            const int m = g.r32(), p = g.pr(), skip2 = g.label();
+            g.e("and.b32 %%r%d, %%r%d, 3;", m, tid);
+            g.e("setp.ne.u32 %%p%d, %%r%d, 0;", p, m);
+            g.e("@%%p%d bra L%d;", p, skip2);
+            for (int e = 0; e < NE; ++e) {
+                int64_t off = 0;
+                for (int i = 0; i < R; ++i)
+                    if ((e >> i) & 1) off += step0[i];
+                const int q = g.rd();
+                g.e("add.s64 %%rd%d, %%rd%d, %lld;", q, pbase, (long long)off);
+                g.e("prefetch.global.L2 [%%rd%d];", q);
+            }
+            g.e("L%d:", skip2);
+        }
+        g.e("L%d:", skip);
+    }
+    // ---- rounds ----
+    for (int r = 0; r < nrounds; ++r) {
+        const qfb_round_header *rh = rounds[r].rh;
+        st.tfull = g.rd();
+        g.e("or.b64 %%rd%d, %%rd%d, %%rd%d;", st.tfull, higb, tg[r]);
+        st.scalar_live = false;
+        const uint8_t *op = rounds[r].ops;
+        for (;;) {
+            OpView v;
+            memcpy(&v.h, op, sizeof(v.h));
+            v.payload = op + sizeof(qfb_op_header);
+            if (v.h.handler == QFB_H_END) break;
+            const int rc = emit_op(g, st, v, err);
+            if (rc != QFB_OK) return rc;
+            op += v.h.bytes;
+        }
+        if (st.scalar_live) {
+            const int ns = g.fd();
+            g.e("neg.f64 %%fd%d, %%fd%d;", ns, st.phi);
+            for (int e = 0; e < NE; ++e) cmul_fresh(g, st.a[e], st.phr, st.phi, ns);
+        }
+        if (r + 1 == nrounds) break;
+        // exchange: this round's assignment out, the next round's in
+        {
+            const XchgAddr x = exchange_addresses(g, smem, stb[r], rh->regpos);
+            for (int e = 0; e < NE; ++e)
+                g.e("st.shared.v2.f64 [%%r%d+%u], {%%fd%d, %%fd%d};", x.base[x.low[e]], x.high[e], st.a[e].re, st.a[e].im);
+        }
+        g.e("bar.sync 0;");
+        {
+            const XchgAddr x = exchange_addresses(g, smem, stb[r + 1], rounds[r + 1].rh->regpos);
+            for (int e = 0; e < NE; ++e) {
+                st.a[e].re = g.fd();
+                st.a[e].im = g.fd();
+                g.e("ld.shared.v2.f64 {%%fd%d, %%fd%d}, [%%r%d+%u];", st.a[e].re, st.a[e].im, x.base[x.low[e]], x.high[e]);
+            }
+        }
+        g.e("bar.sync 0;");
+    }
+    // ---- store: amplitude i goes to address i ^ store_xor; tile bit j is stored at spos[j] ----
+    if (store_sync) g.e("bar.sync 0;");
+    {
+        const int idx = g.rd(), sbase = g.rd();
+        g.e("or.b64 %%rd%d, %%rd%d, %%rd%d;", idx, gb, tg_store);
+        uint64_t regmask = 0;
+        for (int i = 0; i < R; ++i) regmask |= 1ull << store_ipos[store_rh->regpos[i]];
+        const uint64_t fixed_xor = sh.store_xor & ~regmask;
+        if (fixed_xor) g.e("xor.b64 %%rd%d, %%rd%d, %llu;", idx, idx, (unsigned long long)fixed_xor);
+        g.e("shl.b64 %%rd%d, %%rd%d, 4;", idx, idx);
+        g.e("add.u64 %%rd%d, %%rd%d, %%rd%d;", sbase, state, idx);
+        for (int e = 0; e < NE; ++e) {
+            int64_t off = 0;
+            for (int i = 0; i < R; ++i) {
+                const int bit = store_ipos[store_rh->regpos[i]];
+                const int flipped = (int)((sh.store_xor >> bit) & 1ull);
+                if (((e >> i) & 1) ^ flipped) off += (int64_t)16 << bit;
+            }
+            const int addr = g.rd();
+            g.e("add.s64 %%rd%d, %%rd%d, %lld;", addr, sbase, (long long)off);
+            g.e("st.global.cs.v2.f64 [%%rd%d], {%%fd%d, %%fd%d};", addr, st.a[e].re, st.a[e].im);
+        }
+    }
+    // ---- next tile ----
+    g.e("mov.u64 %%rd%d, %%rd%d;", tile, tile_next);
+    g.e("mov.u64 %%rd%d, %%rd%d;", gb, gb_next);
+    g.e("@%%p%d bra L_TILE;", has_next);
+    g.e("L_EXIT:");
+    g.e("ret;");
+
+    const int minb = (M >= 13) ? 1 : (M == 12) ? 3 : (M == 11) ? 6 : 8;
+    const size_t coef_bytes = std::max<size_t>(16, (g.coef.size() * 8 + 15) / 16 * 16);
+    char head[1024];
+    snprintf(head, sizeof(head),
+             ".version 8.7\n.target sm_100a\n.address_size 64\n"
+             ".const .align 16 .b8 qfb_coef[%zu];\n"
+             ".extern .shared .align 128 .b8 qfb_smem[];\n"
+             ".visible .entry qfb_sweep(.param .u64 p_state, .param .u64 p_hi)\n"
+             ".maxntid %d, 1, 1\n.minnctapersm %d\n{\n"
+             ".reg .f64 %%fd<%d>;\n.reg .b64 %%rd<%d>;\n.reg .b32 %%r<%d>;\n.reg .pred %%p<%d>;\n",
+             coef_bytes, T, minb, g.nfd + 1, g.nrd + 1, g.nr + 1, g.np + 1);
+    out.ptx = std::string(head) + g.body + "}\n";
+    out.coef = g.coef;
+    out.coef_bytes = coef_bytes;
+    out.threads = T;
+    out.smem_bytes = (size_t)16 << M;
+    out.nholes = nholes;
+    return QFB_OK;
+}
+
+// ---- PTX -> cubin (no GPU needed) ---------------------------------------------------------------------------
+
+int jit_compile(const std::string &ptx, std::vector<char> &cubin, std::string &log) {
+    nvPTXCompilerHandle c = nullptr;
+    if (nvPTXCompilerCreate(&c, ptx.size(), ptx.c_str()) != NVPTXCOMPILE_SUCCESS) {
+        log = "nvPTXCompilerCreate failed";
+        return QFB_ERR_CUDA;
+    }
+    const char *opts[] = {"--gpu-name=sm_100a", "-O3", "--verbose"};
+    const nvPTXCompileResult res = nvPTXCompilerCompile(c, 3, opts);
+    size_t n = 0;
+    if (res != NVPTXCOMPILE_SUCCESS) {
+        nvPTXCompilerGetErrorLogSize(c, &n);
+        std::vector<char> buf(n + 1, 0);
+        if (n) nvPTXCompilerGetErrorLog(c, buf.data());
+        log = std::string("ptx compilation failed: ") + buf.data();
+        nvPTXCompilerDestroy(&c);
+        return QFB_ERR_CUDA;
+    }
+    nvPTXCompilerGetInfoLogSize(c, &n);
+    if (n) {
+        std::vector<char> buf(n + 1, 0);
+        nvPTXCompilerGetInfoLog(c, buf.data());
+        log = buf.data();
+    }
+    nvPTXCompilerGetCompiledProgramSize(c, &n);
+    cubin.resize(n);
+    nvPTXCompilerGetCompiledProgram(c, cubin.data());
+    nvPTXCompilerDestroy(&c);
+    return QFB_OK;
+}
+
+// ---- compiled-image cache: one image per sweep STRUCTURE (the PTX text holds no coefficient value) ----------
+
+namespace {
+std::mutex g_cache_mutex;
+std::map<std::string, std::shared_ptr<std::vector<char>>> g_cache;
+uint64_t g_cache_hits = 0, g_cache_misses = 0;
+}  // namespace
+
+static int compile_cached(const std::string &ptx, std::shared_ptr<std::vector<char>> &image, std::string &log) {
+    {
+        std::lock_guard<std::mutex> lock(g_cache_mutex);
+        auto it = g_cache.find(ptx);
+        if (it != g_cache.end()) {
+            image = it->second;
+            ++g_cache_hits;
+            return QFB_OK;
+        }
+    }
+    auto cubin = std::make_shared<std::vector<char>>();
+    const int rc = jit_compile(ptx, *cubin, log);
+    if (rc != QFB_OK) return rc;
+    std::lock_guard<std::mutex> lock(g_cache_mutex);
+    ++g_cache_misses;
+    image = g_cache.emplace(ptx, cubin).first->second;
+    return QFB_OK;
+}
+
+void jit_cache_stats(uint64_t *hits, uint64_t *misses) {
+    std::lock_guard<std::mutex> lock(g_cache_mutex);
+    if (hits) *hits = g_cache_hits;
+    if (misses) *misses = g_cache_misses;
+}
+
+// ---- driver API (resolved at run time: the library must load on a machine without libcuda) -------------------
+
+namespace {
+struct Driver {
+    CUresult (*ModuleLoadData)(CUmodule *, const void *) = nullptr;
+    CUresult (*ModuleUnload)(CUmodule) = nullptr;
+    CUresult (*ModuleGetFunction)(CUfunction *, CUmodule, const char *) = nullptr;
+    CUresult (*ModuleGetGlobal)(CUdeviceptr *, size_t *, CUmodule, const char *) = nullptr;
+    CUresult (*MemcpyHtoD)(CUdeviceptr, const void *, size_t) = nullptr;
+    CUresult (*FuncSetAttribute)(CUfunction, CUfunction_attribute, int) = nullptr;
+    CUresult (*OccupancyMaxActiveBlocksPerMultiprocessor)(int *, CUfunction, int, size_t) = nullptr;
+    CUresult (*LaunchKernel)(CUfunction, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, CUstream,
+                             void **, void **) = nullptr;
+    CUresult (*GetErrorString)(CUresult, const char **) = nullptr;
+    bool ok = false;
+};
+
+const Driver &driver() {
+    static Driver d = [] {
+        Driver x;
+        void *h = dlopen("libcuda.so.1", RTLD_NOW | RTLD_GLOBAL);
+        if (!h) return x;
+#define QFB_SYM(field, name) *(void **)(&x.field) = dlsym(h, name)
+        QFB_SYM(ModuleLoadData, "cuModuleLoadData");
+        QFB_SYM(ModuleUnload, "cuModuleUnload");
+        QFB_SYM(ModuleGetFunction, "cuModuleGetFunction");
+        QFB_SYM(ModuleGetGlobal, "cuModuleGetGlobal_v2");
+        QFB_SYM(MemcpyHtoD, "cuMemcpyHtoD_v2");
+        QFB_SYM(FuncSetAttribute, "cuFuncSetAttribute");
+        QFB_SYM(OccupancyMaxActiveBlocksPerMultiprocessor, "cuOccupancyMaxActiveBlocksPerMultiprocessor");
+        QFB_SYM(LaunchKernel, "cuLaunchKernel");
+        QFB_SYM(GetErrorString, "cuGetErrorString");
+#undef QFB_SYM
+        x.ok = x.ModuleLoadData && x.ModuleUnload && x.ModuleGetFunction && x.ModuleGetGlobal && x.MemcpyHtoD &&
+               x.FuncSetAttribute && x.OccupancyMaxActiveBlocksPerMultiprocessor && x.LaunchKernel;
+        return x;
+    }();
+    return d;
+}
+
+const char *cu_error(CUresult r) {
+    const char *s = nullptr;
+    if (driver().GetErrorString) driver().GetErrorString(r, &s);
+    return s ? s : "unknown driver error";
+}
+}  // namespace
+
+#define QFB_CU(call)                                                                          \
+    do {                                                                                      \
+        CUresult r__ = (call);                                                                \
+        if (r__ != CUDA_SUCCESS) {                                                            \
+            set_error("%s failed at %s:%d: %s", #call, __FILE__, __LINE__, cu_error(r__));    \
+            return QFB_ERR_CUDA;                                                              \
+        }                                                                                     \
+    } while (0)
+
+struct JitSweep {
+    CUmodule module = nullptr;
+    CUfunction func = nullptr;
+    int threads = 0, grid = 0;
+    size_t smem = 0;
+};
+
+void jit_destroy(JitSweep *s) {
+    if (!s) return;
+    if (s->module && driver().ok) driver().ModuleUnload(s->module);
+    delete s;
+}
+
+// Generate + compile every sweep of a validated plan (parallel over host threads), then load the images into the
+// current context and write the coefficients. `offsets` = byte offset of every sweep record in the plan.
+int jit_build_plan(const uint8_t *plan, const std::vector<size_t> &offsets, int nbits, int M,
+                   std::vector<JitSweep *> &out) {
+    const Driver &d = driver();
+    if (!d.ok) {
+        set_error("jit: the CUDA driver library (libcuda.so.1) is not available");
+        return QFB_ERR_CUDA;
+    }
+    const size_t n = offsets.size();
+    std::vector<JitSource> src(n);
+    std::vector<std::shared_ptr<std::vector<char>>> image(n);
+    std::vector<std::string> logs(n);
+    std::vector<int> rcs(n, QFB_OK);
+    const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+    const size_t nthreads = std::min<size_t>(n, std::min<unsigned>(hw, 16));
+    std::vector<std::thread> pool;
+    for (size_t w = 0; w < nthreads; ++w) {
+        pool.emplace_back([&, w] {
+            for (size_t i = w; i < n; i += nthreads) {
+                rcs[i] = jit_generate(plan + offsets[i], nbits, M, src[i], logs[i]);
+                if (rcs[i] == QFB_OK) rcs[i] = compile_cached(src[i].ptx, image[i], logs[i]);
+            }
+        });
+    }
+    for (auto &t : pool) t.join();
+    for (size_t i = 0; i < n; ++i) {
+        if (rcs[i] != QFB_OK) {
+            set_error("jit: sweep %zu: %s", i, logs[i].c_str());
+            return rcs[i];
+        }
+    }
+    int sms = sm_count_cached();
+    for (size_t i = 0; i < n; ++i) {
+        JitSweep *s = new JitSweep();
+        out.push_back(s);
+        QFB_CU(d.ModuleLoadData(&s->module, image[i]->data()));
+        QFB_CU(d.ModuleGetFunction(&s->func, s->module, "qfb_sweep"));
+        CUdeviceptr cptr = 0;
+        size_t cbytes = 0;
+        QFB_CU(d.ModuleGetGlobal(&cptr, &cbytes, s->module, "qfb_coef"));
+        if (cbytes < src[i].coef.size() * 8) {
+            set_error("jit: coefficient bank too small");
+            return QFB_ERR_CUDA;
+        }
+        if (!src[i].coef.empty()) QFB_CU(d.MemcpyHtoD(cptr, src[i].coef.data(), src[i].coef.size() * 8));
+        s->threads = src[i].threads;
+        s->smem = src[i].smem_bytes;
+        QFB_CU(d.FuncSetAttribute(s->func, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)s->smem));
+        int resident = 0;
+        QFB_CU(d.OccupancyMaxActiveBlocksPerMultiprocessor(&resident, s->func, s->threads, s->smem));
+        resident = std::max(1, resident);
+        const uint64_t ntiles = 1ull << src[i].nholes;
+        s->grid = (int)std::min<uint64_t>(ntiles, (uint64_t)sms * resident);
+    }
+    return QFB_OK;
+}
+
+int jit_launch(JitSweep *s, void *state, uint64_t hi_shifted, cudaStream_t st) {
+    void *args[2] = {&state, &hi_shifted};
+    QFB_CU(driver().LaunchKernel(s->func, s->grid, 1, 1, s->threads, 1, 1, (unsigned)s->smem, (CUstream)st, args, nullptr));
+    count_launch();
+    return QFB_OK;
+}
+
+}  // namespace qfb

@@ -21,6 +21,7 @@
 #include <algorithm>
 #include <vector>
 #include "qfb_common.cuh"
+#include "qfb_jit.h"
 #include "qfb_plan.h"
 #include "qfb_oploop.inc"
 
@@ -263,9 +264,21 @@ struct PlanHandle {
     uint32_t magic;
     int nbits, tile_bits, device;
     std::vector<SweepInfo> sweeps;
+    std::vector<JitSweep *> jit;   // sweep-specialised kernels (qfb_jit.cu); empty = the interpreter runs the plan
     void *dev;
     size_t dev_bytes;
 };
+
+// QFB_JIT: 0 = interpreter only, 1 = sweep-specialised kernels for every plan the generator supports, unset = for
+// states of at least QFB_JIT_MIN_BITS index bits (default 24: below that a sweep is so short that compiling it --
+// a few hundred milliseconds per distinct sweep structure -- never pays off)
+static bool jit_wanted(int nbits, int tile_bits) {
+    if (tile_bits - R < 3) return false;
+    const char *v = getenv("QFB_JIT");
+    if (v && *v) return atoi(v) != 0;
+    const char *m = getenv("QFB_JIT_MIN_BITS");
+    return nbits >= (m && *m ? atoi(m) : 24);
+}
 
 // register-bit pairs (j0 > j1) in handler order
 static const int J0[10] = {1, 2, 2, 3, 3, 3, 4, 4, 4, 4}, J1[10] = {0, 0, 1, 0, 1, 2, 0, 1, 2, 3};
@@ -551,6 +564,17 @@ int qfb_plan_upload(const void *plan_host, size_t plan_bytes, void **handle_out,
         return QFB_ERR_CUDA;
     }
     h->dev_bytes = plan_bytes;
+    if (jit_wanted(h->nbits, h->tile_bits)) {
+        std::vector<size_t> offsets;
+        for (const SweepInfo &s : h->sweeps) offsets.push_back(s.offset);
+        rc = jit_build_plan((const uint8_t *)plan_host, offsets, h->nbits, h->tile_bits, h->jit);
+        if (rc != QFB_OK) {
+            for (JitSweep *j : h->jit) jit_destroy(j);
+            cudaFree(h->dev);
+            delete h;
+            return rc;
+        }
+    }
     *handle_out = h;
     return QFB_OK;
 }
@@ -560,6 +584,14 @@ int qfb_plan_launch(void *handle, void *state, int nbits, uint64_t index_hi, voi
     QFB_CHECK_ARG(h && h->magic == HANDLE_MAGIC, "qfb_plan_launch: bad handle");
     QFB_CHECK_ARG(state, "qfb_plan_launch: null state");
     QFB_CHECK_ARG(nbits == h->nbits, "qfb_plan_launch: plan built for %d bits, state has %d", h->nbits, nbits);
+    if (!h->jit.empty()) {
+        const uint64_t hi_shifted = (nbits >= 64) ? 0ull : (index_hi << nbits);
+        for (JitSweep *j : h->jit) {
+            int rc = jit_launch(j, state, hi_shifted, (cudaStream_t)stream);
+            if (rc != QFB_OK) return rc;
+        }
+        return QFB_OK;
+    }
     for (const SweepInfo &s : h->sweeps) {
         int rc = launch_sweep_dispatch(h->tile_bits, s.has_g2, (c128 *)state, (const uint8_t *)h->dev + s.offset, s.bytes,
                                        nbits, index_hi, (cudaStream_t)stream);
@@ -572,8 +604,64 @@ int qfb_plan_destroy(void *handle) {
     PlanHandle *h = (PlanHandle *)handle;
     QFB_CHECK_ARG(h && h->magic == HANDLE_MAGIC, "qfb_plan_destroy: bad handle");
     h->magic = 0;
+    for (JitSweep *j : h->jit) jit_destroy(j);
     if (h->dev) cudaFree(h->dev);
     delete h;
+    return QFB_OK;
+}
+
+int qfb_jit_ptx(const void *plan_host, size_t plan_bytes, int sweep, char *buf, size_t cap, size_t *needed,
+                size_t *ncoef) {
+    std::vector<SweepInfo> sweeps;
+    int nbits = 0, M = 0;
+    int rc = validate_plan((const uint8_t *)plan_host, plan_bytes, sweeps, nbits, M);
+    if (rc != QFB_OK) return rc;
+    QFB_CHECK_ARG(sweep >= 0 && (size_t)sweep < sweeps.size(), "qfb_jit_ptx: no sweep %d", sweep);
+    JitSource src;
+    std::string err;
+    rc = jit_generate((const uint8_t *)plan_host + sweeps[sweep].offset, nbits, M, src, err);
+    if (rc != QFB_OK) {
+        set_error("%s", err.c_str());
+        return rc;
+    }
+    if (needed) *needed = src.ptx.size() + 1;
+    if (ncoef) *ncoef = src.coef.size();
+    if (buf && cap) {
+        const size_t n = std::min(cap - 1, src.ptx.size());
+        memcpy(buf, src.ptx.data(), n);
+        buf[n] = 0;
+    }
+    return QFB_OK;
+}
+
+int qfb_jit_check(const void *plan_host, size_t plan_bytes, char *log, size_t cap) {
+    std::vector<SweepInfo> sweeps;
+    int nbits = 0, M = 0;
+    int rc = validate_plan((const uint8_t *)plan_host, plan_bytes, sweeps, nbits, M);
+    if (rc != QFB_OK) return rc;
+    std::string all;
+    for (size_t i = 0; i < sweeps.size(); ++i) {
+        JitSource src;
+        std::string err, info;
+        rc = jit_generate((const uint8_t *)plan_host + sweeps[i].offset, nbits, M, src, err);
+        if (rc != QFB_OK) {
+            set_error("sweep %zu: %s", i, err.c_str());
+            return rc;
+        }
+        std::vector<char> cubin;
+        rc = jit_compile(src.ptx, cubin, info);
+        if (rc != QFB_OK) {
+            set_error("sweep %zu: %s", i, info.c_str());
+            return rc;
+        }
+        all += "sweep " + std::to_string(i) + ": " + std::to_string(src.ptx.size()) + " bytes of PTX, " +
+               std::to_string(src.coef.size()) + " coefficients, image " + std::to_string(cubin.size()) + " bytes\n" + info + "\n";
+    }
+    if (log && cap) {
+        const size_t n = std::min(cap - 1, all.size());
+        memcpy(log, all.data(), n);
+        log[n] = 0;
+    }
     return QFB_OK;
 }
 
