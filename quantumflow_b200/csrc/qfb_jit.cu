@@ -34,8 +34,11 @@ namespace qfb {
 
 namespace {
 
-constexpr int R = QFB_PLAN_REG_BITS;
-constexpr int NE = 1 << R;
+// Register bits of the plan being generated: 5, or 4 (half the code per operator; the straight-line code of a sweep
+// has to fit the SM's 32 KiB instruction cache, profiles/r2_icache_probe.jsonl). Set per generating thread.
+constexpr int RMAX = QFB_PLAN_REG_BITS, NEMAX = 1 << RMAX;
+constexpr int HS = 5;                  // handler ids are laid out for 5 register bits
+thread_local int R = RMAX, NE = NEMAX;
 const int J0[10] = {1, 2, 2, 3, 3, 3, 4, 4, 4, 4}, J1[10] = {0, 0, 1, 0, 1, 2, 0, 1, 2, 3};
 
 uint32_t swz(uint32_t idx) {
@@ -152,7 +155,7 @@ int thread_stb(Gen &g, int tid32, const uint8_t *thrpos, int nthr) {
 // the register bits occupy different tile positions, so only the three swizzled low index bits need an XOR
 struct XchgAddr {
     int base[8];      // 32-bit registers: smem + (stb ^ (k << 4)), -1 when unused
-    uint32_t low[NE], high[NE];
+    uint32_t low[NEMAX], high[NEMAX];
 };
 
 XchgAddr exchange_addresses(Gen &g, int smem32, int stb32, const uint8_t *regpos) {
@@ -266,7 +269,7 @@ void general_pair(Gen &g, Amp &x, Amp &y, const int *c, const int *n, bool inpla
 }
 
 struct RoundState {
-    Amp a[NE];
+    Amp a[NEMAX];
     int tfull;       // 64-bit register: rank bits | tile bits | thread bits of the first amplitude
     int phr, phi;    // running per-thread scalar (has_scalar rounds)
     bool scalar_live;
@@ -282,7 +285,7 @@ int emit_op(Gen &g, RoundState &st, const OpView &op, std::string &err) {
     const int rcm = op.h.reg_cmask;
     const uint64_t icm = op.h.idx_cmask;
     if (hd >= QFB_H_G1_GENERAL && hd < QFB_H_G1C_GENERAL) {
-        const int kind = hd / R, j = hd % R;
+        const int kind = hd / HS, j = hd % HS;
         if (kind == 0) {
             int c[8], n[8];
             load_matrix(g, op, c, n);
@@ -351,7 +354,7 @@ int emit_op(Gen &g, RoundState &st, const OpView &op, std::string &err) {
         if (p >= 0) g.e("L%d:", skip);
         return QFB_OK;
     }
-    if (hd >= QFB_H_G1C_SWAPX && hd < QFB_H_G1C_SWAPX + R) {
+    if (hd >= QFB_H_G1C_SWAPX && hd < QFB_H_G1C_SWAPX + HS) {
         const int j = hd - QFB_H_G1C_SWAPX;
         const int p = thread_predicate(g, icm, st.tfull);
         for (int q = 0; q < NE / 2; ++q) {
@@ -472,7 +475,7 @@ int emit_op(Gen &g, RoundState &st, const OpView &op, std::string &err) {
         }
         const int skip = g.label();
         if (p >= 0) g.e("@!%%p%d bra L%d;", p, skip);
-        int others[R], no = 0;
+        int others[RMAX], no = 0;
         for (int b = 0; b < R; ++b)
             if (b != j0 && b != j1) others[no++] = b;
         for (int q = 0; q < (1 << no); ++q) {
@@ -525,7 +528,7 @@ int emit_op(Gen &g, RoundState &st, const OpView &op, std::string &err) {
         for (int i = 0; i < 8; ++i) c[i] = g.cst(payload_f64(op, i));
         const int skip = g.label();
         if (p >= 0) g.e("@!%%p%d bra L%d;", p, skip);
-        int others[R], no = 0;
+        int others[RMAX], no = 0;
         for (int b = 0; b < R; ++b)
             if (b != j0 && b != j1) others[no++] = b;
         for (int q = 0; q < (1 << no); ++q) {
@@ -563,9 +566,33 @@ int emit_op(Gen &g, RoundState &st, const OpView &op, std::string &err) {
 
 }  // namespace
 
+// QFB_JIT_ASYNC (default 1): the tile of the NEXT iteration is copied global -> shared with cp.async (LDGSTS, no
+// registers involved) into the exchange buffer as soon as the current tile has left it for the last time, i.e. the
+// copy overlaps the last round's arithmetic and the stores; every thread copies exactly the amplitudes it will read
+// back itself (its round-0 slots), so the hand-over needs no barrier, only cp.async.wait_group. 0 = LDG straight
+// into registers at the top of the iteration (plus an L2 prefetch of the next tile), as the interpreter does.
+static bool jit_async() {
+    const char *v = getenv("QFB_JIT_ASYNC");
+    return !(v && *v) || atoi(v) != 0;
+}
+
 // ---- one sweep -> PTX --------------------------------------------------------------------------------------
 
-int jit_generate(const uint8_t *rec, int nbits, int M, JitSource &out, std::string &err) {
+// QFB_JIT_GROUPS: tiles a CTA works on side by side (one group of 2^(M-R) threads per tile). With G > 1 the groups
+// walk the same straight-line code between the same CTA-wide barriers, so an instruction line fetched for one warp
+// serves the warps of the other groups on its SM sub-partition (the code of a sweep is far larger than the
+// instruction caches and every warp executes each line once per tile).
+static int jit_groups(int M) {
+    const char *v = getenv("QFB_JIT_GROUPS");
+    int g = (v && *v) ? atoi(v) : 1;
+    if (g < 1) g = 1;
+    while (g > 1 && (((size_t)16 << M) * g > 200 * 1024 || (g << (M - R)) > 1024)) --g;
+    return g;
+}
+
+int jit_generate(const uint8_t *rec, int nbits, int M, int reg_bits, JitSource &out, std::string &err) {
+    R = reg_bits;
+    NE = 1 << reg_bits;
     qfb_sweep_header sh;
     memcpy(&sh, rec, sizeof(sh));
     const int nholes = nbits - M, nthr = M - R, T = 1 << nthr;
@@ -590,12 +617,18 @@ int jit_generate(const uint8_t *rec, int nbits, int M, JitSource &out, std::stri
     g.M = M;
     g.nbits = nbits;
     g.T = T;
+    const int G = jit_groups(M);
     // ---- prologue (tile independent) ----
-    const int tid = g.r32(), cta = g.r32(), ncta = g.r32(), smem = g.r32();
+    const int tid = g.r32(), cta = g.r32(), ncta = g.r32(), smem = g.r32(), grp = g.r32();
     g.e("mov.u32 %%r%d, %%tid.x;", tid);
+    g.e("shr.u32 %%r%d, %%r%d, %d;", grp, tid, nthr);
+    g.e("and.b32 %%r%d, %%r%d, %d;", tid, tid, T - 1);
     g.e("mov.u32 %%r%d, %%ctaid.x;", cta);
+    g.e("mad.lo.u32 %%r%d, %%r%d, %d, %%r%d;", cta, cta, G, grp);          // first tile of this group
     g.e("mov.u32 %%r%d, %%nctaid.x;", ncta);
+    g.e("mul.lo.u32 %%r%d, %%r%d, %d;", ncta, ncta, G);
     g.e("mov.u32 %%r%d, qfb_smem;", smem);
+    g.e("mad.lo.u32 %%r%d, %%r%d, %d, %%r%d;", smem, grp, 16 << M, smem);
     const int state = g.rd(), hi = g.rd();
     g.e("ld.param.u64 %%rd%d, [p_state];", state);
     g.e("cvta.to.global.u64 %%rd%d, %%rd%d;", state, state);
@@ -618,7 +651,7 @@ int jit_generate(const uint8_t *rec, int nbits, int M, JitSource &out, std::stri
     // (lane k takes the register indices whose top three bits are k); koff = byte offset of lane k's first line
     const qfb_round_header *r0 = rounds[0].rh;
     const bool lane_lines = sh.gpos[r0->thrpos[0]] == 0 && sh.gpos[r0->thrpos[1]] == 1 && sh.gpos[r0->thrpos[2]] == 2;
-    int64_t step0[R];
+    int64_t step0[RMAX];
     for (int i = 0; i < R; ++i) step0[i] = (int64_t)16 << sh.gpos[r0->regpos[i]];
     int koff = -1;
     if (lane_lines) {
@@ -643,43 +676,115 @@ int jit_generate(const uint8_t *rec, int nbits, int M, JitSource &out, std::stri
     g.e("cvt.u64.u32 %%rd%d, %%r%d;", tile, cta);
     g.e("cvt.u64.u32 %%rd%d, %%r%d;", stride, ncta);
     const unsigned long long ntiles = 1ull << nholes;
+    // With G groups the CTA leaves the loop as a whole (CTA-wide barriers): the loop runs while the CTA's FIRST group
+    // has a tile; a group past the end works on the last tile again and keeps its stores to itself (`active`).
+    const int grp64 = g.rd(), lead = g.rd(), active = g.pr(), tclamp = g.rd();
+    g.e("cvt.u64.u32 %%rd%d, %%r%d;", grp64, grp);
     {
         const int p = g.pr();
-        g.e("setp.ge.u64 %%p%d, %%rd%d, %llu;", p, tile, ntiles);
+        g.e("sub.u64 %%rd%d, %%rd%d, %%rd%d;", lead, tile, grp64);
+        g.e("setp.ge.u64 %%p%d, %%rd%d, %llu;", p, lead, ntiles);
         g.e("@%%p%d bra L_EXIT;", p);
     }
+    g.e("setp.lt.u64 %%p%d, %%rd%d, %llu;", active, tile, ntiles);
+    g.e("min.u64 %%rd%d, %%rd%d, %llu;", tclamp, tile, ntiles - 1);
     {
-        const int first = deposit64_from64(g, tile, hole, nholes);
+        const int first = deposit64_from64(g, tclamp, hole, nholes);
         g.e("mov.u64 %%rd%d, %%rd%d;", gb, first);
+    }
+    {
+        // QFB_JIT_STAGGER="K:D" (experiments): CTA b sleeps (b % K) * D nanoseconds before its first tile, so that the
+        // CTAs of the grid do not walk through their load / compute / store phases in step
+        const char *v = getenv("QFB_JIT_STAGGER");
+        int K = 0, D = 0;
+        if (v && sscanf(v, "%d:%d", &K, &D) == 2 && K > 1 && D > 0) {
+            const int c = g.r32(), d = g.r32();
+            g.e("mov.u32 %%r%d, %%ctaid.x;", c);
+            g.e("rem.u32 %%r%d, %%r%d, %d;", d, c, K);
+            g.e("mul.lo.u32 %%r%d, %%r%d, %d;", d, d, D);
+            g.e("nanosleep.u32 %%r%d;", d);
+        }
+    }
+    if (jit_async()) {
+        // the first tile's copy (every later one is started by the iteration before it)
+        const int idx = g.rd(), base = g.rd();
+        g.e("or.b64 %%rd%d, %%rd%d, %%rd%d;", idx, gb, tg[0]);
+        g.e("shl.b64 %%rd%d, %%rd%d, 4;", idx, idx);
+        g.e("add.u64 %%rd%d, %%rd%d, %%rd%d;", base, state, idx);
+        const XchgAddr x = exchange_addresses(g, smem, stb[0], r0->regpos);
+        for (int e = 0; e < NE; ++e) {
+            int64_t off = 0;
+            for (int i = 0; i < R; ++i)
+                if ((e >> i) & 1) off += step0[i];
+            const int addr = g.rd();
+            g.e("add.s64 %%rd%d, %%rd%d, %lld;", addr, base, (long long)off);
+            g.e("cp.async.cg.shared.global [%%r%d+%u], [%%rd%d], 16;", x.base[x.low[e]], x.high[e], addr);
+        }
+        g.e("cp.async.commit_group;");
     }
     g.e("L_TILE:");
     // next tile (for the prefetch and for the next iteration)
-    const int tile_next = g.rd(), has_next = g.pr();
+    const int tile_next = g.rd(), has_next = g.pr(), tnclamp = g.rd();
     g.e("add.u64 %%rd%d, %%rd%d, %%rd%d;", tile_next, tile, stride);
-    g.e("setp.lt.u64 %%p%d, %%rd%d, %llu;", has_next, tile_next, ntiles);
-    const int gb_next = deposit64_from64(g, tile_next, hole, nholes);
+    g.e("sub.u64 %%rd%d, %%rd%d, %%rd%d;", lead, tile_next, grp64);
+    g.e("setp.lt.u64 %%p%d, %%rd%d, %llu;", has_next, lead, ntiles);
+    g.e("min.u64 %%rd%d, %%rd%d, %llu;", tnclamp, tile_next, ntiles - 1);
+    const int gb_next = deposit64_from64(g, tnclamp, hole, nholes);
     const int higb = g.rd();
     g.e("or.b64 %%rd%d, %%rd%d, %%rd%d;", higb, hi, gb);
 
     RoundState st;
     st.scalar_live = false;
     st.phr = st.phi = -1;
-    // ---- round 0: coalesced loads straight into registers ----
-    const int base0 = g.rd();
-    {
-        const int idx = g.rd();
-        g.e("or.b64 %%rd%d, %%rd%d, %%rd%d;", idx, gb, tg[0]);
-        g.e("shl.b64 %%rd%d, %%rd%d, 4;", idx, idx);
-        g.e("add.u64 %%rd%d, %%rd%d, %%rd%d;", base0, state, idx);
-    }
+    const bool async = jit_async();
+    int64_t off0[NEMAX];
     for (int e = 0; e < NE; ++e) {
-        int64_t off = 0;
+        off0[e] = 0;
         for (int i = 0; i < R; ++i)
-            if ((e >> i) & 1) off += step0[i];
+            if ((e >> i) & 1) off0[e] += step0[i];
+    }
+    // global base address of the thread's first amplitude of a tile (round-0 assignment)
+    auto tile_base = [&](int gbreg) {
+        const int idx = g.rd(), base = g.rd();
+        g.e("or.b64 %%rd%d, %%rd%d, %%rd%d;", idx, gbreg, tg[0]);
+        g.e("shl.b64 %%rd%d, %%rd%d, 4;", idx, idx);
+        g.e("add.u64 %%rd%d, %%rd%d, %%rd%d;", base, state, idx);
+        return base;
+    };
+    // asynchronous copy of a tile into the thread's own round-0 slots of the exchange buffer
+    auto async_copy = [&](int basereg) {
+        const XchgAddr x = exchange_addresses(g, smem, stb[0], r0->regpos);
+        for (int e = 0; e < NE; ++e) {
+            const int addr = g.rd();
+            g.e("add.s64 %%rd%d, %%rd%d, %lld;", addr, basereg, (long long)off0[e]);
+            g.e("cp.async.cg.shared.global [%%r%d+%u], [%%rd%d], 16;", x.base[x.low[e]], x.high[e], addr);
+        }
+        g.e("cp.async.commit_group;");
+    };
+    if (async) {
+        // ---- round 0: the tile was copied into shared memory during the previous iteration ----
+        g.e("cp.async.wait_group 0;");
+        const XchgAddr x = exchange_addresses(g, smem, stb[0], r0->regpos);
+        for (int e = 0; e < NE; ++e) {
+            st.a[e].re = g.fd();
+            st.a[e].im = g.fd();
+            g.e("ld.shared.v2.f64 {%%fd%d, %%fd%d}, [%%r%d+%u];", st.a[e].re, st.a[e].im, x.base[x.low[e]], x.high[e]);
+        }
+        if (nrounds == 1) {
+            // no exchange in this sweep: the buffer is the thread's own, the next copy can start at once
+            const int skip = g.label();
+            g.e("@!%%p%d bra L%d;", has_next, skip);
+            async_copy(tile_base(gb_next));
+            g.e("L%d:", skip);
+        }
+    } else {
+    // ---- round 0: coalesced loads straight into registers ----
+    const int base0 = tile_base(gb);
+    for (int e = 0; e < NE; ++e) {
         st.a[e].re = g.fd();
         st.a[e].im = g.fd();
         const int addr = g.rd();
-        g.e("add.s64 %%rd%d, %%rd%d, %lld;", addr, base0, (long long)off);
+        g.e("add.s64 %%rd%d, %%rd%d, %lld;", addr, base0, (long long)off0[e]);
         g.e("ld.global.cs.v2.f64 {%%fd%d, %%fd%d}, [%%rd%d];", st.a[e].re, st.a[e].im, addr);
     }
     {
@@ -707,16 +812,14 @@ int jit_generate(const uint8_t *rec, int nbits, int M, JitSource &out, std::stri
             g.e("setp.ne.u32 %%p%d, %%r%d, 0;", p, m);
             g.e("@%%p%d bra L%d;", p, skip2);
             for (int e = 0; e < NE; ++e) {
-                int64_t off = 0;
-                for (int i = 0; i < R; ++i)
-                    if ((e >> i) & 1) off += step0[i];
                 const int q = g.rd();
-                g.e("add.s64 %%rd%d, %%rd%d, %lld;", q, pbase, (long long)off);
+                g.e("add.s64 %%rd%d, %%rd%d, %lld;", q, pbase, (long long)off0[e]);
                 g.e("prefetch.global.L2 [%%rd%d];", q);
             }
             g.e("L%d:", skip2);
         }
         g.e("L%d:", skip);
+    }
     }
     // ---- rounds ----
     for (int r = 0; r < nrounds; ++r) {
@@ -756,6 +859,13 @@ int jit_generate(const uint8_t *rec, int nbits, int M, JitSource &out, std::stri
             }
         }
         g.e("bar.sync 0;");
+        if (async && r + 2 == nrounds) {
+            // the tile has left the exchange buffer for the last time: the next tile's copy runs under the last round
+            const int skip = g.label();
+            g.e("@!%%p%d bra L%d;", has_next, skip);
+            async_copy(tile_base(gb_next));
+            g.e("L%d:", skip);
+        }
     }
     // ---- store: amplitude i goes to address i ^ store_xor; tile bit j is stored at spos[j] ----
     if (store_sync) g.e("bar.sync 0;");
@@ -777,17 +887,23 @@ int jit_generate(const uint8_t *rec, int nbits, int M, JitSource &out, std::stri
             }
             const int addr = g.rd();
             g.e("add.s64 %%rd%d, %%rd%d, %lld;", addr, sbase, (long long)off);
-            g.e("st.global.cs.v2.f64 [%%rd%d], {%%fd%d, %%fd%d};", addr, st.a[e].re, st.a[e].im);
+            if (G > 1)
+                g.e("@%%p%d st.global.cs.v2.f64 [%%rd%d], {%%fd%d, %%fd%d};", active, addr, st.a[e].re, st.a[e].im);
+            else
+                g.e("st.global.cs.v2.f64 [%%rd%d], {%%fd%d, %%fd%d};", addr, st.a[e].re, st.a[e].im);
         }
     }
     // ---- next tile ----
     g.e("mov.u64 %%rd%d, %%rd%d;", tile, tile_next);
     g.e("mov.u64 %%rd%d, %%rd%d;", gb, gb_next);
+    g.e("setp.lt.u64 %%p%d, %%rd%d, %llu;", active, tile, ntiles);
     g.e("@%%p%d bra L_TILE;", has_next);
     g.e("L_EXIT:");
     g.e("ret;");
 
-    const int minb = (M >= 13) ? 1 : (M == 12) ? 3 : (M == 11) ? 6 : 8;
+    // resident CTAs the register file allows: 2^R amplitudes = 4 * 2^R registers + ~40 per thread
+    const int regs_per_thread = (R == 5) ? 168 : 128;
+    const int minb = std::max(1, std::min(8, (65536 / (regs_per_thread * T)) / G));
     const size_t coef_bytes = std::max<size_t>(16, (g.coef.size() * 8 + 15) / 16 * 16);
     char head[1024];
     snprintf(head, sizeof(head),
@@ -797,13 +913,14 @@ int jit_generate(const uint8_t *rec, int nbits, int M, JitSource &out, std::stri
              ".visible .entry qfb_sweep(.param .u64 p_state, .param .u64 p_hi)\n"
              ".maxntid %d, 1, 1\n.minnctapersm %d\n{\n"
              ".reg .f64 %%fd<%d>;\n.reg .b64 %%rd<%d>;\n.reg .b32 %%r<%d>;\n.reg .pred %%p<%d>;\n",
-             coef_bytes, T, minb, g.nfd + 1, g.nrd + 1, g.nr + 1, g.np + 1);
+             coef_bytes, T * G, minb, g.nfd + 1, g.nrd + 1, g.nr + 1, g.np + 1);
     out.ptx = std::string(head) + g.body + "}\n";
     out.coef = g.coef;
     out.coef_bytes = coef_bytes;
-    out.threads = T;
-    out.smem_bytes = (size_t)16 << M;
+    out.threads = T * G;
+    out.smem_bytes = ((size_t)16 << M) * G;
     out.nholes = nholes;
+    out.groups = G;
     return QFB_OK;
 }
 
@@ -943,7 +1060,7 @@ void jit_destroy(JitSweep *s) {
 
 // Generate + compile every sweep of a validated plan (parallel over host threads), then load the images into the
 // current context and write the coefficients. `offsets` = byte offset of every sweep record in the plan.
-int jit_build_plan(const uint8_t *plan, const std::vector<size_t> &offsets, int nbits, int M,
+int jit_build_plan(const uint8_t *plan, const std::vector<size_t> &offsets, int nbits, int M, int reg_bits,
                    std::vector<JitSweep *> &out) {
     const Driver &d = driver();
     if (!d.ok) {
@@ -961,7 +1078,7 @@ int jit_build_plan(const uint8_t *plan, const std::vector<size_t> &offsets, int 
     for (size_t w = 0; w < nthreads; ++w) {
         pool.emplace_back([&, w] {
             for (size_t i = w; i < n; i += nthreads) {
-                rcs[i] = jit_generate(plan + offsets[i], nbits, M, src[i], logs[i]);
+                rcs[i] = jit_generate(plan + offsets[i], nbits, M, reg_bits, src[i], logs[i]);
                 if (rcs[i] == QFB_OK) rcs[i] = compile_cached(src[i].ptx, image[i], logs[i]);
             }
         });
@@ -994,7 +1111,8 @@ int jit_build_plan(const uint8_t *plan, const std::vector<size_t> &offsets, int 
         QFB_CU(d.OccupancyMaxActiveBlocksPerMultiprocessor(&resident, s->func, s->threads, s->smem));
         resident = std::max(1, resident);
         const uint64_t ntiles = 1ull << src[i].nholes;
-        s->grid = (int)std::min<uint64_t>(ntiles, (uint64_t)sms * resident);
+        const uint64_t nctas = (ntiles + src[i].groups - 1) / src[i].groups;
+        s->grid = (int)std::min<uint64_t>(nctas, (uint64_t)sms * resident);
     }
     return QFB_OK;
 }

@@ -14,17 +14,18 @@ struct JitSource {
     int threads = 0;
     size_t smem_bytes = 0;
     int nholes = 0;
+    int groups = 1;               // tiles a CTA works on side by side
 };
 
 struct JitSweep;                  // a loaded module + launch geometry
 
 // PTX text and coefficients of the sweep record at `rec` (a record of a VALIDATED plan)
-int jit_generate(const uint8_t *rec, int nbits, int tile_bits, JitSource &out, std::string &err);
+int jit_generate(const uint8_t *rec, int nbits, int tile_bits, int reg_bits, JitSource &out, std::string &err);
 // PTX -> sm_100a image with the statically linked PTX compiler (no GPU, no driver needed); `log` = ptxas -v output
 int jit_compile(const std::string &ptx, std::vector<char> &cubin, std::string &log);
 // all sweeps of a plan: generate + compile in parallel (images cached per process by PTX text), load into the current
 // context, write the coefficient banks
-int jit_build_plan(const uint8_t *plan, const std::vector<size_t> &offsets, int nbits, int tile_bits,
+int jit_build_plan(const uint8_t *plan, const std::vector<size_t> &offsets, int nbits, int tile_bits, int reg_bits,
                    std::vector<JitSweep *> &out);
 int jit_launch(JitSweep *s, void *state, uint64_t hi_shifted, cudaStream_t st);
 void jit_destroy(JitSweep *s);

@@ -262,7 +262,7 @@ struct SweepInfo {
 
 struct PlanHandle {
     uint32_t magic;
-    int nbits, tile_bits, device;
+    int nbits, tile_bits, reg_bits, device;
     std::vector<SweepInfo> sweeps;
     std::vector<JitSweep *> jit;   // sweep-specialised kernels (qfb_jit.cu); empty = the interpreter runs the plan
     void *dev;
@@ -272,7 +272,8 @@ struct PlanHandle {
 // QFB_JIT: 0 = interpreter only, 1 = sweep-specialised kernels for every plan the generator supports, unset = for
 // states of at least QFB_JIT_MIN_BITS index bits (default 24: below that a sweep is so short that compiling it --
 // a few hundred milliseconds per distinct sweep structure -- never pays off)
-static bool jit_wanted(int nbits, int tile_bits) {
+static bool jit_wanted(int nbits, int tile_bits, int reg_bits) {
+    if (reg_bits != R) return true;     // only the sweep-specialised kernels run plans with 4 register bits
     if (tile_bits - R < 3) return false;
     const char *v = getenv("QFB_JIT");
     if (v && *v) return atoi(v) != 0;
@@ -291,14 +292,18 @@ static uint32_t swz_host(uint32_t idx) {
     return idx ^ ((x ^ (x >> 3) ^ (x >> 6) ^ (x >> 9)) & 7u);
 }
 
-static int validate_plan(const uint8_t *p, size_t nbytes, std::vector<SweepInfo> &sweeps, int &nbits, int &M) {
+static int validate_plan(const uint8_t *p, size_t nbytes, std::vector<SweepInfo> &sweeps, int &nbits, int &M,
+                         int *reg_bits_out = nullptr) {
     QFB_CHECK_ARG(p && nbytes >= sizeof(qfb_plan_header), "plan: too small");
     qfb_plan_header h;
     memcpy(&h, p, sizeof(h));
     QFB_CHECK_ARG(h.magic == QFB_PLAN_MAGIC && h.version == QFB_PLAN_VERSION, "plan: bad magic/version");
     QFB_CHECK_ARG(h.total_bytes == nbytes, "plan: size mismatch (%llu vs %llu)", (unsigned long long)h.total_bytes,
                   (unsigned long long)nbytes);
-    QFB_CHECK_ARG(h.reg_bits == (uint32_t)R, "plan: reg_bits=%u unsupported", h.reg_bits);
+    // 5 register bits: interpreter (sweep_kernel) and sweep-specialised kernels; 4: sweep-specialised kernels only
+    QFB_CHECK_ARG(h.reg_bits == 5u || h.reg_bits == 4u, "plan: reg_bits=%u unsupported", h.reg_bits);
+    const int RB = (int)h.reg_bits, NEB = 1 << RB;   // handler ids keep their stride of R = 5 register bits
+    if (reg_bits_out) *reg_bits_out = RB;
     QFB_CHECK_ARG(h.tile_bits >= QFB_PLAN_MIN_TILE_BITS && h.tile_bits <= QFB_PLAN_MAX_TILE_BITS &&
                       h.tile_bits <= h.nbits,
                   "plan: tile_bits=%u unsupported (nbits=%u)", h.tile_bits, h.nbits);
@@ -353,13 +358,13 @@ static int validate_plan(const uint8_t *p, size_t nbytes, std::vector<SweepInfo>
             const bool store_rec = r == sh.nrounds;
             const uint8_t *ipos = store_rec ? sh.spos : sh.gpos;   // index-bit images used by this record
             if (store_rec) {
-                QFB_CHECK_ARG(rh.nops == 0 && memcmp(rh.regpos, last_rh.regpos, R) == 0 &&
+                QFB_CHECK_ARG(rh.nops == 0 && memcmp(rh.regpos, last_rh.regpos, RB) == 0 &&
                                   memcmp(rh.thrpos, last_rh.thrpos, 12) == 0,
                               "plan: sweep %u store record does not match the last round", s);
             }
             sweep_g2 = sweep_g2 || rh.has_g2;
             uint32_t tseen = 0;
-            for (int i = 0; i < R; ++i) {
+            for (int i = 0; i < RB; ++i) {
                 QFB_CHECK_ARG(rh.regpos[i] < M && !((tseen >> rh.regpos[i]) & 1u), "plan: bad regpos");
                 tseen |= 1u << rh.regpos[i];
                 const int64_t gbytes = (int64_t)16 << sh.gpos[rh.regpos[i]];
@@ -369,15 +374,15 @@ static int validate_plan(const uint8_t *p, size_t nbytes, std::vector<SweepInfo>
                                   rh.rst[i] == (flipped ? -sbytes : sbytes),
                               "plan: sweep %u round %u bad register-bit images", s, r);
             }
-            for (int t = 0; t < M - R; ++t) {
+            for (int t = 0; t < M - RB; ++t) {
                 QFB_CHECK_ARG(rh.thrpos[t] < M && !((tseen >> rh.thrpos[t]) & 1u), "plan: bad thrpos");
                 tseen |= 1u << rh.thrpos[t];
             }
             // thread LUTs must reproduce the deposit of the thread bits through thrpos / gpos
-            for (int t = 0; t < (1 << (M - R)); ++t) {
+            for (int t = 0; t < (1 << (M - RB)); ++t) {
                 uint32_t tb = 0;
                 uint64_t tg = 0;
-                for (int b = 0; b < M - R; ++b) {
+                for (int b = 0; b < M - RB; ++b) {
                     if ((t >> b) & 1) {
                         tb |= 1u << rh.thrpos[b];
                         tg |= 1ull << ipos[rh.thrpos[b]];
@@ -398,6 +403,8 @@ static int validate_plan(const uint8_t *p, size_t nbytes, std::vector<SweepInfo>
                 QFB_CHECK_ARG(bytes % 16 == 0 && bytes >= sizeof(oh) && ooff + bytes <= rend, "plan: op bad size");
                 const int hd = (int)oh.handler;
                 const int rcm = oh.reg_cmask;
+                // register bits an op names must exist in this plan
+                if (hd < QFB_H_CPH_SCALAR) QFB_CHECK_ARG(hd % R < RB, "plan: op on a register bit the plan does not have");
                 if (o == rh.nops) {
                     QFB_CHECK_ARG(hd == QFB_H_END && bytes == 16, "plan: round does not end with an END record");
                     ended = true;
@@ -413,7 +420,7 @@ static int validate_plan(const uint8_t *p, size_t nbytes, std::vector<SweepInfo>
                         memcpy(&one, p + ooff + 16, 8);
                         QFB_CHECK_ARG(bytes == 32 && one == 1.0, "plan: controlled X needs the payload 1.0");
                     }
-                    QFB_CHECK_ARG(bytes == want && !((rcm >> j) & 1) && rcm < NE, "plan: bad controlled G1 op");
+                    QFB_CHECK_ARG(bytes == want && !((rcm >> j) & 1) && rcm < NEB, "plan: bad controlled G1 op");
                 } else if (hd == QFB_H_CPH_SCALAR) {
                     QFB_CHECK_ARG(bytes == 32 && rcm == 0 && rh.has_scalar == 1, "plan: bad scalar CPH op");
                 } else if (hd >= QFB_H_CPH_REG1 && hd < QFB_H_CPH_NEG2) {
@@ -427,20 +434,20 @@ static int validate_plan(const uint8_t *p, size_t nbytes, std::vector<SweepInfo>
                     const int pi = hd - QFB_H_CPH_NEG2;
                     QFB_CHECK_ARG(bytes == 32 && rcm == ((1 << J0[pi]) | (1 << J1[pi])), "plan: bad 2-bit CPH op");
                 } else if (hd == QFB_H_CPH_REGM || hd == QFB_H_CPH_NEGM) {
-                    QFB_CHECK_ARG(bytes == 32 && rcm > 0 && rcm < NE, "plan: bad CPH op");
+                    QFB_CHECK_ARG(bytes == 32 && rcm > 0 && rcm < NEB, "plan: bad CPH op");
                 } else if (hd == QFB_H_CPH_TABLE) {
-                    QFB_CHECK_ARG(bytes == 16 + 16 * NE && oh.idx_cmask == 0 && rcm < NE && oh.flag <= 1 &&
+                    QFB_CHECK_ARG(bytes == 16 + 16 * NE && oh.idx_cmask == 0 && rcm < NEB && oh.flag <= 1 &&
                                       (rcm != 0 || oh.flag == 1),
                                   "plan: bad diagonal table op");
                 } else if (hd >= QFB_H_G2 && hd < QFB_H_G2 + NPAIRS) {
                     const int j0 = J0[hd - QFB_H_G2], j1 = J1[hd - QFB_H_G2];
                     QFB_CHECK_ARG(rh.has_g2 == 1 && bytes == 16 + 272 && !((rcm >> j0) & 1) && !((rcm >> j1) & 1) &&
-                                      rcm < NE,
+                                      rcm < NEB,
                                   "plan: bad G2 op");
                 } else if (hd >= QFB_H_G2X && hd < QFB_H_G2X + NPAIRS) {
                     const int j0 = J0[hd - QFB_H_G2X], j1 = J1[hd - QFB_H_G2X];
                     QFB_CHECK_ARG(rh.has_g2 == 1 && bytes == 16 + 64 && !((rcm >> j0) & 1) && !((rcm >> j1) & 1) &&
-                                      rcm < NE,
+                                      rcm < NEB,
                                   "plan: bad X-shaped G2 op");
                 } else {
                     QFB_CHECK_ARG(false, "plan: unknown handler %d", hd);
@@ -547,7 +554,7 @@ int qfb_plan_upload(const void *plan_host, size_t plan_bytes, void **handle_out,
     PlanHandle *h = new PlanHandle();
     h->magic = HANDLE_MAGIC;
     h->dev = nullptr;
-    int rc = validate_plan((const uint8_t *)plan_host, plan_bytes, h->sweeps, h->nbits, h->tile_bits);
+    int rc = validate_plan((const uint8_t *)plan_host, plan_bytes, h->sweeps, h->nbits, h->tile_bits, &h->reg_bits);
     if (rc != QFB_OK) {
         delete h;
         return rc;
@@ -564,10 +571,10 @@ int qfb_plan_upload(const void *plan_host, size_t plan_bytes, void **handle_out,
         return QFB_ERR_CUDA;
     }
     h->dev_bytes = plan_bytes;
-    if (jit_wanted(h->nbits, h->tile_bits)) {
+    if (jit_wanted(h->nbits, h->tile_bits, h->reg_bits)) {
         std::vector<size_t> offsets;
         for (const SweepInfo &s : h->sweeps) offsets.push_back(s.offset);
-        rc = jit_build_plan((const uint8_t *)plan_host, offsets, h->nbits, h->tile_bits, h->jit);
+        rc = jit_build_plan((const uint8_t *)plan_host, offsets, h->nbits, h->tile_bits, h->reg_bits, h->jit);
         if (rc != QFB_OK) {
             for (JitSweep *j : h->jit) jit_destroy(j);
             cudaFree(h->dev);
@@ -613,13 +620,13 @@ int qfb_plan_destroy(void *handle) {
 int qfb_jit_ptx(const void *plan_host, size_t plan_bytes, int sweep, char *buf, size_t cap, size_t *needed,
                 size_t *ncoef) {
     std::vector<SweepInfo> sweeps;
-    int nbits = 0, M = 0;
-    int rc = validate_plan((const uint8_t *)plan_host, plan_bytes, sweeps, nbits, M);
+    int nbits = 0, M = 0, RB = 0;
+    int rc = validate_plan((const uint8_t *)plan_host, plan_bytes, sweeps, nbits, M, &RB);
     if (rc != QFB_OK) return rc;
     QFB_CHECK_ARG(sweep >= 0 && (size_t)sweep < sweeps.size(), "qfb_jit_ptx: no sweep %d", sweep);
     JitSource src;
     std::string err;
-    rc = jit_generate((const uint8_t *)plan_host + sweeps[sweep].offset, nbits, M, src, err);
+    rc = jit_generate((const uint8_t *)plan_host + sweeps[sweep].offset, nbits, M, RB, src, err);
     if (rc != QFB_OK) {
         set_error("%s", err.c_str());
         return rc;
@@ -636,14 +643,14 @@ int qfb_jit_ptx(const void *plan_host, size_t plan_bytes, int sweep, char *buf, 
 
 int qfb_jit_check(const void *plan_host, size_t plan_bytes, char *log, size_t cap) {
     std::vector<SweepInfo> sweeps;
-    int nbits = 0, M = 0;
-    int rc = validate_plan((const uint8_t *)plan_host, plan_bytes, sweeps, nbits, M);
+    int nbits = 0, M = 0, RB = 0;
+    int rc = validate_plan((const uint8_t *)plan_host, plan_bytes, sweeps, nbits, M, &RB);
     if (rc != QFB_OK) return rc;
     std::string all;
     for (size_t i = 0; i < sweeps.size(); ++i) {
         JitSource src;
         std::string err, info;
-        rc = jit_generate((const uint8_t *)plan_host + sweeps[i].offset, nbits, M, src, err);
+        rc = jit_generate((const uint8_t *)plan_host + sweeps[i].offset, nbits, M, RB, src, err);
         if (rc != QFB_OK) {
             set_error("sweep %zu: %s", i, err.c_str());
             return rc;

@@ -23,6 +23,7 @@ Passes, all order preserving up to commutation:
               sums only; RX / RY: two fused multiply-adds per amplitude); the pivots of a sweep are multiplied
               into one uniform scalar that is applied once.
 """
+import os
 import random
 import struct
 from typing import Dict, List, Optional, Sequence, Tuple
@@ -33,7 +34,9 @@ from . import classify
 
 PLAN_MAGIC = 0x50424651
 PLAN_VERSION = 13
-REG_BITS = 5
+REG_BITS = 5                # register bits of the interpreter's plans; sweep-specialised kernels also take 4
+HANDLER_STRIDE = 5          # handler ids are laid out for 5 register bits whatever a plan uses
+TABLE_ENTRIES = 32
 MAX_TILE_BITS = 13
 MIN_TILE_BITS = 6
 MAX_HOLES = 48
@@ -43,7 +46,7 @@ MAX_DIAG_BITS = 5
 (H_G1_GENERAL, H_G1_SUMDIFF, H_G1_LU_R, H_G1_LU_I, H_G1C_GENERAL, H_G1C_SWAPX, H_CPH_SCALAR, H_CPH_REG1,
  H_CPH_RSC1, H_CPH_NEG1, H_CPH_NEG2, H_CPH_REGM, H_CPH_NEGM, H_END, H_G2, H_G2X, H_CPH_TABLE) = \
     0, 5, 10, 15, 20, 25, 30, 31, 36, 41, 46, 56, 57, 58, 59, 69, 79
-G2_PAIRS = [(j0, j1) for j0 in range(REG_BITS) for j1 in range(j0)]
+G2_PAIRS = [(j0, j1) for j0 in range(HANDLER_STRIDE) for j1 in range(j0)]
 SWEEP_FLAG_G2, SWEEP_FLAG_STORE_SYNC, SWEEP_FLAG_STORE_PERM = 1, 2, 4
 
 
@@ -59,7 +62,7 @@ def is_scalar_term(record: bytes) -> bool:
 
 def _round_header(nops, nbytes, regs, thrpad, has_scalar, has_g2, rgb, rst) -> bytes:
     """qfb_round_header without the thread LUTs (192 bytes)."""
-    pad8 = [0] * (8 - REG_BITS)
+    pad8 = [0] * (8 - len(regs))
     return struct.pack('<II8B12BBB2x8I8q8q', nops, nbytes, *regs, *pad8, *thrpad, has_scalar, has_g2,
                        *[swz(1 << p) << 4 for p in regs], *pad8, *rgb, *pad8, *rst, *pad8)
 
@@ -431,6 +434,21 @@ def _conflicts(op: POp, def_any: set, def_mix: set) -> bool:
     return bool(op.mixset & def_any) or bool(op.diagset & def_mix)
 
 
+def default_reg_bits(nbits: int) -> int:
+    """Register bits of a plan: 5 (32 amplitudes per thread) for the interpreter; 4 for states that run the sweep-
+    specialised kernels (csrc/qfb_jit.cu), whose straight-line code must fit the SM's 32 KiB instruction cache
+    (profiles/r2_icache_probe.jsonl): half the amplitudes per thread is half the code per operator. The rule is
+    the library's (jit_wanted, csrc/qfb_sweep.cu): QFB_JIT=0 switches the kernels off, otherwise states of at
+    least QFB_JIT_MIN_BITS (24) index bits use them. QFB_REG_BITS overrides (experiments)."""
+    v = os.environ.get('QFB_REG_BITS')
+    if v:
+        return int(v)
+    jit = os.environ.get('QFB_JIT')
+    if jit:
+        return 4 if int(jit) != 0 else 5
+    return 4 if nbits >= int(os.environ.get('QFB_JIT_MIN_BITS') or 24) else 5
+
+
 def swizzle_class(pos: int) -> int:
     return pos if pos < 3 else (pos - 3) % 3
 
@@ -458,8 +476,11 @@ class SweepPlan:
 
 class Planner:
     def __init__(self, nbits: int, tile_bits: int = None, low_bits: int = None, max_cost: float = None,
-                 tries: int = None, refine: bool = None):
+                 tries: int = None, refine: bool = None, reg_bits: int = None):
         self.nbits = int(nbits)
+        self.R = default_reg_bits(self.nbits) if reg_bits is None else int(reg_bits)
+        if self.R not in (4, 5):
+            raise ValueError('reg_bits must be 4 or 5')
         m = DEFAULT_TILE_BITS if tile_bits is None else int(tile_bits)
         m = min(m, self.nbits, MAX_TILE_BITS)
         if m < MIN_TILE_BITS:
@@ -468,7 +489,9 @@ class Planner:
             raise ValueError('state too large for one plan')
         self.M = m
         low = DEFAULT_LOW_BITS if low_bits is None else int(low_bits)
-        self.L = max(0, min(low, m - REG_BITS))
+        if m - self.R < 3:
+            self.R = REG_BITS          # tiny tiles: only the interpreter runs them
+        self.L = max(0, min(low, m - self.R))
         self.max_cost = DEFAULT_MAX_COST if max_cost is None else float(max_cost)
         self.tries = DEFAULT_TRIES if tries is None else int(tries)
         self.refine = True if refine is None else bool(refine)
@@ -652,7 +675,7 @@ class Planner:
                     need = [pos_of[b] for b in op.mix if pos_of[b] not in regs]
                     if first and any(pos_of[b] < self.L for b in op.mix):
                         ok = False
-                    elif len(regs) + len(need) > REG_BITS:
+                    elif len(regs) + len(need) > self.R:
                         ok = False
                     elif need and regs and rnd is not None and rnd.random() > p_new:
                         ok = False
@@ -695,7 +718,7 @@ class Planner:
             # fill up to R register bits with high free positions (never low ones on edge rounds)
             cand = [p for p in range(self.M - 1, -1, -1) if p not in regs and (p >= self.L or not edge)]
             # prefer a spread of swizzle classes so that lane bits always find three distinct classes
-            while len(regs) < REG_BITS:
+            while len(regs) < self.R:
                 counts = {c: sum(1 for p in regs if swizzle_class(p) == c) for c in range(3)}
                 cand.sort(key=lambda p: (counts[swizzle_class(p)], -p))
                 regs.append(cand.pop(0))
@@ -773,7 +796,7 @@ class Planner:
                 elif bin(mask).count('1') == len(op.dbits) and allin[r] >= 2:
                     cost = 0.04 - 0.001 * min(allin[r], 20)
                 else:
-                    touched = (1 << REG_BITS) >> bin(mask).count('1')
+                    touched = (1 << self.R) >> bin(mask).count('1')
                     cost = (0.1 if op.mat == -1 else 0.5) * touched / 8.0
                 if best is None or cost < best[0]:
                     best = (cost, r, mask)
@@ -879,12 +902,12 @@ class Planner:
             sweep.store_xor = sum(1 << mapping.get(b, b) for b in range(nb) if (sweep.store_xor >> b) & 1)
             if not sweep.rounds:
                 # bare sweep: a load round (lanes on index bits 0.. under tile[]) before the store round
-                regs = [p for p in range(self.M - 1, -1, -1) if p >= self.L][:REG_BITS]
+                regs = [p for p in range(self.M - 1, -1, -1) if p >= self.L][:self.R]
                 regs.sort()
                 sweep.rounds.append(Round(regs, self._thread_order(regs, True), []))
             # store round: the lanes walk the tile positions that are stored to index bits 0, 1, 2 ...
-            lanes = [sweep.spos.index(t) for t in range(min(self.L, self.M - REG_BITS))]
-            regs = [p for p in range(self.M - 1, -1, -1) if p not in lanes][:REG_BITS]
+            lanes = [sweep.spos.index(t) for t in range(min(self.L, self.M - self.R))]
+            regs = [p for p in range(self.M - 1, -1, -1) if p not in lanes][:self.R]
             regs.sort()
             thr = lanes + [p for p in range(self.M) if p not in lanes and p not in regs]
             sweep.rounds.append(Round(regs, thr, []))
@@ -1019,7 +1042,7 @@ class Planner:
             else:
                 reg_cmask |= 1 << ri
         factor = complex(factor)
-        regs = [i for i in range(REG_BITS) if (reg_cmask >> i) & 1]
+        regs = [i for i in range(HANDLER_STRIDE) if (reg_cmask >> i) & 1]
         if not regs:
             handler = H_CPH_SCALAR
         elif factor == -1:
@@ -1108,8 +1131,8 @@ class Planner:
         union = 0
         for mask, _ in masks:
             union |= mask
-        entries = np.ones(1 << REG_BITS, dtype=np.complex128)
-        for e in range(1 << REG_BITS):
+        entries = np.ones(TABLE_ENTRIES, dtype=np.complex128)
+        for e in range(TABLE_ENTRIES):
             for mask, factor in masks:
                 if (e & mask) == mask:
                     entries[e] *= factor
@@ -1200,7 +1223,7 @@ class Planner:
             body += struct.pack('<IIII16B48BQ8x16B', size, len(sweep.rounds), nops, flags, *gpos, *hole,
                                 sweep.store_xor, *spos) + rounds_blob
         total = 32 + len(body)
-        header = struct.pack('<IIIIIIQ', PLAN_MAGIC, PLAN_VERSION, self.nbits, self.M, REG_BITS, len(sweeps), total)
+        header = struct.pack('<IIIIIIQ', PLAN_MAGIC, PLAN_VERSION, self.nbits, self.M, self.R, len(sweeps), total)
         return header + body
 
 
@@ -1257,19 +1280,22 @@ def item_bitop(item) -> Tuple[np.ndarray, List[int]]:
 
 
 def build_segments(nbits: int, bitops: Sequence[Tuple[np.ndarray, Sequence[int]]], tile_bits: int = None,
-                   low_bits: int = None, max_cost: float = None, final_perm: Sequence[int] = None) -> List[Segment]:
+                   low_bits: int = None, max_cost: float = None, final_perm: Sequence[int] = None,
+                   reg_bits: int = None) -> List[Segment]:
     """Plan a list of (matrix, bits) operators for a state with `nbits` local index bits. `final_perm` (destination
     bit j <- source bit final_perm[j]) is an in-place bit permutation executed after the last operator, fused into
     the last sweep when its tile holds the moved bits (the local half of a qubit remap, sharded.py)."""
-    return build_segments_from_items(nbits, classify_all(bitops), tile_bits, low_bits, max_cost, final_perm)
+    return build_segments_from_items(nbits, classify_all(bitops), tile_bits, low_bits, max_cost, final_perm,
+                                     reg_bits=reg_bits)
 
 
 def build_segments_from_items(nbits: int, items: Sequence[object], tile_bits: int = None, low_bits: int = None,
                               max_cost: float = None, final_perm: Sequence[int] = None,
-                              preset: Sequence[Tuple[int, Optional[Sequence[int]]]] = None) -> List[Segment]:
+                              preset: Sequence[Tuple[int, Optional[Sequence[int]]]] = None,
+                              reg_bits: int = None) -> List[Segment]:
     """build_segments for operators that are already classified (POp / Fallback, see classify_all). `preset`
     fixes the split into sweeps: (number of items, tile bits) per sweep in order, (1, None) for a Fallback."""
-    planner = Planner(nbits, tile_bits, low_bits, max_cost)
+    planner = Planner(nbits, tile_bits, low_bits, max_cost, reg_bits=reg_bits)
     segments: List[Segment] = []
     pending: List[POp] = []
     groups: List[Tuple[List[POp], List[int]]] = []      # preset sweeps, consumed from the end as items stream by

@@ -9,8 +9,10 @@ import struct
 
 import numpy as np
 
-R = 5
+R = 5              # register bits of the plan being parsed / executed (parse() sets it from the header: 4 or 5)
 NE = 1 << R
+HS = 5             # handler ids are laid out for 5 register bits
+TABLE = 32         # entries of a diagonal table record
 
 
 def swz(idx):
@@ -18,7 +20,7 @@ def swz(idx):
     return idx ^ ((x ^ (x >> 3) ^ (x >> 6) ^ (x >> 9)) & 7)
 
 
-G2_PAIRS = [(j0, j1) for j0 in range(R) for j1 in range(j0)]
+G2_PAIRS = [(j0, j1) for j0 in range(HS) for j1 in range(j0)]
 (H_G1_GENERAL, H_G1_SUMDIFF, H_G1_ROT_R, H_G1_ROT_I, H_G1C_GENERAL, H_G1C_SWAPX, H_CPH_SCALAR, H_CPH_REG1,
  H_CPH_RSC1, H_CPH_NEG1, H_CPH_NEG2, H_CPH_REGM, H_CPH_NEGM, H_END, H_G2, H_G2X, H_CPH_TABLE) = \
     0, 5, 10, 15, 20, 25, 30, 31, 36, 41, 46, 56, 57, 58, 59, 69, 79
@@ -26,8 +28,10 @@ SWEEP_HEADER, ROUND_HEADER = 112, 192 + 768
 
 
 def parse(blob: bytes):
+    global R, NE
     magic, version, nbits, M, rbits, nsweeps, total = struct.unpack_from('<IIIIIIQ', blob, 0)
-    assert magic == 0x50424651 and version == 13 and rbits == R and total == len(blob)
+    assert magic == 0x50424651 and version == 13 and rbits in (4, 5) and total == len(blob)
+    R, NE = rbits, 1 << rbits
     off = 32
     sweeps = []
     for _ in range(nsweeps):
@@ -77,21 +81,23 @@ def parse(blob: bytes):
                     break
                 if handler == H_CPH_TABLE:
                     # diagonal table over the register index; flag 1 = acts on every amplitude (entry 0 included)
-                    assert obytes == 16 + 16 * NE and icm == 0 and flag in (0, 1) and (rcm != 0 or flag == 1)
+                    assert obytes == 16 + 16 * TABLE and icm == 0 and flag in (0, 1) and (rcm != 0 or flag == 1)
                     typ, kind, j0, j1 = 4, 'table', 0, 0
-                    tbl = np.frombuffer(payload, dtype=np.complex128, count=NE)
+                    tbl = np.frombuffer(payload, dtype=np.complex128, count=TABLE)
+                    assert rcm < NE
                     if not flag:
                         assert all(tbl[e] == tbl[e & rcm] for e in range(NE)) and tbl[0] == 1
                 elif handler < H_G1C_GENERAL:
                     assert rcm == 0 and icm == 0
-                    kind = ['general', 'sumdiff', 'rot_r', 'rot_i'][handler // R]
+                    kind = ['general', 'sumdiff', 'rot_r', 'rot_i'][handler // HS]
                     assert obytes == (80 if kind == 'general' else 32)
-                    typ, j0, j1 = 1, handler % R, 0
+                    typ, j0, j1 = 1, handler % HS, 0
+                    assert j0 < R
                 elif handler < H_CPH_SCALAR:
                     kind = 'general' if handler < H_G1C_SWAPX else 'swapx'
                     assert obytes == (80 if kind == 'general' else 32)
-                    typ, j0, j1 = 1, handler % R, 0
-                    assert not (rcm >> j0) & 1
+                    typ, j0, j1 = 1, handler % HS, 0
+                    assert j0 < R and not (rcm >> j0) & 1
                 elif handler < H_END:
                     typ, j0, j1 = 3, 0, 0
                     assert obytes == 32
@@ -281,7 +287,7 @@ def execute(blob: bytes, state: np.ndarray, index_hi: int = 0, check_layout: boo
                     for op in rd['ops']:
                         on = (tfull & op['idx_cmask']) == op['idx_cmask']
                         if op['type'] == 4:
-                            tbl = np.frombuffer(op['payload'], dtype=np.complex128, count=NE)
+                            tbl = np.frombuffer(op['payload'], dtype=np.complex128, count=TABLE)
                             for e in range(NE):
                                 if op['flag'] or (e & op['reg_cmask']):
                                     a[e] = tbl[e] * a[e]

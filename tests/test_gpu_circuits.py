@@ -264,3 +264,24 @@ def test_run_pipelined_matches_run_on_host_resident_states():
         assert np.abs(out.numpy() - want).max() < AMP_TOL
     with pytest.raises(ValueError):
         circ.run_pipelined([torch.zeros(1 << n, dtype=torch.complex128)], outs[:1])      # not pinned
+
+
+@pytest.mark.parametrize('reg_bits', ['4', '5'])
+def test_sweep_specialised_kernels_match_reference(golden, monkeypatch, reg_bits):
+    """The same fixtures through the sweep-specialised kernels (csrc/qfb_jit.cu), forced on for small states, with 4
+    and 5 register bits, and agreement with the interpreter on a density workload."""
+    data = golden('workloads.npz')
+    monkeypatch.setenv('QFB_JIT', '1')
+    monkeypatch.setenv('QFB_REG_BITS', reg_bits)
+    before = engine.launch_count()
+    for seed in (0, 1):
+        got = amps(workloads.wb_circuit(qf, 12, 20, seed).run())
+        assert np.abs(got - data['wb12_seed{}'.format(seed)]).max() < AMP_TOL
+    assert np.abs(amps(workloads.wb_circuit(qf, 16, 8, 3).run()) - data['wb16_d8_seed3']).max() < AMP_TOL
+    assert np.abs(amps(workloads.wa_circuit(qf, 16, 1).run()) - data['wa16_seed1']).max() < AMP_TOL
+    rho_jit = qf.asarray(workloads.wd_circuit(qf, 6, 3, 2).evolve().tensor).reshape(-1)
+    assert engine.launch_count() > before
+    monkeypatch.setenv('QFB_JIT', '0')
+    monkeypatch.setenv('QFB_REG_BITS', '5')
+    rho_int = qf.asarray(workloads.wd_circuit(qf, 6, 3, 2).evolve().tensor).reshape(-1)
+    assert np.abs(rho_jit - rho_int).max() < AMP_TOL

@@ -370,3 +370,87 @@ def test_native_tile_search_matches_its_python_statement(seed):
         again = ctypes.c_uint64(0)
         assert lib.qfb_plan_refine_tile_lookahead(*args, tmask, fmask, keep, max_cost, room, 6, 3,
                                                   ctypes.byref(again), None) == 0 and again.value == la.value
+
+
+# ---------------------------------------------------------------------------------------------------------
+# round 2: plans with 4 register bits (sweep-specialised kernels), diagonal tables, phase terms that sink across
+# sweeps, and the PTX generator (compiled here with the static PTX compiler, no GPU involved)
+# ---------------------------------------------------------------------------------------------------------
+
+@pytest.mark.parametrize('n,depth,seed,tile', [(12, 20, 0, 12), (12, 6, 1, 8), (11, 5, 2, 11), (9, 4, 3, 7),
+                                                (13, 3, 5, 13)])
+def test_wb_plan_with_four_register_bits_matches_oracle(n, depth, seed, tile):
+    specs = workloads.wb_gate_list(n, depth, seed)
+    segments = planner.build_segments(n, bitops_of(specs, n), tile_bits=tile, reg_bits=4)
+    assert all(E.parse(s.blob)['sweeps'] is not None for s in segments if s.kind == 'plan')
+    assert E.R == 4
+    got = run_segments(segments, zero(n))
+    assert np.abs(got - O.run_specs(specs, n).reshape(-1)).max() < AMP_TOL
+
+
+def test_phase_terms_sink_to_their_anchor_and_form_tables():
+    """T / RZ / CZ-heavy circuit: phase terms move to the sweep and round of the operator that next mixes their bit
+    and are multiplied into diagonal tables there; the result is unchanged."""
+    n = 12
+    rnd = random.Random(7)
+    specs = []
+    for layer in range(10):
+        for q in range(n):
+            kind = rnd.choice(['T', 'RZ', 'S', 'H', 'RX'])
+            specs.append((kind, (rnd.uniform(0, 6.28),) if kind in ('RZ', 'RX') else (), (q,)))
+        qs = list(range(n))
+        rnd.shuffle(qs)
+        for a, b in zip(qs[::2], qs[1::2]):
+            specs.append((rnd.choice(['CZ', 'CNOT']), (), (a, b)))
+    for tile, rb in ((8, 5), (8, 4), (12, 4)):
+        segments = planner.build_segments(n, bitops_of(specs, n), tile_bits=tile, reg_bits=rb)
+        ntables = sum(1 for s in segments for sw in E.parse(s.blob)['sweeps'] for rd in sw['rounds']
+                      for op in rd['ops'] if op['type'] == 4)
+        assert ntables > 0
+        got = run_segments(segments, zero(n))
+        assert np.abs(got - O.run_specs(specs, n).reshape(-1)).max() < AMP_TOL
+
+
+def test_sink_phase_terms_keeps_every_operator_and_moves_terms_forward_only():
+    n = 10
+    specs = workloads.wb_gate_list(n, 8, 3)
+    items = [it for it in planner.classify_all(bitops_of(specs, n)) if not isinstance(it, planner.Fallback)]
+    pl = planner.Planner(n, tile_bits=7)
+    parts = pl._partition(items)
+    sunk = planner.sink_phase_terms(parts)
+    before = [id(op) for chosen, _ in parts for op in chosen]
+    after = [id(op) for chosen, _ in sunk for op in chosen]
+    assert sorted(before) == sorted(after)
+    where_before = {id(op): si for si, (chosen, _) in enumerate(parts) for op in chosen}
+    where_after = {id(op): si for si, (chosen, _) in enumerate(sunk) for op in chosen}
+    assert all(where_after[k] >= where_before[k] for k in where_before)
+    # mixing operators never move
+    assert [id(op) for chosen, _ in parts for op in chosen if op.kind == 'G'] == \
+        [id(op) for chosen, _ in sunk for op in chosen if op.kind == 'G']
+
+
+@pytest.mark.parametrize('reg_bits', [4, 5])
+def test_sweep_specialised_ptx_compiles_for_sm100a(reg_bits):
+    """qfb_jit_check: every sweep of a plan -> PTX -> sm_100a image with the statically linked PTX compiler (host
+    code only). Checks the generator's output is valid PTX and that the code of a 4-register-bit sweep stays near
+    the 32 KiB instruction cache."""
+    import ctypes
+    from quantumflow_b200 import _lib
+    n = 20
+    specs = workloads.wb_gate_list(n, 6, 1)
+    segments = planner.build_segments(n, bitops_of(specs, n), reg_bits=reg_bits)
+    lib = _lib.load()
+    for seg in segments:
+        log = ctypes.create_string_buffer(1 << 16)
+        rc = lib.qfb_jit_check(seg.blob, len(seg.blob), log, len(log))
+        assert rc == 0, lib.qfb_last_error()
+        text = log.value.decode()
+        assert 'Used' in text and 'qfb_sweep' in text
+        need, ncoef = ctypes.c_size_t(0), ctypes.c_size_t(0)
+        assert lib.qfb_jit_ptx(seg.blob, len(seg.blob), 0, None, 0, ctypes.byref(need), ctypes.byref(ncoef)) == 0
+        buf = ctypes.create_string_buffer(need.value)
+        assert lib.qfb_jit_ptx(seg.blob, len(seg.blob), 0, buf, need.value, None, None) == 0
+        ptx = buf.value.decode()
+        assert '.target sm_100a' in ptx and 'cp.async.cg.shared.global' in ptx and 'ld.const.f64' in ptx
+        # structure only: no coefficient value appears in the text (one image serves every parameter value)
+        assert ptx.count('ld.const.f64') == ncoef.value
