@@ -34,7 +34,12 @@ def parse_args():
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=5)
     ap.add_argument('--warmup', type=int, default=3)
-    ap.add_argument('--qubits', type=int, default=None, help='qubits per GPU (default 30)')
+    ap.add_argument('--qubits', type=int, default=None,
+                    help='qubits per GPU (default 30 on one GPU, 33 when sharded: BASELINE.json configs[3] / [4])')
+    ap.add_argument('--config', default='headline', choices=['headline', 'c1', 'c2', 'c3'],
+                    help='headline = the W-B circuit of BASELINE.json metric; c1 / c2 / c3 = the other configurations '
+                         '(20-qubit circuit, QAOA gradient step, 14-qubit density evolution), one JSON line each')
+    ap.add_argument('--no-parity', action='store_true', help='skip the sharded-vs-single-GPU parity run (N > 1)')
     ap.add_argument('--depth', type=int, default=20)
     ap.add_argument('--seed', type=int, default=0)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
@@ -114,16 +119,17 @@ def measured_peak_gbs():
 
 
 def ncu_traffic_bytes(nbits: int):
-    """dram read+write bytes per sweep launch from the committed ncu --set full capture (profiles/), if any."""
+    """(dram read+write bytes per sweep launch, where the figure comes from): the committed `ncu --set full` capture
+    of this round's kernel on the same workload (profiles/sweep_traffic.json names the report), or (None, why)."""
     path = os.path.join(ROOT, 'profiles', 'sweep_traffic.json')
     try:
         with open(path) as f:
             rec = json.load(f)
         if int(rec.get('nbits', -1)) == nbits:
-            return float(rec['dram_bytes_per_launch'])
+            return float(rec['dram_bytes_per_launch']), rec.get('source', 'profiles/sweep_traffic.json')
     except Exception:
         pass
-    return None
+    return None, 'no ncu capture for {} index bits per GPU'.format(nbits)
 
 
 # ---------------------------------------------------------------------------------------------------------
@@ -153,8 +159,19 @@ def cpu_baseline_c_port(nq: int, depth: int, seed: int, target_seconds: float) -
                       'numpybk.tensormul (oracle/qf_oracle_c.c), {:.1f} s'.format(done, len(specs), nq, dt)}
 
 
-def reference_einsum_step(nq: int, specs, start: int, ngates: int, state):
-    """`ngates` gates of the circuit with the reference's own np.einsum call (numpybk.py:159-214)."""
+REFERENCE_PROBE_QUBITS = 26      # the reference arm's bounded sample runs at this size (1 GiB state, ~1 s per gate)
+
+
+def representative_gates(m: int):
+    """1-qubit / 2-qubit gates on low / middle / high axes: np.einsum's cost depends on the
+    axis, so the sample cycles through all of them."""
+    lo, mid, hi = 1, m // 2, m - 2
+    return [('H', (), (hi,)), ('CNOT', (), (lo, mid)), ('RX', (0.7,), (mid,)), ('CZ', (), (mid, hi)),
+            ('RY', (0.9,), (lo,)), ('CNOT', (), (hi, lo)), ('T', (), (mid,)), ('CNOT', (), (mid + 1, mid))]
+
+
+def reference_einsum_step(specs, start: int, ngates: int, state):
+    """`ngates` gates with the reference's own np.einsum call (numpybk.py:159-214), cycling through `specs`."""
     from oracle import qf_oracle as O
     t0 = time.perf_counter()
     for i in range(ngates):
@@ -164,7 +181,11 @@ def reference_einsum_step(nq: int, specs, start: int, ngates: int, state):
 
 
 def run_reference_arm(args):
-    """bench.py --impl reference: the reference's algorithm on the host (single-threaded np.einsum)."""
+    """bench.py --impl reference: the reference's algorithm on the host (single-threaded np.einsum, the reference's
+    own subscripts). A full 30-qubit gate takes ~25 s, so every step is a bounded sample: a few representative
+    gates (1q / 2q x low / mid / high axis) on a 2^26-amplitude state, scaled to the benchmark's size by the
+    measured linear cost of einsum in the number of amplitudes (labelled as extrapolated in `sample`). Sized so
+    that the whole --steps / --warmup run ends within a few minutes whatever the number of GPUs of the main arm."""
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
@@ -172,47 +193,56 @@ def run_reference_arm(args):
     from quantumflow_b200 import workloads
     world = max(1, args.gpus)
     p = world.bit_length() - 1
-    nq = (args.qubits or 30) + p
-    specs = workloads.wb_gate_list(nq, args.depth, args.seed)
-    # bounded sample: the circuit's gates are taken in order, `per_step` gates per step
-    probe_n = min(nq, 24)
-    probe = np.zeros([2] * probe_n, dtype=np.complex128)
-    probe[(0,) * probe_n] = 1
-    dt_probe, _ = reference_einsum_step(probe_n, workloads.wb_gate_list(probe_n, 1, 0), 0, 4, probe)
-    est_gate = dt_probe / 4 * (2 ** (nq - probe_n))
-    budget = 150.0 / max(1, args.steps + args.warmup)
-    per_step = max(1, int(budget / max(est_gate, 1e-6)))
-    per_step = min(per_step, len(specs))
-    try:
-        state = np.zeros([2] * nq, dtype=np.complex128)
-        state[(0,) * nq] = 1
-    except MemoryError:
-        print(json.dumps({'impl': 'reference', 'unavailable': 'host cannot hold a {}-qubit state'.format(nq)}))
-        return
-    pos = 0
+    nq = default_local_qubits(args, world) + p
+    ngates = workloads.wb_gate_count(nq, args.depth)
+    m = min(nq, REFERENCE_PROBE_QUBITS)
+    specs = representative_gates(m)
+    state = np.zeros([2] * m, dtype=np.complex128)
+    state[(0,) * m] = 1
+    dt_probe, state = reference_einsum_step(specs, 0, 2, state)
+    budget = 120.0 / max(1, args.steps + args.warmup)              # seconds per step
+    per_step = max(1, min(len(specs), int(budget / max(dt_probe / 2, 1e-6))))
+    pos = 2
     for _ in range(args.warmup):
-        _, state = reference_einsum_step(nq, specs, pos, per_step, state)
+        _, state = reference_einsum_step(specs, pos, per_step, state)
         pos += per_step
     total = 0.0
     for _ in range(args.steps):
-        dt, state = reference_einsum_step(nq, specs, pos, per_step, state)
+        dt, state = reference_einsum_step(specs, pos, per_step, state)
         pos += per_step
         total += dt
-    gates_per_s = per_step * args.steps / total
-    value = gates_per_s * world          # shard-gates/s, see main arm
-    sample = ('{} consecutive gates of the {}-qubit circuit per step (np.einsum with the reference subscripts, '
-              'single thread), {} steps'.format(per_step, nq, args.steps))
+    rate_m = per_step * args.steps / total                          # gates/s on 2^m amplitudes
+    gates_per_s = rate_m / 2.0 ** (nq - m)                          # extrapolated to the benchmark's 2^nq amplitudes
+    value = gates_per_s * 2.0 ** (nq - 30)                          # the main arm's unit (30-qubit equivalents)
+    sample = ('{} representative gates per step (H / RX / RY / T / CNOT / CZ on low, middle and high axes) on a '
+              '{}-qubit state with the reference subscripts of np.einsum, single thread, {} steps: {:.3f} gates/s '
+              'measured at {} qubits, EXTRAPOLATED x 2^-{} to {} qubits (einsum cost is linear in the number of '
+              'amplitudes; a full {}-qubit run of the {} gates would take {:.1f} h)'.format(
+                  per_step, m, args.steps, rate_m, m, nq - m, nq, nq, ngates, ngates / gates_per_s / 3600.0))
     line = {
-        'impl': 'reference', 'metric': 'gates/s', 'value': value, 'unit': 'gates/s', 'n_gpus': world,
+        'impl': 'reference', 'metric': 'gates/s', 'value': value, 'unit': value_unit(world), 'n_gpus': world,
         'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * total / args.steps,
         'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'complex128',
         'data': 'synthetic',
-        'config': workload_config(nq, args.depth, args.seed, world, len(specs)),
-        'cpu_baseline': {'value': value, 'unit': 'gates/s', 'cores': 1, 'kind': 'port', 'sample': sample},
-        'e2e': {'value': value, 'unit': 'gates/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'config': workload_config(nq, args.depth, args.seed, world, ngates),
+        'circuit_gates_per_s': gates_per_s,
+        'cpu_baseline': {'value': value, 'unit': value_unit(world), 'cores': 1, 'kind': 'port', 'sample': sample},
+        'e2e': {'value': value, 'unit': value_unit(world), 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
     }
     print(json.dumps(line))
+
+
+def default_local_qubits(args, world: int) -> int:
+    """Qubits per GPU: BASELINE.json configs[3] (30 qubits) on one GPU, configs[4] (33 per GPU: 34 / 35 / 36 qubits on
+    2 / 4 / 8 GPUs) when sharded."""
+    if args.qubits:
+        return args.qubits
+    return 30 if world == 1 else 33
+
+
+def value_unit(world: int) -> str:
+    return 'gates/s' if world == 1 else 'gates/s in 30-qubit equivalents (circuit gates/s x 2^(qubits-30))'
 
 
 def workload_config(nq, depth, seed, world, ngates):
@@ -221,8 +251,10 @@ def workload_config(nq, depth, seed, world, ngates):
                             depth, nq, seed, ngates),
             'qubits': nq, 'depth': depth, 'gates': ngates, 'seed': seed,
             'sharding': 'none' if world == 1 else 'top {} qubits over {} GPUs'.format(world.bit_length() - 1, world),
-            'unit_of_work': 'one gate applied to one 2^(qubits per GPU)-amplitude shard '
-                            '(value = circuit gates/s x n_gpus; identical to plain gates/s at n_gpus=1)',
+            'unit_of_work': 'one gate of the circuit applied to 2^30 amplitudes: value = circuit gates/s x 2^(qubits-30), '
+                            'plain gates/s for the 30-qubit circuit on one GPU; a sharded run of q qubits does '
+                            '2^(q-30) such units per gate, so value / (n_gpus x one-GPU value) is the weak-scaling '
+                            'efficiency; the raw rate is circuit_gates_per_s',
             'l2': 'state is {} MiB per GPU, far larger than the 126 MB L2 (no flush needed)'.format(
                 (16 << (nq - (world.bit_length() - 1))) >> 20)}
 
@@ -231,10 +263,71 @@ def workload_config(nq, depth, seed, world, ngates):
 # B200 arm
 # ---------------------------------------------------------------------------------------------------------
 
+def sharded_parity(qf, world: int, rank: int, dev) -> float:
+    """Multi-GPU parity inside the bench (no test can skip it): a 21-qubit-per-GPU W-B circuit through the sharded
+    path (sweep-specialised kernels forced on, 1 MiB staging chunks on the NCCL path) against the single-GPU engine
+    running the whole circuit on this rank's device with the interpreter. max-abs amplitude difference over all
+    ranks (tolerance 1e-10, BASELINE.json north_star)."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from quantumflow_b200 import sharded, workloads
+    p = world.bit_length() - 1
+    n = 21 + p
+    saved = {k: os.environ.get(k) for k in ('QFB_JIT', 'QFB_REG_BITS')}
+    try:
+        os.environ['QFB_JIT'] = '1'
+        circ = workloads.wb_circuit(qf, n, 8, 11)
+        runner = sharded.ShardedCircuit(circ, n, world, rank, staging_bytes=1 << 20)
+        shard = torch.zeros(1 << runner.nl, dtype=torch.complex128, device=dev)
+        if rank == 0:
+            shard[0] = 1.0
+        shard = runner.execute(shard)
+        os.environ['QFB_JIT'] = '0'
+        full = qf.asarray(workloads.wb_circuit(qf, n, 8, 11).run().tensor).reshape(-1)
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+    local = np.arange(1 << runner.nl, dtype=np.int64) | (np.int64(rank) << runner.nl)
+    logical = np.zeros_like(local)
+    for b, pos in enumerate(runner.final_phys_of):
+        logical |= ((local >> pos) & 1) << b
+    err = float(np.abs(shard.cpu().numpy() - full[logical]).max())
+    t = torch.tensor([err], dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def spot_amplitudes(state, nlocal: int, nq: int, rank: int, world: int, phys_of, dev):
+    """16 amplitudes at fixed logical indices (a 1-GPU run of the same circuit and seed reproduces them where the
+    state fits one GPU): [[logical index, re, im], ...]."""
+    import torch
+    import torch.distributed as dist
+    out = torch.zeros(16, 2, dtype=torch.float64, device=dev)
+    indices = [(i * 0x9E3779B97F4A7C15 + 12345) % (1 << nq) for i in range(16)]
+    for k, logical in enumerate(indices):
+        physical = 0
+        for b in range(nq):
+            physical |= ((logical >> b) & 1) << (phys_of[b] if phys_of is not None else b)
+        if physical >> nlocal == rank:
+            amp = state[physical & ((1 << nlocal) - 1)]
+            out[k, 0], out[k, 1] = amp.real, amp.imag
+    if world > 1:
+        dist.all_reduce(out)
+    vals = out.cpu().tolist()
+    return [[int(i), v[0], v[1]] for i, v in zip(indices, vals)]
+
+
 def main():
     args = parse_args()
     if args.impl == 'reference':
         run_reference_arm(args)
+        return
+    if args.config != 'headline':
+        run_config(args)
         return
 
     import numpy as np
@@ -249,18 +342,23 @@ def main():
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
+    dev = torch.device('cuda', local_rank)
+    torch.zeros(1, device=dev)                      # CUDA context (not part of the cold-start figure)
+    torch.cuda.synchronize()
 
     import quantumflow_b200 as qf
     from quantumflow_b200 import engine, planner, workloads
 
     p = world.bit_length() - 1
     assert (1 << p) == world, 'number of GPUs must be a power of two'
-    nlocal = args.qubits or 30
+    nlocal = default_local_qubits(args, world)
     nq = nlocal + p
     specs = workloads.wb_gate_list(nq, args.depth, args.seed)
     ngates = len(specs)
+    scale30 = 2.0 ** (nq - 30)                      # 30-qubit equivalents per gate of this circuit
 
-    t_plan0 = time.perf_counter()
+    # ---- cold start: circuit -> plan -> sweep-specialised kernels (PTX generation + compilation) -> first run ----
+    t_cold0 = time.perf_counter()
     circ = workloads.circuit_from_specs(qf, specs)
     if world == 1:
         bitops = [(g.matrix(), [nq - 1 - q for q in g.qubits]) for g in circ.elements]
@@ -272,13 +370,17 @@ def main():
         runner = sharded.ShardedCircuit(circ, nq, world, rank, tile_bits=args.tile_bits, low_bits=args.low_bits,
                                         max_cost=args.max_cost)
         segments = runner.local_segments()
-    plan_seconds = time.perf_counter() - t_plan0
+    plan_seconds = time.perf_counter() - t_cold0
+    t_jit0 = time.perf_counter()
+    for seg in segments:
+        if seg.kind == 'plan' and seg.uploaded is None:
+            seg.uploaded = engine.UploadedPlan(seg.blob)     # validates, compiles (cached per structure), loads
+    jit_seconds = time.perf_counter() - t_jit0
     stats = planner.plan_stats(segments)
-    # fingerprint of the executed plan (all sweep records): lets a reader check which plan a number belongs to
     import hashlib
     stats['plan_sha256'] = hashlib.sha256(b''.join(s.blob for s in segments if s.blob)).hexdigest()[:16]
+    stats['reg_bits'] = planner.default_reg_bits(nlocal)
 
-    dev = torch.device('cuda', local_rank)
     state = torch.zeros(1 << nlocal, dtype=torch.complex128, device=dev)
     if rank == 0:
         state[0] = 1.0
@@ -288,14 +390,28 @@ def main():
         if runner is None:
             qf.Circuit._execute(segments, state)
         else:
-            state = runner.execute(state)     # in place (the remaps exchange blocks through staging chunks)
+            state = runner.execute(state)     # in place (peer-memory block exchange at the remaps)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(args.warmup):
+    step()
+    barrier()
+    cold_seconds = time.perf_counter() - t_cold0
+    spots = spot_amplitudes(state, nlocal, nq, rank, world, runner.final_phys_of if runner is not None else None, dev)
+    cold = {'plan_seconds': plan_seconds, 'kernel_build_seconds': jit_seconds, 'total_seconds': cold_seconds,
+            'value': ngates / cold_seconds * scale30, 'unit': value_unit(world),
+            'what': 'first Circuit.run of a fresh process: build the circuit, plan it, generate + compile + load the '
+                    'sweep-specialised kernels, allocate |0..0>, run once (CUDA context creation excluded)'}
+
+    # ---- parity of the sharded path (N > 1), inside the run the driver records ----
+    parity = None
+    if world > 1 and not args.no_parity:
+        parity = sharded_parity(qf, world, rank, dev)
+
+    for _ in range(max(0, args.warmup - 1)):
         step()
     barrier()
     if runner is not None:
@@ -324,7 +440,7 @@ def main():
     clocks = sampler.stop(t0, t1) if rank == 0 else None
     ms_step = ms_total / args.steps
     gates_per_s = ngates / (ms_step * 1e-3)
-    value = gates_per_s * world
+    value = gates_per_s * scale30
 
     # unitarity check after all steps: the state must still be normalised (work was really done, correctly)
     n2 = engine.norm2(state)
@@ -339,65 +455,28 @@ def main():
     algo_bytes = 32.0 * (1 << nlocal)
     peak, peak_src = measured_peak_gbs()
     achieved = algo_bytes / (sweep_ms * 1e-3) / 1e9
+    traffic, traffic_src = ncu_traffic_bytes(nlocal)
     roofline = {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
-                'traffic': ncu_traffic_bytes(nlocal), 'kernel': 'sweep_kernel<{}>'.format(
+                'traffic': traffic, 'traffic_source': traffic_src,
+                'kernel': 'qfb_sweep (sweep-specialised, {} register bits, tile 2^{})'.format(
+                    stats['reg_bits'], args.tile_bits or planner.DEFAULT_TILE_BITS)
+                if os.environ.get('QFB_JIT', '1') != '0' else 'sweep_kernel<{}> (interpreter)'.format(
                     args.tile_bits or planner.DEFAULT_TILE_BITS),
                 'algorithmic_bytes_per_launch': algo_bytes, 'launches_per_step': nsweeps,
                 'avg_launch_ms': sweep_ms, 'peak_source': peak_src}
 
-    # end-to-end through the public API with host buffers (N=1: State from pinned host memory -> Circuit.run ->
-    # result back in pinned host memory). At N>1 each rank does the same with its shard.
+    # ---- end to end with HOST buffers ----
     e2e = None
-    if not args.no_e2e and nlocal <= 31:     # 2 x 16 GiB of pinned host memory per rank at 30 qubits per GPU
-        nbytes = 16 << nlocal
+    e2e_ref_shaped = None
+    nbytes = 16 << nlocal
+    if not args.no_e2e:
         del state
         torch.cuda.empty_cache()
-        try:
-            host_in = torch.zeros(1 << nlocal, dtype=torch.complex128).pin_memory()
-            if rank == 0:
-                host_in[0] = 1.0
-            host_out = torch.empty(1 << nlocal, dtype=torch.complex128).pin_memory()
-            pinned_ok = 1
-        except (RuntimeError, MemoryError):
-            host_in = host_out = None
-            pinned_ok = 0
-        if world > 1:       # every rank must take the same branch: the e2e loop contains collectives
-            flag = torch.tensor([pinned_ok], dtype=torch.int32, device=dev)
-            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
-            pinned_ok = int(flag.item())
-    if not args.no_e2e and nlocal <= 31 and not pinned_ok:
-        e2e = {'value': None, 'unit': 'gates/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0,
-               'skipped': 'pinned host buffers (2 x {} GiB per rank) could not be allocated'.format(nbytes >> 30)}
-    elif not args.no_e2e and nlocal <= 31:
-        # N=1: Circuit.run_pipelined streams the states through upload / sweeps / download on three streams
-        # (every step's 16 GiB input and 16 GiB result cross PCIe inside the timed region; pipeline fill and
-        # drain are inside it too). N>1: each rank uploads its shard, runs the sharded circuit, downloads it.
-        e2e_steps = max(args.steps, 16) if runner is None else max(1, min(args.steps, 3))
-
-        def e2e_steps_run(count):
-            if runner is None:
-                circ.run_pipelined([host_in] * count, [host_out] * count, depth=3)
-            else:
-                for _ in range(count):
-                    dstate = runner.execute(host_in.to(dev, non_blocking=False))
-                    host_out.copy_(dstate, non_blocking=False)
-
-        e2e_steps_run(1)      # warm-up (the first call also builds and uploads the plan)
-        barrier()
-        tw0 = time.perf_counter()
-        e2e_steps_run(e2e_steps)
-        barrier()
-        e2e_ms = 1e3 * (time.perf_counter() - tw0) / e2e_steps
-        if world > 1:
-            t = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            e2e_ms = float(t.item())
-        e2e = {'value': ngates / (e2e_ms * 1e-3) * world, 'unit': 'gates/s', 'h2d_bytes_per_step': nbytes * world,
-               'd2h_bytes_per_step': nbytes * world, 'ms_per_step': e2e_ms, 'steps': e2e_steps,
-               'api': ('Circuit.run_pipelined(pinned host states -> pinned host results), 3 device buffers, upload / '
-                       'sweeps / download overlapped across consecutive steps') if runner is None else
-                      'pinned host shard -> ShardedCircuit.execute -> pinned host shard'}
-        del host_in, host_out
+        if nlocal <= 31:
+            e2e, e2e_ref_shaped = e2e_resident_host(args, qf, circ, runner, nlocal, nq, ngates, scale30, world, rank,
+                                                    dev, barrier)
+        else:
+            e2e = e2e_streamed(args, runner, nlocal, ngates, scale30, world, rank, dev, barrier)
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -408,22 +487,249 @@ def main():
 
     if rank == 0:
         line = {
-            'metric': 'gates/s', 'value': value, 'unit': 'gates/s', 'n_gpus': world, 'steps': args.steps,
+            'metric': 'gates/s', 'value': value, 'unit': value_unit(world), 'n_gpus': world, 'steps': args.steps,
             'warmup': args.warmup, 'ms_per_step': ms_step, 'higher_is_better': True, 'scaling': 'weak',
             'vs_baseline': None, 'dtype': 'complex128', 'data': 'synthetic',
             'config': workload_config(nq, args.depth, args.seed, world, ngates),
-            'plan': dict(stats, plan_seconds=plan_seconds, tile_bits=args.tile_bits or planner.DEFAULT_TILE_BITS),
+            'plan': dict(stats, plan_seconds=plan_seconds, kernel_build_seconds=jit_seconds,
+                         tile_bits=args.tile_bits or planner.DEFAULT_TILE_BITS),
             'circuit_gates_per_s': gates_per_s,
             'unfused_equivalent_gbs': ngates * algo_bytes / (ms_step * 1e-3) / 1e9,
-            'norm_error_after_run': norm_err,
-            'roofline': roofline, 'cpu_baseline': cpu, 'e2e': e2e, 'gpu_launches': int(launches),
-            'clocks': clocks,
+            'norm_error_after_run': norm_err, 'parity_max_abs': parity, 'spot_amplitudes': spots,
+            'roofline': roofline, 'cpu_baseline': cpu, 'e2e': e2e, 'e2e_reference_shaped': e2e_ref_shaped,
+            'e2e_cold': cold, 'gpu_launches': int(launches), 'clocks': clocks,
         }
         if runner is not None:
             line['comm'] = runner.comm_summary()
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def run_config(args):
+    """bench.py --config c1|c2|c3: the BASELINE.json configurations that are parity cases rather than the headline
+    (SURVEY 8d W-B 20 qubits, W-Q QAOA gradient step, W-D 14-qubit density evolution), through the public API on
+    one GPU, one JSON line. Timed with CUDA events around `steps` calls after `warmup` calls; the state is created
+    inside the timed call as the reference's Circuit.run() does."""
+    import numpy as np
+    import torch
+    torch.cuda.set_device(0)
+    import quantumflow_b200 as qf
+    from quantumflow_b200 import engine, workloads
+    peak, peak_src = measured_peak_gbs()
+    line = None
+    if args.config == 'c1':
+        n = args.qubits or 20
+        circ = workloads.wb_circuit(qf, n, args.depth, args.seed)
+        units, unit, what = len(circ.elements), 'gates/s', 'Circuit.run() of the W-B circuit, {} qubits depth {}, {} gates'.format(n, args.depth, len(circ.elements))
+        call = lambda: circ.run()                                                       # noqa: E731
+        state_bytes = 16 << n
+    elif args.config == 'c3':
+        n = args.qubits or 14
+        circ = workloads.wd_circuit(qf, n, args.depth, args.seed, kraus=True)
+        units, unit, what = len(circ.elements), 'ops/s', ('Circuit.evolve() of the W-D density workload, {} qubits depth {}: '
+                                                         '{} operations (RX, CNOT, Depolarizing(0.01) as Kraus), rho = {} MiB'
+                                                         .format(n, args.depth, len(circ.elements), (16 << (2 * n)) >> 20))
+        call = lambda: circ.evolve()                                                    # noqa: E731
+        state_bytes = 16 << (2 * n)
+    else:
+        import networkx as nx
+        n, steps_p = args.qubits or 6, 5
+        graph = nx.gnp_random_graph(n, 0.5, seed=args.seed)
+        cuts = qf.graph_cuts(graph)
+        np.random.seed(args.seed)
+        beta = torch.tensor(np.random.normal(0.5, 0.01, size=steps_p), requires_grad=True)
+        gamma = torch.tensor(np.random.normal(0.5, 0.01, size=steps_p), requires_grad=True)
+
+        def call():
+            circ = qf.qubo_circuit(graph, steps_p, beta, gamma)
+            expect = circ.run().expectation(cuts)
+            (-expect).backward()
+            with torch.no_grad():
+                beta.sub_(0.01 * beta.grad)
+                gamma.sub_(0.01 * gamma.grad)
+            beta.grad = None
+            gamma.grad = None
+            return expect
+        units, unit = 1, 'gradient steps/s'
+        what = ('QAOA MaxCut gradient step (examples/qaoa_maxcut.py): gnp_random_graph({}, 0.5, seed {}) with {} edges, '
+                '{} QAOA steps, forward + backward through the torch.autograd bridge + plain gradient descent'
+                .format(n, args.seed, graph.number_of_edges(), steps_p))
+        state_bytes = 16 << n
+    for _ in range(max(1, args.warmup)):
+        call()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(0)
+    sampler.start()
+    time.sleep(0.3)
+    launches0 = engine.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.time()
+    tw0 = time.perf_counter()
+    ev0.record()
+    for _ in range(args.steps):
+        call()
+    ev1.record()
+    torch.cuda.synchronize()
+    wall_ms = 1e3 * (time.perf_counter() - tw0) / args.steps
+    t1 = time.time()
+    ms = ev0.elapsed_time(ev1) / args.steps
+    launches = (engine.launch_count() - launches0) / args.steps
+    clocks = sampler.stop(t0, t1)
+    line = {'metric': unit, 'value': units / (ms * 1e-3), 'unit': unit, 'n_gpus': 1, 'steps': args.steps,
+            'warmup': args.warmup, 'ms_per_step': ms, 'wall_ms_per_step': wall_ms, 'higher_is_better': True,
+            'scaling': 'weak', 'vs_baseline': None, 'dtype': 'complex128', 'data': 'synthetic',
+            'config': {'workload': what, 'name': args.config},
+            'gpu_launches': launches * args.steps, 'launches_per_step': launches, 'clocks': clocks}
+    if args.config == 'c3':
+        segs = [seg for cache in [circ.__dict__.get('_plan_cache', {})] for hit in cache.values() for seg in hit[0]]
+        nsweeps = sum(seg.nsweeps for seg in segs)
+        algo = 2.0 * state_bytes
+        line['roofline'] = {'bound': 'hbm', 'achieved': nsweeps * algo / (ms * 1e-3) / 1e9, 'peak': peak, 'unit': 'GB/s',
+                            'frac': nsweeps * algo / (ms * 1e-3) / 1e9 / peak, 'traffic': None,
+                            'algorithmic_bytes_per_launch': algo, 'launches_per_step': nsweeps,
+                            'avg_launch_ms': ms / max(1, nsweeps), 'peak_source': peak_src,
+                            'note': 'every sweep of rho carries dense 2-bit superoperators (16 or 4 FP64 instructions per '
+                                    'amplitude each): the FP64 pipe, not HBM, bounds these sweeps (DESIGN.md section 4)'}
+    else:
+        line['roofline'] = {'bound': 'launch latency', 'achieved': None, 'peak': None, 'unit': 'GB/s', 'frac': None,
+                            'traffic': None,
+                            'note': 'state of {} bytes is L2 / cache resident: the step is bound by kernel launches and '
+                                    'host-side work, not by HBM (SURVEY 8d)'.format(state_bytes)}
+    print(json.dumps(line))
+
+
+def e2e_resident_host(args, qf, circ, runner, nlocal, nq, ngates, scale30, world, rank, dev, barrier):
+    """States that fit pinned host memory (<= 31 qubits per GPU). N=1: Circuit.run_pipelined streams host states
+    through upload / sweeps / download on three streams, plus the reference-shaped sequence State(host array) ->
+    Circuit.run -> asarray. N>1: each rank uploads its shard, runs the sharded circuit, downloads it."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    nbytes = 16 << nlocal
+    try:
+        host_in = torch.zeros(1 << nlocal, dtype=torch.complex128).pin_memory()
+        if rank == 0:
+            host_in[0] = 1.0
+        host_out = torch.empty(1 << nlocal, dtype=torch.complex128).pin_memory()
+        pinned_ok = 1
+    except (RuntimeError, MemoryError):
+        host_in = host_out = None
+        pinned_ok = 0
+    if world > 1:       # every rank must take the same branch: the e2e loop contains collectives
+        flag = torch.tensor([pinned_ok], dtype=torch.int32, device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        pinned_ok = int(flag.item())
+    if not pinned_ok:
+        return ({'value': None, 'unit': value_unit(world), 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0,
+                 'skipped': 'pinned host buffers (2 x {} GiB per rank) could not be allocated'.format(nbytes >> 30)},
+                None)
+    e2e_steps = max(args.steps, 16) if runner is None else max(1, min(args.steps, 3))
+
+    def e2e_steps_run(count):
+        if runner is None:
+            circ.run_pipelined([host_in] * count, [host_out] * count, depth=3)
+        else:
+            for _ in range(count):
+                dstate = runner.execute(host_in.to(dev, non_blocking=False))
+                host_out.copy_(dstate, non_blocking=False)
+
+    e2e_steps_run(1)      # warm-up
+    barrier()
+    tw0 = time.perf_counter()
+    e2e_steps_run(e2e_steps)
+    barrier()
+    e2e_ms = 1e3 * (time.perf_counter() - tw0) / e2e_steps
+    if world > 1:
+        t = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_ms = float(t.item())
+    e2e = {'value': ngates / (e2e_ms * 1e-3) * scale30, 'unit': value_unit(world),
+           'h2d_bytes_per_step': nbytes * world, 'd2h_bytes_per_step': nbytes * world, 'ms_per_step': e2e_ms,
+           'steps': e2e_steps,
+           'api': ('Circuit.run_pipelined(pinned host states -> pinned host results), 3 device buffers, upload / '
+                   'sweeps / download overlapped across consecutive steps') if runner is None else
+                  'pinned host shard -> ShardedCircuit.execute -> pinned host shard'}
+    ref_shaped = None
+    if runner is None:
+        # the reference's own call sequence (qf.State(array) -> Circuit.run -> asarray), pageable numpy arrays
+        del host_out
+        host_np = host_in.numpy().reshape([2] * nq)
+        times = []
+        for _ in range(2):
+            torch.cuda.synchronize()
+            tr0 = time.perf_counter()
+            ket = qf.State(host_np)
+            out = circ.run(ket)
+            res = qf.asarray(out.tensor)
+            times.append(time.perf_counter() - tr0)
+            assert abs(float(np.vdot(res[(0,) * nq], res[(0,) * nq]).real)) >= 0.0
+            del ket, out, res
+        ref_ms = 1e3 * min(times)
+        ref_shaped = {'value': ngates / (ref_ms * 1e-3), 'unit': 'gates/s', 'ms_per_step': ref_ms,
+                      'h2d_bytes_per_step': nbytes, 'd2h_bytes_per_step': nbytes,
+                      'api': 'qf.State(host numpy array) -> Circuit.run(ket) -> qf.asarray(result): the reference\'s '
+                             'call sequence, un-pipelined (upload, clone of the caller\'s state, sweeps, download in a row)'}
+    return e2e, ref_shaped
+
+
+def e2e_streamed(args, runner, nlocal, ngates, scale30, world, rank, dev, barrier):
+    """Shards that do not fit pinned host memory (33 qubits per GPU = 128 GiB per rank): the shard crosses PCIe in
+    1 GiB pieces through two pinned staging buffers, host -> device before the circuit and device -> host after it,
+    inside the timed region. The host never holds the whole shard: the input pieces are produced in the staging
+    buffer (|0..0>: zeros, amplitude 1 in rank 0's first piece), the result pieces are overwritten after a checksum."""
+    import torch
+    import torch.distributed as dist
+    nbytes = 16 << nlocal
+    piece = 1 << 26                                    # amplitudes per piece (1 GiB)
+    npieces = (1 << nlocal) // piece
+    stage = [torch.zeros(piece, dtype=torch.complex128).pin_memory() for _ in range(2)]
+    shard = torch.empty(1 << nlocal, dtype=torch.complex128, device=dev)
+    copy_stream = torch.cuda.Stream(dev)
+
+    def one_step():
+        nonlocal shard
+        with torch.cuda.stream(copy_stream):
+            for i in range(npieces):
+                buf = stage[i % 2]
+                if i < 2:
+                    buf.zero_()
+                    if rank == 0 and i == 0:
+                        buf[0] = 1.0
+                elif rank == 0 and i == 2:
+                    stage[0][0] = 0.0
+                shard[i * piece:(i + 1) * piece].copy_(buf, non_blocking=True)
+        copy_stream.synchronize()
+        shard = runner.execute(shard)
+        torch.cuda.synchronize()
+        acc = 0.0
+        with torch.cuda.stream(copy_stream):
+            for i in range(npieces):
+                buf = stage[i % 2]
+                buf.copy_(shard[i * piece:(i + 1) * piece], non_blocking=True)
+                if i % 2 == 1:
+                    copy_stream.synchronize()
+                    acc += float(stage[0][0].real) + float(stage[1][0].real)
+        copy_stream.synchronize()
+        return acc
+
+    steps = 1 if args.steps < 4 else 2
+    barrier()
+    tw0 = time.perf_counter()
+    for _ in range(steps):
+        one_step()
+    barrier()
+    e2e_ms = 1e3 * (time.perf_counter() - tw0) / steps
+    t = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_ms = float(t.item())
+    del shard
+    return {'value': ngates / (e2e_ms * 1e-3) * scale30, 'unit': value_unit(world),
+            'h2d_bytes_per_step': nbytes * world, 'd2h_bytes_per_step': nbytes * world, 'ms_per_step': e2e_ms,
+            'steps': steps,
+            'api': 'each rank: host pieces of 1 GiB (two pinned staging buffers) -> shard -> ShardedCircuit.execute -> '
+                   'host pieces; {} GiB up and {} GiB down per rank and step inside the timed region; the host '
+                   'never holds a whole shard'.format(nbytes >> 30, nbytes >> 30)}
 
 
 if __name__ == '__main__':

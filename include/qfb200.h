@@ -149,6 +149,15 @@ int qfb_plan_refine_tile_lookahead(const uint64_t *mix, const uint64_t *diag, co
                                    uint64_t tmask, uint64_t fmask, uint64_t keep, double max_cost, int64_t room,
                                    int passes, int lookahead_passes, uint64_t *tmask_out, int *score_out);
 
+/* ---- sharded states: the exchange half of a qubit remap (csrc/qfb_remap.cu; the reference has no distributed
+ * path) ---- */
+/* For i < npairs: the `nelems[i]` complex128 amplitudes at local_blocks[i] (this GPU) and at remote_blocks[i] (a
+ * peer GPU's shard, mapped into this process, e.g. through CUDA IPC) trade places, in one kernel over NVLink.
+ * Both ranks of a pair call it for disjoint halves of the pair's blocks. Stream ordered; the caller orders it
+ * against the peers' work (a barrier before and after). Host arrays. */
+int qfb_remap_swap(int npairs, void *const *local_blocks, void *const *remote_blocks, const uint64_t *nelems,
+                   void *stream);
+
 /* ---- autograd bridge ---- */
 /* grad_mat[r][c] = sum_groups g[base|off[r]] * conj(psi[base|off[c]])   (k <= 3), written to out_dev (4^k c128) */
 int qfb_gate_grad(const void *g, const void *psi, int nbits, int k, const int *bits, void *out_dev, void *stream);

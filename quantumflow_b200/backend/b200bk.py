@@ -39,6 +39,10 @@ EINSUM_SUBSCRIPTS = string.ascii_lowercase + string.ascii_uppercase
 
 DEVICE = 'gpu'
 
+# largest host tensor that tensormul treats as an operator (a 6-qubit channel has 4^6 = 4096 elements ... 2^16 covers
+# 8-qubit gates); anything larger on the host is an amplitude tensor in the wrong place
+HOST_OPERATOR_LIMIT = 1 << 16
+
 from math import pi  # noqa: E402,F401  (the reference backends re-export pi)
 
 
@@ -337,6 +341,12 @@ def tensormul(tensor0: BKTensor, tensor1: BKTensor, indices: typing.List[int]) -
         raise ValueError('tensormul: bad indices {}'.format(indices))
 
     if not is_amplitudes(tensor1):
+        # operator (x) operator algebra of the planner (Gate @ Gate, aschannel): at most a few thousand elements.
+        # A state-sized tensor on the host is a usage error: amplitudes live in HBM and there is no CPU path.
+        if size(tensor1) > HOST_OPERATOR_LIMIT:
+            raise RuntimeError('tensormul: a {}-element tensor on the host is not an operator; states and densities '
+                               'must be amplitude tensors (bk.asamplitudes / qf.State) -- there is no CPU path'
+                               .format(size(tensor1)))
         return _host_tensormul(astensor(tensor0), astensor(tensor1), indices)
 
     from ..autograd import needs_grad, tensormul_autograd

@@ -186,8 +186,13 @@ class Gate(Operation):
 
 
 def _format_param(obj: Any) -> str:
+    """Quil text of a gate parameter (quantumflow/ops.py:204-210): floats as small fractions (of pi) when they are."""
     if isinstance(obj, float):
-        return repr(round(obj, 12)) if obj != int(obj) else str(obj)
+        from .utils import symbolize
+        try:
+            return symbolize(obj)
+        except (ValueError, OverflowError):
+            return '{}'.format(obj)
     return str(obj)
 
 

@@ -20,6 +20,8 @@ kept on the host, so "swapping back" is never needed.
 so the scheduling and exchange logic is testable on CPU with gloo and the oracle standing in for the kernels
 (tests/test_sharded_cpu.py); on GPU the callables are the libqfb200 paths.
 """
+import ctypes
+import os
 import time
 from typing import Callable, Dict, List, Optional, Sequence, Tuple
 
@@ -104,12 +106,17 @@ def schedule(nbits: int, p: int, bitops: Sequence[BitOp], tile_bits: int = None,
     # variants - picking the variant that does most work NOW is exactly what it is there to avoid
     for tries, lookahead in [(t, False) for t in SWEEP_TRIES_CANDIDATES] + [(0, True)]:
         for cand in (THIN_CANDIDATES[1:3] if lookahead else THIN_CANDIDATES):     # the look-ahead is the slow one
-            steps, phys_of, nsweeps = _schedule_once(nbits, p, bitops, tile_bits, low_bits, max_cost, cand, tries,
-                                                     lookahead)
+            try:
+                steps, phys_of, nsweeps = _schedule_once(nbits, p, bitops, tile_bits, low_bits, max_cost, cand, tries,
+                                                         lookahead)
+            except RuntimeError:
+                continue          # one candidate that cannot be scheduled must not abort the others
             cost = nsweeps + sum(REMAP_COST_PER_FRACTION * (1.0 - 0.5 ** len(st.rank_positions))
                                  for st in steps if isinstance(st, Remap))
             if best is None or cost < best[0] - 1e-9:
                 best = (cost, steps, phys_of)
+    if best is None:
+        raise RuntimeError('no schedule found')
     return best[1], best[2]
 
 
@@ -188,12 +195,14 @@ def _schedule_once(nbits: int, p: int, bitops: Sequence[BitOp], tile_bits: int, 
     nbare = 0                            # remaps whose local permutation needs a bare sweep of its own
     before_last: Optional[List[object]] = None    # the operator list the stage's last sweep was formed from
     fresh = True                         # no sweep yet since the last remap: take the next one whatever its size
+    force = False                        # the remap rule found nothing to exchange: take the thin sweep after all
     while remaining:
         glob = frozenset(b for b in range(nbits) if phys_of[b] >= nl)
         chosen, rest, waiting, tile = next_sweep(glob, remaining)
         work = sum(getattr(o, 'cost', 1.0) for o in chosen)
         thin = bool(costs) and work < thin_fraction * (sum(costs) / len(costs))
-        if chosen and not (waiting and thin and not fresh):
+        if chosen and not (waiting and thin and not fresh and not force):
+            force = False
             before_last = remaining
             take(chosen, tile)
             costs.append(work)
@@ -215,6 +224,12 @@ def _schedule_once(nbits: int, p: int, bitops: Sequence[BitOp], tile_bits: int, 
         incoming = sorted(cur_global - new_global, key=lambda b: phys_of[b])     # rank -> local
         k = len(outgoing)
         if k == 0:
+            # Belady keeps the current global bits (the waiting operators' bits are used farthest in the future):
+            # a remap would change nothing. If the stage was cut short because the next sweep is thin, run that
+            # sweep instead (it is what unblocks the order); only a truly stuck schedule is an error.
+            if chosen and not force:
+                force = True
+                continue
             raise RuntimeError('scheduler made no progress')
         # local permutation: outgoing logical bits move to the top-k local positions nl-k .. nl-1
         top = list(range(nl - k, nl))
@@ -295,6 +310,9 @@ class ShardedCircuit:
         self._permute = permute            # test double only (out of place); the GPU path fuses it into the plan
         self._staging_bytes = int(staging_bytes)
         self._staging = None
+        self._peers = None             # peers' shards mapped into this process (CUDA IPC), see _map_peers
+        self._peer_key = None
+        self._token = None
         self._comm_seconds = 0.0
         self._comm_bytes = 0
         self._remaps = 0
@@ -331,14 +349,81 @@ class ShardedCircuit:
         ex = max(1, self._executions)
         return {'remaps_per_step': self._remaps / ex, 'bytes_sent_per_rank_per_step': self._comm_bytes / ex,
                 'ms_per_step': self.comm_ms_per_step(),
-                'note': 'in-place pairwise block exchange (isend/irecv, XOR pairing) of k rank bits with the top-k '
-                        'local bits, chunked through two staging buffers; the local bit permutation is fused '
-                        'into the last sweep of the preceding stage; not overlapped with compute yet'}
+                'path': self._exchange_path,
+                'note': 'in-place pairwise block exchange of k rank bits with the top-k local bits; path "peer": one '
+                        'kernel per remap and rank swaps its half of every pair over peer memory (qfb_remap_swap, '
+                        'NVLink loads / stores on the IPC-mapped shards, no staging, no NCCL call); path "nccl": '
+                        'isend / irecv chunks through two staging buffers. The local bit permutation is fused into '
+                        'the last sweep of the preceding stage; the exchange is not overlapped with sweeps'}
 
     def reset_comm_counters(self) -> None:
         self._comm_seconds, self._comm_bytes, self._remaps, self._executions = 0.0, 0, 0, 0
 
     # ---- execution ---------------------------------------------------------------------------------
+    _exchange_path = 'nccl'
+
+    def _map_peers(self, shard: torch.Tensor) -> None:
+        """Map every peer's shard into this process through CUDA IPC (one process per GPU on one box): afterwards
+        self._peers[r] is a device pointer to rank r's shard that this GPU's kernels can load from and store to
+        over NVLink. Collective; done once per shard buffer."""
+        key = (shard.data_ptr(), shard.numel())
+        if self._peer_key == key:
+            return
+        storage = shard.untyped_storage()
+        mine = (storage._share_cuda_(), shard.storage_offset() * shard.element_size())
+        gathered = [None] * self.world
+        dist.all_gather_object(gathered, mine, group=self.group)
+        self._peer_storages, self._peers = [], [0] * self.world
+        for r, (handle, offset) in enumerate(gathered):
+            if r == self.rank:
+                self._peers[r] = shard.data_ptr()
+                continue
+            # open the peer's allocation with THIS rank's device current: cudaIpcOpenMemHandle then enables peer
+            # access from this GPU to the GPU that owns the memory (the tuple's first entry is the owner's device)
+            st = torch.UntypedStorage._new_shared_cuda(shard.device.index, *handle[1:])
+            self._peer_storages.append(st)                 # keeps the mapping alive
+            self._peers[r] = st.data_ptr() + offset
+        self._peer_key = key
+        self._token = torch.zeros(1, dtype=torch.int32, device=shard.device)
+
+    def _rank_barrier(self) -> None:
+        """Stream-ordered barrier across the ranks: nobody's later work starts before everybody's earlier work
+        (on the current streams) is complete. One 4-byte all-reduce."""
+        dist.all_reduce(self._token, group=self.group)
+
+    def _exchange_peer(self, shard: torch.Tensor, rank_positions: List[int]) -> None:
+        """The exchange as ONE kernel over peer memory (csrc/qfb_remap.cu): block j of this rank trades places
+        with block `mine` of the peer whose selected rank bits equal j; of every pair's block the lower rank swaps
+        the first half and the higher rank the second half."""
+        from . import _lib, engine
+        self._map_peers(shard)
+        k = len(rank_positions)
+        blk = shard.numel() >> k
+        mine = 0
+        for i, t in enumerate(rank_positions):
+            mine |= ((self.rank >> t) & 1) << i
+        es = shard.element_size()
+        local, remote, counts = [], [], []
+        for s in range(1, 1 << k):
+            j = mine ^ s
+            peer = self.rank
+            for i, t in enumerate(rank_positions):
+                peer = (peer & ~(1 << t)) | (((j >> i) & 1) << t)
+            half = blk // 2
+            off, n = (0, half) if self.rank < peer else (half, blk - half)
+            if n == 0:
+                continue
+            local.append(shard.data_ptr() + (j * blk + off) * es)
+            remote.append(self._peers[peer] + (mine * blk + off) * es)
+            counts.append(n)
+            self._comm_bytes += n * es * 2        # leaves this GPU: n by its own remote stores, n pulled by the peer
+        self._rank_barrier()
+        npairs = len(local)
+        lib = _lib.load()
+        _lib.check(lib.qfb_remap_swap(npairs, (ctypes.c_void_p * npairs)(*local), (ctypes.c_void_p * npairs)(*remote),
+                                      (ctypes.c_uint64 * npairs)(*counts), engine._stream()))
+        self._rank_barrier()
+
     def _exchange(self, shard: torch.Tensor, rank_positions: List[int]) -> None:
         """In place: block j of this rank (top-k local bits = j) is swapped with block `mine` of the peer whose
         selected rank bits equal j. Step s pairs mine with mine ^ s on every rank, so both sides of a pair issue
@@ -396,7 +481,11 @@ class ShardedCircuit:
                 ev0.record()
             else:
                 t0 = time.perf_counter()
-            self._exchange(shard, st.rank_positions)
+            if timed and os.environ.get('QFB_REMAP', 'peer') != 'nccl':
+                self._exchange_path = 'peer'
+                self._exchange_peer(shard, st.rank_positions)
+            else:
+                self._exchange(shard, st.rank_positions)
             self._remaps += 1
             if timed:
                 ev1.record()

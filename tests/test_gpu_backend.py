@@ -219,3 +219,41 @@ def test_no_cpu_path_for_amplitudes(bk):
     assert ket.tensor.is_cuda and not qf.H(0).tensor.is_cuda
     assert qf.H(0).run(ket).tensor.is_cuda
     assert bk.gpu_available() and bk.DEVICE == 'gpu'
+
+
+def test_plugin_backend_for_the_reference_classes_runs_on_the_device(bk):
+    """b200ref is the module the reference's backend package star-imports: everything the
+    reference builds through bk.astensorproduct (quantumflow/qubits.py:103) is an amplitude tensor in HBM and every
+    tensormul launches a libqfb200 kernel -- no silent CPU path (round-1 review, missing #1)."""
+    from oracle import qf_oracle as O
+    from quantumflow_b200 import engine
+    from quantumflow_b200.backend import b200ref as ref
+    rng = np.random.RandomState(3)
+    n = 7
+    psi = rng.normal(size=[2] * n) + 1j * rng.normal(size=[2] * n)
+    ket = ref.astensorproduct(psi)                 # what quantumflow.states.State.__init__ calls
+    assert ket.is_cuda and tuple(ket.shape) == (2,) * n
+    gate = ref.astensorproduct(O.gate_matrix('CNOT', ()))     # what quantumflow.ops.Gate.__init__ calls
+    assert gate.is_cuda and tuple(gate.shape) == (2,) * 4
+    before = engine.launch_count()
+    out = ref.tensormul(gate, ket, [5, 2])
+    assert engine.launch_count() > before and out.is_cuda
+    want = O.tensormul(O.as_tensor(O.gate_matrix('CNOT', ())), psi, [5, 2])
+    assert np.abs(ref.evaluate(out) - want).max() < 1e-12
+    # a gate tensor derived on the device (no remembered host copy) and a host tensor1 both end up in the kernels
+    rx = ref.astensorproduct(O.gate_matrix('RX', (0.3,)))
+    before = engine.launch_count()
+    out2 = ref.tensormul(ref.conj(rx), psi, [4])
+    assert engine.launch_count() > before and out2.is_cuda
+    want2 = O.tensormul(O.as_tensor(O.gate_matrix('RX', (0.3,)).conj()), psi, [4])
+    assert np.abs(ref.evaluate(out2) - want2).max() < 1e-12
+    # gate (x) gate as the reference's Gate.__matmul__ does it (ops.py:187-198): tensor1 is a [2]*2K gate tensor
+    cz = ref.astensorproduct(O.gate_matrix('CZ', ()))
+    prod = ref.tensormul(rx, cz, [1])
+    want3 = O.tensormul(O.as_tensor(O.gate_matrix('RX', (0.3,))), O.as_tensor(O.gate_matrix('CZ', ())), [1])
+    assert np.abs(ref.evaluate(prod) - want3).max() < 1e-12
+    assert abs(complex(ref.evaluate(ref.inner(psi, psi))) - np.vdot(psi, psi)) < 1e-10
+    # the mirror package's backend refuses a state-sized tensor on the host instead of multiplying it on the CPU
+    big = np.zeros([2] * 17, dtype=np.complex128)
+    with pytest.raises(RuntimeError):
+        bk.tensormul(bk.astensorproduct(O.gate_matrix('H', ())), bk.astensorproduct(big), [3])

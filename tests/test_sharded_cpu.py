@@ -266,3 +266,33 @@ def test_sharded_readout_reductions(tmp_path, world, n, seed):
     agree = samples == logical
     assert agree.mean() > 0.9                           # rounding at span edges may move a draw to a neighbour
     assert np.all(probs[samples] > 0)
+
+
+def test_thin_sweep_with_nothing_to_exchange_is_taken_instead_of_raising():
+    """Reproducer of a scheduler crash (round-1 review): many 2-qubit gates on the low bits, one layer over every
+    other local bit, then H on the global bit. The stage used to end before the thin sweep while Belady kept the
+    same global bit, so the remap exchanged nothing ('scheduler made no progress')."""
+    import random
+    rnd = random.Random(5)
+    for n in (16, 17):
+        p, nl = 1, n - 1
+        ops = []
+        for _ in range(200):
+            a, b = rnd.sample(range(12), 2)
+            ops.append((O.gate_matrix('CAN', (0.1, 0.2, 0.3)), [a, b]))
+        free = list(range(3, nl))
+        for a, b in zip(free[::2], free[1::2]):
+            ops.append((O.gate_matrix('CAN', (0.3, 0.1, 0.2)), [a, b]))
+        ops.append((O.gate_matrix('H', ()), [n - 1]))
+        for thin in (0.0, 0.6, 0.9):
+            steps, phys_of, _ = sharded._schedule_once(n, p, ops, None, None, None, thin)
+            assert sorted(phys_of) == list(range(n))
+            done = sum(len(st.items) for st in steps if isinstance(st, sharded.Stage))
+            assert done >= len(ops)
+            for st in steps:
+                if isinstance(st, sharded.Stage):
+                    for mat, bits in st.bitops:
+                        mix, _ = sharded._mixing_and_diag_bits(np.asarray(mat), list(bits))
+                        assert all(b < nl for b in mix)
+        steps, phys_of = sharded.schedule(n, p, ops)
+        assert any(isinstance(st, sharded.Remap) for st in steps)
