@@ -158,6 +158,18 @@ int qfb_plan_refine_tile_lookahead(const uint64_t *mix, const uint64_t *diag, co
 int qfb_remap_swap(int npairs, void *const *local_blocks, void *const *remote_blocks, const uint64_t *nelems,
                    void *stream);
 
+/* ---- batched stochastic trajectories (Kraus.run / UnitaryMixture.run, quantumflow/channels.py:70-77, 119-125, for
+ * 2^nbatch_bits pure states of nstate qubits in one buffer: trajectory index = the top index bits) ---- */
+/* out_dev[4 t .. 4 t + 3] = (sum |x|^2, sum |y|^2, Re sum x conj(y), Im sum x conj(y)) over the amplitude pairs
+ * (x: bit = 0, y: bit = 1) of trajectory t: the 1-qubit reduced density from which the host gets every branch
+ * probability w_k tr(K_k rho K_k^dagger). workspace_dev: qfb_batch_rho1_workspace() bytes. Deterministic. */
+int qfb_batch_rho1(const void *state, int nstate, int nbatch_bits, int bit, double *out_dev, void *workspace_dev,
+                   size_t workspace_bytes, void *stream);
+size_t qfb_batch_rho1_workspace(int nstate, int nbatch_bits);
+/* psi_t <- M_t psi_t in place, M_t = mats_dev[8 t .. 8 t + 7] (row-major 2x2 complex128, DEVICE memory, 16-byte
+ * aligned): the Kraus branch drawn for trajectory t, already divided by its norm. */
+int qfb_batch_apply1(void *state, int nstate, int nbatch_bits, int bit, const double *mats_dev, void *stream);
+
 /* ---- autograd bridge ---- */
 /* grad_mat[r][c] = sum_groups g[base|off[r]] * conj(psi[base|off[c]])   (k <= 3), written to out_dev (4^k c128) */
 int qfb_gate_grad(const void *g, const void *psi, int nbits, int k, const int *bits, void *out_dev, void *stream);

@@ -20,7 +20,8 @@ from .dagcircuit import *                   # noqa: F401,F403
 from .programs import *                     # noqa: F401,F403
 from .measures import *                     # noqa: F401,F403
 from .qaoa import *                         # noqa: F401,F403
-from . import utils, workloads, planner, engine, classify, stateio   # noqa: F401
+from .trajectories import StateBatch       # noqa: F401  (engine-only: batched stochastic trajectories)
+from . import utils, workloads, planner, engine, classify, stateio, trajectories   # noqa: F401
 
 from .config import version as __version__  # noqa: F401
 

@@ -53,6 +53,9 @@ PROTOTYPES = {
     'qfb_plan_refine_tile_lookahead': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
                                                c_uint64, c_uint64, c_uint64, c_double, c_int64, c_int, c_int,
                                                POINTER(c_uint64), _c_int_p]),
+    'qfb_batch_rho1': (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
+    'qfb_batch_rho1_workspace': (c_size_t, [c_int, c_int]),
+    'qfb_batch_apply1': (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
     'qfb_remap_swap': (c_int, [c_int, POINTER(c_void_p), POINTER(c_void_p), POINTER(c_uint64), c_void_p]),
     'qfb_gate_grad': (c_int, [c_void_p, c_void_p, c_int, c_int, _c_int_p, c_void_p, c_void_p]),
 }

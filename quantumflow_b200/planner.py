@@ -481,6 +481,15 @@ class Planner:
         self.R = default_reg_bits(self.nbits) if reg_bits is None else int(reg_bits)
         if self.R not in (4, 5):
             raise ValueError('reg_bits must be 4 or 5')
+        # Diagonal tables (and the placement of phase terms that feeds them) change WHERE a phase is multiplied in.
+        # That is exact in real arithmetic but not in floating point: amplitudes that cancel to an exact 0 in the
+        # reference's gate-by-gate arithmetic may end as 1e-17 (measured: tools/zero_pattern.py), and
+        # np.random.multinomial consumes no random number for a zero-probability bin -- so the bit-exact sampling
+        # fixtures only hold with the plain placement. Plans of the interpreter (5 register bits: states below
+        # QFB_JIT_MIN_BITS, where the whole probability vector goes to the host's numpy calls) keep it; plans of
+        # the sweep-specialised kernels (4 register bits: large states, sampled on the device) take the tables.
+        v = os.environ.get('QFB_PLAN_TABLES')
+        self.tables = (self.R == 4) if not v else v != '0'
         m = DEFAULT_TILE_BITS if tile_bits is None else int(tile_bits)
         m = min(m, self.nbits, MAX_TILE_BITS)
         if m < MIN_TILE_BITS:
@@ -726,7 +735,8 @@ class Planner:
             final.append(Round(regs, self._thread_order(regs, edge), chosen))
         sweep.rounds = final
         self._relocate_phase_terms(sweep)
-        self._form_tables(sweep)
+        if self.tables:
+            self._form_tables(sweep)
 
     def _relocate_phase_terms(self, sweep: SweepPlan) -> None:
         """Move every phase term, inside its commutation window, to the round where it is cheapest."""
@@ -793,7 +803,7 @@ class Planner:
                 mask = reg_mask(op, r)
                 if mask == 0:
                     cost = 0.05 if r in scalar_rounds else 1.05
-                elif bin(mask).count('1') == len(op.dbits) and allin[r] >= 2:
+                elif self.tables and bin(mask).count('1') == len(op.dbits) and allin[r] >= 2:
                     cost = 0.04 - 0.001 * min(allin[r], 20)
                 else:
                     touched = (1 << self.R) >> bin(mask).count('1')
@@ -1008,7 +1018,8 @@ class Planner:
                 if len(set(tile)) != self.M or tile[:self.L] != list(range(self.L)) or tile[-1] >= self.nbits or \
                         any(not op.mixset <= set(tile) for op in chosen):
                     raise ValueError('preset sweep does not fit its tile')
-        parts = [(chosen, tile) for chosen, tile in sink_phase_terms(parts) if chosen]
+        if os.environ.get('QFB_PLAN_SINK', '1') != '0':          # experiments: 0 keeps every phase term in its sweep
+            parts = [(chosen, tile) for chosen, tile in sink_phase_terms(parts) if chosen]
         for index, (chosen, tile) in enumerate(parts):
             remaining = index + 1 < len(parts)
             ops, store_xor = absorb_frame(chosen, scale)
@@ -1169,7 +1180,7 @@ class Planner:
             # by the plan's last sweep (or earlier, when it leaves a range that is safe for the stored amplitudes'
             # exponents), inside a diagonal table if the sweep has one -- otherwise as a per-thread scalar term.
             carry *= scalar
-            last = si + 1 == len(sweeps)
+            last = si + 1 == len(sweeps) or os.environ.get('QFB_PLAN_CARRY', '1') == '0'
             due = carry != 1 and (last or not 2.0 ** -200 < abs(carry) < 2.0 ** 200)
             if due:
                 host = next(((i, k) for i, (_, bl) in enumerate(encoded) for k, b in enumerate(bl)

@@ -406,7 +406,9 @@ def test_phase_terms_sink_to_their_anchor_and_form_tables():
         segments = planner.build_segments(n, bitops_of(specs, n), tile_bits=tile, reg_bits=rb)
         ntables = sum(1 for s in segments for sw in E.parse(s.blob)['sweeps'] for rd in sw['rounds']
                       for op in rd['ops'] if op['type'] == 4)
-        assert ntables > 0
+        # tables belong to the plans of the sweep-specialised kernels (4 register bits); interpreter plans keep the
+        # plain phase placement that the bit-exact sampling fixtures were pinned with
+        assert (ntables > 0) == (rb == 4)
         got = run_segments(segments, zero(n))
         assert np.abs(got - O.run_specs(specs, n).reshape(-1)).max() < AMP_TOL
 
