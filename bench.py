@@ -470,13 +470,14 @@ def main():
     e2e_ref_shaped = None
     nbytes = 16 << nlocal
     if not args.no_e2e:
-        del state
-        torch.cuda.empty_cache()
         if nlocal <= 31:
+            del state
+            torch.cuda.empty_cache()
             e2e, e2e_ref_shaped = e2e_resident_host(args, qf, circ, runner, nlocal, nq, ngates, scale30, world, rank,
                                                     dev, barrier)
         else:
-            e2e = e2e_streamed(args, runner, nlocal, ngates, scale30, world, rank, dev, barrier)
+            # the shard buffer is reused (it is mapped into the peers' address spaces for the remaps)
+            e2e = e2e_streamed(args, runner, state, nlocal, ngates, scale30, world, rank, dev, barrier)
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -673,7 +674,7 @@ def e2e_resident_host(args, qf, circ, runner, nlocal, nq, ngates, scale30, world
     return e2e, ref_shaped
 
 
-def e2e_streamed(args, runner, nlocal, ngates, scale30, world, rank, dev, barrier):
+def e2e_streamed(args, runner, shard, nlocal, ngates, scale30, world, rank, dev, barrier):
     """Shards that do not fit pinned host memory (33 qubits per GPU = 128 GiB per rank): the shard crosses PCIe in
     1 GiB pieces through two pinned staging buffers, host -> device before the circuit and device -> host after it,
     inside the timed region. The host never holds the whole shard: the input pieces are produced in the staging
@@ -684,7 +685,6 @@ def e2e_streamed(args, runner, nlocal, ngates, scale30, world, rank, dev, barrie
     piece = 1 << 26                                    # amplitudes per piece (1 GiB)
     npieces = (1 << nlocal) // piece
     stage = [torch.zeros(piece, dtype=torch.complex128).pin_memory() for _ in range(2)]
-    shard = torch.empty(1 << nlocal, dtype=torch.complex128, device=dev)
     copy_stream = torch.cuda.Stream(dev)
 
     def one_step():
@@ -723,7 +723,6 @@ def e2e_streamed(args, runner, nlocal, ngates, scale30, world, rank, dev, barrie
     t = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_ms = float(t.item())
-    del shard
     return {'value': ngates / (e2e_ms * 1e-3) * scale30, 'unit': value_unit(world),
             'h2d_bytes_per_step': nbytes * world, 'd2h_bytes_per_step': nbytes * world, 'ms_per_step': e2e_ms,
             'steps': steps,

@@ -42,6 +42,7 @@ DEVICE = 'gpu'
 # largest host tensor that tensormul treats as an operator (a 6-qubit channel has 4^6 = 4096 elements ... 2^16 covers
 # 8-qubit gates); anything larger on the host is an amplitude tensor in the wrong place
 HOST_OPERATOR_LIMIT = 1 << 16
+_STAGED_MIN_BYTES = 1 << 28            # host <-> device copies of at least 256 MiB go through engine.upload / download
 
 from math import pi  # noqa: E402,F401  (the reference backends re-export pi)
 
@@ -108,6 +109,12 @@ def astensorproduct(array: TensorLike) -> BKTensor:
 
 def asamplitudes(array: TensorLike) -> BKTensor:
     """Product tensor resident in HBM (contiguous complex128 on the CUDA device)."""
+    if isinstance(array, np.ndarray) and array.nbytes >= _STAGED_MIN_BYTES and array.size == 1 << int(
+            math.log2(array.size)):
+        # a state-sized host array: pieces through pinned staging buffers instead of one pageable copy
+        from .. import engine
+        n = int(math.log2(array.size))
+        return engine.upload(array, device()).reshape([2] * n)
     tensor = astensorproduct(array)
     if not tensor.is_cuda:
         tensor = tensor.to(device())
@@ -117,6 +124,10 @@ def asamplitudes(array: TensorLike) -> BKTensor:
 def evaluate(tensor: BKTensor) -> TensorLike:
     """Value of a tensor as a numpy array (device -> host copy for amplitude tensors)."""
     if isinstance(tensor, torch.Tensor):
+        if tensor.is_cuda and tensor.dtype == CTYPE and tensor.numel() * 16 >= _STAGED_MIN_BYTES \
+                and tensor.is_contiguous():
+            from .. import engine
+            return engine.download(tensor).reshape(tuple(tensor.shape))
         return tensor.detach().cpu().numpy()
     return np.asarray(tensor)
 

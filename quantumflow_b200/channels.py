@@ -49,10 +49,13 @@ class Kraus(Operation):
 
     def superoperator_matrix(self) -> np.ndarray:
         """4^K x 4^K host matrix of `aschannel()`, bit order [ket qubits..., bra qubits...]."""
-        if self._superop is None:
+        # cached per (operators, weights): replacing an operator or a weight after a first evolve() must not replay
+        # the stale superoperator (the reference recomputes on every call)
+        key = (tuple(id(op) for op in self.operators), tuple(self.weights))
+        if self._superop is None or self._superop[0] != key:
             dim = 4 ** len(self.qubits)
-            self._superop = np.ascontiguousarray(asarray(self.aschannel().tensor).reshape(dim, dim))
-        return self._superop
+            self._superop = (key, np.ascontiguousarray(asarray(self.aschannel().tensor).reshape(dim, dim)))
+        return self._superop[1]
 
     def run(self, ket: State) -> State:
         """Pick one Kraus branch with probability w_k <psi|K_k^dagger K_k|psi>, then renormalise."""

@@ -537,23 +537,46 @@ int qfb_sample_search(const double *probs_dev, uint64_t n, const double *u_host,
     }
     const double total = run;
     std::vector<double> chunk(SB);
+    // draws sorted by chunk: every chunk of probabilities is fetched once, whatever the number of draws in it
+    std::vector<std::pair<uint64_t, int>> order(nu);
     for (int j = 0; j < nu; ++j) {
         const double target = u_host[j] * total;
         uint64_t c = std::upper_bound(cum.begin(), cum.end(), target) - cum.begin();
         if (c >= nchunks) c = nchunks - 1;
+        order[j] = std::make_pair(c, j);
+    }
+    std::sort(order.begin(), order.end());
+    uint64_t loaded = ~0ull;
+    for (int k = 0; k < nu; ++k) {
+        const uint64_t c = order[k].first;
+        const int j = order[k].second;
+        const double target = u_host[j] * total;
         const uint64_t lo = c * SB;
         const uint64_t len = std::min<uint64_t>(SB, n - lo);
-        QFB_CUDA(cudaMemcpyAsync(chunk.data(), probs_dev + lo, sizeof(double) * len, cudaMemcpyDeviceToHost, st));
-        QFB_CUDA(cudaStreamSynchronize(st));
+        if (c != loaded) {
+            QFB_CUDA(cudaMemcpyAsync(chunk.data(), probs_dev + lo, sizeof(double) * len, cudaMemcpyDeviceToHost, st));
+            QFB_CUDA(cudaStreamSynchronize(st));
+            loaded = c;
+        }
         double acc = (c == 0) ? 0.0 : cum[c - 1];
-        uint64_t pick = lo + len - 1;
+        // The chunk totals come from a tree reduction, this walk is sequential: their roundings differ, so the walk
+        // may end without exceeding the target. The fallback is the LAST entry with a non-zero probability (never
+        // a zero-probability basis state such as the padded tail of a chunk).
+        uint64_t pick = lo, last_nonzero = lo;
+        bool found = false, any = false;
         for (uint64_t t = 0; t < len; ++t) {
+            if (chunk[t] > 0.0) {
+                last_nonzero = lo + t;
+                any = true;
+            }
             acc += chunk[t];
             if (acc > target) {
                 pick = lo + t;
+                found = true;
                 break;
             }
         }
+        if (!found) pick = any ? last_nonzero : lo + len - 1;
         out_idx_host[j] = pick;
     }
     return QFB_OK;

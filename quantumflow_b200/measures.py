@@ -34,8 +34,10 @@ def states_close(state0: State, state1: State, tolerance: float = TOLERANCE) -> 
 
 
 def purity(rho: Density) -> bk.BKTensor:
-    """tr(rho^2) = sum |rho_ij|^2 for Hermitian rho: one squared-norm reduction on the device."""
-    return rho.vec.norm()
+    """tr(rho . rho) as the reference computes it (quantumflow/measures.py:59-64), a complex backend scalar: the
+    inner product <rho^H, rho> = sum_ij rho_ji rho_ij -- a conjugate-transpose sweep (qfb_permute_bits) and one
+    vdot reduction on the device. Equals sum |rho_ij|^2 only for Hermitian rho; intermediates of non-CP maps are not."""
+    return bk.inner(rho.vec.H.tensor, rho.tensor)
 
 
 def _operator(rho: Density) -> np.ndarray:

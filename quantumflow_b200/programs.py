@@ -116,7 +116,10 @@ class Program(Instruction):
     def _basic_blocks(self) -> Dict[int, Tuple[int, Circuit]]:
         """start pc -> (end pc, Circuit) for every maximal run of >= BLOCK_MIN_CALLS gate calls. Cached on the
         identities of the instructions, so a program that is extended after a run is analysed again."""
-        key = tuple(id(i) for i in self.instructions)
+        # keyed on the instructions AND on what a Call resolves to: changing Call.params / gatename / qubits after a
+        # run must not replay the stale fused circuit (the reference re-resolves every instruction on each run)
+        key = tuple((id(i), i.gatename, tuple(map(_hashable, i.params)), tuple(i.qubits)) if isinstance(i, Call)
+                    else id(i) for i in self.instructions)
         hit = self._blocks.get(key)
         if hit is not None:
             return hit
@@ -177,6 +180,14 @@ def _keep_memory(new: State, old: State) -> State:
     """A block of unitary gates never touches classical memory; carry the interpreter's over whatever the circuit
     executor returned."""
     return type(new)(new.tensor, new.qubits, old.memory)
+
+
+def _hashable(value):
+    try:
+        hash(value)
+        return value
+    except TypeError:
+        return id(value)
 
 
 def _as_gate(instr) -> Optional[Gate]:

@@ -92,3 +92,32 @@ def load_state(path: str, qubits=None, chunk_bytes: int = 1 << 28):
     nqubits = nbits // rank
     labels = tuple(range(nqubits)) if qubits is None else tuple(qubits)
     return (Density if rank == 2 else State)(tensor, labels)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# pyQuil wavefunction order (quantumflow/forest/__init__.py:350-366)
+# ---------------------------------------------------------------------------------------------------------
+# pyQuil labels basis states backwards: its flat amplitude vector is the reference's [2]*N tensor with the axes
+# reversed (`amplitudes.transpose().reshape(size)`), i.e. the flat index with its N bits in reverse order. pyquil
+# itself is not needed for the layout half (and is not installed); the functions below return / accept the flat
+# vector a `pyquil.Wavefunction` holds. The bit reversal runs on the device (qfb_permute_bits).
+
+def state_to_wavefunction_amplitudes(state) -> np.ndarray:
+    """Flat complex128 vector in pyQuil's order: what `forest.state_to_wavefunction(state).amplitudes` holds."""
+    from . import engine
+    n = state.qubit_nb
+    reversed_bits = engine.permute_bits(state.tensor.reshape(-1), list(range(n - 1, -1, -1)))
+    return reversed_bits.cpu().numpy().reshape(-1)
+
+
+def state_from_pyquil_order(amplitudes, qubits=None):
+    """Inverse of state_to_wavefunction_amplitudes: the state whose pyQuil-ordered flat vector is `amplitudes`.
+    (The reference's own `wavefunction_to_state` transposes a 1-D array, which is a no-op, so it re-reads the vector
+    in QuantumFlow order, forest/__init__.py:361-364; this function performs the bit reversal.)"""
+    from . import engine
+    from .states import State
+    vec = np.asarray(amplitudes, dtype=np.complex128).reshape(-1)
+    n = int(np.log2(vec.size))
+    st = State(vec.reshape([2] * n), qubits)
+    tensor = engine.permute_bits(st.tensor.reshape(-1), list(range(n - 1, -1, -1)))
+    return State(tensor.reshape([2] * n), st.qubits)

@@ -257,3 +257,28 @@ def test_plugin_backend_for_the_reference_classes_runs_on_the_device(bk):
     big = np.zeros([2] * 17, dtype=np.complex128)
     with pytest.raises(RuntimeError):
         bk.tensormul(bk.astensorproduct(O.gate_matrix('H', ())), bk.astensorproduct(big), [3])
+
+
+def test_staged_transfer_of_large_host_arrays(bk):
+    """State(host array) / asarray(result) of state-sized arrays go through the pinned staging ring (engine.upload /
+    engine.download): byte-exact round trip, several pieces, ragged last piece."""
+    from quantumflow_b200 import engine
+    rng = np.random.RandomState(2)
+    old = engine._STAGE_BYTES
+    try:
+        engine._STAGE_BYTES = 1 << 20                  # 64 Ki amplitudes per piece: many pieces at test size
+        engine._stage_buffers.clear()
+        n = (1 << 18) + 12345                          # not a multiple of the piece
+        host = rng.normal(size=n) + 1j * rng.normal(size=n)
+        dev = engine.upload(host, bk.device())
+        assert dev.is_cuda and np.array_equal(dev.cpu().numpy(), host)
+        assert np.array_equal(engine.download(dev), host)
+    finally:
+        engine._STAGE_BYTES = old
+        engine._stage_buffers.clear()
+    # the public path: a 2^24-amplitude numpy array (256 MiB) becomes a resident State and comes back unchanged
+    import quantumflow_b200 as qf
+    big = rng.normal(size=1 << 24) + 1j * rng.normal(size=1 << 24)
+    ket = qf.State(big.reshape([2] * 24))
+    assert ket.tensor.is_cuda
+    assert np.array_equal(qf.asarray(ket.tensor).reshape(-1), big)

@@ -172,7 +172,7 @@ def test_density_workloads_match_reference(golden):
         assert np.abs(qf.asarray(rho.asoperator()) - want).max() < AMP_TOL
         assert abs(complex(qf.asarray(rho.trace())) - 1) < 1e-12
     # SURVEY Appendix G golden values
-    assert abs(float(qf.asarray(qf.purity(rho))) - 0.104522702942447) < 1e-12
+    assert abs(float(np.real(qf.asarray(qf.purity(rho)))) - 0.104522702942447) < 1e-12
     rho = workloads.wd_circuit(qf, 8, 4, 1, kraus=True).evolve()
     assert np.abs(qf.asarray(rho.asoperator()) - data['wd8_d4_seed1_kraus']).max() < AMP_TOL
     import math
@@ -208,7 +208,7 @@ def test_density_11q_properties():
         circ = workloads.circuit_from_specs(qf, specs[layer * per_layer:(layer + 1) * per_layer])
         rho = circ.evolve(rho)
         assert abs(complex(qf.asarray(rho.trace())) - 1) < 1e-10
-        pur = float(qf.asarray(qf.purity(rho)))
+        pur = float(np.real(qf.asarray(qf.purity(rho))))
         assert pur <= prev
         prev = pur
     op = rho.asoperator()

@@ -144,9 +144,9 @@ def test_density_api():
     assert abs(complex(qf.asarray(rho.trace())) - 1) < 1e-14
     assert np.abs(qf.asarray(rho.asoperator()) - np.outer(amps(ket), amps(ket).conj())).max() < 1e-15
     assert np.abs(np.real(qf.asarray(rho.probabilities())) - qf.asarray(ket.probabilities())).max() < 1e-15
-    assert abs(float(qf.asarray(qf.purity(rho))) - 1) < 1e-13
+    assert abs(float(np.real(qf.asarray(qf.purity(rho)))) - 1) < 1e-13
     mixed = qf.mixed_density(2)
-    assert abs(float(qf.asarray(qf.purity(mixed))) - 0.25) < 1e-15
+    assert abs(float(np.real(qf.asarray(qf.purity(mixed)))) - 0.25) < 1e-15
     assert qf.densities_close(qf.Density(qf.asarray(rho.asoperator()) * 2).normalize(), rho)
     # partial trace (read-out path)
     bell = qf.Circuit([qf.H(0), qf.CNOT(0, 1)]).run(qf.zero_state(3)).asdensity()
@@ -287,3 +287,32 @@ def test_state_dump_round_trip(tmp_path):
     back = stateio.load_state(path, qubits=rho.qubits)
     assert isinstance(back, qf.Density) and back.qubit_nb == 4
     assert np.array_equal(qf.asarray(back.tensor), qf.asarray(rho.tensor))
+
+
+def test_pyquil_wavefunction_order():
+    """quantumflow/forest/__init__.py:350-358: the pyQuil vector is the [2]*N tensor with reversed axes, flattened."""
+    from quantumflow_b200 import stateio
+    rng = np.random.RandomState(4)
+    n = 9
+    psi = rng.normal(size=[2] * n) + 1j * rng.normal(size=[2] * n)
+    ket = qf.State(psi)
+    got = stateio.state_to_wavefunction_amplitudes(ket)
+    want = psi.transpose().reshape(psi.size)           # the reference's two lines
+    assert np.array_equal(got, want)
+    back = stateio.state_from_pyquil_order(got)
+    assert np.array_equal(qf.asarray(back.tensor), psi)
+    # |q0 q1 q2> = |1 0 0> : QuantumFlow index 4, pyQuil index 1
+    ket = qf.Circuit([qf.X(0)]).run(qf.zero_state(3))
+    assert np.argmax(np.abs(stateio.state_to_wavefunction_amplitudes(ket))) == 1
+
+
+def test_purity_is_trace_of_rho_squared_also_for_non_hermitian_tensors():
+    """quantumflow/measures.py:59-64 computes tr(rho . rho) as a complex scalar; sum |rho_ij|^2 only equals it for
+    Hermitian rho (review finding): checked on a non-Hermitian tensor."""
+    rng = np.random.RandomState(6)
+    n = 4
+    mat = rng.normal(size=(1 << n, 1 << n)) + 1j * rng.normal(size=(1 << n, 1 << n))
+    rho = qf.Density(mat.reshape([2] * (2 * n)))
+    got = complex(qf.asarray(qf.purity(rho)))
+    assert abs(got - np.trace(mat @ mat)) < 1e-10
+    assert abs(got - np.sum(np.abs(mat) ** 2)) > 1.0
