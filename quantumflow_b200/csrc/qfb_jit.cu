@@ -571,10 +571,15 @@ int emit_op(Gen &g, RoundState &st, const OpView &op, std::string &err) {
 // copy overlaps the last round's arithmetic and the stores; every thread copies exactly the amplitudes it will read
 // back itself (its round-0 slots), so the hand-over needs no barrier, only cp.async.wait_group. 0 = LDG straight
 // into registers at the top of the iteration (plus an L2 prefetch of the next tile), as the interpreter does.
-static bool jit_async() {
+static int jit_async_mode() {
     const char *v = getenv("QFB_JIT_ASYNC");
-    return !(v && *v) || atoi(v) != 0;
+    return (v && *v) ? atoi(v) : 1;
 }
+static bool jit_async() { return jit_async_mode() != 0; }
+// QFB_JIT_ASYNC=2: the copy lands in a SECOND buffer of the CTA (shared memory doubles), so it can start as soon as the
+// current tile has been read out of that buffer -- a whole tile period ahead instead of one round. Worth it when the
+// tile is small enough to keep three CTAs per SM (tile 2^11: 64 KiB per CTA).
+static bool jit_landing_buffer() { return jit_async_mode() == 2; }
 
 // ---- one sweep -> PTX --------------------------------------------------------------------------------------
 
@@ -629,6 +634,12 @@ int jit_generate(const uint8_t *rec, int nbits, int M, int reg_bits, JitSource &
     g.e("mul.lo.u32 %%r%d, %%r%d, %d;", ncta, ncta, G);
     g.e("mov.u32 %%r%d, qfb_smem;", smem);
     g.e("mad.lo.u32 %%r%d, %%r%d, %d, %%r%d;", smem, grp, 16 << M, smem);
+    const bool landing = jit_landing_buffer() && jit_async() && ((size_t)32 << M) * G <= 200 * 1024;
+    int land = smem;                       // where the asynchronous copy lands: the exchange buffer, or a buffer of its own
+    if (landing) {
+        land = g.r32();
+        g.e("add.u32 %%r%d, %%r%d, %d;", land, smem, (16 << M) * G);
+    }
     const int state = g.rd(), hi = g.rd();
     g.e("ld.param.u64 %%rd%d, [p_state];", state);
     g.e("cvta.to.global.u64 %%rd%d, %%rd%d;", state, state);
@@ -711,7 +722,7 @@ int jit_generate(const uint8_t *rec, int nbits, int M, int reg_bits, JitSource &
         g.e("or.b64 %%rd%d, %%rd%d, %%rd%d;", idx, gb, tg[0]);
         g.e("shl.b64 %%rd%d, %%rd%d, 4;", idx, idx);
         g.e("add.u64 %%rd%d, %%rd%d, %%rd%d;", base, state, idx);
-        const XchgAddr x = exchange_addresses(g, smem, stb[0], r0->regpos);
+        const XchgAddr x = exchange_addresses(g, land, stb[0], r0->regpos);
         for (int e = 0; e < NE; ++e) {
             int64_t off = 0;
             for (int i = 0; i < R; ++i)
@@ -753,7 +764,7 @@ int jit_generate(const uint8_t *rec, int nbits, int M, int reg_bits, JitSource &
     };
     // asynchronous copy of a tile into the thread's own round-0 slots of the exchange buffer
     auto async_copy = [&](int basereg) {
-        const XchgAddr x = exchange_addresses(g, smem, stb[0], r0->regpos);
+        const XchgAddr x = exchange_addresses(g, land, stb[0], r0->regpos);
         for (int e = 0; e < NE; ++e) {
             const int addr = g.rd();
             g.e("add.s64 %%rd%d, %%rd%d, %lld;", addr, basereg, (long long)off0[e]);
@@ -764,13 +775,13 @@ int jit_generate(const uint8_t *rec, int nbits, int M, int reg_bits, JitSource &
     if (async) {
         // ---- round 0: the tile was copied into shared memory during the previous iteration ----
         g.e("cp.async.wait_group 0;");
-        const XchgAddr x = exchange_addresses(g, smem, stb[0], r0->regpos);
+        const XchgAddr x = exchange_addresses(g, land, stb[0], r0->regpos);
         for (int e = 0; e < NE; ++e) {
             st.a[e].re = g.fd();
             st.a[e].im = g.fd();
             g.e("ld.shared.v2.f64 {%%fd%d, %%fd%d}, [%%r%d+%u];", st.a[e].re, st.a[e].im, x.base[x.low[e]], x.high[e]);
         }
-        if (nrounds == 1) {
+        if (nrounds == 1 || landing) {
             // no exchange in this sweep: the buffer is the thread's own, the next copy can start at once
             const int skip = g.label();
             g.e("@!%%p%d bra L%d;", has_next, skip);
@@ -859,7 +870,7 @@ int jit_generate(const uint8_t *rec, int nbits, int M, int reg_bits, JitSource &
             }
         }
         g.e("bar.sync 0;");
-        if (async && r + 2 == nrounds) {
+        if (async && !landing && r + 2 == nrounds) {
             // the tile has left the exchange buffer for the last time: the next tile's copy runs under the last round
             const int skip = g.label();
             g.e("@!%%p%d bra L%d;", has_next, skip);
@@ -903,7 +914,9 @@ int jit_generate(const uint8_t *rec, int nbits, int M, int reg_bits, JitSource &
 
     // resident CTAs the register file allows: 2^R amplitudes = 4 * 2^R registers + ~40 per thread
     const int regs_per_thread = (R == 5) ? 168 : 128;
-    const int minb = std::max(1, std::min(8, (65536 / (regs_per_thread * T)) / G));
+    const size_t smem_per_cta = ((size_t)16 << M) * G * (landing ? 2 : 1);
+    const int by_regs = (65536 / (regs_per_thread * T)) / G, by_smem = (int)((227 * 1024) / (smem_per_cta + 1024));
+    const int minb = std::max(1, std::min(8, std::min(by_regs, by_smem)));
     const size_t coef_bytes = std::max<size_t>(16, (g.coef.size() * 8 + 15) / 16 * 16);
     char head[1024];
     snprintf(head, sizeof(head),
@@ -918,7 +931,7 @@ int jit_generate(const uint8_t *rec, int nbits, int M, int reg_bits, JitSource &
     out.coef = g.coef;
     out.coef_bytes = coef_bytes;
     out.threads = T * G;
-    out.smem_bytes = ((size_t)16 << M) * G;
+    out.smem_bytes = smem_per_cta;
     out.nholes = nholes;
     out.groups = G;
     return QFB_OK;

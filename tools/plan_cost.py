@@ -16,10 +16,11 @@ def popcount(x):
 
 
 def op_cost(op, handler_names=None):
-    """(fp64, alu) instructions per thread of one decoded op."""
+    """(fp64, alu) instructions per thread of one decoded op (E.NE amplitudes per thread: 32 or 16)."""
     rc = popcount(op['reg_cmask'])
+    ne = E.NE
     if op['type'] == 1:
-        pairs = 16 >> rc
+        pairs = (ne // 2) >> rc
         k = op['kind']
         if k == 'general':
             return 16 * pairs, 0
@@ -27,14 +28,14 @@ def op_cost(op, handler_names=None):
             return (0, 0) if op.get('free') else (6 * pairs, 0)
         return 4 * pairs, 0
     if op['type'] == 2:
-        groups = 8 >> rc
+        groups = (ne // 4) >> rc
         return (16 * groups if op['kind'] == 'xshape' else 128 * groups), 0
     if op['type'] == 4:     # diagonal table
-        return (128 if op['flag'] else 4 * (32 - (32 >> popcount(op['reg_cmask'])))), 0
+        return (4 * ne if op['flag'] else 4 * (ne - (ne >> popcount(op['reg_cmask'])))), 0
     # phase terms
     if op['reg_cmask'] == 0:
         return 4, 0
-    touched = 32 >> rc
+    touched = ne >> rc
     if op['kind'] == 'neg':
         return 0, 2 * touched
     return (2 if op.get('real') else 4) * touched, 0
@@ -51,7 +52,7 @@ def plan_cost(blob):
                 fp += f
                 alu += a
             if rd['has_scalar']:
-                fp += 128
+                fp += 4 * E.NE
         rows.append((len(sw['rounds']), sum(len(rd['ops']) for rd in sw['rounds']), fp, alu))
     return rows
 
