@@ -459,9 +459,9 @@ def main():
     roofline = {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
                 'traffic': traffic, 'traffic_source': traffic_src,
                 'kernel': 'qfb_sweep (sweep-specialised, {} register bits, tile 2^{})'.format(
-                    stats['reg_bits'], args.tile_bits or planner.DEFAULT_TILE_BITS)
+                    stats['reg_bits'], args.tile_bits or planner.default_tile_bits(stats['reg_bits']))
                 if os.environ.get('QFB_JIT', '1') != '0' else 'sweep_kernel<{}> (interpreter)'.format(
-                    args.tile_bits or planner.DEFAULT_TILE_BITS),
+                    args.tile_bits or planner.default_tile_bits(stats['reg_bits'])),
                 'algorithmic_bytes_per_launch': algo_bytes, 'launches_per_step': nsweeps,
                 'avg_launch_ms': sweep_ms, 'peak_source': peak_src}
 
@@ -493,7 +493,7 @@ def main():
             'vs_baseline': None, 'dtype': 'complex128', 'data': 'synthetic',
             'config': workload_config(nq, args.depth, args.seed, world, ngates),
             'plan': dict(stats, plan_seconds=plan_seconds, kernel_build_seconds=jit_seconds,
-                         tile_bits=args.tile_bits or planner.DEFAULT_TILE_BITS),
+                         tile_bits=args.tile_bits or planner.default_tile_bits(stats['reg_bits'])),
             'circuit_gates_per_s': gates_per_s,
             'unfused_equivalent_gbs': ngates * algo_bytes / (ms_step * 1e-3) / 1e9,
             'norm_error_after_run': norm_err, 'parity_max_abs': parity, 'spot_amplitudes': spots,

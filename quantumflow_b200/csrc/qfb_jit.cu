@@ -73,9 +73,16 @@ struct Gen {
     int pr() { return np++; }
     int label() { return nlabel++; }
     // a coefficient of the plan: an operand from the module's constant bank (value-independent code)
+    // QFB_JIT_COEF_PIN (default 1): the constant-bank address carries a term that is zero at run time but depends on
+    // the tile (coef_base, set per tile), so ptxas cannot hoist the coefficient loads out of the tile loop -- it did,
+    // ran out of registers, spilled them and re-read them with LDL + R2UR (51 LDL, 54 STL, 83 R2UR per tile and thread)
+    int coef_base = -1;
     int cst(double v) {
         const int reg = fd();
-        e("ld.const.f64 %%fd%d, [qfb_coef+%zu];", reg, coef.size() * 8);
+        if (coef_base >= 0)
+            e("ld.const.f64 %%fd%d, [%%rd%d+%zu];", reg, coef_base, coef.size() * 8);
+        else
+            e("ld.const.f64 %%fd%d, [qfb_coef+%zu];", reg, coef.size() * 8);
         coef.push_back(v);
         return reg;
     }
@@ -184,6 +191,35 @@ XchgAddr exchange_addresses(Gen &g, int smem32, int stb32, const uint8_t *regpos
     }
     return x;
 }
+
+// Global address of `base + off` as an operand text: offsets are split into a part that needs a register of its own
+// (bits of 2^22 bytes and above: one 64-bit add per distinct high part) and an immediate, so that 16 accesses of a
+// tile need a handful of address registers instead of 16 (less register pressure, fewer integer instructions).
+struct AddrSet {
+    std::map<long long, int> bases;      // high part -> 64-bit register
+    int root;
+    explicit AddrSet(int root_reg) : root(root_reg) {}
+    std::string operand(Gen &g, long long off) {
+        const long long lo = ((off % (1ll << 22)) + (1ll << 22)) % (1ll << 22), hi = off - lo;
+        int reg = root;
+        if (hi != 0) {
+            auto it = bases.find(hi);
+            if (it == bases.end()) {
+                reg = g.rd();
+                g.e("add.s64 %%rd%d, %%rd%d, %lld;", reg, root, hi);
+                bases[hi] = reg;
+            } else {
+                reg = it->second;
+            }
+        }
+        char buf[64];
+        if (lo)
+            snprintf(buf, sizeof(buf), "[%%rd%d+%lld]", reg, lo);
+        else
+            snprintf(buf, sizeof(buf), "[%%rd%d]", reg);
+        return buf;
+    }
+};
 
 struct OpView {
     qfb_op_header h;
@@ -644,20 +680,37 @@ int jit_generate(const uint8_t *rec, int nbits, int M, int reg_bits, JitSource &
     g.e("ld.param.u64 %%rd%d, [p_state];", state);
     g.e("cvta.to.global.u64 %%rd%d, %%rd%d;", state, state);
     g.e("ld.param.u64 %%rd%d, [p_hi];", hi);
+    const int zmask = g.rd();
+    g.e("ld.param.u64 %%rd%d, [p_zero];", zmask);
     // thread-bit images per round: index-bit image (64-bit) and exchange offset (32-bit)
-    std::vector<int> tg(nrounds), stb(nrounds);
-    for (int r = 0; r < nrounds; ++r) {
+    // QFB_JIT_REMAT=1 (experiments): the images are recomputed from the thread id where they are used (a dozen integer
+    // instructions each) instead of being kept across the tile loop. Measured: no gain once the coefficient loads
+    // stay inside the loop (Gen::cst), which is what had caused the spills.
+    const char *remat_env = getenv("QFB_JIT_REMAT");
+    const bool remat = remat_env && *remat_env && atoi(remat_env) != 0;
+    std::vector<int> tg_pro(nrounds, -1), stb_pro(nrounds, -1);
+    auto make_tg = [&](int r) {
         int pos[16];
         for (int t = 0; t < nthr; ++t) pos[t] = sh.gpos[rounds[r].rh->thrpos[t]];
-        tg[r] = deposit64(g, tid, pos, nthr);
-        stb[r] = thread_stb(g, tid, rounds[r].rh->thrpos, nthr);
-    }
-    int tg_store;
-    {
+        return deposit64(g, tid, pos, nthr);
+    };
+    auto make_stb = [&](int r) { return thread_stb(g, tid, rounds[r].rh->thrpos, nthr); };
+    auto make_tg_store = [&]() {
         int pos[16];
         for (int t = 0; t < nthr; ++t) pos[t] = store_ipos[store_rh->thrpos[t]];
-        tg_store = deposit64(g, tid, pos, nthr);
+        return deposit64(g, tid, pos, nthr);
+    };
+    int tg_store_pro = -1;
+    if (!remat) {
+        for (int r = 0; r < nrounds; ++r) {
+            tg_pro[r] = make_tg(r);
+            stb_pro[r] = make_stb(r);
+        }
+        tg_store_pro = make_tg_store();
     }
+    auto tg = [&](int r) { return remat ? make_tg(r) : tg_pro[r]; };
+    auto stb = [&](int r) { return remat ? make_stb(r) : stb_pro[r]; };
+    auto tg_store_fn = [&]() { return remat ? make_tg_store() : tg_store_pro; };
     // L2 prefetch of the next tile: the 8 lanes that share the thread's 128-byte lines split its 2^R lines
     // (lane k takes the register indices whose top three bits are k); koff = byte offset of lane k's first line
     const qfb_round_header *r0 = rounds[0].rh;
@@ -719,17 +772,17 @@ int jit_generate(const uint8_t *rec, int nbits, int M, int reg_bits, JitSource &
     if (jit_async()) {
         // the first tile's copy (every later one is started by the iteration before it)
         const int idx = g.rd(), base = g.rd();
-        g.e("or.b64 %%rd%d, %%rd%d, %%rd%d;", idx, gb, tg[0]);
+        g.e("or.b64 %%rd%d, %%rd%d, %%rd%d;", idx, gb, tg(0));
         g.e("shl.b64 %%rd%d, %%rd%d, 4;", idx, idx);
         g.e("add.u64 %%rd%d, %%rd%d, %%rd%d;", base, state, idx);
-        const XchgAddr x = exchange_addresses(g, land, stb[0], r0->regpos);
+        const XchgAddr x = exchange_addresses(g, land, stb(0), r0->regpos);
+        AddrSet as(base);
         for (int e = 0; e < NE; ++e) {
             int64_t off = 0;
             for (int i = 0; i < R; ++i)
                 if ((e >> i) & 1) off += step0[i];
-            const int addr = g.rd();
-            g.e("add.s64 %%rd%d, %%rd%d, %lld;", addr, base, (long long)off);
-            g.e("cp.async.cg.shared.global [%%r%d+%u], [%%rd%d], 16;", x.base[x.low[e]], x.high[e], addr);
+            const std::string src = as.operand(g, off);
+            g.e("cp.async.cg.shared.global [%%r%d+%u], %s, 16;", x.base[x.low[e]], x.high[e], src.c_str());
         }
         g.e("cp.async.commit_group;");
     }
@@ -743,6 +796,16 @@ int jit_generate(const uint8_t *rec, int nbits, int M, int reg_bits, JitSource &
     const int gb_next = deposit64_from64(g, tnclamp, hole, nholes);
     const int higb = g.rd();
     g.e("or.b64 %%rd%d, %%rd%d, %%rd%d;", higb, hi, gb);
+    {
+        const char *v = getenv("QFB_JIT_COEF_PIN");
+        if (!(v && *v) || atoi(v) != 0) {
+            const int z = g.rd(), cb = g.rd();
+            g.e("and.b64 %%rd%d, %%rd%d, %%rd%d;", z, tile, zmask);       // zmask = 0 at run time
+            g.e("mov.u64 %%rd%d, qfb_coef;", cb);
+            g.e("add.u64 %%rd%d, %%rd%d, %%rd%d;", cb, cb, z);
+            g.coef_base = cb;
+        }
+    }
 
     RoundState st;
     st.scalar_live = false;
@@ -757,25 +820,25 @@ int jit_generate(const uint8_t *rec, int nbits, int M, int reg_bits, JitSource &
     // global base address of the thread's first amplitude of a tile (round-0 assignment)
     auto tile_base = [&](int gbreg) {
         const int idx = g.rd(), base = g.rd();
-        g.e("or.b64 %%rd%d, %%rd%d, %%rd%d;", idx, gbreg, tg[0]);
+        g.e("or.b64 %%rd%d, %%rd%d, %%rd%d;", idx, gbreg, tg(0));
         g.e("shl.b64 %%rd%d, %%rd%d, 4;", idx, idx);
         g.e("add.u64 %%rd%d, %%rd%d, %%rd%d;", base, state, idx);
         return base;
     };
     // asynchronous copy of a tile into the thread's own round-0 slots of the exchange buffer
     auto async_copy = [&](int basereg) {
-        const XchgAddr x = exchange_addresses(g, land, stb[0], r0->regpos);
+        const XchgAddr x = exchange_addresses(g, land, stb(0), r0->regpos);
+        AddrSet as(basereg);
         for (int e = 0; e < NE; ++e) {
-            const int addr = g.rd();
-            g.e("add.s64 %%rd%d, %%rd%d, %lld;", addr, basereg, (long long)off0[e]);
-            g.e("cp.async.cg.shared.global [%%r%d+%u], [%%rd%d], 16;", x.base[x.low[e]], x.high[e], addr);
+            const std::string src = as.operand(g, off0[e]);
+            g.e("cp.async.cg.shared.global [%%r%d+%u], %s, 16;", x.base[x.low[e]], x.high[e], src.c_str());
         }
         g.e("cp.async.commit_group;");
     };
     if (async) {
         // ---- round 0: the tile was copied into shared memory during the previous iteration ----
         g.e("cp.async.wait_group 0;");
-        const XchgAddr x = exchange_addresses(g, land, stb[0], r0->regpos);
+        const XchgAddr x = exchange_addresses(g, land, stb(0), r0->regpos);
         for (int e = 0; e < NE; ++e) {
             st.a[e].re = g.fd();
             st.a[e].im = g.fd();
@@ -791,12 +854,12 @@ int jit_generate(const uint8_t *rec, int nbits, int M, int reg_bits, JitSource &
     } else {
     // ---- round 0: coalesced loads straight into registers ----
     const int base0 = tile_base(gb);
+    AddrSet as0(base0);
     for (int e = 0; e < NE; ++e) {
         st.a[e].re = g.fd();
         st.a[e].im = g.fd();
-        const int addr = g.rd();
-        g.e("add.s64 %%rd%d, %%rd%d, %lld;", addr, base0, (long long)off0[e]);
-        g.e("ld.global.cs.v2.f64 {%%fd%d, %%fd%d}, [%%rd%d];", st.a[e].re, st.a[e].im, addr);
+        const std::string src = as0.operand(g, off0[e]);
+        g.e("ld.global.cs.v2.f64 {%%fd%d, %%fd%d}, %s;", st.a[e].re, st.a[e].im, src.c_str());
     }
     {
         // prefetch: delta = 16 * (gb_next - gb)
@@ -836,7 +899,7 @@ int jit_generate(const uint8_t *rec, int nbits, int M, int reg_bits, JitSource &
     for (int r = 0; r < nrounds; ++r) {
         const qfb_round_header *rh = rounds[r].rh;
         st.tfull = g.rd();
-        g.e("or.b64 %%rd%d, %%rd%d, %%rd%d;", st.tfull, higb, tg[r]);
+        g.e("or.b64 %%rd%d, %%rd%d, %%rd%d;", st.tfull, higb, tg(r));
         st.scalar_live = false;
         const uint8_t *op = rounds[r].ops;
         for (;;) {
@@ -856,13 +919,13 @@ int jit_generate(const uint8_t *rec, int nbits, int M, int reg_bits, JitSource &
         if (r + 1 == nrounds) break;
         // exchange: this round's assignment out, the next round's in
         {
-            const XchgAddr x = exchange_addresses(g, smem, stb[r], rh->regpos);
+            const XchgAddr x = exchange_addresses(g, smem, stb(r), rh->regpos);
             for (int e = 0; e < NE; ++e)
                 g.e("st.shared.v2.f64 [%%r%d+%u], {%%fd%d, %%fd%d};", x.base[x.low[e]], x.high[e], st.a[e].re, st.a[e].im);
         }
         g.e("bar.sync 0;");
         {
-            const XchgAddr x = exchange_addresses(g, smem, stb[r + 1], rounds[r + 1].rh->regpos);
+            const XchgAddr x = exchange_addresses(g, smem, stb(r + 1), rounds[r + 1].rh->regpos);
             for (int e = 0; e < NE; ++e) {
                 st.a[e].re = g.fd();
                 st.a[e].im = g.fd();
@@ -882,13 +945,14 @@ int jit_generate(const uint8_t *rec, int nbits, int M, int reg_bits, JitSource &
     if (store_sync) g.e("bar.sync 0;");
     {
         const int idx = g.rd(), sbase = g.rd();
-        g.e("or.b64 %%rd%d, %%rd%d, %%rd%d;", idx, gb, tg_store);
+        g.e("or.b64 %%rd%d, %%rd%d, %%rd%d;", idx, gb, tg_store_fn());
         uint64_t regmask = 0;
         for (int i = 0; i < R; ++i) regmask |= 1ull << store_ipos[store_rh->regpos[i]];
         const uint64_t fixed_xor = sh.store_xor & ~regmask;
         if (fixed_xor) g.e("xor.b64 %%rd%d, %%rd%d, %llu;", idx, idx, (unsigned long long)fixed_xor);
         g.e("shl.b64 %%rd%d, %%rd%d, 4;", idx, idx);
         g.e("add.u64 %%rd%d, %%rd%d, %%rd%d;", sbase, state, idx);
+        AddrSet sas(sbase);
         for (int e = 0; e < NE; ++e) {
             int64_t off = 0;
             for (int i = 0; i < R; ++i) {
@@ -896,12 +960,11 @@ int jit_generate(const uint8_t *rec, int nbits, int M, int reg_bits, JitSource &
                 const int flipped = (int)((sh.store_xor >> bit) & 1ull);
                 if (((e >> i) & 1) ^ flipped) off += (int64_t)16 << bit;
             }
-            const int addr = g.rd();
-            g.e("add.s64 %%rd%d, %%rd%d, %lld;", addr, sbase, (long long)off);
+            const std::string dst = sas.operand(g, off);
             if (G > 1)
-                g.e("@%%p%d st.global.cs.v2.f64 [%%rd%d], {%%fd%d, %%fd%d};", active, addr, st.a[e].re, st.a[e].im);
+                g.e("@%%p%d st.global.cs.v2.f64 %s, {%%fd%d, %%fd%d};", active, dst.c_str(), st.a[e].re, st.a[e].im);
             else
-                g.e("st.global.cs.v2.f64 [%%rd%d], {%%fd%d, %%fd%d};", addr, st.a[e].re, st.a[e].im);
+                g.e("st.global.cs.v2.f64 %s, {%%fd%d, %%fd%d};", dst.c_str(), st.a[e].re, st.a[e].im);
         }
     }
     // ---- next tile ----
@@ -913,17 +976,20 @@ int jit_generate(const uint8_t *rec, int nbits, int M, int reg_bits, JitSource &
     g.e("ret;");
 
     // resident CTAs the register file allows: 2^R amplitudes = 4 * 2^R registers + ~40 per thread
-    const int regs_per_thread = (R == 5) ? 168 : 128;
+    const int regs_per_thread = (R == 5) ? 168 : (R == 4) ? 128 : 64;
     const size_t smem_per_cta = ((size_t)16 << M) * G * (landing ? 2 : 1);
     const int by_regs = (65536 / (regs_per_thread * T)) / G, by_smem = (int)((227 * 1024) / (smem_per_cta + 1024));
-    const int minb = std::max(1, std::min(8, std::min(by_regs, by_smem)));
+    int minb = std::max(1, std::min(8, std::min(by_regs, by_smem)));
+    if (const char *v = getenv("QFB_JIT_MINB")) {        // experiments: resident CTAs per SM the register budget is cut for
+        if (*v && atoi(v) > 0) minb = std::min(atoi(v), by_smem);
+    }
     const size_t coef_bytes = std::max<size_t>(16, (g.coef.size() * 8 + 15) / 16 * 16);
     char head[1024];
     snprintf(head, sizeof(head),
              ".version 8.7\n.target sm_100a\n.address_size 64\n"
              ".const .align 16 .b8 qfb_coef[%zu];\n"
              ".extern .shared .align 128 .b8 qfb_smem[];\n"
-             ".visible .entry qfb_sweep(.param .u64 p_state, .param .u64 p_hi)\n"
+             ".visible .entry qfb_sweep(.param .u64 p_state, .param .u64 p_hi, .param .u64 p_zero)\n"
              ".maxntid %d, 1, 1\n.minnctapersm %d\n{\n"
              ".reg .f64 %%fd<%d>;\n.reg .b64 %%rd<%d>;\n.reg .b32 %%r<%d>;\n.reg .pred %%p<%d>;\n",
              coef_bytes, T * G, minb, g.nfd + 1, g.nrd + 1, g.nr + 1, g.np + 1);
@@ -1131,7 +1197,8 @@ int jit_build_plan(const uint8_t *plan, const std::vector<size_t> &offsets, int 
 }
 
 int jit_launch(JitSweep *s, void *state, uint64_t hi_shifted, cudaStream_t st) {
-    void *args[2] = {&state, &hi_shifted};
+    uint64_t zero = 0;      // see Gen::cst
+    void *args[3] = {&state, &hi_shifted, &zero};
     QFB_CU(driver().LaunchKernel(s->func, s->grid, 1, 1, s->threads, 1, 1, (unsigned)s->smem, (CUstream)st, args, nullptr));
     count_launch();
     return QFB_OK;

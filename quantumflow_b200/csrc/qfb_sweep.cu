@@ -300,8 +300,8 @@ static int validate_plan(const uint8_t *p, size_t nbytes, std::vector<SweepInfo>
     QFB_CHECK_ARG(h.magic == QFB_PLAN_MAGIC && h.version == QFB_PLAN_VERSION, "plan: bad magic/version");
     QFB_CHECK_ARG(h.total_bytes == nbytes, "plan: size mismatch (%llu vs %llu)", (unsigned long long)h.total_bytes,
                   (unsigned long long)nbytes);
-    // 5 register bits: interpreter (sweep_kernel) and sweep-specialised kernels; 4: sweep-specialised kernels only
-    QFB_CHECK_ARG(h.reg_bits == 5u || h.reg_bits == 4u, "plan: reg_bits=%u unsupported", h.reg_bits);
+    // 5 register bits: interpreter (sweep_kernel) and sweep-specialised kernels; 3 or 4: sweep-specialised kernels only
+    QFB_CHECK_ARG(h.reg_bits >= 3u && h.reg_bits <= 5u, "plan: reg_bits=%u unsupported", h.reg_bits);
     const int RB = (int)h.reg_bits, NEB = 1 << RB;   // handler ids keep their stride of R = 5 register bits
     if (reg_bits_out) *reg_bits_out = RB;
     QFB_CHECK_ARG(h.tile_bits >= QFB_PLAN_MIN_TILE_BITS && h.tile_bits <= QFB_PLAN_MAX_TILE_BITS &&

@@ -79,7 +79,13 @@ ROUND_HEADER_BYTES = 192 + 16 * (16 + 32)
 # QFB_G1_* kinds (csrc/qfb_plan.h)
 K_GENERAL, K_REAL, K_RXLIKE, K_SWAPX, K_ANTIDIAG, K_SUMDIFF, K_LU_R, K_LU_I = range(8)
 
-DEFAULT_TILE_BITS = 12
+DEFAULT_TILE_BITS = 12          # interpreter plans (5 register bits)
+DEFAULT_TILE_BITS_SPECIALISED = 11   # plans of the sweep-specialised kernels: 4 CTAs of 128 threads per SM instead of 2 of
+                                    # 256 -- more tiles in different phases per SM (146.6 against 151.3 ms on the benchmark)
+
+
+def default_tile_bits(reg_bits: int) -> int:
+    return DEFAULT_TILE_BITS if reg_bits == REG_BITS else DEFAULT_TILE_BITS_SPECIALISED
 DEFAULT_LOW_BITS = 3
 # cost units ~ FP64 work per amplitude relative to a dense 1-bit operator (16 FP64 ops per amplitude pair)
 COST = {K_GENERAL: 1.0, K_REAL: 1.0, K_RXLIKE: 1.0, K_SWAPX: 0.3, K_ANTIDIAG: 1.0, K_SUMDIFF: 0.25, K_LU_R: 0.25,
@@ -479,8 +485,8 @@ class Planner:
                  tries: int = None, refine: bool = None, reg_bits: int = None):
         self.nbits = int(nbits)
         self.R = default_reg_bits(self.nbits) if reg_bits is None else int(reg_bits)
-        if self.R not in (4, 5):
-            raise ValueError('reg_bits must be 4 or 5')
+        if self.R not in (3, 4, 5):
+            raise ValueError('reg_bits must be 3, 4 or 5')
         # Diagonal tables (and the placement of phase terms that feeds them) change WHERE a phase is multiplied in.
         # That is exact in real arithmetic but not in floating point: amplitudes that cancel to an exact 0 in the
         # reference's gate-by-gate arithmetic may end as 1e-17 (measured: tools/zero_pattern.py), and
@@ -489,8 +495,8 @@ class Planner:
         # QFB_JIT_MIN_BITS, where the whole probability vector goes to the host's numpy calls) keep it; plans of
         # the sweep-specialised kernels (4 register bits: large states, sampled on the device) take the tables.
         v = os.environ.get('QFB_PLAN_TABLES')
-        self.tables = (self.R == 4) if not v else v != '0'
-        m = DEFAULT_TILE_BITS if tile_bits is None else int(tile_bits)
+        self.tables = (self.R != REG_BITS) if not v else v != '0'
+        m = default_tile_bits(self.R) if tile_bits is None else int(tile_bits)
         m = min(m, self.nbits, MAX_TILE_BITS)
         if m < MIN_TILE_BITS:
             raise ValueError('state too small for the tiled executor (need >= {} bits)'.format(MIN_TILE_BITS))
@@ -500,6 +506,8 @@ class Planner:
         low = DEFAULT_LOW_BITS if low_bits is None else int(low_bits)
         if m - self.R < 3:
             self.R = REG_BITS          # tiny tiles: only the interpreter runs them
+        while m - self.R > 9:
+            self.R += 1                # the thread tables of a round record hold 9 thread bits
         self.L = max(0, min(low, m - self.R))
         self.max_cost = DEFAULT_MAX_COST if max_cost is None else float(max_cost)
         self.tries = DEFAULT_TRIES if tries is None else int(tries)

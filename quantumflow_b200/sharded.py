@@ -141,7 +141,7 @@ def _schedule_once(nbits: int, p: int, bitops: Sequence[BitOp], tile_bits: int, 
     phys_of = list(range(nbits))                       # identity: the top p qubits' bits are global
     remaining = planner.classify_all(bitops)
     # tiles are formed here in logical bits and handed to the stage planner (nl local bits): same tile size
-    tb = min(planner.DEFAULT_TILE_BITS if tile_bits is None else int(tile_bits), nl)
+    tb = min(planner.default_tile_bits(planner.default_reg_bits(nl)) if tile_bits is None else int(tile_bits), nl)
     pl = planner.Planner(nbits, tb, low_bits, max_cost) if nl >= planner.MIN_TILE_BITS else None
     pinned = set(range(pl.L)) if pl is not None else set()
 

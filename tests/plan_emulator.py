@@ -30,7 +30,7 @@ SWEEP_HEADER, ROUND_HEADER = 112, 192 + 768
 def parse(blob: bytes):
     global R, NE
     magic, version, nbits, M, rbits, nsweeps, total = struct.unpack_from('<IIIIIIQ', blob, 0)
-    assert magic == 0x50424651 and version == 13 and rbits in (4, 5) and total == len(blob)
+    assert magic == 0x50424651 and version == 13 and rbits in (3, 4, 5) and total == len(blob)
     R, NE = rbits, 1 << rbits
     off = 32
     sweeps = []
