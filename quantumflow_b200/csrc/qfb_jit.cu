@@ -86,6 +86,19 @@ struct Gen {
         coef.push_back(v);
         return reg;
     }
+    // the negative of a coefficient that is already in a register: neg.f64 folds into the consumer's operand modifier,
+    // so it costs neither a constant load (LDC: an issue slot and two registers each) nor an instruction.
+    // QFB_JIT_NEGFOLD=0 loads the negated value as a coefficient of its own (experiments).
+    int neg_of(int reg, double v) {
+        static const bool fold = [] {
+            const char *e = getenv("QFB_JIT_NEGFOLD");
+            return !(e && *e) || atoi(e) != 0;
+        }();
+        if (!fold) return cst(-v);
+        const int out = fd();
+        this->e("neg.f64 %%fd%d, %%fd%d;", out, reg);
+        return out;
+    }
 };
 
 struct RoundInfo {
@@ -188,6 +201,56 @@ XchgAddr exchange_addresses(Gen &g, int smem32, int stb32, const uint8_t *regpos
                 g.e("xor.b32 %%r%d, %%r%d, %d;", x.base[k], sum, k << 4);
             }
         }
+    }
+    return x;
+}
+
+// The same for the write side of an exchange when conditional flips are pending (RoundState::pend): in the threads
+// where predicate pend[j] holds, the register with index e carries the amplitude of index e ^ (1 << j) and goes to THAT
+// slot. swz is linear over GF(2), so the slot of e ^ F is slot(e) ^ slot(F): the thread's part of the address takes the
+// XOR of the selected slot(1 << j); the pending bits themselves then cannot go into the immediate (their address bits
+// are thread dependent), so there is one set of base registers per value v of the pending bits.
+struct XchgStore {
+    int reg[NEMAX];
+    uint32_t imm[NEMAX];
+};
+
+XchgStore exchange_store_addresses(Gen &g, int smem32, int stb32, const uint8_t *regpos, const int *pend) {
+    XchgStore x;
+    auto slot = [&](int e) {
+        uint32_t rb = 0;
+        for (int i = 0; i < R; ++i)
+            if ((e >> i) & 1) rb |= 1u << regpos[i];
+        return swz(rb);
+    };
+    int jm = 0, t = stb32;
+    for (int j = 0; j < R; ++j) {
+        if (pend[j] < 0) continue;
+        jm |= 1 << j;
+        const int sel = g.r32(), nt = g.r32();
+        g.e("selp.b32 %%r%d, %u, 0, %%p%d;", sel, slot(1 << j) << 4, pend[j]);
+        g.e("xor.b32 %%r%d, %%r%d, %%r%d;", nt, t, sel);
+        t = nt;
+    }
+    std::map<uint32_t, int> bases;       // (v, k) -> register
+    for (int e = 0; e < NE; ++e) {
+        const int v = e & jm, rest = e & ~jm;
+        const uint32_t sr = slot(rest), k = sr & 7u;
+        const uint32_t key = ((uint32_t)v << 3) | k;
+        auto it = bases.find(key);
+        if (it == bases.end()) {
+            const uint32_t c = (slot(v) << 4) ^ (k << 4);
+            const int tv = g.r32(), b = g.r32();
+            if (c) {
+                g.e("xor.b32 %%r%d, %%r%d, %u;", tv, t, c);
+                g.e("add.u32 %%r%d, %%r%d, %%r%d;", b, smem32, tv);
+            } else {
+                g.e("add.u32 %%r%d, %%r%d, %%r%d;", b, smem32, t);
+            }
+            it = bases.emplace(key, b).first;
+        }
+        x.reg[e] = it->second;
+        x.imm[e] = (sr & ~7u) << 4;
     }
     return x;
 }
@@ -309,11 +372,56 @@ struct RoundState {
     int tfull;       // 64-bit register: rank bits | tile bits | thread bits of the first amplitude
     int phr, phi;    // running per-thread scalar (has_scalar rounds)
     bool scalar_live;
+    // Pending conditional flips: pend[j] >= 0 is a predicate register q; in the threads where q holds the amplitude
+    // of register index e sits in a[e ^ (1 << j)] (a thread-controlled X on register bit j that has not been carried
+    // out). A flip stays pending while no later operator of the round looks at bit j; what is still pending at the end
+    // of the round goes into the ADDRESSES of the exchange (or of the final store) -- a dozen integer instructions
+    // instead of 8 selects per amplitude pair.
+    int pend[RMAX];
 };
+
+// QFB_JIT_DEFER (default 1): 0 = every thread-controlled X is carried out at once with selects
+bool defer_flips() {
+    static const bool on = [] {
+        const char *e = getenv("QFB_JIT_DEFER");
+        return !(e && *e) || atoi(e) != 0;
+    }();
+    return on;
+}
+
+// carry out the pending flip of register bit j
+void flush_flip(Gen &g, RoundState &st, int j) {
+    const int q = st.pend[j];
+    if (q < 0) return;
+    st.pend[j] = -1;
+    for (int k = 0; k < NE / 2; ++k) {
+        int e0, e1;
+        pairs_of(j, k, e0, e1);
+        Amp &x = st.a[e0], &y = st.a[e1];
+        const int xr = g.fd(), xi = g.fd(), yr = g.fd(), yi = g.fd();
+        g.e("selp.f64 %%fd%d, %%fd%d, %%fd%d, %%p%d;", xr, y.re, x.re, q);
+        g.e("selp.f64 %%fd%d, %%fd%d, %%fd%d, %%p%d;", xi, y.im, x.im, q);
+        g.e("selp.f64 %%fd%d, %%fd%d, %%fd%d, %%p%d;", yr, x.re, y.re, q);
+        g.e("selp.f64 %%fd%d, %%fd%d, %%fd%d, %%p%d;", yi, x.im, y.im, q);
+        x.re = xr; x.im = xi; y.re = yr; y.im = yi;
+    }
+}
+
+void flush_mask(Gen &g, RoundState &st, int mask) {
+    for (int j = 0; j < R; ++j)
+        if ((mask >> j) & 1) flush_flip(g, st, j);
+}
+
+int pending_mask(const RoundState &st) {
+    int m = 0;
+    for (int j = 0; j < R; ++j)
+        if (st.pend[j] >= 0) m |= 1 << j;
+    return m;
+}
 
 void load_matrix(Gen &g, const OpView &op, int *c, int *n) {
     for (int i = 0; i < 8; ++i) c[i] = g.cst(payload_f64(op, i));
-    for (int i = 1; i < 8; i += 2) n[i] = g.cst(-payload_f64(op, i));
+    for (int i = 1; i < 8; i += 2) n[i] = g.neg_of(c[i], payload_f64(op, i));
 }
 
 int emit_op(Gen &g, RoundState &st, const OpView &op, std::string &err) {
@@ -322,6 +430,7 @@ int emit_op(Gen &g, RoundState &st, const OpView &op, std::string &err) {
     const uint64_t icm = op.h.idx_cmask;
     if (hd >= QFB_H_G1_GENERAL && hd < QFB_H_G1C_GENERAL) {
         const int kind = hd / HS, j = hd % HS;
+        flush_flip(g, st, j);
         if (kind == 0) {
             int c[8], n[8];
             load_matrix(g, op, c, n);
@@ -359,7 +468,7 @@ int emit_op(Gen &g, RoundState &st, const OpView &op, std::string &err) {
             }
         } else {                         // LU_I: x += i a y ; y += i b x
             const double a = payload_f64(op, 0), b = payload_f64(op, 1);
-            const int ca = g.cst(a), cb = g.cst(b), na = g.cst(-a), nb = g.cst(-b);
+            const int ca = g.cst(a), cb = g.cst(b), na = g.neg_of(ca, a), nb = g.neg_of(cb, b);
             for (int p = 0; p < NE / 2; ++p) {
                 int e0, e1;
                 pairs_of(j, p, e0, e1);
@@ -376,6 +485,7 @@ int emit_op(Gen &g, RoundState &st, const OpView &op, std::string &err) {
     }
     if (hd >= QFB_H_G1C_GENERAL && hd < QFB_H_G1C_SWAPX) {
         const int j = hd - QFB_H_G1C_GENERAL;
+        flush_mask(g, st, rcm | (1 << j));
         const int p = thread_predicate(g, icm, st.tfull);
         int c[8], n[8];
         load_matrix(g, op, c, n);
@@ -392,7 +502,19 @@ int emit_op(Gen &g, RoundState &st, const OpView &op, std::string &err) {
     }
     if (hd >= QFB_H_G1C_SWAPX && hd < QFB_H_G1C_SWAPX + HS) {
         const int j = hd - QFB_H_G1C_SWAPX;
+        flush_mask(g, st, rcm);            // a pending X on the target commutes with this X, one on a control does not
         const int p = thread_predicate(g, icm, st.tfull);
+        if (p >= 0 && rcm == 0 && defer_flips()) {
+            if (st.pend[j] < 0) {
+                st.pend[j] = p;
+            } else {
+                const int both = g.pr();
+                g.e("xor.pred %%p%d, %%p%d, %%p%d;", both, st.pend[j], p);
+                st.pend[j] = both;
+            }
+            return QFB_OK;
+        }
+        if (p >= 0) flush_flip(g, st, j);
         for (int q = 0; q < NE / 2; ++q) {
             int e0, e1;
             pairs_of(j, q, e0, e1);
@@ -440,9 +562,10 @@ int emit_op(Gen &g, RoundState &st, const OpView &op, std::string &err) {
     }
     if ((hd >= QFB_H_CPH_REG1 && hd < QFB_H_CPH_NEG1) || hd == QFB_H_CPH_REGM) {
         const bool real_scale = hd >= QFB_H_CPH_RSC1 && hd < QFB_H_CPH_NEG1;
+        flush_mask(g, st, rcm);
         const double fr = payload_f64(op, 0), fi = payload_f64(op, 1);
         const int c = g.cst(fr);
-        const int s = real_scale ? -1 : g.cst(fi), ns = real_scale ? -1 : g.cst(-fi);
+        const int s = real_scale ? -1 : g.cst(fi), ns = real_scale ? -1 : g.neg_of(s, fi);
         const int p = thread_predicate(g, icm, st.tfull);
         const int skip = g.label();
         if (p >= 0) g.e("@!%%p%d bra L%d;", p, skip);
@@ -470,6 +593,27 @@ int emit_op(Gen &g, RoundState &st, const OpView &op, std::string &err) {
     }
     if ((hd >= QFB_H_CPH_NEG1 && hd < QFB_H_CPH_REGM) || hd == QFB_H_CPH_NEGM) {
         const int p = thread_predicate(g, icm, st.tfull);
+        const int pm = pending_mask(st) & rcm;
+        if (pm != 0 && (rcm & (rcm - 1)) == 0) {
+            // sign flip on ONE register bit j whose X is pending (predicate q): the amplitudes with bit j = 1 sit in the
+            // registers with bit j = 1 where q is false and in those with bit j = 0 where q is true
+            const int q = st.pend[__builtin_ctz(rcm)];
+            const int p1 = g.pr(), p0 = g.pr();
+            if (p >= 0) {
+                g.e("and.pred %%p%d, %%p%d, !%%p%d;", p1, p, q);
+                g.e("and.pred %%p%d, %%p%d, %%p%d;", p0, p, q);
+            } else {
+                g.e("not.pred %%p%d, %%p%d;", p1, q);
+                g.e("mov.pred %%p%d, %%p%d;", p0, q);
+            }
+            for (int e = 0; e < NE; ++e) {
+                const int pe = (e & rcm) ? p1 : p0;
+                g.e("@%%p%d xor.b64 %%fd%d, %%fd%d, 0x8000000000000000;", pe, st.a[e].re, st.a[e].re);
+                g.e("@%%p%d xor.b64 %%fd%d, %%fd%d, 0x8000000000000000;", pe, st.a[e].im, st.a[e].im);
+            }
+            return QFB_OK;
+        }
+        flush_mask(g, st, rcm);
         for (int e = 0; e < NE; ++e) {
             if ((e & rcm) != rcm) continue;
             if (p >= 0) {
@@ -488,16 +632,18 @@ int emit_op(Gen &g, RoundState &st, const OpView &op, std::string &err) {
     }
     if (hd == QFB_H_CPH_TABLE) {
         const bool whole = op.h.flag != 0;
+        flush_mask(g, st, whole ? NE - 1 : rcm);
         for (int e = 0; e < NE; ++e) {
             if (!whole && (e & rcm) == 0) continue;
             const double fr = payload_f64(op, 2 * e), fi = payload_f64(op, 2 * e + 1);
-            const int c = g.cst(fr), s = g.cst(fi), ns = g.cst(-fi);
+            const int c = g.cst(fr), s = g.cst(fi), ns = g.neg_of(s, fi);
             cmul_fresh(g, st.a[e], c, s, ns);
         }
         return QFB_OK;
     }
     if (hd >= QFB_H_G2 && hd < QFB_H_G2 + 10) {
         const int j0 = J0[hd - QFB_H_G2], j1 = J1[hd - QFB_H_G2];
+        flush_mask(g, st, rcm | (1 << j0) | (1 << j1));
         uint32_t nz;
         memcpy(&nz, op.payload + 256, 4);
         const int p = thread_predicate(g, icm, st.tfull);
@@ -507,7 +653,7 @@ int emit_op(Gen &g, RoundState &st, const OpView &op, std::string &err) {
             if (!((nz >> i) & 1)) continue;
             c[2 * i] = g.cst(payload_f64(op, 2 * i));
             c[2 * i + 1] = g.cst(payload_f64(op, 2 * i + 1));
-            n[2 * i + 1] = g.cst(-payload_f64(op, 2 * i + 1));
+            n[2 * i + 1] = g.neg_of(c[2 * i + 1], payload_f64(op, 2 * i + 1));
         }
         const int skip = g.label();
         if (p >= 0) g.e("@!%%p%d bra L%d;", p, skip);
@@ -559,6 +705,7 @@ int emit_op(Gen &g, RoundState &st, const OpView &op, std::string &err) {
     }
     if (hd >= QFB_H_G2X && hd < QFB_H_G2X + 10) {
         const int j0 = J0[hd - QFB_H_G2X], j1 = J1[hd - QFB_H_G2X];
+        flush_mask(g, st, rcm | (1 << j0) | (1 << j1));
         const int p = thread_predicate(g, icm, st.tfull);
         int c[8];
         for (int i = 0; i < 8; ++i) c[i] = g.cst(payload_f64(op, i));
@@ -662,8 +809,12 @@ int jit_generate(const uint8_t *rec, int nbits, int M, int reg_bits, JitSource &
     // ---- prologue (tile independent) ----
     const int tid = g.r32(), cta = g.r32(), ncta = g.r32(), smem = g.r32(), grp = g.r32();
     g.e("mov.u32 %%r%d, %%tid.x;", tid);
-    g.e("shr.u32 %%r%d, %%r%d, %d;", grp, tid, nthr);
-    g.e("and.b32 %%r%d, %%r%d, %d;", tid, tid, T - 1);
+    if (G > 1) {
+        g.e("shr.u32 %%r%d, %%r%d, %d;", grp, tid, nthr);
+        g.e("and.b32 %%r%d, %%r%d, %d;", tid, tid, T - 1);
+    } else {
+        g.e("mov.u32 %%r%d, 0;", grp);       // one group: the loop control is provably CTA-uniform
+    }
     g.e("mov.u32 %%r%d, %%ctaid.x;", cta);
     g.e("mad.lo.u32 %%r%d, %%r%d, %d, %%r%d;", cta, cta, G, grp);          // first tile of this group
     g.e("mov.u32 %%r%d, %%nctaid.x;", ncta);
@@ -786,6 +937,8 @@ int jit_generate(const uint8_t *rec, int nbits, int M, int reg_bits, JitSource &
         }
         g.e("cp.async.commit_group;");
     }
+    const int iter32 = g.r32();
+    g.e("mov.u32 %%r%d, 0;", iter32);
     g.e("L_TILE:");
     // next tile (for the prefetch and for the next iteration)
     const int tile_next = g.rd(), has_next = g.pr(), tnclamp = g.rd();
@@ -798,7 +951,21 @@ int jit_generate(const uint8_t *rec, int nbits, int M, int reg_bits, JitSource &
     g.e("or.b64 %%rd%d, %%rd%d, %%rd%d;", higb, hi, gb);
     {
         const char *v = getenv("QFB_JIT_COEF_PIN");
-        if (!(v && *v) || atoi(v) != 0) {
+        const int mode = (v && *v) ? atoi(v) : 1;
+        if (mode == 2) {
+            // the same with a CTA-uniform 32-bit iteration counter of its own (not the 64-bit tile index, which lives in
+            // vector registers because thread-dependent addresses are derived from it): ptxas can prove the address
+            // uniform and reads the coefficients on the uniform datapath (LDCU into uniform registers, no vector
+            // registers and no LDC latency)
+            const int z32 = g.r32(), z = g.rd(), cb = g.rd(), zm32 = g.r32();
+            g.e("cvt.u32.u64 %%r%d, %%rd%d;", zm32, zmask);
+            g.e("and.b32 %%r%d, %%r%d, %%r%d;", z32, iter32, zm32);
+            g.e("add.u32 %%r%d, %%r%d, 1;", iter32, iter32);
+            g.e("cvt.u64.u32 %%rd%d, %%r%d;", z, z32);
+            g.e("mov.u64 %%rd%d, qfb_coef;", cb);
+            g.e("add.u64 %%rd%d, %%rd%d, %%rd%d;", cb, cb, z);
+            g.coef_base = cb;
+        } else if (mode != 0) {
             const int z = g.rd(), cb = g.rd();
             g.e("and.b64 %%rd%d, %%rd%d, %%rd%d;", z, tile, zmask);       // zmask = 0 at run time
             g.e("mov.u64 %%rd%d, qfb_coef;", cb);
@@ -835,7 +1002,46 @@ int jit_generate(const uint8_t *rec, int nbits, int M, int reg_bits, JitSource &
         }
         g.e("cp.async.commit_group;");
     };
+    // L2 prefetch of the tile whose first amplitude (of this thread) is at `pbase`: the 8 lanes that share the thread's
+    // 128-byte lines split its 2^R lines between them
+    auto l2_prefetch = [&](int pbase) {
+        if (lane_lines) {
+            const int pb = g.rd();
+            g.e("add.s64 %%rd%d, %%rd%d, %%rd%d;", pb, pbase, koff);
+            for (int j = 0; j < (1 << (R - 3)); ++j) {
+                int64_t off = 0;
+                for (int i = 0; i < R - 3; ++i)
+                    if ((j >> i) & 1) off += step0[i];
+                const int q = g.rd();
+                g.e("add.s64 %%rd%d, %%rd%d, %lld;", q, pb, (long long)off);
+                g.e("prefetch.global.L2 [%%rd%d];", q);
+                g.e("prefetch.global.L2 [%%rd%d+64];", q);
+            }
+        } else {
+            const int m = g.r32(), p = g.pr(), skip2 = g.label();
+            g.e("and.b32 %%r%d, %%r%d, 3;", m, tid);
+            g.e("setp.ne.u32 %%p%d, %%r%d, 0;", p, m);
+            g.e("@%%p%d bra L%d;", p, skip2);
+            for (int e = 0; e < NE; ++e) {
+                const int q = g.rd();
+                g.e("add.s64 %%rd%d, %%rd%d, %lld;", q, pbase, (long long)off0[e]);
+                g.e("prefetch.global.L2 [%%rd%d];", q);
+            }
+            g.e("L%d:", skip2);
+        }
+    };
+    // QFB_JIT_L2PF=1 (experiments; measured 1 % SLOWER, default off): with the asynchronous copy the next tile is also
+    // prefetched into L2 at the TOP of the iteration, most of a tile period before its copy is issued (the copy starts
+    // under the last round only, because the exchange buffer is busy until then)
+    const char *l2pf_env = getenv("QFB_JIT_L2PF");
+    const bool l2pf = l2pf_env && *l2pf_env && atoi(l2pf_env) != 0;
     if (async) {
+        if (l2pf && nrounds > 1 && !landing) {
+            const int skip = g.label();
+            g.e("@!%%p%d bra L%d;", has_next, skip);
+            l2_prefetch(tile_base(gb_next));
+            g.e("L%d:", skip);
+        }
         // ---- round 0: the tile was copied into shared memory during the previous iteration ----
         g.e("cp.async.wait_group 0;");
         const XchgAddr x = exchange_addresses(g, land, stb(0), r0->regpos);
@@ -869,38 +1075,19 @@ int jit_generate(const uint8_t *rec, int nbits, int M, int reg_bits, JitSource &
         g.e("sub.s64 %%rd%d, %%rd%d, %%rd%d;", delta, gb_next, gb);
         g.e("shl.b64 %%rd%d, %%rd%d, 4;", delta, delta);
         g.e("add.s64 %%rd%d, %%rd%d, %%rd%d;", pbase, base0, delta);
-        if (lane_lines) {
-            g.e("add.s64 %%rd%d, %%rd%d, %%rd%d;", pbase, pbase, koff);
-            for (int j = 0; j < (1 << (R - 3)); ++j) {
-                int64_t off = 0;
-                for (int i = 0; i < R - 3; ++i)
-                    if ((j >> i) & 1) off += step0[i];
-                const int q = g.rd();
-                g.e("add.s64 %%rd%d, %%rd%d, %lld;", q, pbase, (long long)off);
-                g.e("prefetch.global.L2 [%%rd%d];", q);
-                g.e("prefetch.global.L2 [%%rd%d+64];", q);
-            }
-        } else {
-            const int m = g.r32(), p = g.pr(), skip2 = g.label();
-            g.e("and.b32 %%r%d, %%r%d, 3;", m, tid);
-            g.e("setp.ne.u32 %%p%d, %%r%d, 0;", p, m);
-            g.e("@%%p%d bra L%d;", p, skip2);
-            for (int e = 0; e < NE; ++e) {
-                const int q = g.rd();
-                g.e("add.s64 %%rd%d, %%rd%d, %lld;", q, pbase, (long long)off0[e]);
-                g.e("prefetch.global.L2 [%%rd%d];", q);
-            }
-            g.e("L%d:", skip2);
-        }
+        l2_prefetch(pbase);
         g.e("L%d:", skip);
     }
     }
     // ---- rounds ----
+    const char *barb_env = getenv("QFB_JIT_BARB");
+    const bool keep_barriers = barb_env && *barb_env && atoi(barb_env) != 0;
     for (int r = 0; r < nrounds; ++r) {
         const qfb_round_header *rh = rounds[r].rh;
         st.tfull = g.rd();
         g.e("or.b64 %%rd%d, %%rd%d, %%rd%d;", st.tfull, higb, tg(r));
         st.scalar_live = false;
+        for (int j = 0; j < RMAX; ++j) st.pend[j] = -1;
         const uint8_t *op = rounds[r].ops;
         for (;;) {
             OpView v;
@@ -919,9 +1106,16 @@ int jit_generate(const uint8_t *rec, int nbits, int M, int reg_bits, JitSource &
         if (r + 1 == nrounds) break;
         // exchange: this round's assignment out, the next round's in
         {
-            const XchgAddr x = exchange_addresses(g, smem, stb(r), rh->regpos);
-            for (int e = 0; e < NE; ++e)
-                g.e("st.shared.v2.f64 [%%r%d+%u], {%%fd%d, %%fd%d};", x.base[x.low[e]], x.high[e], st.a[e].re, st.a[e].im);
+            if (pending_mask(st) == 0) {
+                const XchgAddr x = exchange_addresses(g, smem, stb(r), rh->regpos);
+                for (int e = 0; e < NE; ++e)
+                    g.e("st.shared.v2.f64 [%%r%d+%u], {%%fd%d, %%fd%d};", x.base[x.low[e]], x.high[e], st.a[e].re,
+                        st.a[e].im);
+            } else {
+                const XchgStore x = exchange_store_addresses(g, smem, stb(r), rh->regpos, st.pend);
+                for (int e = 0; e < NE; ++e)
+                    g.e("st.shared.v2.f64 [%%r%d+%u], {%%fd%d, %%fd%d};", x.reg[e], x.imm[e], st.a[e].re, st.a[e].im);
+            }
         }
         g.e("bar.sync 0;");
         {
@@ -932,7 +1126,12 @@ int jit_generate(const uint8_t *rec, int nbits, int M, int reg_bits, JitSource &
                 g.e("ld.shared.v2.f64 {%%fd%d, %%fd%d}, [%%r%d+%u];", st.a[e].re, st.a[e].im, x.base[x.low[e]], x.high[e]);
             }
         }
-        g.e("bar.sync 0;");
+        // The barrier after the read-back protects the buffer against the NEXT writer. Between two exchanges of a tile
+        // that writer is the thread itself (it writes the slots of its own assignment of round r + 1, which nobody else
+        // read), so the barrier is only needed after the LAST exchange: there the asynchronous copy of the next tile (or,
+        // without it, the next tile's first exchange) writes round-0 slots that other threads may still be reading.
+        // QFB_JIT_BARB=1 keeps every barrier (experiments).
+        if (r + 2 == nrounds || keep_barriers) g.e("bar.sync 0;");
         if (async && !landing && r + 2 == nrounds) {
             // the tile has left the exchange buffer for the last time: the next tile's copy runs under the last round
             const int skip = g.label();
@@ -952,15 +1151,34 @@ int jit_generate(const uint8_t *rec, int nbits, int M, int reg_bits, JitSource &
         if (fixed_xor) g.e("xor.b64 %%rd%d, %%rd%d, %llu;", idx, idx, (unsigned long long)fixed_xor);
         g.e("shl.b64 %%rd%d, %%rd%d, 4;", idx, idx);
         g.e("add.u64 %%rd%d, %%rd%d, %%rd%d;", sbase, state, idx);
-        AddrSet sas(sbase);
+        // pending conditional flips of the last round go into the store address: bit j of the destination is
+        // e_j ^ (static flip) ^ (predicate), so every value v of the pending bits gets a root address of its own
+        const int jm = pending_mask(st);
+        std::map<int, AddrSet> roots;
+        for (int v = 0; v < NE; ++v) {
+            if (v & ~jm) continue;
+            int root = sbase;
+            for (int j = 0; j < R; ++j) {
+                if (!((jm >> j) & 1)) continue;
+                const int bit = store_ipos[store_rh->regpos[j]];
+                const int a = ((v >> j) & 1) ^ (int)((sh.store_xor >> bit) & 1ull);
+                const int sel = g.rd(), nr = g.rd();
+                const long long step = (long long)16 << bit;
+                g.e("selp.b64 %%rd%d, %lld, %lld, %%p%d;", sel, a ? 0ll : step, a ? step : 0ll, st.pend[j]);
+                g.e("add.u64 %%rd%d, %%rd%d, %%rd%d;", nr, root, sel);
+                root = nr;
+            }
+            roots.emplace(v, AddrSet(root));
+        }
         for (int e = 0; e < NE; ++e) {
             int64_t off = 0;
             for (int i = 0; i < R; ++i) {
+                if ((jm >> i) & 1) continue;
                 const int bit = store_ipos[store_rh->regpos[i]];
                 const int flipped = (int)((sh.store_xor >> bit) & 1ull);
                 if (((e >> i) & 1) ^ flipped) off += (int64_t)16 << bit;
             }
-            const std::string dst = sas.operand(g, off);
+            const std::string dst = roots.at(e & jm).operand(g, off);
             if (G > 1)
                 g.e("@%%p%d st.global.cs.v2.f64 %s, {%%fd%d, %%fd%d};", active, dst.c_str(), st.a[e].re, st.a[e].im);
             else
@@ -976,7 +1194,9 @@ int jit_generate(const uint8_t *rec, int nbits, int M, int reg_bits, JitSource &
     g.e("ret;");
 
     // resident CTAs the register file allows: 2^R amplitudes = 4 * 2^R registers + ~40 per thread
-    const int regs_per_thread = (R == 5) ? 168 : (R == 4) ? 128 : 64;
+    // (R = 4: 96 registers = 5 CTAs of 128 threads; ptxas then keeps the coefficients in uniform registers (LDCU) and
+    // spills ~10 words per thread; measured 137.3 against 141.3 ms per step with 128 registers = 4 CTAs)
+    const int regs_per_thread = (R == 5) ? 168 : (R == 4) ? 96 : 64;
     const size_t smem_per_cta = ((size_t)16 << M) * G * (landing ? 2 : 1);
     const int by_regs = (65536 / (regs_per_thread * T)) / G, by_smem = (int)((227 * 1024) / (smem_per_cta + 1024));
     int minb = std::max(1, std::min(8, std::min(by_regs, by_smem)));

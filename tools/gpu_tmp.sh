@@ -1,7 +1,6 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 900 ncu --set full --clock-control none -k regex:qfb_sweep -s 19 -c 2 -f -o gpurun_out/prof_jit_final \
-  python bench.py --steps 1 --warmup 1 --no-e2e --no-cpu-baseline > gpurun_out/ncu_jit_final.log 2>&1
-tail -2 gpurun_out/ncu_jit_final.log
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 0 -c 120 --csv --log-file gpurun_out/r2_launches.csv python bench.py --steps 2 --warmup 1 --no-e2e --no-cpu-baseline > gpurun_out/b.log 2>&1
-tail -3 gpurun_out/r2_launches.csv
+timeout 900 python -m pytest tests/test_gpu_circuits.py -m gpu -q --timeout 800 -p no:cacheprovider -x -k "specialised or wb24 or wb28 or round_trip" > gpurun_out/pytest_jit.log 2>&1; echo "pytest rc=$?"; tail -n 5 gpurun_out/pytest_jit.log
+bash tools/gpu_bench_matrix.sh "|" "QFB_JIT_DEFER=0|" "QFB_JIT_MINB=4|" "QFB_JIT_MINB=6|" "QFB_JIT_COEF_PIN=2|" "QFB_JIT_BARB=1|"
+timeout 600 compute-sanitizer --tool racecheck --error-exitcode 9 python -m pytest tests/test_gpu_circuits.py -m gpu -q -p no:cacheprovider -x -k "sweep_specialised" > gpurun_out/r2_sanitizer_racecheck_jit.log 2>&1
+echo "== racecheck rc=$?"; grep -E "ERROR SUMMARY|passed|failed|RACECHECK SUMMARY" gpurun_out/r2_sanitizer_racecheck_jit.log | tail -4
