@@ -496,6 +496,9 @@ class Planner:
         # the sweep-specialised kernels (4 register bits: large states, sampled on the device) take the tables.
         v = os.environ.get('QFB_PLAN_TABLES')
         self.tables = (self.R != REG_BITS) if not v else v != '0'
+        # latest-possible rounds (see _split_rounds): plans of the sweep-specialised kernels only, for the same reason
+        v = os.environ.get('QFB_PLAN_LATE')
+        self.late_rounds = (self.R != REG_BITS) if not v else v != '0'
         m = default_tile_bits(self.R) if tile_bits is None else int(tile_bits)
         m = min(m, self.nbits, MAX_TILE_BITS)
         if m < MIN_TILE_BITS:
@@ -673,9 +676,18 @@ class Planner:
         rest = [p for p in free if p not in head]
         return head + rest
 
-    def _split_rounds(self, sweep: SweepPlan, rnd=None, p_new: float = 1.0) -> List[Tuple[List[int], List[POp]]]:
+    def _split_rounds(self, sweep: SweepPlan, rnd=None, p_new: float = 1.0,
+                      backward: bool = False) -> List[Tuple[List[int], List[POp]]]:
         """Greedy split of a sweep's operators into rounds of R register bits; with `rnd`, an operator that needs
-        a NEW register bit is only admitted with probability p_new (randomised variants, see _form_rounds)."""
+        a NEW register bit is only admitted with probability p_new (randomised variants, see _form_rounds).
+        `backward`: the same greedy on the reversed operator list (commutation is symmetric, and so are the
+        constraints of the two rounds that touch HBM), i.e. every operator goes to the LATEST round that can take
+        it: the full rounds end up at the end of the sweep, where the sweep-specialised kernels hide the
+        asynchronous copy of the next tile (it can only start after the last exchange)."""
+        if backward:
+            mirror = SweepPlan(sweep.tile, list(reversed(sweep.ops)))
+            rounds = self._split_rounds(mirror, rnd, p_new)
+            return [(regs, list(reversed(chosen))) for regs, chosen in reversed(rounds)]
         pos_of = {b: j for j, b in enumerate(sweep.tile)}
         remaining = list(sweep.ops)
         rounds: List[Tuple[List[int], List[POp]]] = []
@@ -726,6 +738,18 @@ class Planner:
                     break
                 cand = self._split_rounds(sweep, random.Random(trial), 0.85)
                 if len(cand) < len(rounds):
+                    rounds = cand
+        if self.late_rounds and len(rounds) > 1:
+            # the latest-possible split, kept when it needs no more rounds and leaves more work behind the last
+            # exchange (cost of the last round's operators)
+            def tail(split):
+                return sum(op.cost for op in split[-1][1])
+            cands = [self._split_rounds(sweep, backward=True)]
+            if len(sweep.ops) >= 16:
+                cands += [self._split_rounds(sweep, random.Random(trial), 0.85, backward=True)
+                          for trial in range(1, 1 + self.tries)]
+            for cand in cands:
+                if len(cand) < len(rounds) or (len(cand) == len(rounds) and tail(cand) > tail(rounds)):
                     rounds = cand
         final: List[Round] = []
         nr = len(rounds)

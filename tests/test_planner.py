@@ -456,3 +456,22 @@ def test_sweep_specialised_ptx_compiles_for_sm100a(reg_bits):
         assert '.target sm_100a' in ptx and 'cp.async.cg.shared.global' in ptx and 'ld.const.f64' in ptx
         # structure only: no coefficient value appears in the text (one image serves every parameter value)
         assert ptx.count('ld.const.f64') == ncoef.value
+
+
+def test_latest_possible_rounds_need_no_more_exchanges_and_end_full(monkeypatch):
+    """Plans of the sweep-specialised kernels split a sweep's operators into rounds from the back (every operator in
+    the latest round that can take it): never more rounds than the forward split, the work sits behind the last
+    exchange (where the next tile's asynchronous copy is hidden), and the result is the same."""
+    n = 14
+    specs = workloads.wb_gate_list(n, 12, 4)
+    shapes = {}
+    for late in ('0', '1'):
+        monkeypatch.setenv('QFB_PLAN_LATE', late)
+        segments = planner.build_segments(n, bitops_of(specs, n), tile_bits=11, reg_bits=4)
+        sweeps = [sw for s in segments for sw in E.parse(s.blob)['sweeps']]
+        shapes[late] = [[len(rd['ops']) for rd in sw['rounds']] for sw in sweeps]
+        got = run_segments(segments, zero(n))
+        assert np.abs(got - O.run_specs(specs, n).reshape(-1)).max() < AMP_TOL
+    assert sum(map(len, shapes['1'])) <= sum(map(len, shapes['0']))
+    multi = [s for s in shapes['1'] if len(s) > 1]
+    assert multi and sum(s[-1] for s in multi) >= sum(s[0] for s in multi)
