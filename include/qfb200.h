@@ -79,6 +79,14 @@ int qfb_plan_validate(const void *plan_host, size_t plan_bytes);
 /* Upload a plan once and replay it (plans are immutable); handle is freed with qfb_plan_destroy. */
 int qfb_plan_upload(const void *plan_host, size_t plan_bytes, void **handle_out, void *stream);
 int qfb_plan_launch(void *handle, void *state, int nbits, uint64_t index_hi, void *stream);
+/* Sweeps [first_sweep, first_sweep + nsweeps) of an uploaded plan, optionally on a slice of the state: the amplitudes
+ * whose index bits `fix_mask` equal `fix_value` (bits outside the tile of every launched sweep; needs the sweep-
+ * specialised kernels, whose slice variants are built on first use); ctas_per_sm bounds the resident CTAs per SM of a
+ * slice launch (0 = all that fit, -1 = one fewer: room for the exchange kernel of another slice). qfb_plan_sweep_info: number of sweeps, the
+ * non-tile index bits of one sweep, whether the plan runs on sweep-specialised kernels (any pointer may be NULL). */
+int qfb_plan_launch_part(void *handle, void *state, int nbits, uint64_t index_hi, int first_sweep, int nsweeps,
+                         uint64_t fix_mask, uint64_t fix_value, int ctas_per_sm, void *stream);
+int qfb_plan_sweep_info(void *handle, int sweep, int *nsweeps, uint64_t *nontile_mask, int *specialised);
 int qfb_plan_destroy(void *handle);
 /* Sweep-specialised kernels (csrc/qfb_jit.cu): qfb_plan_upload emits every sweep of the plan as straight-line PTX,
  * compiles it in-process for sm_100a and loads it (environment: QFB_JIT=0/1, QFB_JIT_MIN_BITS). The two entry
@@ -157,6 +165,17 @@ int qfb_plan_refine_tile_lookahead(const uint64_t *mix, const uint64_t *diag, co
  * against the peers' work (a barrier before and after). Host arrays. */
 int qfb_remap_swap(int npairs, void *const *local_blocks, void *const *remote_blocks, const uint64_t *nelems,
                    void *stream);
+/* The same for a SLICE of every run: only the amplitudes whose offset inside the run has the bits selpos[0..nsel)
+ * (ascending, nsel <= 4) equal to `selval` trade places; `ctas_per_sm` (0 = default) bounds the kernel's share of
+ * every SM so that it can run beside a sweep on another stream. Sharded states pipeline a remap slice by slice:
+ * last sweep of the stage on slice s+1 | exchange of slice s | first sweep of the next stage on slice s-1. */
+int qfb_remap_swap_slice(int npairs, void *const *local_blocks, void *const *remote_blocks, const uint64_t *nelems,
+                         int nsel, const int *selpos, uint64_t selval, int ctas_per_sm, void *stream);
+/* Stream-ordered barrier across the GPUs of one box through peer memory (no host involvement, no NCCL kernel that
+ * would need a free SM): flags_of_ranks[r] = rank r's array of `world` uint32 (flags_of_ranks[rank] = flags_local),
+ * epochs must increase call by call; *error_dev (uint32) is set to the epoch if a peer does not arrive within ~10 s. */
+int qfb_peer_barrier(void *flags_local, void *const *flags_of_ranks, int world, int rank, uint32_t epoch,
+                     void *error_dev, void *stream);
 
 /* ---- batched stochastic trajectories (Kraus.run / UnitaryMixture.run, quantumflow/channels.py:70-77, 119-125, for
  * 2^nbatch_bits pure states of nstate qubits in one buffer: trajectory index = the top index bits) ---- */

@@ -25,6 +25,9 @@ PROTOTYPES = {
     'qfb_plan_upload': (c_int, [c_void_p, c_size_t, POINTER(c_void_p), c_void_p]),
     'qfb_plan_launch': (c_int, [c_void_p, c_void_p, c_int, c_uint64, c_void_p]),
     'qfb_plan_destroy': (c_int, [c_void_p]),
+    'qfb_plan_launch_part': (c_int, [c_void_p, c_void_p, c_int, c_uint64, c_int, c_int, c_uint64, c_uint64, c_int,
+                                     c_void_p]),
+    'qfb_plan_sweep_info': (c_int, [c_void_p, c_int, POINTER(c_int), POINTER(c_uint64), POINTER(c_int)]),
     'qfb_jit_ptx': (c_int, [c_void_p, c_size_t, c_int, c_char_p, c_size_t, POINTER(c_size_t), POINTER(c_size_t)]),
     'qfb_jit_check': (c_int, [c_void_p, c_size_t, c_char_p, c_size_t]),
     'qfb_launch_count': (c_uint64, []),
@@ -57,6 +60,9 @@ PROTOTYPES = {
     'qfb_batch_rho1_workspace': (c_size_t, [c_int, c_int]),
     'qfb_batch_apply1': (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
     'qfb_remap_swap': (c_int, [c_int, POINTER(c_void_p), POINTER(c_void_p), POINTER(c_uint64), c_void_p]),
+    'qfb_remap_swap_slice': (c_int, [c_int, POINTER(c_void_p), POINTER(c_void_p), POINTER(c_uint64), c_int,
+                                     POINTER(c_int), c_uint64, c_int, c_void_p]),
+    'qfb_peer_barrier': (c_int, [c_void_p, POINTER(c_void_p), c_int, c_int, ctypes.c_uint32, c_void_p, c_void_p]),
     'qfb_gate_grad': (c_int, [c_void_p, c_void_p, c_int, c_int, _c_int_p, c_void_p, c_void_p]),
 }
 

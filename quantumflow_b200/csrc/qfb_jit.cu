@@ -778,7 +778,8 @@ static int jit_groups(int M) {
     return g;
 }
 
-int jit_generate(const uint8_t *rec, int nbits, int M, int reg_bits, JitSource &out, std::string &err) {
+int jit_generate(const uint8_t *rec, int nbits, int M, int reg_bits, JitSource &out, std::string &err,
+                 uint64_t fix_mask) {
     R = reg_bits;
     NE = 1 << reg_bits;
     qfb_sweep_header sh;
@@ -833,6 +834,11 @@ int jit_generate(const uint8_t *rec, int nbits, int M, int reg_bits, JitSource &
     g.e("ld.param.u64 %%rd%d, [p_hi];", hi);
     const int zmask = g.rd();
     g.e("ld.param.u64 %%rd%d, [p_zero];", zmask);
+    // index bits that are the same for every tile of this launch (kernel parameter): 0 for a launch over the whole
+    // state; a launch over a SLICE of the state takes the index bits of `fix_mask` (non-tile bits) from here and
+    // enumerates the others (jit_build_variant: sharded states pipeline a qubit remap slice by slice)
+    const int fixv = g.rd();
+    g.e("ld.param.u64 %%rd%d, [p_fix];", fixv);
     // thread-bit images per round: index-bit image (64-bit) and exchange offset (32-bit)
     // QFB_JIT_REMAT=1 (experiments): the images are recomputed from the thread id where they are used (a dozen integer
     // instructions each) instead of being kept across the tile loop. Measured: no gain once the coefficient loads
@@ -885,12 +891,21 @@ int jit_generate(const uint8_t *rec, int nbits, int M, int reg_bits, JitSource &
         }
     }
     int hole[QFB_PLAN_MAX_HOLES];
-    for (int i = 0; i < nholes; ++i) hole[i] = sh.hole[i];
+    int nfree = 0;
+    uint64_t hole_mask = 0;
+    for (int i = 0; i < nholes; ++i) {
+        hole_mask |= 1ull << sh.hole[i];
+        if (!((fix_mask >> sh.hole[i]) & 1ull)) hole[nfree++] = sh.hole[i];
+    }
+    if (fix_mask & ~hole_mask) {
+        err = "jit: a slice can only fix index bits outside the sweep's tile";
+        return QFB_ERR_UNSUPPORTED;
+    }
     // ---- tile loop: tile = ctaid, ctaid + nctaid, ... ----
     const int tile = g.rd(), stride = g.rd(), gb = g.rd();
     g.e("cvt.u64.u32 %%rd%d, %%r%d;", tile, cta);
     g.e("cvt.u64.u32 %%rd%d, %%r%d;", stride, ncta);
-    const unsigned long long ntiles = 1ull << nholes;
+    const unsigned long long ntiles = 1ull << nfree;
     // With G groups the CTA leaves the loop as a whole (CTA-wide barriers): the loop runs while the CTA's FIRST group
     // has a tile; a group past the end works on the last tile again and keeps its stores to itself (`active`).
     const int grp64 = g.rd(), lead = g.rd(), active = g.pr(), tclamp = g.rd();
@@ -904,8 +919,8 @@ int jit_generate(const uint8_t *rec, int nbits, int M, int reg_bits, JitSource &
     g.e("setp.lt.u64 %%p%d, %%rd%d, %llu;", active, tile, ntiles);
     g.e("min.u64 %%rd%d, %%rd%d, %llu;", tclamp, tile, ntiles - 1);
     {
-        const int first = deposit64_from64(g, tclamp, hole, nholes);
-        g.e("mov.u64 %%rd%d, %%rd%d;", gb, first);
+        const int first = deposit64_from64(g, tclamp, hole, nfree);
+        g.e("or.b64 %%rd%d, %%rd%d, %%rd%d;", gb, first, fixv);
     }
     {
         // QFB_JIT_STAGGER="K:D" (experiments): CTA b sleeps (b % K) * D nanoseconds before its first tile, so that the
@@ -946,7 +961,11 @@ int jit_generate(const uint8_t *rec, int nbits, int M, int reg_bits, JitSource &
     g.e("sub.u64 %%rd%d, %%rd%d, %%rd%d;", lead, tile_next, grp64);
     g.e("setp.lt.u64 %%p%d, %%rd%d, %llu;", has_next, lead, ntiles);
     g.e("min.u64 %%rd%d, %%rd%d, %llu;", tnclamp, tile_next, ntiles - 1);
-    const int gb_next = deposit64_from64(g, tnclamp, hole, nholes);
+    const int gb_next = g.rd();
+    {
+        const int dep = deposit64_from64(g, tnclamp, hole, nfree);
+        g.e("or.b64 %%rd%d, %%rd%d, %%rd%d;", gb_next, dep, fixv);
+    }
     const int higb = g.rd();
     g.e("or.b64 %%rd%d, %%rd%d, %%rd%d;", higb, hi, gb);
     {
@@ -1209,7 +1228,7 @@ int jit_generate(const uint8_t *rec, int nbits, int M, int reg_bits, JitSource &
              ".version 8.7\n.target sm_100a\n.address_size 64\n"
              ".const .align 16 .b8 qfb_coef[%zu];\n"
              ".extern .shared .align 128 .b8 qfb_smem[];\n"
-             ".visible .entry qfb_sweep(.param .u64 p_state, .param .u64 p_hi, .param .u64 p_zero)\n"
+             ".visible .entry qfb_sweep(.param .u64 p_state, .param .u64 p_hi, .param .u64 p_zero, .param .u64 p_fix)\n"
              ".maxntid %d, 1, 1\n.minnctapersm %d\n{\n"
              ".reg .f64 %%fd<%d>;\n.reg .b64 %%rd<%d>;\n.reg .b32 %%r<%d>;\n.reg .pred %%p<%d>;\n",
              coef_bytes, T * G, minb, g.nfd + 1, g.nrd + 1, g.nr + 1, g.np + 1);
@@ -1218,7 +1237,7 @@ int jit_generate(const uint8_t *rec, int nbits, int M, int reg_bits, JitSource &
     out.coef_bytes = coef_bytes;
     out.threads = T * G;
     out.smem_bytes = smem_per_cta;
-    out.nholes = nholes;
+    out.nholes = nfree;
     out.groups = G;
     return QFB_OK;
 }
@@ -1347,7 +1366,8 @@ const char *cu_error(CUresult r) {
 struct JitSweep {
     CUmodule module = nullptr;
     CUfunction func = nullptr;
-    int threads = 0, grid = 0;
+    int threads = 0, grid = 0, resident = 0;
+    uint64_t nctas = 0;
     size_t smem = 0;
 };
 
@@ -1355,6 +1375,35 @@ void jit_destroy(JitSweep *s) {
     if (!s) return;
     if (s->module && driver().ok) driver().ModuleUnload(s->module);
     delete s;
+}
+
+// load a compiled sweep into the current context, write its coefficients, size its grid
+static int load_sweep(const JitSource &src, const std::vector<char> &image, JitSweep **out) {
+    const Driver &d = driver();
+    JitSweep *s = new JitSweep();
+    *out = s;
+    QFB_CU(d.ModuleLoadData(&s->module, image.data()));
+    QFB_CU(d.ModuleGetFunction(&s->func, s->module, "qfb_sweep"));
+    CUdeviceptr cptr = 0;
+    size_t cbytes = 0;
+    QFB_CU(d.ModuleGetGlobal(&cptr, &cbytes, s->module, "qfb_coef"));
+    if (cbytes < src.coef.size() * 8) {
+        set_error("jit: coefficient bank too small");
+        return QFB_ERR_CUDA;
+    }
+    if (!src.coef.empty()) QFB_CU(d.MemcpyHtoD(cptr, src.coef.data(), src.coef.size() * 8));
+    s->threads = src.threads;
+    s->smem = src.smem_bytes;
+    QFB_CU(d.FuncSetAttribute(s->func, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)s->smem));
+    int resident = 0;
+    QFB_CU(d.OccupancyMaxActiveBlocksPerMultiprocessor(&resident, s->func, s->threads, s->smem));
+    resident = std::max(1, resident);
+    const uint64_t ntiles = 1ull << src.nholes;
+    const uint64_t nctas = (ntiles + src.groups - 1) / src.groups;
+    s->grid = (int)std::min<uint64_t>(nctas, (uint64_t)sm_count_cached() * resident);
+    s->resident = resident;
+    s->nctas = nctas;
+    return QFB_OK;
 }
 
 // Generate + compile every sweep of a validated plan (parallel over host threads), then load the images into the
@@ -1389,37 +1438,51 @@ int jit_build_plan(const uint8_t *plan, const std::vector<size_t> &offsets, int 
             return rcs[i];
         }
     }
-    int sms = sm_count_cached();
     for (size_t i = 0; i < n; ++i) {
-        JitSweep *s = new JitSweep();
-        out.push_back(s);
-        QFB_CU(d.ModuleLoadData(&s->module, image[i]->data()));
-        QFB_CU(d.ModuleGetFunction(&s->func, s->module, "qfb_sweep"));
-        CUdeviceptr cptr = 0;
-        size_t cbytes = 0;
-        QFB_CU(d.ModuleGetGlobal(&cptr, &cbytes, s->module, "qfb_coef"));
-        if (cbytes < src[i].coef.size() * 8) {
-            set_error("jit: coefficient bank too small");
-            return QFB_ERR_CUDA;
-        }
-        if (!src[i].coef.empty()) QFB_CU(d.MemcpyHtoD(cptr, src[i].coef.data(), src[i].coef.size() * 8));
-        s->threads = src[i].threads;
-        s->smem = src[i].smem_bytes;
-        QFB_CU(d.FuncSetAttribute(s->func, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)s->smem));
-        int resident = 0;
-        QFB_CU(d.OccupancyMaxActiveBlocksPerMultiprocessor(&resident, s->func, s->threads, s->smem));
-        resident = std::max(1, resident);
-        const uint64_t ntiles = 1ull << src[i].nholes;
-        const uint64_t nctas = (ntiles + src[i].groups - 1) / src[i].groups;
-        s->grid = (int)std::min<uint64_t>(nctas, (uint64_t)sms * resident);
+        JitSweep *s = nullptr;
+        const int rc = load_sweep(src[i], *image[i], &s);
+        if (s) out.push_back(s);
+        if (rc != QFB_OK) return rc;
     }
     return QFB_OK;
 }
 
-int jit_launch(JitSweep *s, void *state, uint64_t hi_shifted, cudaStream_t st) {
+// One sweep restricted to the slice of the state whose index bits `fix_mask` (non-tile bits of the sweep) are given at
+// launch time (jit_launch's fix_value): same code, the tile loop enumerates the remaining non-tile bits only.
+int jit_build_variant(const uint8_t *rec, int nbits, int M, int reg_bits, uint64_t fix_mask, JitSweep **out) {
+    *out = nullptr;
+    if (!driver().ok) {
+        set_error("jit: the CUDA driver library (libcuda.so.1) is not available");
+        return QFB_ERR_CUDA;
+    }
+    JitSource src;
+    std::string log;
+    int rc = jit_generate(rec, nbits, M, reg_bits, src, log, fix_mask);
+    std::shared_ptr<std::vector<char>> image;
+    if (rc == QFB_OK) rc = compile_cached(src.ptx, image, log);
+    if (rc != QFB_OK) {
+        set_error("jit: slice variant: %s", log.c_str());
+        return rc;
+    }
+    rc = load_sweep(src, *image, out);
+    if (rc != QFB_OK && *out) {
+        jit_destroy(*out);
+        *out = nullptr;
+    }
+    return rc;
+}
+
+int jit_launch(JitSweep *s, void *state, uint64_t hi_shifted, cudaStream_t st, uint64_t fix_value, int ctas_per_sm) {
     uint64_t zero = 0;      // see Gen::cst
-    void *args[3] = {&state, &hi_shifted, &zero};
-    QFB_CU(driver().LaunchKernel(s->func, s->grid, 1, 1, s->threads, 1, 1, (unsigned)s->smem, (CUstream)st, args, nullptr));
+    void *args[4] = {&state, &hi_shifted, &zero, &fix_value};
+    // the CTAs are persistent (a tile loop each), so a kernel on another stream only finds room on an SM if this launch
+    // leaves it: ctas_per_sm > 0 bounds the resident CTAs per SM (negative: that many fewer than fit)
+    int grid = s->grid;
+    if (ctas_per_sm != 0) {
+        const int per_sm = ctas_per_sm > 0 ? std::min(ctas_per_sm, s->resident) : std::max(1, s->resident + ctas_per_sm);
+        grid = (int)std::min<uint64_t>(s->nctas, (uint64_t)sm_count_cached() * per_sm);
+    }
+    QFB_CU(driver().LaunchKernel(s->func, grid, 1, 1, s->threads, 1, 1, (unsigned)s->smem, (CUstream)st, args, nullptr));
     count_launch();
     return QFB_OK;
 }

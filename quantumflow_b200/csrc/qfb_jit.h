@@ -20,14 +20,19 @@ struct JitSource {
 struct JitSweep;                  // a loaded module + launch geometry
 
 // PTX text and coefficients of the sweep record at `rec` (a record of a VALIDATED plan)
-int jit_generate(const uint8_t *rec, int nbits, int tile_bits, int reg_bits, JitSource &out, std::string &err);
+// (fix_mask: index bits outside the tile that a launch fixes through the kernel's p_fix parameter, see jit_build_variant)
+int jit_generate(const uint8_t *rec, int nbits, int tile_bits, int reg_bits, JitSource &out, std::string &err,
+                 uint64_t fix_mask = 0);
 // PTX -> sm_100a image with the statically linked PTX compiler (no GPU, no driver needed); `log` = ptxas -v output
 int jit_compile(const std::string &ptx, std::vector<char> &cubin, std::string &log);
 // all sweeps of a plan: generate + compile in parallel (images cached per process by PTX text), load into the current
 // context, write the coefficient banks
 int jit_build_plan(const uint8_t *plan, const std::vector<size_t> &offsets, int nbits, int tile_bits, int reg_bits,
                    std::vector<JitSweep *> &out);
-int jit_launch(JitSweep *s, void *state, uint64_t hi_shifted, cudaStream_t st);
+// one sweep for launches over a slice of the state: the index bits `fix_mask` come from jit_launch's fix_value
+int jit_build_variant(const uint8_t *rec, int nbits, int tile_bits, int reg_bits, uint64_t fix_mask, JitSweep **out);
+int jit_launch(JitSweep *s, void *state, uint64_t hi_shifted, cudaStream_t st, uint64_t fix_value = 0,
+               int ctas_per_sm = 0);
 void jit_destroy(JitSweep *s);
 void jit_cache_stats(uint64_t *hits, uint64_t *misses);
 

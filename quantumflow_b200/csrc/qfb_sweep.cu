@@ -19,6 +19,7 @@
 // bandwidth are the secondary limits ("sweep kernel").
 #include <stdlib.h>
 #include <algorithm>
+#include <map>
 #include <vector>
 #include "qfb_common.cuh"
 #include "qfb_jit.h"
@@ -267,6 +268,9 @@ struct PlanHandle {
     std::vector<JitSweep *> jit;   // sweep-specialised kernels (qfb_jit.cu); empty = the interpreter runs the plan
     void *dev;
     size_t dev_bytes;
+    // slice launches (qfb_plan_launch_part): host copy of the plan and the kernels built for (sweep, fixed bits)
+    std::vector<uint8_t> host;
+    std::map<std::pair<int, uint64_t>, JitSweep *> variants;
 };
 
 // QFB_JIT: 0 = interpreter only, 1 = sweep-specialised kernels for every plan the generator supports, unset = for
@@ -582,7 +586,63 @@ int qfb_plan_upload(const void *plan_host, size_t plan_bytes, void **handle_out,
             return rc;
         }
     }
+    h->host.assign((const uint8_t *)plan_host, (const uint8_t *)plan_host + plan_bytes);
     *handle_out = h;
+    return QFB_OK;
+}
+
+int qfb_plan_sweep_info(void *handle, int sweep, int *nsweeps, uint64_t *nontile_mask, int *specialised) {
+    PlanHandle *h = (PlanHandle *)handle;
+    QFB_CHECK_ARG(h && h->magic == HANDLE_MAGIC, "qfb_plan_sweep_info: bad handle");
+    if (nsweeps) *nsweeps = (int)h->sweeps.size();
+    if (specialised) *specialised = h->jit.empty() ? 0 : 1;
+    if (nontile_mask) {
+        QFB_CHECK_ARG(sweep >= 0 && (size_t)sweep < h->sweeps.size(), "qfb_plan_sweep_info: no sweep %d", sweep);
+        qfb_sweep_header sh;
+        memcpy(&sh, h->host.data() + h->sweeps[sweep].offset, sizeof(sh));
+        uint64_t m = 0;
+        for (int i = 0; i < h->nbits - h->tile_bits; ++i) m |= 1ull << sh.hole[i];
+        *nontile_mask = m;
+    }
+    return QFB_OK;
+}
+
+int qfb_plan_launch_part(void *handle, void *state, int nbits, uint64_t index_hi, int first_sweep, int nsweeps,
+                         uint64_t fix_mask, uint64_t fix_value, int ctas_per_sm, void *stream) {
+    PlanHandle *h = (PlanHandle *)handle;
+    QFB_CHECK_ARG(h && h->magic == HANDLE_MAGIC, "qfb_plan_launch_part: bad handle");
+    QFB_CHECK_ARG(state, "qfb_plan_launch_part: null state");
+    QFB_CHECK_ARG(nbits == h->nbits, "qfb_plan_launch_part: plan built for %d bits, state has %d", h->nbits, nbits);
+    QFB_CHECK_ARG(first_sweep >= 0 && nsweeps >= 0 && (size_t)first_sweep + nsweeps <= h->sweeps.size(),
+                  "qfb_plan_launch_part: sweeps [%d, %d) out of range", first_sweep, first_sweep + nsweeps);
+    QFB_CHECK_ARG((fix_value & ~fix_mask) == 0 && (nbits >= 64 || (fix_mask >> nbits) == 0),
+                  "qfb_plan_launch_part: fixed bits outside the mask / the state");
+    const uint64_t hi_shifted = (nbits >= 64) ? 0ull : (index_hi << nbits);
+    for (int i = first_sweep; i < first_sweep + nsweeps; ++i) {
+        const SweepInfo &s = h->sweeps[i];
+        if (fix_mask == 0) {
+            int rc = h->jit.empty() ? launch_sweep_dispatch(h->tile_bits, s.has_g2, (c128 *)state,
+                                                            (const uint8_t *)h->dev + s.offset, s.bytes, nbits, index_hi,
+                                                            (cudaStream_t)stream)
+                                    : jit_launch(h->jit[i], state, hi_shifted, (cudaStream_t)stream);
+            if (rc != QFB_OK) return rc;
+            continue;
+        }
+        if (h->jit.empty()) {
+            set_error("qfb_plan_launch_part: slices need the sweep-specialised kernels (QFB_JIT, QFB_JIT_MIN_BITS)");
+            return QFB_ERR_UNSUPPORTED;
+        }
+        const auto key = std::make_pair(i, fix_mask);
+        auto it = h->variants.find(key);
+        if (it == h->variants.end()) {
+            JitSweep *v = nullptr;
+            int rc = jit_build_variant(h->host.data() + s.offset, h->nbits, h->tile_bits, h->reg_bits, fix_mask, &v);
+            if (rc != QFB_OK) return rc;
+            it = h->variants.emplace(key, v).first;
+        }
+        int rc = jit_launch(it->second, state, hi_shifted, (cudaStream_t)stream, fix_value, ctas_per_sm);
+        if (rc != QFB_OK) return rc;
+    }
     return QFB_OK;
 }
 
@@ -612,6 +672,7 @@ int qfb_plan_destroy(void *handle) {
     QFB_CHECK_ARG(h && h->magic == HANDLE_MAGIC, "qfb_plan_destroy: bad handle");
     h->magic = 0;
     for (JitSweep *j : h->jit) jit_destroy(j);
+    for (auto &kv : h->variants) jit_destroy(kv.second);
     if (h->dev) cudaFree(h->dev);
     delete h;
     return QFB_OK;

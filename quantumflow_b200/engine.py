@@ -368,6 +368,36 @@ class UploadedPlan:
         _lib.check(self._lib.qfb_plan_launch(self._handle, src.data_ptr(), nbits_of(src), int(index_hi),
                                              _stream()))
 
+    def _info(self, sweep: int = 0):
+        n, mask, spec = ctypes.c_int(0), ctypes.c_uint64(0), ctypes.c_int(0)
+        _lib.check(self._lib.qfb_plan_sweep_info(self._handle, int(sweep), ctypes.byref(n), ctypes.byref(mask),
+                                                 ctypes.byref(spec)))
+        return n.value, mask.value, bool(spec.value)
+
+    @property
+    def nsweeps(self) -> int:
+        return self._info()[0]
+
+    @property
+    def specialised(self) -> bool:
+        """Does the plan run on sweep-specialised kernels (csrc/qfb_jit.cu)? Only those can be launched on slices."""
+        return self._info()[2]
+
+    def nontile_mask(self, sweep: int) -> int:
+        """Index bits outside the tile of sweep `sweep`: amplitudes that differ in one of them never meet in it."""
+        return self._info(sweep)[1]
+
+    def launch_part(self, tensor: torch.Tensor, first_sweep: int, nsweeps: int, index_hi: int = 0,
+                    fix_mask: int = 0, fix_value: int = 0, ctas_per_sm: int = 0) -> None:
+        """Sweeps [first_sweep, first_sweep + nsweeps) in place on `tensor`; with fix_mask on the slice of the state
+        whose index bits fix_mask equal fix_value (bits of nontile_mask of every launched sweep)."""
+        src = _require_amplitudes(tensor)
+        if src.data_ptr() != tensor.data_ptr():
+            raise ValueError('plan execution is in place and needs a contiguous tensor')
+        _lib.check(self._lib.qfb_plan_launch_part(self._handle, src.data_ptr(), nbits_of(src), int(index_hi),
+                                                  int(first_sweep), int(nsweeps), int(fix_mask), int(fix_value),
+                                                  int(ctas_per_sm), _stream()))
+
     def close(self) -> None:
         if self._handle is not None and self._handle.value:
             self._lib.qfb_plan_destroy(self._handle)

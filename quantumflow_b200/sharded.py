@@ -317,6 +317,9 @@ class ShardedCircuit:
         self._comm_bytes = 0
         self._remaps = 0
         self._executions = 0
+        self._pipelined = 0
+        self._comm_events = []          # (start, end) CUDA events of exchange kernels, resolved lazily (no host sync)
+        self._comm_stream = None
         for st in self.steps:
             if isinstance(st, Stage):
                 st.segments = planner.build_segments_from_items(self.nl, st.items, final_perm=st.final_perm,
@@ -342,7 +345,18 @@ class ShardedCircuit:
                 out.extend(st.segments)
         return out
 
+    def _resolve_comm_events(self) -> None:
+        if self._comm_events:
+            torch.cuda.synchronize()
+            for t0, t1 in self._comm_events:
+                self._comm_seconds += t0.elapsed_time(t1) * 1e-3
+            self._comm_events = []
+            if getattr(self, '_barrier_error', None) is not None and int(self._barrier_error.item()) != 0:
+                raise RuntimeError('peer barrier {} timed out: a rank did not arrive'.format(
+                    int(self._barrier_error.item())))
+
     def comm_ms_per_step(self) -> float:
+        self._resolve_comm_events()
         return 1e3 * self._comm_seconds / max(1, self._executions)
 
     def comm_summary(self) -> dict:
@@ -350,14 +364,19 @@ class ShardedCircuit:
         return {'remaps_per_step': self._remaps / ex, 'bytes_sent_per_rank_per_step': self._comm_bytes / ex,
                 'ms_per_step': self.comm_ms_per_step(),
                 'path': self._exchange_path,
+                'pipelined_remaps_per_step': self._pipelined / ex,
                 'note': 'in-place pairwise block exchange of k rank bits with the top-k local bits; path "peer": one '
                         'kernel per remap and rank swaps its half of every pair over peer memory (qfb_remap_swap, '
                         'NVLink loads / stores on the IPC-mapped shards, no staging, no NCCL call); path "nccl": '
                         'isend / irecv chunks through two staging buffers. The local bit permutation is fused into '
-                        'the last sweep of the preceding stage; the exchange is not overlapped with sweeps'}
+                        'the last sweep of the preceding stage. Pipelined remaps: the last sweep of the stage, the exchange and the '
+                        'first sweep of the next stage run slice by slice (slices = index bits outside both tiles), the exchange '
+                        'of slice s beside the sweeps of its neighbours, ranks ordered by a peer-memory barrier; '
+                        'ms_per_step is the device time of the exchange kernels (overlapped with sweeps when pipelined)'}
 
     def reset_comm_counters(self) -> None:
-        self._comm_seconds, self._comm_bytes, self._remaps, self._executions = 0.0, 0, 0, 0
+        self._resolve_comm_events()
+        self._comm_seconds, self._comm_bytes, self._remaps, self._executions, self._pipelined = 0.0, 0, 0, 0, 0
 
     # ---- execution ---------------------------------------------------------------------------------
     _exchange_path = 'nccl'
@@ -385,6 +404,23 @@ class ShardedCircuit:
             self._peers[r] = st.data_ptr() + offset
         self._peer_key = key
         self._token = torch.zeros(1, dtype=torch.int32, device=shard.device)
+        # flag words of the peer-memory barrier (qfb_peer_barrier), mapped the same way
+        self._flags = torch.zeros(64, dtype=torch.int32, device=shard.device)
+        self._barrier_error = torch.zeros(1, dtype=torch.int32, device=shard.device)
+        torch.cuda.synchronize(shard.device)
+        fl = (self._flags.untyped_storage()._share_cuda_(), self._flags.storage_offset() * 4)
+        gathered = [None] * self.world
+        dist.all_gather_object(gathered, fl, group=self.group)
+        self._flag_ptrs = [0] * self.world
+        for r, (handle, offset) in enumerate(gathered):
+            if r == self.rank:
+                self._flag_ptrs[r] = self._flags.data_ptr()
+                continue
+            st = torch.UntypedStorage._new_shared_cuda(shard.device.index, *handle[1:])
+            self._peer_storages.append(st)
+            self._flag_ptrs[r] = st.data_ptr() + offset
+        self._epoch = 0
+        dist.barrier(group=self.group)         # nobody signals before everybody's flags are zero and mapped
 
     def _rank_barrier(self) -> None:
         """Stream-ordered barrier across the ranks: nobody's later work starts before everybody's earlier work
@@ -397,6 +433,16 @@ class ShardedCircuit:
         the first half and the higher rank the second half."""
         from . import _lib, engine
         self._map_peers(shard)
+        local, remote, counts = self._swap_runs(shard, rank_positions)
+        self._rank_barrier()
+        npairs = len(local)
+        lib = _lib.load()
+        _lib.check(lib.qfb_remap_swap(npairs, (ctypes.c_void_p * npairs)(*local), (ctypes.c_void_p * npairs)(*remote),
+                                      (ctypes.c_uint64 * npairs)(*counts), engine._stream()))
+        self._rank_barrier()
+
+    def _swap_runs(self, shard: torch.Tensor, rank_positions: List[int]):
+        """(local addresses, peer addresses, amplitude counts) of the runs this rank swaps in a remap."""
         k = len(rank_positions)
         blk = shard.numel() >> k
         mine = 0
@@ -417,12 +463,7 @@ class ShardedCircuit:
             remote.append(self._peers[peer] + (mine * blk + off) * es)
             counts.append(n)
             self._comm_bytes += n * es * 2        # leaves this GPU: n by its own remote stores, n pulled by the peer
-        self._rank_barrier()
-        npairs = len(local)
-        lib = _lib.load()
-        _lib.check(lib.qfb_remap_swap(npairs, (ctypes.c_void_p * npairs)(*local), (ctypes.c_void_p * npairs)(*remote),
-                                      (ctypes.c_uint64 * npairs)(*counts), engine._stream()))
-        self._rank_barrier()
+        return local, remote, counts
 
     def _exchange(self, shard: torch.Tensor, rank_positions: List[int]) -> None:
         """In place: block j of this rank (top-k local bits = j) is swapped with block `mine` of the peer whose
@@ -464,10 +505,149 @@ class ShardedCircuit:
                 req.wait()
             pending[1].copy_(pending[2])
 
+    # ---- pipelined remaps (GPU, peer-memory path) ---------------------------------------------------------
+    # A remap sits between the last sweep A of a stage and the first sweep B of the next. Index bits that are outside
+    # the tiles of A and of B and below the exchanged block bits cut the shard into 2^v SLICES that never meet in A,
+    # in the exchange or in B, so the three are pipelined slice by slice: A runs on slice s+1 while the exchange
+    # kernel (another stream, a bounded share of every SM) moves slice s over NVLink and B follows one barrier
+    # behind. The ranks are ordered by a barrier through peer memory (qfb_peer_barrier) between the steps of the
+    # exchange stream: no host synchronisation, no NCCL kernel that would have to wait for a free SM.
+    def _uploaded(self, seg):
+        from . import engine
+        if seg.uploaded is None:
+            seg.uploaded = engine.UploadedPlan(seg.blob)
+        return seg.uploaded
+
+    def _pipeline_bits(self, prev: 'Stage', remap: 'Remap', nxt: 'Stage') -> Optional[List[int]]:
+        """Selector bits (ascending) of the slices of this remap, or None when it cannot be pipelined."""
+        want = int(os.environ.get('QFB_REMAP_SLICE_BITS', '2'))
+        if want <= 0 or not prev.segments or not nxt.segments:
+            return None
+        a_seg, b_seg = prev.segments[-1], nxt.segments[0]
+        if a_seg.kind != 'plan' or b_seg.kind != 'plan':
+            return None
+        a, b = self._uploaded(a_seg), self._uploaded(b_seg)
+        if not (a.specialised and b.specialised):
+            return None
+        k = len(remap.rank_positions)
+        common = a.nontile_mask(a.nsweeps - 1) & b.nontile_mask(0)
+        # below the half-block split of the exchange; runs of at least 2^12 amplitudes (64 KiB) stay contiguous
+        cand = [pos for pos in range(12, self.nl - k - 1) if (common >> pos) & 1]
+        if not cand:
+            return None
+        return cand[-want:]
+
+    def _peer_barrier(self) -> None:
+        from . import _lib, engine
+        self._epoch += 1
+        ptrs = (ctypes.c_void_p * self.world)(*self._flag_ptrs)
+        _lib.check(_lib.load().qfb_peer_barrier(self._flags.data_ptr(), ptrs, self.world, self.rank, self._epoch,
+                                                self._barrier_error.data_ptr(), engine._stream()))
+
+    def _run_stage_part(self, stage: 'Stage', shard: torch.Tensor, skip_first: bool, skip_last: bool) -> None:
+        from . import engine
+        segs = stage.segments
+        for idx, seg in enumerate(segs):
+            if seg.kind != 'plan':
+                engine.apply_operator(shard, seg.mat, seg.bits, inplace=True, index_hi=self.rank)
+                continue
+            up = self._uploaded(seg)
+            first = 1 if (skip_first and idx == 0) else 0
+            last = up.nsweeps - 1 if (skip_last and idx == len(segs) - 1) else up.nsweeps
+            if last > first:
+                up.launch_part(shard, first, last - first, index_hi=self.rank)
+
+    def _remap_pipelined(self, shard: torch.Tensor, prev: 'Stage', remap: 'Remap', nxt: 'Stage',
+                         bits: List[int]) -> None:
+        from . import _lib, engine
+        lib = _lib.load()
+        main = torch.cuda.current_stream(shard.device)
+        if getattr(self, '_comm_stream', None) is None:
+            self._comm_stream = torch.cuda.Stream(device=shard.device, priority=-1)
+        comm = self._comm_stream
+        a, b = self._uploaded(prev.segments[-1]), self._uploaded(nxt.segments[0])
+        local, remote, counts = self._swap_runs(shard, remap.rank_positions)
+        npairs = len(local)
+        c_local, c_remote = (ctypes.c_void_p * npairs)(*local), (ctypes.c_void_p * npairs)(*remote)
+        c_counts, c_pos = (ctypes.c_uint64 * npairs)(*counts), (ctypes.c_int * len(bits))(*bits)
+        mask = sum(1 << pos for pos in bits)
+        # the sweeps' CTAs are persistent: a slice launch leaves room for one exchange CTA per SM (QFB_SLICE_ROOM=0: none)
+        ctas = int(os.environ.get('QFB_REMAP_CTAS', '1'))
+        room = -int(os.environ.get('QFB_SLICE_ROOM', '1'))
+        nslices = 1 << len(bits)
+        values = [sum(((sl >> t) & 1) << pos for t, pos in enumerate(bits)) for sl in range(nslices)]
+        arrived = []
+        for sl in range(nslices):
+            a.launch_part(shard, a.nsweeps - 1, 1, index_hi=self.rank, fix_mask=mask, fix_value=values[sl],
+                          ctas_per_sm=room)
+            ev_a = torch.cuda.Event()
+            ev_a.record(main)
+            with torch.cuda.stream(comm):
+                comm.wait_event(ev_a)
+                # everybody's slice is final (and, from the second slice on, everybody's previous exchange complete)
+                self._peer_barrier()
+                if sl > 0:
+                    ev_x = torch.cuda.Event()
+                    ev_x.record(comm)
+                    arrived.append(ev_x)
+                t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                t0.record(comm)
+                _lib.check(lib.qfb_remap_swap_slice(npairs, c_local, c_remote, c_counts, len(bits), c_pos, values[sl],
+                                                    ctas, comm.cuda_stream))
+                t1.record(comm)
+                self._comm_events.append((t0, t1))
+        with torch.cuda.stream(comm):
+            self._peer_barrier()
+            ev_x = torch.cuda.Event()
+            ev_x.record(comm)
+            arrived.append(ev_x)
+        for sl in range(nslices):
+            main.wait_event(arrived[sl])
+            b.launch_part(shard, 0, 1, index_hi=self.rank, fix_mask=mask, fix_value=values[sl], ctas_per_sm=room)
+
+    def _execute_overlapped(self, shard: torch.Tensor) -> torch.Tensor:
+        self._exchange_path = 'peer'
+        self._map_peers(shard)
+        steps = self.steps
+        skip_first = False
+        i = 0
+        while i < len(steps):
+            st = steps[i]
+            if isinstance(st, Remap):           # a remap that no stage's pipeline has taken
+                t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                t0.record()
+                self._exchange_peer(shard, st.rank_positions)
+                t1.record()
+                self._comm_events.append((t0, t1))
+                self._remaps += 1
+                i += 1
+                continue
+            remap = steps[i + 1] if i + 1 < len(steps) and isinstance(steps[i + 1], Remap) else None
+            nxt = steps[i + 2] if remap is not None and i + 2 < len(steps) and isinstance(steps[i + 2], Stage) else None
+            bits = self._pipeline_bits(st, remap, nxt) if nxt is not None else None
+            # a stage that is one sweep in all cannot be the tail of one pipeline and the head of the next
+            if bits is not None and skip_first and len(st.segments) == 1 and self._uploaded(st.segments[0]).nsweeps == 1:
+                bits = None
+            self._run_stage_part(st, shard, skip_first, bits is not None)
+            skip_first = False
+            if bits is not None:
+                self._remap_pipelined(shard, st, remap, nxt, bits)
+                self._pipelined += 1
+                self._remaps += 1
+                skip_first = True
+                i += 2
+            else:
+                i += 1
+        self._executions += 1
+        return shard
+
     def execute(self, shard: torch.Tensor) -> torch.Tensor:
         """Runs the circuit in place on this rank's shard and returns it (the same tensor)."""
         assert shard.numel() == 1 << self.nl and shard.is_contiguous()
         timed = shard.is_cuda
+        if (timed and self.world > 1 and self._run_stage == self._run_stage_gpu
+                and os.environ.get('QFB_REMAP', 'peer') != 'nccl' and os.environ.get('QFB_REMAP_OVERLAP', '1') != '0'):
+            return self._execute_overlapped(shard)
         for st in self.steps:
             if isinstance(st, Stage):
                 self._run_stage(st, shard)
@@ -489,8 +669,7 @@ class ShardedCircuit:
             self._remaps += 1
             if timed:
                 ev1.record()
-                ev1.synchronize()
-                self._comm_seconds += ev0.elapsed_time(ev1) * 1e-3
+                self._comm_events.append((ev0, ev1))       # resolved when the figures are read: no host sync here
             else:
                 self._comm_seconds += time.perf_counter() - t0
         self._executions += 1

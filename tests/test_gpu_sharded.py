@@ -19,10 +19,12 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _worker(rank, world, port, n, depth, seed, out_dir):
+def _worker(rank, world, port, n, depth, seed, out_dir, jit=False):
     import torch.distributed as dist
     os.environ['MASTER_ADDR'] = '127.0.0.1'
     os.environ['MASTER_PORT'] = str(port)
+    if jit:
+        os.environ['QFB_JIT'] = '1'      # sweep-specialised kernels: the remaps are pipelined slice by slice
     torch.cuda.set_device(rank)
     dist.init_process_group('nccl', rank=rank, world_size=world, device_id=torch.device('cuda', rank))
     try:
@@ -36,25 +38,35 @@ def _worker(rank, world, port, n, depth, seed, out_dir):
         if rank == 0:
             shard[0] = 1
         shard = runner.execute(shard)
+        if jit:
+            # a second execution from the same start: the peer-memory barrier's epochs carry on
+            again = torch.zeros_like(shard)
+            if rank == 0:
+                again[0] = 1
+            again = runner.execute(again)
+            assert torch.equal(again, shard)
         n2 = engine.norm2(shard)
         dist.all_reduce(n2)
         np.save(os.path.join(out_dir, 'shard{}.npy'.format(rank)), shard.cpu().numpy())
         if rank == 0:
-            np.save(os.path.join(out_dir, 'meta.npy'), np.asarray(list(runner.final_phys_of) + [runner._remaps]))
+            np.save(os.path.join(out_dir, 'meta.npy'),
+                    np.asarray(list(runner.final_phys_of) + [runner._remaps, runner._pipelined]))
             np.save(os.path.join(out_dir, 'norm.npy'), np.asarray([float(n2)]))
     finally:
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize('world,n,depth,seed', [(2, 20, 6, 0), (2, 22, 4, 1), (4, 21, 5, 2), (8, 22, 4, 3)])
-def test_sharded_matches_single_gpu_and_oracle(tmp_path, world, n, depth, seed):
+@pytest.mark.parametrize('world,n,depth,seed,jit', [(2, 20, 6, 0, False), (2, 22, 4, 1, False), (4, 21, 5, 2, False),
+                                                     (8, 22, 4, 3, False), (2, 22, 8, 4, True), (4, 23, 6, 5, True),
+                                                     (8, 24, 5, 6, True)])
+def test_sharded_matches_single_gpu_and_oracle(tmp_path, world, n, depth, seed, jit):
     if torch.cuda.device_count() < world:
         pytest.skip('needs {} GPUs'.format(world))
     import torch.multiprocessing as mp
     from oracle import c_oracle
     from oracle import qf_oracle as O
     from quantumflow_b200 import sharded, workloads
-    mp.spawn(_worker, args=(world, _free_port(), n, depth, seed, str(tmp_path)), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, _free_port(), n, depth, seed, str(tmp_path), jit), nprocs=world, join=True)
     p = world.bit_length() - 1
     shards = [np.load(os.path.join(str(tmp_path), 'shard{}.npy'.format(r))) for r in range(world)]
     meta = list(np.load(os.path.join(str(tmp_path), 'meta.npy')))
@@ -63,6 +75,8 @@ def test_sharded_matches_single_gpu_and_oracle(tmp_path, world, n, depth, seed):
     assert np.abs(got - want).max() < AMP_TOL
     assert abs(float(np.load(os.path.join(str(tmp_path), 'norm.npy'))[0]) - 1) < 1e-10
     assert int(meta[n]) >= 1
+    if jit:
+        assert int(meta[n + 1]) >= 1, 'no remap was pipelined'
 
 
 def _readout_worker(rank, world, port, n, phys_of, phys, diag, uniforms, out_dir):
