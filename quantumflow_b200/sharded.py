@@ -318,6 +318,7 @@ class ShardedCircuit:
         self._remaps = 0
         self._executions = 0
         self._pipelined = 0
+        self._pipelined_sweeps = 0
         self._comm_events = []          # (start, end) CUDA events of exchange kernels, resolved lazily (no host sync)
         self._comm_stream = None
         for st in self.steps:
@@ -365,6 +366,7 @@ class ShardedCircuit:
                 'ms_per_step': self.comm_ms_per_step(),
                 'path': self._exchange_path,
                 'pipelined_remaps_per_step': self._pipelined / ex,
+                'sweeps_inside_pipelines_per_step': self._pipelined_sweeps / ex,
                 'note': 'in-place pairwise block exchange of k rank bits with the top-k local bits; path "peer": one '
                         'kernel per remap and rank swaps its half of every pair over peer memory (qfb_remap_swap, '
                         'NVLink loads / stores on the IPC-mapped shards, no staging, no NCCL call); path "nccl": '
@@ -377,6 +379,7 @@ class ShardedCircuit:
     def reset_comm_counters(self) -> None:
         self._resolve_comm_events()
         self._comm_seconds, self._comm_bytes, self._remaps, self._executions, self._pipelined = 0.0, 0, 0, 0, 0
+        self._pipelined_sweeps = 0
 
     # ---- execution ---------------------------------------------------------------------------------
     _exchange_path = 'nccl'
@@ -518,10 +521,15 @@ class ShardedCircuit:
             seg.uploaded = engine.UploadedPlan(seg.blob)
         return seg.uploaded
 
-    def _pipeline_bits(self, prev: 'Stage', remap: 'Remap', nxt: 'Stage') -> Optional[List[int]]:
-        """Selector bits (ascending) of the slices of this remap, or None when it cannot be pipelined."""
-        want = int(os.environ.get('QFB_REMAP_SLICE_BITS', '2'))
-        if want <= 0 or not prev.segments or not nxt.segments:
+    def _pipeline_shape(self, prev: 'Stage', remap: 'Remap', nxt: 'Stage', used_first: int, nxt_has_remap: bool):
+        """(selector bits ascending, da, db) of this remap's pipeline, or None when it cannot be pipelined: the last da
+        sweeps of `prev` and the first db sweeps of `nxt` run slice by slice around the exchange. Deeper chains hide
+        more of the exchange (it runs beside 2 (da + db) / 2^v ... of sweep work instead of 2), but every sweep of a
+        chain must keep the selector bits outside its tile. `used_first`: leading sweeps of prev's first plan that the
+        previous remap's pipeline has already run."""
+        want = int(os.environ.get('QFB_REMAP_SLICE_BITS', '3'))
+        depth = int(os.environ.get('QFB_REMAP_CHAIN', '3'))
+        if want <= 0 or depth <= 0 or not prev.segments or not nxt.segments:
             return None
         a_seg, b_seg = prev.segments[-1], nxt.segments[0]
         if a_seg.kind != 'plan' or b_seg.kind != 'plan':
@@ -530,12 +538,36 @@ class ShardedCircuit:
         if not (a.specialised and b.specialised):
             return None
         k = len(remap.rank_positions)
-        common = a.nontile_mask(a.nsweeps - 1) & b.nontile_mask(0)
-        # below the half-block split of the exchange; runs of at least 2^12 amplitudes (64 KiB) stay contiguous
-        cand = [pos for pos in range(12, self.nl - k - 1) if (common >> pos) & 1]
-        if not cand:
+        na, nb = a.nsweeps, b.nsweeps
+        da_max = min(depth, na - (used_first if len(prev.segments) == 1 else 0))
+        # a one-plan stage that feeds the next remap's pipeline keeps at least half of its sweeps for that one
+        db_max = min(depth, nb - (nb + 1) // 2 if (nxt_has_remap and len(nxt.segments) == 1 and nb > 1) else nb)
+        if nxt_has_remap and len(nxt.segments) == 1 and nb == 1:
+            db_max = 0
+        if da_max < 1 or db_max < 1:
             return None
-        return cand[-want:]
+        best = None
+        for da in range(1, da_max + 1):
+            for db in range(1, db_max + 1):
+                common = ~0
+                for i in range(na - da, na):
+                    common &= a.nontile_mask(i)
+                for i in range(db):
+                    common &= b.nontile_mask(i)
+                # below the half-block split of the exchange; runs of at least 2^12 amplitudes (64 KiB) stay contiguous
+                cand = [pos for pos in range(12, self.nl - k - 1) if (common >> pos) & 1]
+                nb_bits = min(want, len(cand))
+                if nb_bits < 1:
+                    continue
+                # time saved ~ (sweep work beside the exchange, at most the exchange itself: a whole-shard exchange
+                # takes about 3.5 sweeps) x (1 - 1 / slices)
+                hidden = min(float(da + db), 3.5 * (1.0 - 0.5 ** k)) * (1.0 - 0.5 ** nb_bits)
+                key = (round(hidden, 6), -(da + db), -abs(da - db))
+                if best is None or key > best[0]:
+                    best = (key, cand[-nb_bits:], da, db)
+        if best is None:
+            return None
+        return best[1], best[2], best[3]
 
     def _peer_barrier(self) -> None:
         from . import _lib, engine
@@ -544,7 +576,9 @@ class ShardedCircuit:
         _lib.check(_lib.load().qfb_peer_barrier(self._flags.data_ptr(), ptrs, self.world, self.rank, self._epoch,
                                                 self._barrier_error.data_ptr(), engine._stream()))
 
-    def _run_stage_part(self, stage: 'Stage', shard: torch.Tensor, skip_first: bool, skip_last: bool) -> None:
+    def _run_stage_part(self, stage: 'Stage', shard: torch.Tensor, skip_first: int, skip_last: int) -> None:
+        """The stage without the first `skip_first` sweeps of its first plan and the last `skip_last` of its last plan
+        (those run inside the pipelines of the neighbouring remaps)."""
         from . import engine
         segs = stage.segments
         for idx, seg in enumerate(segs):
@@ -552,13 +586,13 @@ class ShardedCircuit:
                 engine.apply_operator(shard, seg.mat, seg.bits, inplace=True, index_hi=self.rank)
                 continue
             up = self._uploaded(seg)
-            first = 1 if (skip_first and idx == 0) else 0
-            last = up.nsweeps - 1 if (skip_last and idx == len(segs) - 1) else up.nsweeps
+            first = skip_first if idx == 0 else 0
+            last = up.nsweeps - (skip_last if idx == len(segs) - 1 else 0)
             if last > first:
                 up.launch_part(shard, first, last - first, index_hi=self.rank)
 
     def _remap_pipelined(self, shard: torch.Tensor, prev: 'Stage', remap: 'Remap', nxt: 'Stage',
-                         bits: List[int]) -> None:
+                         bits: List[int], da: int, db: int) -> None:
         from . import _lib, engine
         lib = _lib.load()
         main = torch.cuda.current_stream(shard.device)
@@ -578,7 +612,7 @@ class ShardedCircuit:
         values = [sum(((sl >> t) & 1) << pos for t, pos in enumerate(bits)) for sl in range(nslices)]
         arrived = []
         for sl in range(nslices):
-            a.launch_part(shard, a.nsweeps - 1, 1, index_hi=self.rank, fix_mask=mask, fix_value=values[sl],
+            a.launch_part(shard, a.nsweeps - da, da, index_hi=self.rank, fix_mask=mask, fix_value=values[sl],
                           ctas_per_sm=room)
             ev_a = torch.cuda.Event()
             ev_a.record(main)
@@ -603,13 +637,13 @@ class ShardedCircuit:
             arrived.append(ev_x)
         for sl in range(nslices):
             main.wait_event(arrived[sl])
-            b.launch_part(shard, 0, 1, index_hi=self.rank, fix_mask=mask, fix_value=values[sl], ctas_per_sm=room)
+            b.launch_part(shard, 0, db, index_hi=self.rank, fix_mask=mask, fix_value=values[sl], ctas_per_sm=room)
 
     def _execute_overlapped(self, shard: torch.Tensor) -> torch.Tensor:
         self._exchange_path = 'peer'
         self._map_peers(shard)
         steps = self.steps
-        skip_first = False
+        skip_first = 0
         i = 0
         while i < len(steps):
             st = steps[i]
@@ -624,17 +658,19 @@ class ShardedCircuit:
                 continue
             remap = steps[i + 1] if i + 1 < len(steps) and isinstance(steps[i + 1], Remap) else None
             nxt = steps[i + 2] if remap is not None and i + 2 < len(steps) and isinstance(steps[i + 2], Stage) else None
-            bits = self._pipeline_bits(st, remap, nxt) if nxt is not None else None
-            # a stage that is one sweep in all cannot be the tail of one pipeline and the head of the next
-            if bits is not None and skip_first and len(st.segments) == 1 and self._uploaded(st.segments[0]).nsweeps == 1:
-                bits = None
-            self._run_stage_part(st, shard, skip_first, bits is not None)
-            skip_first = False
-            if bits is not None:
-                self._remap_pipelined(shard, st, remap, nxt, bits)
+            shape = None
+            if nxt is not None:
+                nxt_has_remap = i + 3 < len(steps) and isinstance(steps[i + 3], Remap)
+                shape = self._pipeline_shape(st, remap, nxt, skip_first, nxt_has_remap)
+            self._run_stage_part(st, shard, skip_first, shape[1] if shape else 0)
+            skip_first = 0
+            if shape is not None:
+                bits, da, db = shape
+                self._remap_pipelined(shard, st, remap, nxt, bits, da, db)
                 self._pipelined += 1
+                self._pipelined_sweeps += da + db
                 self._remaps += 1
-                skip_first = True
+                skip_first = db
                 i += 2
             else:
                 i += 1
