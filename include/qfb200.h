@@ -96,6 +96,21 @@ int qfb_plan_destroy(void *handle);
 int qfb_jit_ptx(const void *plan_host, size_t plan_bytes, int sweep, char *buf, size_t cap, size_t *needed,
                 size_t *ncoef);
 int qfb_jit_check(const void *plan_host, size_t plan_bytes, char *log, size_t cap);
+/* Whole circuits on small states in ONE launch (csrc/qfb_small.cu; the QAOA gradient step of
+ * examples/qaoa_maxcut.py:37-87, BASELINE.json configs[1]): the state (<= 13 qubits) stays in the shared memory of one
+ * CTA for all gates; `batch` independent items (states [batch][2^nbits], matrices [batch][mats_stride]) run as one CTA
+ * each. gates_dev: ngates records of 4 int32 {k (1|2), index bit of gate qubit 0, of gate qubit 1, offset of the
+ * row-major 2^k x 2^k matrix in the item's matrix array (complex elements)}; all pointers are device pointers.
+ * qfb_small_circuit_adjoint is the reverse sweep of the adjoint method for UNITARY gates (<= 12 qubits): from the final
+ * state and grad_out = dL/dpsi_final it writes grad_in = dL/dpsi_initial and, per gate, grad[r][c] = sum over groups
+ * of lambda_out[r] conj(psi_in[c]) (qfb_gate_grad's convention) into grad_mats_dev, laid out like mats_dev
+ * ([batch][mats_stride], the gate's entries at its matrix offset); no intermediate state is stored. scratch_dev: qfb_small_circuit_scratch_doubles(batch, ngates) doubles. */
+int qfb_small_circuit_run(void *out, const void *in, int nbits, int batch, int ngates, const void *gates_dev,
+                          const void *mats_dev, size_t mats_stride, void *stream);
+int qfb_small_circuit_adjoint(const void *psi_final, const void *grad_out, int nbits, int batch, int ngates,
+                              const void *gates_dev, const void *mats_dev, size_t mats_stride, void *grad_mats_dev,
+                              void *grad_in_dev, void *scratch_dev, void *stream);
+size_t qfb_small_circuit_scratch_doubles(int batch, int ngates);
 /* number of kernel launches performed by this library in this process (bench.py's gpu_launches) */
 uint64_t qfb_launch_count(void);
 

@@ -11,7 +11,7 @@ import subprocess
 CSRC = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'csrc')
 LIB_PATH = os.path.join(CSRC, 'libqfb200.so')
 STAMP_PATH = os.path.join(CSRC, '.libqfb200.stamp')
-SOURCES = ['qfb_api.cu', 'qfb_apply.cu', 'qfb_reduce.cu', 'qfb_sweep.cu', 'qfb_planhost.cu', 'qfb_jit.cu', 'qfb_remap.cu', 'qfb_batch.cu']
+SOURCES = ['qfb_api.cu', 'qfb_apply.cu', 'qfb_reduce.cu', 'qfb_sweep.cu', 'qfb_planhost.cu', 'qfb_jit.cu', 'qfb_remap.cu', 'qfb_batch.cu', 'qfb_small.cu']
 HEADERS = ['qfb_common.cuh', 'qfb_plan.h', 'qfb_jit.h', 'qfb_oploop.inc', os.path.join('..', '..', 'include', 'qfb200.h')]
 
 NVCC_FLAGS = ['-O3', '-std=c++17', '-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo',

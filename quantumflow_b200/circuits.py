@@ -7,12 +7,14 @@ caller's State is never mutated (gates and states stay immutable by convention),
 Elements that consult the RNG or classical memory (Measure, Kraus, Reset, If ...) are barriers and run through
 their own `.run` / `.evolve`.
 """
+import os
 from collections import defaultdict
 from itertools import chain
 from math import pi
 from typing import Dict, Iterable, Iterator, List, Sequence, Tuple, Type
 
 import numpy as np
+import torch
 
 from . import backend as bk
 from .gates import control_gate, identity_gate
@@ -117,6 +119,24 @@ class Circuit(Operation):
         count = ket.qubit_nb
         i = 0
         while i < len(flat):
+            # differentiable runs on small states: the whole run is one launch and one autograd node each way
+            # (autograd.run_small_circuit; the QAOA gradient step of examples/qaoa_maxcut.py)
+            g_end = i
+            while g_end < len(flat) and isinstance(flat[g_end], Gate):
+                g_end += 1
+            if g_end - i >= 2 and torch.is_grad_enabled() and os.environ.get('QFB_SMALL_CIRCUIT', '1') != '0' and (
+                    getattr(ket.tensor, 'requires_grad', False)
+                    or any(getattr(e.tensor, 'requires_grad', False) for e in flat[i:g_end])):
+                from . import autograd
+                if autograd.small_circuit_shape_ok(flat[i:g_end], count):
+                    where = {q: count - 1 - w for w, q in enumerate(ket.qubits)}
+                    tensor = autograd.run_small_circuit(ket.tensor, flat[i:g_end],
+                                                        lambda g: [where[q] for q in g.qubits])
+                    if tensor is not None:           # None: a gate is not unitary -> gate by gate below
+                        ket = State(tensor, ket.qubits, ket.memory)
+                        owned = True
+                        i = g_end
+                        continue
             j = i
             while j < len(flat) and _plannable_gate(flat[j]):
                 j += 1

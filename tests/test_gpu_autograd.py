@@ -98,3 +98,56 @@ def test_gradient_descent_reaches_the_reference_criterion():
         beta.grad = None
         gamma.grad = None
     assert ratio > 0.95
+
+
+def _random_parametrised_circuit(n, layers, seed, params):
+    """RX / RY / RZ / ZZ / CPHASE gates on random qubits, every angle an entry of `params` (torch, requires_grad),
+    CNOT / H without parameters in between."""
+    rnd = np.random.RandomState(seed)
+    circ = qf.Circuit()
+    at = 0
+    for _ in range(layers):
+        for q in range(n):
+            kind = rnd.choice(['RX', 'RY', 'RZ', 'H'])
+            if kind == 'H':
+                circ += qf.H(q)
+            else:
+                circ += getattr(qf, kind)(params[at], q)
+                at += 1
+        for _ in range(n // 2):
+            a, b = rnd.choice(n, 2, replace=False)
+            kind = rnd.choice(['ZZ', 'CNOT', 'CPHASE'])
+            if kind == 'CNOT':
+                circ += qf.CNOT(int(a), int(b))
+            else:
+                circ += getattr(qf, kind)(params[at], int(a), int(b))
+                at += 1
+    return circ, at
+
+
+@pytest.mark.parametrize('n,layers,seed', [(3, 2, 0), (6, 4, 1), (9, 3, 2), (12, 2, 3)])
+def test_single_launch_circuit_node_matches_the_gate_by_gate_path(monkeypatch, n, layers, seed):
+    """autograd.run_small_circuit (one launch forward, one reverse adjoint sweep that recomputes the intermediate
+    states with U^H) against the per-gate nodes (one saved state per gate): same state, same expectation, same
+    gradient for every parameter and for a differentiable input state."""
+    from quantumflow_b200 import engine
+    rnd = np.random.RandomState(100 + seed)
+    diag = rnd.standard_normal(1 << n).reshape([2] * n)
+    results = {}
+    for mode in ('1', '0'):
+        monkeypatch.setenv('QFB_SMALL_CIRCUIT', mode)
+        params = torch.tensor(np.random.RandomState(7).uniform(0, 2 * np.pi, 400), dtype=torch.float64, requires_grad=True)
+        circ, used = _random_parametrised_circuit(n, layers, seed, params)
+        before = engine.launch_count()
+        ket = circ.run()
+        fwd_launches = engine.launch_count() - before
+        expect = ket.expectation(diag)
+        expect.backward()
+        results[mode] = (qf.asarray(ket.tensor).reshape(-1), float(expect), params.grad.numpy()[:used].copy(),
+                         fwd_launches)
+    fused, plain = results['1'], results['0']
+    assert np.abs(fused[0] - plain[0]).max() < 1e-12
+    assert abs(fused[1] - plain[1]) < 1e-12
+    assert np.abs(fused[2] - plain[2]).max() < 1e-10
+    assert np.abs(plain[2]).max() > 1e-3
+    assert fused[3] <= 3 < plain[3]            # zero state + ONE launch for the whole circuit
