@@ -85,6 +85,9 @@ DEFAULT_TILE_BITS_SPECIALISED = 11   # plans of the sweep-specialised kernels: 4
 
 
 def default_tile_bits(reg_bits: int) -> int:
+    v = os.environ.get('QFB_TILE_BITS')          # experiments
+    if v:
+        return int(v)
     return DEFAULT_TILE_BITS if reg_bits == REG_BITS else DEFAULT_TILE_BITS_SPECIALISED
 DEFAULT_LOW_BITS = 3
 # cost units ~ FP64 work per amplitude relative to a dense 1-bit operator (16 FP64 ops per amplitude pair)
