@@ -756,8 +756,15 @@ int emit_op(Gen &g, RoundState &st, const OpView &op, std::string &err) {
 // into registers at the top of the iteration (plus an L2 prefetch of the next tile), as the interpreter does.
 static int jit_async_mode() {
     const char *v = getenv("QFB_JIT_ASYNC");
-    return (v && *v) ? atoi(v) : 1;
+    return (v && *v) ? atoi(v) : 3;
 }
+// QFB_JIT_ASYNC=3 (default): as 1, but after the last exchange every thread copies the amplitudes of the next tile that
+// belong to the slots it has just read ITSELF (its assignment of the last round), so the copy needs no barrier in front
+// of it and is issued right behind the read-back; the hand-over barrier moves to the top of the next tile, behind
+// cp.async.wait_group. With mode 1 the copy sat behind a barrier, and ptxas moved the whole register arithmetic of the
+// last round in FRONT of that barrier (barriers order memory operations only): the copy was issued just before the
+// stores and 19 % of the warp time went into waiting for it (profiles/r2_sweep_jit_v6_summary.txt).
+static bool jit_own_slot_copy() { return jit_async_mode() == 3; }
 static bool jit_async() { return jit_async_mode() != 0; }
 // QFB_JIT_ASYNC=2: the copy lands in a SECOND buffer of the CTA (shared memory doubles), so it can start as soon as the
 // current tile has been read out of that buffer -- a whole tile period ahead instead of one round. Worth it when the
@@ -1021,6 +1028,26 @@ int jit_generate(const uint8_t *rec, int nbits, int M, int reg_bits, JitSource &
         }
         g.e("cp.async.commit_group;");
     };
+    // the same into the thread's own slots of round rr's assignment (the amplitudes of the tile at `gbreg` that have
+    // this thread's bits of round rr): the slots the thread has just read, no barrier needed in front
+    auto async_copy_round = [&](int gbreg, int rr) {
+        const qfb_round_header *rh = rounds[rr].rh;
+        const int idx = g.rd(), base = g.rd();
+        g.e("or.b64 %%rd%d, %%rd%d, %%rd%d;", idx, gbreg, tg(rr));
+        g.e("shl.b64 %%rd%d, %%rd%d, 4;", idx, idx);
+        g.e("add.u64 %%rd%d, %%rd%d, %%rd%d;", base, state, idx);
+        const XchgAddr x = exchange_addresses(g, land, stb(rr), rh->regpos);
+        AddrSet as(base);
+        for (int e = 0; e < NE; ++e) {
+            int64_t off = 0;
+            for (int i = 0; i < R; ++i)
+                if ((e >> i) & 1) off += (int64_t)16 << sh.gpos[rh->regpos[i]];
+            const std::string src = as.operand(g, off);
+            g.e("cp.async.cg.shared.global [%%r%d+%u], %s, 16;", x.base[x.low[e]], x.high[e], src.c_str());
+        }
+        g.e("cp.async.commit_group;");
+    };
+    const bool own_slot = jit_own_slot_copy() && async && !landing && nrounds > 1;
     // L2 prefetch of the tile whose first amplitude (of this thread) is at `pbase`: the 8 lanes that share the thread's
     // 128-byte lines split its 2^R lines between them
     auto l2_prefetch = [&](int pbase) {
@@ -1063,6 +1090,7 @@ int jit_generate(const uint8_t *rec, int nbits, int M, int reg_bits, JitSource &
         }
         // ---- round 0: the tile was copied into shared memory during the previous iteration ----
         g.e("cp.async.wait_group 0;");
+        if (own_slot) g.e("bar.sync 0;");       // the tile was copied by the threads that owned the slots in the last round
         const XchgAddr x = exchange_addresses(g, land, stb(0), r0->regpos);
         for (int e = 0; e < NE; ++e) {
             st.a[e].re = g.fd();
@@ -1150,6 +1178,32 @@ int jit_generate(const uint8_t *rec, int nbits, int M, int reg_bits, JitSource &
         // read), so the barrier is only needed after the LAST exchange: there the asynchronous copy of the next tile (or,
         // without it, the next tile's first exchange) writes round-0 slots that other threads may still be reading.
         // QFB_JIT_BARB=1 keeps every barrier (experiments).
+        if (own_slot && r + 2 == nrounds) {
+            const int skip = g.label();
+            g.e("@!%%p%d bra L%d;", has_next, skip);
+            async_copy_round(gb_next, r + 1);
+            g.e("L%d:", skip);
+            // The copy has no consumer inside the iteration, so ptxas gives it the lowest priority and lets it sink
+            // behind the whole last round (measured: issued just before the stores, 19 % of the warp time waiting for
+            // it at the top of the next tile). A shared-memory load of one of the slots the copy writes cannot move
+            // in front of it; its value (masked to zero at run time, made warp uniform by a vote so that the
+            // coefficient loads stay on the uniform datapath) goes into the address of the last round's coefficients,
+            // which puts the copy on the critical path of the round's arithmetic.
+            if (g.coef_base >= 0) {
+                const XchgAddr x = exchange_addresses(g, land, stb(r + 1), rounds[r + 1].rh->regpos);
+                const int z = g.r32(), zm = g.r32(), pz = g.pr(), b = g.r32(), b64 = g.rd(), cb2 = g.rd();
+                g.e("ld.shared.u32 %%r%d, [%%r%d+%u];", z, x.base[x.low[0]], x.high[0]);
+                g.e("cvt.u32.u64 %%r%d, %%rd%d;", zm, zmask);
+                g.e("and.b32 %%r%d, %%r%d, %%r%d;", z, z, zm);
+                g.e("setp.ne.u32 %%p%d, %%r%d, 0;", pz, z);
+                g.e("vote.sync.ballot.b32 %%r%d, %%p%d, 0xffffffff;", b, pz);
+                g.e("and.b32 %%r%d, %%r%d, %%r%d;", b, b, zm);
+                g.e("cvt.u64.u32 %%rd%d, %%r%d;", b64, b);
+                g.e("add.u64 %%rd%d, %%rd%d, %%rd%d;", cb2, g.coef_base, b64);
+                g.coef_base = cb2;
+            }
+            continue;
+        }
         if (r + 2 == nrounds || keep_barriers) g.e("bar.sync 0;");
         if (async && !landing && r + 2 == nrounds) {
             // the tile has left the exchange buffer for the last time: the next tile's copy runs under the last round
