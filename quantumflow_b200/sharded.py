@@ -524,8 +524,7 @@ class ShardedCircuit:
     def _pipeline_shape(self, prev: 'Stage', remap: 'Remap', nxt: 'Stage', used_first: int, nxt_has_remap: bool):
         """(selector bits ascending, da, db) of this remap's pipeline, or None when it cannot be pipelined: the last da
         sweeps of `prev` and the first db sweeps of `nxt` run slice by slice around the exchange. Deeper chains hide
-        more of the exchange (it runs beside 2 (da + db) / 2^v ... of sweep work instead of 2), but every sweep of a
-        chain must keep the selector bits outside its tile. `used_first`: leading sweeps of prev's first plan that the
+        more of the exchange, but every sweep of a chain must keep the selector bits outside its tile. `used_first`: leading sweeps of prev's first plan that the
         previous remap's pipeline has already run."""
         want = int(os.environ.get('QFB_REMAP_SLICE_BITS', '3'))
         depth = int(os.environ.get('QFB_REMAP_CHAIN', '3'))
@@ -559,10 +558,10 @@ class ShardedCircuit:
                 nb_bits = min(want, len(cand))
                 if nb_bits < 1:
                     continue
-                # time saved ~ (sweep work beside the exchange, at most the exchange itself: a whole-shard exchange
-                # takes about 3.5 sweeps) x (1 - 1 / slices)
-                hidden = min(float(da + db), 3.5 * (1.0 - 0.5 ** k)) * (1.0 - 0.5 ** nb_bits)
-                key = (round(hidden, 6), -(da + db), -abs(da - db))
+                # at least 4 slices first, then the deepest chains (measured at 34 qubits on 2 GPUs: 1 520 / 1 488 /
+                # 1 478 ms per step with 1 / 2 / 3 sweeps per side, although the exchange alone is only 1.7 sweeps long:
+                # sweeps that run beside the exchange lose HBM bandwidth to it, so more of them fit), then more slices
+                key = (min(nb_bits, 2), da + db, nb_bits, -abs(da - db))
                 if best is None or key > best[0]:
                     best = (key, cand[-nb_bits:], da, db)
         if best is None:
