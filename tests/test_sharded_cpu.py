@@ -296,3 +296,83 @@ def test_thin_sweep_with_nothing_to_exchange_is_taken_instead_of_raising():
                         assert all(b < nl for b in mix)
         steps, phys_of = sharded.schedule(n, p, ops)
         assert any(isinstance(st, sharded.Remap) for st in steps)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# pipelined remaps: the host logic that chooses slices and chains (the kernels are covered by test_gpu_sharded.py)
+# ---------------------------------------------------------------------------------------------------------
+
+class _FakePlan:
+    """Stands in for engine.UploadedPlan: sweep count, non-tile masks, and a record of what was launched."""
+
+    def __init__(self, nontile_masks, log, name):
+        self._masks, self._log, self._name = list(nontile_masks), log, name
+        self.specialised = True
+
+    @property
+    def nsweeps(self):
+        return len(self._masks)
+
+    def nontile_mask(self, sweep):
+        return self._masks[sweep]
+
+    def launch_part(self, tensor, first, count, index_hi=0, fix_mask=0, fix_value=0, ctas_per_sm=0):
+        self._log.append((self._name, first, count, fix_mask, fix_value))
+
+
+def _fake_runner(nl, p, masks_per_stage, log):
+    """A ShardedCircuit shell whose stages are one fake plan each (no planning, no GPU)."""
+    runner = sharded.ShardedCircuit.__new__(sharded.ShardedCircuit)
+    runner.nl, runner.p, runner.world, runner.rank = nl, p, 1 << p, 0
+    stages = []
+    for i, masks in enumerate(masks_per_stage):
+        st = sharded.Stage([], None, None)
+        seg = planner.Segment('plan', blob=b'', nsweeps=len(masks))
+        seg.uploaded = _FakePlan(masks, log, 'stage%d' % i)
+        st.segments = [seg]
+        stages.append(st)
+    return runner, stages
+
+
+def test_pipeline_shape_takes_common_non_tile_bits_below_the_exchanged_blocks(monkeypatch):
+    monkeypatch.delenv('QFB_REMAP_SLICE_BITS', raising=False)
+    monkeypatch.delenv('QFB_REMAP_CHAIN', raising=False)
+    nl, p = 30, 1
+    bit = lambda *pos: sum(1 << b for b in pos)                                   # noqa: E731
+    log = []
+    # stage 0: 4 sweeps; stage 1: 5 sweeps. Bits 20..24 are outside every tile, 28 only outside the nearest sweeps,
+    # 29 is the exchanged block bit region (nl - k - 1 = 28 is the half-block split: not allowed either)
+    s0 = [bit(20, 21, 22, 23, 24), bit(20, 21, 22, 23, 24, 27), bit(20, 21, 22, 23, 24, 27), bit(20, 21, 22, 23, 24, 27, 28)]
+    s1 = [bit(20, 21, 22, 23, 24, 27, 28), bit(20, 21, 22, 23, 24, 27), bit(5, 20, 21, 22, 23, 24), bit(20, 21), bit(20, 21)]
+    runner, (a, b) = _fake_runner(nl, p, [s0, s1], log)
+    remap = sharded.Remap([0])
+    bits, da, db = runner._pipeline_shape(a, remap, b, 0, False)
+    assert (da, db) == (3, 3)                       # three sweeps per side keep 3 common selector bits
+    assert bits == [22, 23, 24] and all(12 <= x < nl - 1 - 1 for x in bits)
+    # the next stage feeds another remap: it keeps at least half of its sweeps for that one
+    bits2, da2, db2 = runner._pipeline_shape(a, remap, b, 0, True)
+    assert db2 == 2 and da2 == 3
+    # sweeps that the previous pipeline has already run are not available
+    assert runner._pipeline_shape(a, remap, b, 2, False)[1] == 2
+    assert runner._pipeline_shape(a, remap, b, 4, False) is None
+    # one selector bit (2 slices) only when nothing better exists; below bit 12 never
+    only = [bit(3, 4, 13)]
+    runner2, (c, d) = _fake_runner(nl, p, [only, only], [])
+    assert runner2._pipeline_shape(c, remap, d, 0, False) == ([13], 1, 1)
+    runner3, (e, f) = _fake_runner(nl, p, [[bit(3, 4)], [bit(3, 4)]], [])
+    assert runner3._pipeline_shape(e, remap, f, 0, False) is None
+    monkeypatch.setenv('QFB_REMAP_CHAIN', '1')
+    assert runner._pipeline_shape(a, remap, b, 0, False)[1:] == (1, 1)
+
+
+def test_stage_parts_skip_exactly_the_sweeps_the_pipelines_run():
+    log = []
+    runner, (a,) = _fake_runner(30, 1, [[1, 1, 1, 1, 1]], log)
+    runner._run_stage_part(a, None, 2, 2)
+    assert log == [('stage0', 2, 1, 0, 0)]
+    log.clear()
+    runner._run_stage_part(a, None, 0, 0)
+    assert log == [('stage0', 0, 5, 0, 0)]
+    log.clear()
+    runner._run_stage_part(a, None, 3, 2)          # nothing left between the two pipelines
+    assert log == []
