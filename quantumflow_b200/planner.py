@@ -96,6 +96,9 @@ COST = {K_GENERAL: 1.0, K_REAL: 1.0, K_RXLIKE: 1.0, K_SWAPX: 0.3, K_ANTIDIAG: 1.
 DEFAULT_MAX_COST = 28.0
 # randomised variants of the greedy sweep split tried by Planner._partition (0 = plain greedy)
 DEFAULT_TRIES = 24
+# randomised variants of the split of a sweep into rounds, for plans of the sweep-specialised kernels (an exchange less
+# is ~1.5 ms of a 30-qubit sweep: 3-round sweeps run at 0.87 of the HBM roofline, 4-round sweeps at 0.70)
+ROUND_TRIES_SPECIALISED = 256
 # tile refinement (Planner._refine_tile): operator lists shorter than this are not worth the search
 REFINE_MIN_OPS = 24
 SWEEP_WINDOW = 4096         # operators of the list that one sweep may draw from
@@ -735,10 +738,11 @@ class Planner:
     def _form_rounds(self, sweep: SweepPlan) -> None:
         # every extra round is one more trip of the tile through shared memory: keep the split with the fewest
         rounds = self._split_rounds(sweep)
+        tries = max(self.tries, ROUND_TRIES_SPECIALISED) if self.late_rounds and self.tries > 0 else self.tries
         if len(sweep.ops) >= 16:
-            for trial in range(1, 1 + self.tries):
-                if len(rounds) <= 2:
-                    break
+            for trial in range(1, 1 + tries):
+                if len(rounds) <= 2 or (trial > self.tries and len(rounds) <= 3):
+                    break           # the long search is for sweeps that still need four rounds
                 cand = self._split_rounds(sweep, random.Random(trial), 0.85)
                 if len(cand) < len(rounds):
                     rounds = cand
@@ -749,8 +753,10 @@ class Planner:
                 return sum(op.cost for op in split[-1][1])
             cands = [self._split_rounds(sweep, backward=True)]
             if len(sweep.ops) >= 16:
-                cands += [self._split_rounds(sweep, random.Random(trial), 0.85, backward=True)
-                          for trial in range(1, 1 + self.tries)]
+                for trial in range(1, 1 + tries):
+                    if trial > self.tries and min(len(rounds), min(len(c) for c in cands)) <= 3:
+                        break
+                    cands.append(self._split_rounds(sweep, random.Random(trial), 0.85, backward=True))
             for cand in cands:
                 if len(cand) < len(rounds) or (len(cand) == len(rounds) and tail(cand) > tail(rounds)):
                     rounds = cand
