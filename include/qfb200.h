@@ -188,7 +188,7 @@ int qfb_remap_swap_slice(int npairs, void *const *local_blocks, void *const *rem
                          int nsel, const int *selpos, uint64_t selval, int ctas_per_sm, void *stream);
 /* Stream-ordered barrier across the GPUs of one box through peer memory (no host involvement, no NCCL kernel that
  * would need a free SM): flags_of_ranks[r] = rank r's array of `world` uint32 (flags_of_ranks[rank] = flags_local),
- * epochs must increase call by call; *error_dev (uint32) is set to the epoch if a peer does not arrive within ~10 s. */
+ * epochs must increase call by call; *error_dev (uint32) is set to the epoch if a peer does not arrive within two minutes. */
 int qfb_peer_barrier(void *flags_local, void *const *flags_of_ranks, int world, int rank, uint32_t epoch,
                      void *error_dev, void *stream);
 

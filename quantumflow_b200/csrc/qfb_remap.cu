@@ -80,7 +80,13 @@ namespace qfb {
 // Barrier across the GPUs of one box through peer memory: every rank writes `epoch` into its slot of every peer's flag
 // array and waits until its own array holds `epoch` in every slot. One CTA of `world` threads; stream ordered, so the
 // kernels queued before it on every rank's stream are complete (and their peer writes visible) when it returns.
-// The wait is bounded (~10 s): on expiry *error is set and the kernel returns, so a lost peer cannot hang the GPU.
+// The wait is bounded (two minutes): on expiry *error is set and the kernel returns, so a lost peer cannot hang the GPU.
+__device__ __forceinline__ unsigned long long global_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
 struct PeerTable {
     uint32_t *p[32];
 };
@@ -93,11 +99,11 @@ __global__ void peer_barrier_kernel(volatile uint32_t *mine, PeerTable peers, in
     volatile uint32_t *dst = (volatile uint32_t *)peers.p[r];
     dst[rank] = epoch;
     __threadfence_system();
-    const long long t0 = clock64();
+    const unsigned long long t0 = global_ns();
     while ((int32_t)(mine[r] - epoch) < 0) {
         __nanosleep(200);
-        if (clock64() - t0 > 20000000000ll) {      // ~10 s at 2 GHz
-            *error = epoch;
+        if (global_ns() - t0 > 120ull * 1000000000ull) {      // two minutes: ranks may arrive seconds apart (e.g. after
+            *error = epoch;                                   // each has staged a 128 GiB shard over PCIe)
             return;
         }
     }
