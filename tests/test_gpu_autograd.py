@@ -151,3 +151,65 @@ def test_single_launch_circuit_node_matches_the_gate_by_gate_path(monkeypatch, n
     assert np.abs(fused[2] - plain[2]).max() < 1e-10
     assert np.abs(plain[2]).max() > 1e-3
     assert fused[3] <= 3 < plain[3]            # zero state + ONE launch for the whole circuit
+
+
+def test_small_circuit_kernels_run_a_batch_of_parameter_sets_as_one_cta_each():
+    """C ABI of csrc/qfb_small.cu with batch > 1 (independent states and matrices per item, shared gate list): forward
+    against the oracle's gate-by-gate arithmetic, adjoint against the per-item results of the batch-1 call."""
+    import ctypes
+    from oracle import qf_oracle as O
+    from quantumflow_b200 import _lib, engine
+    lib = _lib.load()
+    n, batch = 5, 3
+    rnd = np.random.RandomState(5)
+    names = [('RX', 1, (0,)), ('ZZ', 1, (1, 3)), ('H', 0, (2,)), ('CNOT', 0, (4, 0)), ('RY', 1, (3,)), ('CPHASE', 1, (2, 4))]
+    rows, at = [], 0
+    for name, _, qubits in names:
+        bits = [n - 1 - q for q in qubits]
+        rows.append([len(bits), bits[0], bits[1] if len(bits) > 1 else 0, at])
+        at += 1 << (2 * len(bits))
+    stride = at
+    mats = np.zeros((batch, stride), dtype=np.complex128)
+    states = np.zeros((batch, 1 << n), dtype=np.complex128)
+    want = np.zeros_like(states)
+    for b in range(batch):
+        psi = rnd.standard_normal(1 << n) + 1j * rnd.standard_normal(1 << n)
+        psi /= np.linalg.norm(psi)
+        states[b] = psi
+        cur = psi.copy()
+        for (name, npar, qubits), row in zip(names, rows):
+            m = O.gate_matrix(name, tuple(rnd.uniform(0, 6, npar)))
+            mats[b, row[3]:row[3] + m.size] = m.reshape(-1)
+            cur = O.tensormul_flat(m, cur, [n - 1 - q for q in qubits])
+        want[b] = cur
+    dev = torch.device('cuda')
+    d_states = torch.from_numpy(states).to(dev)
+    d_mats = torch.from_numpy(mats).to(dev)
+    d_desc = torch.tensor(rows, dtype=torch.int32, device=dev)
+    out = torch.empty_like(d_states)
+    st = engine._stream()
+    _lib.check(lib.qfb_small_circuit_run(out.data_ptr(), d_states.data_ptr(), n, batch, len(rows), d_desc.data_ptr(),
+                                         d_mats.data_ptr(), stride, st))
+    assert np.abs(out.cpu().numpy() - want).max() < 1e-13
+    grad_out = torch.from_numpy(rnd.standard_normal((batch, 1 << n)) + 1j * rnd.standard_normal((batch, 1 << n))).to(dev)
+
+    def adjoint(psi_final, g, m, nb):
+        gm = torch.zeros((nb, stride), dtype=torch.complex128, device=dev)
+        gin = torch.empty_like(psi_final)
+        scratch = torch.empty(int(lib.qfb_small_circuit_scratch_doubles(nb, len(rows))), dtype=torch.float64, device=dev)
+        _lib.check(lib.qfb_small_circuit_adjoint(psi_final.data_ptr(), g.data_ptr(), n, nb, len(rows), d_desc.data_ptr(),
+                                                 m.data_ptr(), stride, gm.data_ptr(), gin.data_ptr(),
+                                                 scratch.data_ptr(), st))
+        return gm.cpu().numpy(), gin.cpu().numpy()
+
+    gm_all, gin_all = adjoint(out, grad_out, d_mats, batch)
+    for b in range(batch):
+        gm_one, gin_one = adjoint(out[b:b + 1].contiguous(), grad_out[b:b + 1].contiguous(), d_mats[b:b + 1].contiguous(), 1)
+        assert np.array_equal(gm_all[b], gm_one[0]) and np.array_equal(gin_all[b], gin_one[0])
+        # grad_in = U_1^H ... U_G^H grad_out: check against the oracle applied in reverse
+        cur = grad_out[b].cpu().numpy()
+        for (name, npar, qubits), row in reversed(list(zip(names, rows))):
+            dim = 1 << row[0]
+            m = mats[b, row[3]:row[3] + dim * dim].reshape(dim, dim)
+            cur = O.tensormul_flat(m.conj().T.copy(), cur, [n - 1 - q for q in qubits])
+        assert np.abs(gin_all[b] - cur).max() < 1e-12
