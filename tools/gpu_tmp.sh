@@ -1,3 +1,3 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 300 python -m pytest tests/test_gpu_autograd.py -m gpu -q --timeout 200 -p no:cacheprovider -x -k "batch" > gpurun_out/pytest_autograd.log 2>&1; echo "pytest rc=$?"; tail -n 12 gpurun_out/pytest_autograd.log
+timeout 200 python tools/gpu_fuzz_jit.py 100 7 > gpurun_out/r2_fuzz_jit.log 2>&1; echo "fuzz rc=$?"; tail -n 5 gpurun_out/r2_fuzz_jit.log
