@@ -1,3 +1,8 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 200 python tools/gpu_fuzz_jit.py 100 7 > gpurun_out/r2_fuzz_jit.log 2>&1; echo "fuzz rc=$?"; tail -n 5 gpurun_out/r2_fuzz_jit.log
+timeout 600 python bench.py > gpurun_out/r2_bench_1gpu.json 2> gpurun_out/bench_full.err; echo "bench rc=$?"
+python - <<'PY'
+import json
+d=json.loads(open('gpurun_out/r2_bench_1gpu.json').read().strip().splitlines()[-1])
+print(d['ms_per_step'], d['value'], d['roofline']['frac'], d['plan']['rounds'], d['e2e']['value'], d['clocks'])
+PY
