@@ -314,6 +314,18 @@ def test_wb28_depth20_full_vector_against_c_oracle():
     assert _compare_with_c_oracle(28, 20, 0) < AMP_TOL
 
 
+def test_wb30_depth3_spot_amplitudes_against_c_oracle():
+    """The size of the headline number in the default suite: 30 qubits (16 GiB state, the same tiles, non-tile bits
+    and sweep-specialised kernels as the benchmark), depth 3 = 165 gates so that the oracle needs well under a minute;
+    72 spot amplitudes. The full depth-20 circuit is the opt-in test below."""
+    import psutil
+    if psutil.virtual_memory().available < (5 << 32) or torch.cuda.mem_get_info()[0] < (5 << 32):
+        pytest.skip('needs 20 GiB of host and device memory')
+    err = _compare_with_c_oracle(30, 3, 0, spots=72)
+    print('30-qubit depth-3 W-B seed 0: max-abs error over 72 spot amplitudes = {:.3e}'.format(err))
+    assert err < AMP_TOL
+
+
 @pytest.mark.skipif(os.environ.get('QFB_SLOW_TESTS', '0') != '1',
                     reason='about five minutes of host time (930 gates on a 16 GiB vector): set QFB_SLOW_TESTS=1; '
                            'the round-2 run is recorded in profiles/r2_parity_30q.txt')

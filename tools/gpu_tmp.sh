@@ -1,8 +1,3 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 600 python bench.py > gpurun_out/r2_bench_1gpu.json 2> gpurun_out/bench_full.err; echo "bench rc=$?"
-python - <<'PY'
-import json
-d=json.loads(open('gpurun_out/r2_bench_1gpu.json').read().strip().splitlines()[-1])
-print(d['ms_per_step'], d['value'], d['roofline']['frac'], d['plan']['rounds'], d['e2e']['value'], d['clocks'])
-PY
+timeout 300 python -m pytest tests/test_gpu_circuits.py -m gpu -q --timeout 280 -p no:cacheprovider -x -s -k "wb30_depth3" > gpurun_out/pytest_30q_d3.log 2>&1; echo "pytest rc=$?"; tail -n 4 gpurun_out/pytest_30q_d3.log
