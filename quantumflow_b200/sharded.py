@@ -592,7 +592,7 @@ class ShardedCircuit:
 
     def _remap_pipelined(self, shard: torch.Tensor, prev: 'Stage', remap: 'Remap', nxt: 'Stage',
                          bits: List[int], da: int, db: int) -> None:
-        from . import _lib, engine
+        from . import _lib
         lib = _lib.load()
         main = torch.cuda.current_stream(shard.device)
         if getattr(self, '_comm_stream', None) is None:
