@@ -704,6 +704,7 @@ def e2e_streamed(args, runner, shard, nlocal, ngates, scale30, world, rank, dev,
                     if rank == 0 and i == 0:
                         buf[0] = 1.0
                 elif rank == 0 and i == 2:
+                    copy_stream.synchronize()          # piece 0 (the one that holds amplitude 1) has left stage[0]
                     stage[0][0] = 0.0
                 shard[i * piece:(i + 1) * piece].copy_(buf, non_blocking=True)
         copy_stream.synchronize()

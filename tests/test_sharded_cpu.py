@@ -174,11 +174,16 @@ def test_sharded_plans_run_on_the_plan_emulator(n, p, tile, depth, seed):
     print('local permutations: fused into a stage sweep', fused, '/ bare sweep', bare)
 
 
-@pytest.mark.parametrize('n,p', [(31, 1), (32, 2), (33, 3)])
+@pytest.mark.parametrize('n,p', [(32, 2), (34, 1), (35, 2), (36, 3)])
 def test_benchmark_size_sharded_plans_pass_the_library_validation(n, p):
-    """The plans bench.py launches at 2 / 4 / 8 GPUs (30 qubits per GPU), built as ShardedCircuit builds them and
-    checked by the library's plan validation (the host half of qfb_plan_upload); too large to emulate."""
+    """The plans bench.py launches at 2 / 4 / 8 GPUs (33 qubits per GPU: 34 / 35 / 36 qubits, BASELINE.json
+    configs[4]; and the 30-per-GPU shape of round 1), built as ShardedCircuit builds them, checked by the library's
+    plan validation (the host half of qfb_plan_upload) and emitted + compiled for sm_100a as the sweep-specialised
+    kernels (qfb_jit_check); too large to emulate."""
+    import ctypes
+    from quantumflow_b200 import _lib
     from test_planner import validate_with_library
+    lib = _lib.load()
     specs = workloads.wb_gate_list(n, 20, 0)
     steps, phys_of = sharded.schedule(n, p, _bitops(specs, n))
     assert sorted(phys_of) == list(range(n))
@@ -189,10 +194,12 @@ def test_benchmark_size_sharded_plans_pass_the_library_validation(n, p):
             for seg in segs:
                 assert seg.kind == 'plan'
                 validate_with_library(seg.blob)
+                log = ctypes.create_string_buffer(4096)
+                assert lib.qfb_jit_check(seg.blob, len(seg.blob), log, len(log)) == 0, log.value.decode()
             nsweeps += sum(s.nsweeps for s in segs)
         else:
             nremaps += 1
-    assert nsweeps <= 24 and 1 <= nremaps <= 6, (nsweeps, nremaps)
+    assert nsweeps <= 26 and 1 <= nremaps <= 6, (nsweeps, nremaps)
 
 
 def _readout_worker(rank, world, port, n, phys_of, phys, diag, uniforms, out_dir):
