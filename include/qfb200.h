@@ -172,6 +172,21 @@ int qfb_plan_refine_tile_lookahead(const uint64_t *mix, const uint64_t *diag, co
                                    uint64_t tmask, uint64_t fmask, uint64_t keep, double max_cost, int64_t room,
                                    int passes, int lookahead_passes, uint64_t *tmask_out, int *score_out);
 
+/* Threads the tile searches use for the candidates of one pass (results do not depend on it); 0 = back to the
+ * default: QFB_PLAN_THREADS, else min(4, hardware threads / LOCAL_WORLD_SIZE). */
+int qfb_plan_set_threads(int nthreads);
+/* split_rounds: the greedy split of ONE sweep's operators into rounds of `reg_bits` register bits (the planner's
+ * search over randomised variants calls it a few hundred times per sweep). posmask[i] = tile positions of the bits
+ * operator i mixes (0xffffffff for a phase term), low_bits = tile positions that stay on the lanes in the rounds
+ * that touch HBM, rnd[0..nrnd) = the random stream of the variant (NULL: plain greedy), backward != 0: the same on
+ * the reversed list (latest-possible rounds). round_of / regs_of_round (bit masks of tile positions, room for
+ * max_rounds) may be NULL; *tail_out = cost of the last round's operators; *consumed_out = random numbers used, -1
+ * when the stream ran out (nothing else is valid then). */
+int qfb_plan_split_rounds(const uint64_t *mix, const uint64_t *diag, const uint32_t *posmask, const double *cost,
+                          int nops, int reg_bits, int low_bits, const double *rnd, int nrnd, double p_new,
+                          int backward, int *round_of, uint32_t *regs_of_round, int max_rounds, int *nrounds_out,
+                          double *tail_out, int *consumed_out);
+
 /* ---- sharded states: the exchange half of a qubit remap (csrc/qfb_remap.cu; the reference has no distributed
  * path) ---- */
 /* For i < npairs: the `nelems[i]` complex128 amplitudes at local_blocks[i] (this GPU) and at remote_blocks[i] (a

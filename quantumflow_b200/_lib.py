@@ -60,6 +60,10 @@ PROTOTYPES = {
     'qfb_plan_refine_tile_lookahead': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
                                                c_uint64, c_uint64, c_uint64, c_double, c_int64, c_int, c_int,
                                                POINTER(c_uint64), _c_int_p]),
+    'qfb_plan_set_threads': (c_int, [c_int]),
+    'qfb_plan_split_rounds': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_int,
+                                      c_double, c_int, c_void_p, c_void_p, c_int, _c_int_p, POINTER(c_double),
+                                      _c_int_p]),
     'qfb_batch_rho1': (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
     'qfb_batch_rho1_workspace': (c_size_t, [c_int, c_int]),
     'qfb_batch_apply1': (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),

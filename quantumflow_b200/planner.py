@@ -111,13 +111,19 @@ REFINE_WINDOW = 512      # operators of the list that the search scores (a sweep
 PIVOT_RATIO = 1e-3
 
 
+# one operator for the native tile search (qfb_plan_refine_tile): mix mask, diag mask, cost, record bytes
+OP_ROW = struct.Struct('<QQdI4x')
+OP_ROW_DTYPE = np.dtype([('mix', '<u8'), ('diag', '<u8'), ('cost', '<f8'), ('bytes', '<u4'), ('pad', '<u4')])
+
+
 class POp:
     """A classified operator: kind 'G' (mixing) or 'P' (phase term)."""
     __slots__ = ('kind', 'mix', 'ctrl', 'dbits', 'mat', 'cost', 'mixset', 'diagset', 'anyset', 'gate_index', 'enc',
-                 'mixmask', 'diagmask', 'plan_bytes', 'terms')
+                 'mixmask', 'diagmask', 'plan_bytes', 'terms', 'row')
 
     def __init__(self, kind, mix=(), ctrl=(), dbits=(), mat=None, cost=1.0, gate_index=-1, enc=None, terms=None):
         self.enc = enc          # (kind, payload, scalar) chosen by absorb_scales for an uncontrolled 1-bit operator
+        self.row = None         # (nbits, packed OP_ROW) for the native tile search, filled on first use (_refine_tile)
         self.terms = terms      # kind 'T' (diagonal table over register bits): [(bits, factor)], see _form_tables
         self.kind = kind
         self.mix = tuple(int(b) for b in mix)
@@ -486,6 +492,73 @@ class SweepPlan:
         self.spos = list(tile)       # index-bit position tile bit j is stored to (!= tile: in-place bit permutation)
 
 
+# length of the random streams handed to qfb_plan_split_rounds (a split consumes one number per operator that asks
+# for a new register bit, a few hundred at most; a split that runs out is redone in Python)
+ROUND_STREAM_LEN = 1024
+_round_streams: Dict[int, np.ndarray] = {}
+
+
+def _round_stream(trial: int) -> np.ndarray:
+    """The first ROUND_STREAM_LEN numbers of random.Random(trial): what Planner._split_rounds draws for that trial."""
+    stream = _round_streams.get(trial)
+    if stream is None:
+        draw = random.Random(trial).random
+        stream = np.fromiter((draw() for _ in range(ROUND_STREAM_LEN)), dtype=np.float64, count=ROUND_STREAM_LEN)
+        _round_streams[trial] = stream
+    return stream
+
+
+class _RoundSplitter:
+    """The operators of one sweep as arrays for qfb_plan_split_rounds (csrc/qfb_planhost.cu), the native statement of
+    Planner._split_rounds: score() = (number of rounds, cost of the last round's operators) of one split, rounds() =
+    the split itself as _split_rounds returns it. Trial 0 is the plain greedy, trial t > 0 the randomised variant
+    with random.Random(t) and p_new = 0.85."""
+
+    def __init__(self, planner: 'Planner', sweep: 'SweepPlan'):
+        from . import _lib
+        self.ops = sweep.ops
+        self.R, self.L = planner.R, planner.L
+        n = len(self.ops)
+        pos_of = {b: j for j, b in enumerate(sweep.tile)}
+        self.lib = _lib.load()
+        try:
+            self.mix = np.fromiter((op.mixmask for op in self.ops), dtype=np.uint64, count=n)
+            self.diag = np.fromiter((op.diagmask for op in self.ops), dtype=np.uint64, count=n)
+            self.pos = np.fromiter((sum(1 << pos_of[b] for b in op.mix) if op.kind == 'G' else 0xffffffff
+                                    for op in self.ops), dtype=np.uint32, count=n)
+            self.cost = np.fromiter((op.cost for op in self.ops), dtype=np.float64, count=n)
+        except OverflowError:           # index bits beyond 63: the Python loop handles them
+            self.lib = None
+
+    def _call(self, trial: int, backward: bool, round_of, regs, max_rounds: int):
+        import ctypes
+        from . import _lib
+        stream = _round_stream(trial) if trial else None
+        nrounds, consumed, tail = ctypes.c_int(0), ctypes.c_int(0), ctypes.c_double(0.0)
+        _lib.check(self.lib.qfb_plan_split_rounds(
+            self.mix.ctypes.data, self.diag.ctypes.data, self.pos.ctypes.data, self.cost.ctypes.data, len(self.ops),
+            self.R, self.L, stream.ctypes.data if trial else None, ROUND_STREAM_LEN if trial else 0, 0.85,
+            1 if backward else 0, round_of, regs, max_rounds, ctypes.byref(nrounds), ctypes.byref(tail),
+            ctypes.byref(consumed)))
+        return (nrounds.value, tail.value) if consumed.value >= 0 else None
+
+    def score(self, trial: int, backward: bool) -> Optional[Tuple[int, float]]:
+        if self.lib is None:
+            return None
+        return self._call(trial, backward, None, None, 0)
+
+    def rounds(self, trial: int, backward: bool) -> List[Tuple[List[int], List['POp']]]:
+        n = len(self.ops)
+        round_of = np.zeros(max(n, 1), dtype=np.int32)
+        regs = np.zeros(n + 3, dtype=np.uint32)
+        nrounds, _ = self._call(trial, backward, round_of.ctypes.data, regs.ctypes.data, n + 3)
+        out: List[Tuple[List[int], List[POp]]] = [([p for p in range(32) if (int(regs[r]) >> p) & 1], [])
+                                                  for r in range(nrounds)]
+        for op, r in zip(self.ops, round_of.tolist()):
+            out[r][1].append(op)
+        return out
+
+
 class Planner:
     def __init__(self, nbits: int, tile_bits: int = None, low_bits: int = None, max_cost: float = None,
                  tries: int = None, refine: bool = None, reg_bits: int = None):
@@ -536,9 +609,13 @@ class Planner:
         state, sharded.schedule) are deferred and such bits never pad the tile. The bits of `required` are tile
         bits whatever the operators need (the bit positions a qubit remap moves: the sweep that holds them all
         can store the permutation, attach_permutation)."""
-        tile = set(range(self.L)) | set(required)
-        if len(tile) > self.M:
+        tmask = (1 << self.L) - 1
+        for b in required:
+            tmask |= 1 << b
+        tcount = bin(tmask).count('1')
+        if tcount > self.M:
             raise ValueError('required bits do not fit a tile')
+        fmask = sum(1 << b for b in forbidden)
         # Only the next SWEEP_WINDOW operators are candidates (everything behind them is deferred as it stands:
         # deferring is always legal, and a sweep holds a few hundred operators at most). Keeps the planner linear
         # in the length of the circuit instead of quadratic.
@@ -546,43 +623,45 @@ class Planner:
         ops = ops[:SWEEP_WINDOW] if beyond else ops
         cost = 0.0
         nbytes = SWEEP_HEADER_BYTES + 8 * ROUND_HEADER_BYTES
-        def_any: set = set()
-        def_mix: set = set()
+        cap = MAX_SWEEP_BYTES - 4 * ROUND_HEADER_BYTES
+        da = dm = 0                    # index bits touched / mixed by the operators deferred so far (bit masks)
         started = False
         for op in ops:
-            ok = not _conflicts(op, def_any, def_mix)
-            if ok and op.kind == 'G' and (op.mixset & forbidden):
-                ok = False
+            mm = op.mixmask
+            ok = not ((mm & da) or (op.diagmask & dm))
             if ok and op.kind == 'G':
-                if any(b >= self.nbits for b in op.mix):
-                    raise ValueError('operator mixes bit {} outside the local index; remap first'.format(
-                        max(op.mix)))
-                need = op.mixset - tile
-                if len(tile) + len(need) > self.M:
+                if mm & fmask:
                     ok = False
-                elif need and rnd is not None and started and rnd.random() > p_new:
-                    ok = False
+                else:
+                    if mm >> self.nbits:
+                        raise ValueError('operator mixes bit {} outside the local index; remap first'.format(
+                            max(op.mix)))
+                    need = mm & ~tmask
+                    if tcount + bin(need).count('1') > self.M:
+                        ok = False
+                    elif need and rnd is not None and started and rnd.random() > p_new:
+                        ok = False
             if ok and cost + op.cost > self.max_cost and started:
                 ok = False
-            if ok and nbytes + op.plan_bytes > MAX_SWEEP_BYTES - 4 * ROUND_HEADER_BYTES:
+            if ok and nbytes + op.plan_bytes > cap:
                 break
             if ok:
                 started = True
                 cost += op.cost
                 nbytes += op.plan_bytes
-                if op.kind == 'G':
-                    tile |= op.mixset
+                if op.kind == 'G' and mm & ~tmask:
+                    tmask |= mm
+                    tcount = bin(tmask).count('1')
             else:
-                def_any |= op.anyset
-                def_mix |= op.mixset
+                da |= mm | op.diagmask
+                dm |= mm
         # pad the tile with the lowest free bits (locality of the strided tile accesses)
         b = 0
-        while len(tile) < self.M:
-            if b not in tile and b not in forbidden:
-                tile.add(b)
+        while tcount < self.M:
+            if not ((tmask | fmask) >> b) & 1:
+                tmask |= 1 << b
+                tcount += 1
             b += 1
-        tmask = sum(1 << b for b in tile)
-        fmask = sum(1 << b for b in forbidden)
         if self.refine and len(ops) >= REFINE_MIN_OPS:
             tmask = self._refine_tile(ops, tmask, fmask, sum(1 << b for b in required), lookahead)
         chosen, deferred = self._closure(ops, tmask, fmask)
@@ -650,10 +729,20 @@ class Planner:
         window = ops[:REFINE_WINDOW]
         n = len(window)
         every = (1 << self.nbits) - 1
-        mix = np.fromiter((op.mixmask & every for op in window), dtype=np.uint64, count=n)
-        diag = np.fromiter((op.diagmask & every for op in window), dtype=np.uint64, count=n)
-        cost = np.fromiter((op.cost for op in window), dtype=np.float64, count=n)
-        nbytes = np.fromiter((op.plan_bytes for op in window), dtype=np.uint32, count=n)
+        nb = self.nbits
+        # the operators as parallel arrays; every operator keeps its packed row (the same operators are scanned by
+        # hundreds of searches)
+        rows = []
+        for op in window:
+            row = op.row
+            if row is None or row[0] != nb:
+                row = op.row = (nb, OP_ROW.pack(op.mixmask & every, op.diagmask & every, op.cost, op.plan_bytes))
+            rows.append(row[1])
+        rec = np.frombuffer(b''.join(rows), dtype=OP_ROW_DTYPE)
+        mix = np.ascontiguousarray(rec['mix'])
+        diag = np.ascontiguousarray(rec['diag'])
+        cost = np.ascontiguousarray(rec['cost'])
+        nbytes = np.ascontiguousarray(rec['bytes'])
         room = MAX_SWEEP_BYTES - 4 * ROUND_HEADER_BYTES - (SWEEP_HEADER_BYTES + 8 * ROUND_HEADER_BYTES)
         out = ctypes.c_uint64(0)
         _lib.check(lib.qfb_plan_refine_tile(mix.ctypes.data, diag.ctypes.data, cost.ctypes.data, nbytes.ctypes.data, n,
@@ -736,30 +825,41 @@ class Planner:
         return rounds
 
     def _form_rounds(self, sweep: SweepPlan) -> None:
-        # every extra round is one more trip of the tile through shared memory: keep the split with the fewest
-        rounds = self._split_rounds(sweep)
+        # every extra round is one more trip of the tile through shared memory: keep the split with the fewest.
+        # The search scores a few hundred splits per sweep: they are computed natively (_RoundSplitter) and only the
+        # one that is kept is turned into operator lists. A candidate is (rounds, cost of the last round, split or key).
+        splitter = _RoundSplitter(self, sweep)
+
+        def split(trial: int, backward: bool):
+            scored = splitter.score(trial, backward)
+            if scored is None:          # no native answer (masks beyond 64 bits, random stream too short)
+                rounds = self._split_rounds(sweep, random.Random(trial) if trial else None, 0.85 if trial else 1.0,
+                                            backward)
+                return len(rounds), sum(op.cost for op in rounds[-1][1]), rounds
+            return scored[0], scored[1], (trial, backward)
+
+        best = split(0, False)
         tries = max(self.tries, ROUND_TRIES_SPECIALISED) if self.late_rounds and self.tries > 0 else self.tries
         if len(sweep.ops) >= 16:
             for trial in range(1, 1 + tries):
-                if len(rounds) <= 2 or (trial > self.tries and len(rounds) <= 3):
+                if best[0] <= 2 or (trial > self.tries and best[0] <= 3):
                     break           # the long search is for sweeps that still need four rounds
-                cand = self._split_rounds(sweep, random.Random(trial), 0.85)
-                if len(cand) < len(rounds):
-                    rounds = cand
-        if self.late_rounds and len(rounds) > 1:
+                cand = split(trial, False)
+                if cand[0] < best[0]:
+                    best = cand
+        if self.late_rounds and best[0] > 1:
             # the latest-possible split, kept when it needs no more rounds and leaves more work behind the last
             # exchange (cost of the last round's operators)
-            def tail(split):
-                return sum(op.cost for op in split[-1][1])
-            cands = [self._split_rounds(sweep, backward=True)]
+            cands = [split(0, True)]
             if len(sweep.ops) >= 16:
                 for trial in range(1, 1 + tries):
-                    if trial > self.tries and min(len(rounds), min(len(c) for c in cands)) <= 3:
+                    if trial > self.tries and min(best[0], min(c[0] for c in cands)) <= 3:
                         break
-                    cands.append(self._split_rounds(sweep, random.Random(trial), 0.85, backward=True))
+                    cands.append(split(trial, True))
             for cand in cands:
-                if len(cand) < len(rounds) or (len(cand) == len(rounds) and tail(cand) > tail(rounds)):
-                    rounds = cand
+                if cand[0] < best[0] or (cand[0] == best[0] and cand[1] > best[1]):
+                    best = cand
+        rounds = splitter.rounds(*best[2]) if isinstance(best[2], tuple) else best[2]
         final: List[Round] = []
         nr = len(rounds)
         for r, (regs, chosen) in enumerate(rounds):

@@ -475,3 +475,60 @@ def test_latest_possible_rounds_need_no_more_exchanges_and_end_full(monkeypatch)
     assert sum(map(len, shapes['1'])) <= sum(map(len, shapes['0']))
     multi = [s for s in shapes['1'] if len(s) > 1]
     assert multi and sum(s[-1] for s in multi) >= sum(s[0] for s in multi)
+
+
+@pytest.mark.parametrize('n,depth,seed,reg_bits', [(14, 10, 0, 4), (16, 12, 1, 5), (20, 16, 2, 4)])
+def test_native_round_split_matches_the_python_statement(n, depth, seed, reg_bits):
+    """qfb_plan_split_rounds (what Planner._form_rounds scores a few hundred variants per sweep with) against
+    Planner._split_rounds, the same greedy in Python: plain and randomised variants (the random.Random(trial) stream),
+    forward and latest-possible, same operators per round, same register bits, same cost of the last round."""
+    import random
+    specs = workloads.wb_gate_list(n, depth, seed)
+    items = planner.classify_all(bitops_of(specs, n))
+    pl = planner.Planner(n, reg_bits=reg_bits)
+    sweeps = pl.plan([it for it in items if not isinstance(it, planner.Fallback)])
+    checked = 0
+    for sw in sweeps:
+        ops = [op for rd in sw.rounds for op in rd.ops if op.kind in ('G', 'P')]
+        again = planner.SweepPlan(sw.tile, ops)
+        splitter = planner._RoundSplitter(pl, again)
+        for trial in [0] + list(range(1, 12)):
+            for backward in (False, True):
+                want = pl._split_rounds(again, random.Random(trial) if trial else None, 0.85 if trial else 1.0, backward)
+                nrounds, tail = splitter.score(trial, backward)
+                got = splitter.rounds(trial, backward)
+                assert nrounds == len(want) == len(got)
+                assert tail == sum(op.cost for op in want[-1][1])
+                for (wregs, wops), (gregs, gops) in zip(want, got):
+                    assert sorted(wregs) == gregs
+                    assert [id(op) for op in wops] == [id(op) for op in gops]
+                checked += 1
+    assert checked >= 24
+    # a random stream that is too short is reported, not silently reused
+    long_sweep = max(sweeps, key=lambda sw: len(sw.ops))
+    splitter = planner._RoundSplitter(pl, planner.SweepPlan(long_sweep.tile, [op for rd in long_sweep.rounds
+                                                                           for op in rd.ops if op.kind in ('G', 'P')]))
+    saved = planner.ROUND_STREAM_LEN
+    try:
+        planner.ROUND_STREAM_LEN = 1
+        assert splitter.score(3, False) is None
+    finally:
+        planner.ROUND_STREAM_LEN = saved
+
+
+def test_tile_search_does_not_depend_on_the_number_of_threads():
+    """The candidates of a search pass are scored side by side (csrc/qfb_planhost.cu, PassWorkers); the winner is
+    picked in the serial order afterwards, so plans are byte-identical for any thread count."""
+    from quantumflow_b200 import _lib
+    lib = _lib.load()
+    n = 26
+    specs = workloads.wb_gate_list(n, 10, 3)
+    blobs = {}
+    try:
+        for threads in (1, 4, 3):
+            assert lib.qfb_plan_set_threads(threads) == 0
+            segments = planner.build_segments(n, bitops_of(specs, n))
+            blobs[threads] = b''.join(s.blob for s in segments if s.blob)
+    finally:
+        lib.qfb_plan_set_threads(0)
+    assert blobs[1] == blobs[4] == blobs[3]
