@@ -594,6 +594,10 @@ class Planner:
         self.max_cost = DEFAULT_MAX_COST if max_cost is None else float(max_cost)
         self.tries = DEFAULT_TRIES if tries is None else int(tries)
         self.refine = True if refine is None else bool(refine)
+        # results of the tile searches, keyed by the operators scanned and the start tile: the randomised partitions
+        # of one plan, and even more so the candidate schedules of a sharded circuit (sharded.schedule hands one dict
+        # to all of them), repeat many searches. Only valid while the operator objects are alive (ids in the key).
+        self.search_cache: Optional[Dict[tuple, int]] = None
 
     # ---- pass 2: sweeps ---------------------------------------------------------------------------
     def _form_sweep(self, ops: List[POp], rnd=None, p_new: float = 1.0, forbidden: frozenset = frozenset(),
@@ -728,6 +732,12 @@ class Planner:
         lib = _lib.load()
         window = ops[:REFINE_WINDOW]
         n = len(window)
+        key = None
+        if self.search_cache is not None:
+            key = (tuple(map(id, window)), tmask, fmask, keep, lookahead, self.nbits, self.L, self.M, self.max_cost)
+            hit = self.search_cache.get(key)
+            if hit is not None:
+                return hit
         every = (1 << self.nbits) - 1
         nb = self.nbits
         # the operators as parallel arrays; every operator keeps its packed row (the same operators are scanned by
@@ -755,6 +765,8 @@ class Planner:
                 mix.ctypes.data, diag.ctypes.data, cost.ctypes.data, nbytes.ctypes.data, n, self.nbits, self.L,
                 self.M, int(out.value), fmask, ((1 << self.L) - 1) | keep, float(self.max_cost), room,
                 REFINE_PASSES, LOOKAHEAD_PASSES, ctypes.byref(out), None))
+        if key is not None:
+            self.search_cache[key] = int(out.value)
         return int(out.value)
 
     # ---- pass 3: rounds ---------------------------------------------------------------------------
@@ -1109,6 +1121,16 @@ class Planner:
         """Split the operator list into sweeps. Every sweep costs one pass over the state (the dominant cost), so
         besides the plain greedy walk a few randomised variants are tried (fixed seeds: the plan is deterministic)
         and the split with the fewest sweeps wins."""
+        own_cache = self.search_cache is None
+        if own_cache:
+            self.search_cache = {}          # `pops` keeps the operators alive while it is in use
+        try:
+            return self._partition_search(pops)
+        finally:
+            if own_cache:
+                self.search_cache = None
+
+    def _partition_search(self, pops: List[POp]) -> List[Tuple[List[POp], List[int]]]:
         best = None
         # with tile refinement a trial costs ~0.25 s on 1000 operators of 30 bits: fewer randomised variants
         tries = min(self.tries, REFINE_TRIES) if self.refine else self.tries

@@ -103,13 +103,14 @@ def schedule(nbits: int, p: int, bitops: Sequence[BitOp], tile_bits: int = None,
         return steps, phys_of
     best = None
     items = planner.classify_all(bitops)       # once for all candidates (the scheduler never changes an operator)
+    searches: Dict[tuple, int] = {}            # tile searches shared by the candidates (Planner.search_cache): most repeat
     # (randomised variants per sweep, two-sweep look-ahead of the tile search): the look-ahead runs without
     # variants - picking the variant that does most work NOW is exactly what it is there to avoid
     for tries, lookahead in [(t, False) for t in SWEEP_TRIES_CANDIDATES] + [(0, True)]:
         for cand in (THIN_CANDIDATES[1:3] if lookahead else THIN_CANDIDATES):     # the look-ahead is the slow one
             try:
                 steps, phys_of, nsweeps = _schedule_once(nbits, p, bitops, tile_bits, low_bits, max_cost, cand, tries,
-                                                         lookahead, items=items)
+                                                         lookahead, items=items, searches=searches)
             except RuntimeError:
                 continue          # one candidate that cannot be scheduled must not abort the others
             cost = nsweeps + sum(REMAP_COST_PER_FRACTION * (1.0 - 0.5 ** len(st.rank_positions))
@@ -123,7 +124,8 @@ def schedule(nbits: int, p: int, bitops: Sequence[BitOp], tile_bits: int = None,
 
 def _schedule_once(nbits: int, p: int, bitops: Sequence[BitOp], tile_bits: int, low_bits: int, max_cost: float,
                    thin_fraction: float, sweep_tries: int = 3, lookahead: bool = False,
-                   items: Optional[List[object]] = None) -> Tuple[List[object], List[int], int]:
+                   items: Optional[List[object]] = None, searches: Optional[Dict[tuple, int]] = None
+                   ) -> Tuple[List[object], List[int], int]:
     """Split `bitops` (logical bit positions, program order) into Stage / Remap steps.
 
     Sweeps (passes over the shard) are formed one at a time from the operators that are executable under the
@@ -144,6 +146,9 @@ def _schedule_once(nbits: int, p: int, bitops: Sequence[BitOp], tile_bits: int, 
     # tiles are formed here in logical bits and handed to the stage planner (nl local bits): same tile size
     tb = min(planner.default_tile_bits(planner.default_reg_bits(nl)) if tile_bits is None else int(tile_bits), nl)
     pl = planner.Planner(nbits, tb, low_bits, max_cost) if nl >= planner.MIN_TILE_BITS else None
+    if pl is not None:
+        # without a shared dict: one of its own (the operators of `remaining` stay alive in this call's frame)
+        pl.search_cache = searches if searches is not None else {}
     pinned = set(range(pl.L)) if pl is not None else set()
 
     def mixset(it) -> frozenset:
