@@ -13,7 +13,6 @@ from itertools import chain
 from math import pi
 from typing import Dict, Iterable, Iterator, List, Sequence, Tuple, Type
 
-import numpy as np
 import torch
 
 from . import backend as bk

@@ -71,6 +71,8 @@ def upload(array: np.ndarray, device: torch.device) -> torch.Tensor:
     stage = _staging(device)
     piece = stage[0].numel()
     stream = torch.cuda.Stream(device)
+    # `out` may be a recycled block that work already queued on the current stream still reads: stay behind it
+    stream.wait_stream(torch.cuda.current_stream(device))
     done = [None, None]
     for i, lo in enumerate(range(0, src.numel(), piece)):
         n = min(piece, src.numel() - lo)
@@ -133,6 +135,8 @@ def apply_operator(tensor: torch.Tensor, mat: np.ndarray, bits: Sequence[int], i
     nb = nbits_of(src)
     k = len(bits)
     mat = classify.as_matrix(mat, k)
+    if inplace and src.data_ptr() != tensor.data_ptr():
+        raise ValueError('in-place application needs a contiguous tensor')
     dst = src if inplace else torch.empty_like(src)
     st = _stream()
     bits = [int(b) for b in bits]

@@ -13,7 +13,7 @@ land on labels, so such a run is always entered at its top -- is handed to the s
 40 gates costs a handful of sweeps per iteration instead of 40.
 """
 from abc import ABC
-from typing import Dict, Generator, List, Optional, Tuple, Union
+from typing import Dict, Generator, List, Optional, Tuple
 
 from .cbits import Addr, Register
 from .circuits import Circuit

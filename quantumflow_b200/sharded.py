@@ -7,13 +7,17 @@ kept on the host, so "swapping back" is never needed.
 * diagonal operators and control qubits on rank bits cost no communication: the kernels resolve them from
   `index_hi` (= the rank), see qfb_apply_diag / qfb_run_plan;
 * an operator that MIXES a rank bit triggers a remap: k rank bits are exchanged with the k top local bits by a
-  pairwise block exchange (for k = p this is the all-to-all of SURVEY 8e) over NCCL / NVLink. The outgoing logical
-  qubits are first moved to the top local positions by an in-place bit permutation that rides on the final store
-  of the stage's last sweep (planner.attach_permutation: no extra pass over the shard);
-* the exchange is IN PLACE: block j of the shard is swapped with the matching block of peer (mine ^ s) in step s
-  (XOR pairing, so every pair agrees on the order), chunk by chunk through two small staging buffers - chunk
-  i+1 is on the wire while chunk i is copied out of its staging buffer. Memory: shard + 2 staging chunks, which
-  is what lets a 2^33-amplitude (128 GiB) shard live on a 180 GB GPU;
+  pairwise block exchange (for k = p this is the all-to-all of SURVEY 8e). The outgoing logical qubits are first moved
+  to the top local positions by an in-place bit permutation that rides on the final store of the stage's last sweep
+  (planner.attach_permutation: no extra pass over the shard);
+* the exchange is IN PLACE: block j of the shard trades places with block `mine` of the peer whose selected rank bits
+  equal j. On GPUs it is ONE kernel per remap and rank over NVLink peer memory (csrc/qfb_remap.cu: the peers' shards
+  are mapped through CUDA IPC, of every pair's block the lower rank swaps the first half and the higher rank the
+  second half; no staging buffer, no NCCL call on the data path), and it is PIPELINED slice by slice with the sweeps on
+  either side of it (`_remap_pipelined`: sweeps of slice s+1 | exchange of slice s | sweeps of slice s-1 on two
+  streams, ranks ordered by a barrier kernel through peer memory). Memory = the shard alone, which is what lets a
+  2^33-amplitude (128 GiB) shard live on a 180 GB GPU. The round-1 path (`_exchange`: XOR-paired isend / irecv chunks
+  through two staging buffers) is what the gloo tests run and what QFB_REMAP=nccl selects;
 * which qubits become global is decided Belady-style: the ones whose next mixing use is farthest away.
 
 `ShardedCircuit` only needs three callables for the local work (run segments, permute bits, allocate scratch),
