@@ -66,3 +66,22 @@ def max_threads() -> int:
 
 def set_threads(n: int) -> None:
     load().qfo_set_threads(int(n))
+
+
+def evolve_specs(specs, nqubits: int, gate_matrix, depolarizing_superop) -> np.ndarray:
+    """Circuit.evolve over specs on the flat density (qf_oracle.evolve_specs with the C kernel instead of einsum:
+    rho is a [2]*(2n) tensor, ket axes first, so ket qubit q is index bit 2n-1-q and bra qubit q index bit n-1-q;
+    a gate acts as kron(U, conj U) on (ket qubits, bra qubits), DEPOLARIZING as its Kraus-sum superoperator).
+    Starts from |0..0><0..0|. For densities too large for einsum's temporaries (14 qubits = 2^28 elements)."""
+    n = nqubits
+    rho = np.zeros(1 << (2 * n), dtype=np.complex128)
+    rho[0] = 1.0
+    for name, params, qubits in specs:
+        if name == 'DEPOLARIZING':
+            sup = depolarizing_superop(params[0])
+        else:
+            u = gate_matrix(name, params)
+            sup = np.kron(u, u.conj())
+        bits = [2 * n - 1 - q for q in qubits] + [n - 1 - q for q in qubits]
+        apply_dense(rho, sup, bits)
+    return rho
