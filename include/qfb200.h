@@ -96,6 +96,14 @@ int qfb_plan_destroy(void *handle);
 int qfb_jit_ptx(const void *plan_host, size_t plan_bytes, int sweep, char *buf, size_t cap, size_t *needed,
                 size_t *ncoef);
 int qfb_jit_check(const void *plan_host, size_t plan_bytes, char *log, size_t cap);
+/* Everything a launch of one sweep's kernel consists of, for tools and for the CPU tests that EXECUTE the generated
+ * code on a PTX emulator (tests/ptx_emulator.py): the PTX text (fix_mask != 0: the variant for launches over a slice
+ * of the state, whose index bits fix_mask come from the kernel parameter p_fix), the coefficients in the order of the
+ * module's constant bank qfb_coef, threads per CTA, dynamic shared memory, tiles a CTA works on side by side. Any
+ * output pointer may be NULL. Host code only. */
+int qfb_jit_source(const void *plan_host, size_t plan_bytes, int sweep, uint64_t fix_mask, char *ptx, size_t ptx_cap,
+                   size_t *ptx_needed, double *coef, size_t coef_cap, size_t *ncoef, int *threads,
+                   size_t *smem_bytes, int *groups);
 /* Whole circuits on small states in ONE launch (csrc/qfb_small.cu; the QAOA gradient step of
  * examples/qaoa_maxcut.py:37-87, BASELINE.json configs[1]): the state (<= 13 qubits) stays in the shared memory of one
  * CTA for all gates; `batch` independent items (states [batch][2^nbits], matrices [batch][mats_stride]) run as one CTA

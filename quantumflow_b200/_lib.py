@@ -30,6 +30,8 @@ PROTOTYPES = {
     'qfb_plan_sweep_info': (c_int, [c_void_p, c_int, POINTER(c_int), POINTER(c_uint64), POINTER(c_int)]),
     'qfb_jit_ptx': (c_int, [c_void_p, c_size_t, c_int, c_char_p, c_size_t, POINTER(c_size_t), POINTER(c_size_t)]),
     'qfb_jit_check': (c_int, [c_void_p, c_size_t, c_char_p, c_size_t]),
+    'qfb_jit_source': (c_int, [c_void_p, c_size_t, c_int, c_uint64, c_char_p, c_size_t, POINTER(c_size_t), c_void_p,
+                               c_size_t, POINTER(c_size_t), _c_int_p, POINTER(c_size_t), _c_int_p]),
     'qfb_small_circuit_run': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
     'qfb_small_circuit_adjoint': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_size_t,
                                           c_void_p, c_void_p, c_void_p, c_void_p]),

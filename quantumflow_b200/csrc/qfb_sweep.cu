@@ -702,6 +702,35 @@ int qfb_jit_ptx(const void *plan_host, size_t plan_bytes, int sweep, char *buf, 
     return QFB_OK;
 }
 
+int qfb_jit_source(const void *plan_host, size_t plan_bytes, int sweep, uint64_t fix_mask, char *ptx, size_t ptx_cap,
+                   size_t *ptx_needed, double *coef, size_t coef_cap, size_t *ncoef, int *threads,
+                   size_t *smem_bytes, int *groups) {
+    std::vector<SweepInfo> sweeps;
+    int nbits = 0, M = 0, RB = 0;
+    int rc = validate_plan((const uint8_t *)plan_host, plan_bytes, sweeps, nbits, M, &RB);
+    if (rc != QFB_OK) return rc;
+    QFB_CHECK_ARG(sweep >= 0 && (size_t)sweep < sweeps.size(), "qfb_jit_source: no sweep %d", sweep);
+    JitSource src;
+    std::string err;
+    rc = jit_generate((const uint8_t *)plan_host + sweeps[sweep].offset, nbits, M, RB, src, err, fix_mask);
+    if (rc != QFB_OK) {
+        set_error("%s", err.c_str());
+        return rc;
+    }
+    if (ptx_needed) *ptx_needed = src.ptx.size() + 1;
+    if (ncoef) *ncoef = src.coef.size();
+    if (threads) *threads = src.threads;
+    if (smem_bytes) *smem_bytes = src.smem_bytes;
+    if (groups) *groups = src.groups;
+    if (ptx && ptx_cap) {
+        const size_t n = std::min(ptx_cap - 1, src.ptx.size());
+        memcpy(ptx, src.ptx.data(), n);
+        ptx[n] = 0;
+    }
+    if (coef && coef_cap) memcpy(coef, src.coef.data(), sizeof(double) * std::min(coef_cap, src.coef.size()));
+    return QFB_OK;
+}
+
 int qfb_jit_check(const void *plan_host, size_t plan_bytes, char *log, size_t cap) {
     std::vector<SweepInfo> sweeps;
     int nbits = 0, M = 0, RB = 0;

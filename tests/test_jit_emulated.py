@@ -1,0 +1,206 @@
+"""The sweep-specialised kernels (csrc/qfb_jit.cu) EXECUTED without a GPU: the library emits the PTX of every sweep of
+a plan (qfb_jit_source: text, coefficients, launch geometry -- the same generator call qfb_plan_upload makes), the PTX
+emulator (tests/ptx_emulator.py) runs it thread for thread on a numpy state, and the result is compared with the
+oracle's gate-by-gate arithmetic. Covers what the GPU tests cover for these kernels (4 / 5 register bits, tile sizes,
+every operator handler, dense 2-bit superoperators of density workloads, store permutations and rank-bit controls of
+sharded stages, slice launches of pipelined remaps) in the CPU tier; the ptxas compile check of the same text is
+tests/test_planner.py::test_sweep_specialised_ptx_compiles_for_sm100a."""
+import ctypes
+import random
+
+import numpy as np
+import pytest
+
+import ptx_emulator as PE
+from oracle import qf_oracle as O
+from quantumflow_b200 import _lib, planner, sharded, workloads
+
+AMP_TOL = 1e-10
+
+
+def bitops_of(specs, n):
+    return [(O.gate_matrix(name, params), [n - 1 - q for q in qubits]) for name, params, qubits in specs]
+
+
+def sweep_source(blob: bytes, sweep: int, fix_mask: int = 0):
+    """(ptx, coefficients, threads, shared-memory bytes, groups) of one sweep of a plan."""
+    lib = _lib.load()
+    need, ncoef, smem = ctypes.c_size_t(0), ctypes.c_size_t(0), ctypes.c_size_t(0)
+    threads, groups = ctypes.c_int(0), ctypes.c_int(0)
+    rc = lib.qfb_jit_source(blob, len(blob), sweep, fix_mask, None, 0, ctypes.byref(need), None, 0, ctypes.byref(ncoef),
+                            ctypes.byref(threads), ctypes.byref(smem), ctypes.byref(groups))
+    assert rc == 0, lib.qfb_last_error()
+    text = ctypes.create_string_buffer(need.value)
+    coef = np.zeros(max(1, ncoef.value), dtype=np.float64)
+    rc = lib.qfb_jit_source(blob, len(blob), sweep, fix_mask, text, need.value, None, coef.ctypes.data, ncoef.value,
+                            None, None, None, None)
+    assert rc == 0, lib.qfb_last_error()
+    return text.value.decode(), coef[:ncoef.value], threads.value, smem.value, groups.value
+
+
+def run_plan_emulated(blob: bytes, nsweeps: int, state: np.ndarray, index_hi: int = 0, grid: int = 2) -> None:
+    for i in range(nsweeps):
+        ptx, coef, threads, smem, groups = sweep_source(blob, i)
+        assert PE.Kernel(ptx).threads == threads
+        PE.run_sweep(ptx, coef, state, index_hi=index_hi, grid=grid, smem_bytes=smem, groups=groups)
+
+
+def run_segments_emulated(segments, state: np.ndarray, index_hi: int = 0, grid: int = 2) -> None:
+    for seg in segments:
+        if seg.kind == 'plan':
+            run_plan_emulated(seg.blob, seg.nsweeps, state, index_hi, grid)
+        else:
+            state[:] = O.tensormul_flat(np.asarray(seg.mat), state, list(seg.bits))
+
+
+def zero(n):
+    state = np.zeros(1 << n, dtype=np.complex128)
+    state[0] = 1.0
+    return state
+
+
+@pytest.mark.parametrize('n,depth,seed,tile,reg_bits,grid', [
+    (12, 6, 0, None, 4, 2), (13, 10, 1, None, 4, 3), (14, 12, 2, None, 4, 1), (12, 8, 3, 9, 4, 2),
+    (13, 8, 4, None, 5, 2), (11, 8, 5, 8, 4, 5), (12, 20, 6, 10, 5, 2)])
+def test_generated_kernels_run_the_benchmark_circuit_family(n, depth, seed, tile, reg_bits, grid):
+    """W-B circuits (the benchmark's family: H / X / T / RX / RY / RZ layers + CNOT / CZ matchings): every sweep of the
+    plan through its generated kernel, any grid size, against the oracle."""
+    specs = workloads.wb_gate_list(n, depth, seed)
+    segments = planner.build_segments(n, bitops_of(specs, n), tile_bits=tile, reg_bits=reg_bits)
+    assert any(seg.kind == 'plan' for seg in segments)
+    state = zero(n)
+    run_segments_emulated(segments, state, grid=grid)
+    want = O.run_specs(specs, n).reshape(-1)
+    assert np.abs(state - want).max() < AMP_TOL
+
+
+@pytest.mark.parametrize('seed', [11, 12, 13, 14, 15, 16])
+def test_generated_kernels_on_random_circuits_with_every_gate_kind(seed):
+    """The circuits of the GPU fuzz (tools/gpu_fuzz_jit.py): layered random circuits with extra CNOT / CZ / SWAP / ISWAP
+    / CCNOT anywhere, random sizes and tiles; plus controlled phases and rotations that exercise the diagonal tables."""
+    rnd = random.Random(seed)
+    n = rnd.randint(10, 13)
+    depth = rnd.randint(2, 6)
+    tile = rnd.randint(8, min(n, 11))
+    specs = workloads.wb_gate_list(n, depth, rnd.randint(0, 10 ** 6))
+    for _ in range(rnd.randint(3, 10)):
+        kind = rnd.choice(['CNOT', 'CZ', 'SWAP', 'ISWAP', 'CCNOT', 'CPHASE', 'ZZ', 'S', 'Y', 'TX'])
+        if kind == 'CCNOT':
+            qs, params = tuple(rnd.sample(range(n), 3)), ()
+        elif kind in ('S', 'Y'):
+            qs, params = (rnd.randrange(n),), ()
+        elif kind == 'TX':
+            qs, params = (rnd.randrange(n),), (rnd.uniform(0, 2),)
+        else:
+            qs = tuple(rnd.sample(range(n), 2))
+            params = (rnd.uniform(0, 6.28),) if kind in ('CPHASE', 'ZZ') else ()
+        specs.insert(rnd.randint(0, len(specs)), (kind, params, qs))
+    segments = planner.build_segments(n, bitops_of(specs, n), tile_bits=tile, reg_bits=4)
+    rng = np.random.RandomState(seed)
+    state = rng.normal(size=1 << n) + 1j * rng.normal(size=1 << n)
+    state /= np.linalg.norm(state)
+    want = O.run_specs(specs, n, state.reshape([2] * n)).reshape(-1)
+    run_segments_emulated(segments, state, grid=rnd.randint(1, 4))
+    assert np.abs(state - want).max() < AMP_TOL
+
+
+@pytest.mark.parametrize('n,depth,seed,reg_bits', [(5, 3, 0, 4), (6, 2, 1, 4), (6, 2, 2, 5)])
+def test_generated_kernels_on_density_workloads(n, depth, seed, reg_bits):
+    """W-D (config C3's family): RX, CNOT and depolarising channels on rho as a 2n-bit vector -- gates as U on the ket
+    bits and conj(U) on the bra bits, channels as dense 2-bit superoperators (the G2 handlers)."""
+    specs = workloads.wd_gate_list(n, depth, seed)
+    ops = []
+    for name, params, qubits in specs:
+        ket = [2 * n - 1 - q for q in qubits]
+        bra = [n - 1 - q for q in qubits]
+        if name == 'DEPOLARIZING':
+            ops.append((O.depolarizing_superop(params[0]), ket + bra))
+        else:
+            u = O.gate_matrix(name, params)
+            ops.append((u, ket))
+            ops.append((u.conj(), bra))
+    segments = planner.build_segments(2 * n, ops, reg_bits=reg_bits)
+    rho = zero(2 * n)
+    run_segments_emulated(segments, rho, grid=2)
+    want = O.evolve_specs(specs, n).reshape(-1)
+    assert np.abs(rho - want).max() < AMP_TOL
+    assert abs(rho.reshape(1 << n, 1 << n).trace() - 1) < 1e-12
+
+
+def _swap_index_bits(vec, pairs):
+    idx = np.arange(vec.size, dtype=np.int64)
+    src = idx.copy()
+    for a, b in pairs:
+        ba, bb = (idx >> a) & 1, (idx >> b) & 1
+        src = (src & ~((1 << a) | (1 << b))) | (bb << a) | (ba << b)
+    return vec[src]
+
+
+@pytest.mark.parametrize('n,p,tile,depth,seed', [(13, 1, 9, 6, 0), (13, 2, 8, 5, 1), (14, 3, 9, 4, 2)])
+def test_generated_kernels_run_sharded_stages(n, p, tile, depth, seed):
+    """The GPU path of a sharded circuit, minus the GPU: stages planned as ShardedCircuit plans them (preset sweeps,
+    the remap's local permutation fused into the last sweep's store or appended as a bare sweep), every rank's shard
+    through the generated kernels with index_hi = rank (controls and phases on rank bits), remaps as index-bit swaps
+    of the concatenated shards."""
+    specs = workloads.wb_gate_list(n, depth, seed)
+    nl = n - p
+    steps, phys_of = sharded.schedule(n, p, bitops_of(specs, n), tile_bits=tile)
+    rng = np.random.RandomState(seed)
+    full = rng.normal(size=1 << n) + 1j * rng.normal(size=1 << n)
+    full /= np.linalg.norm(full)
+    phys = full.copy()
+    nplans = 0
+    for st in steps:
+        if isinstance(st, sharded.Stage):
+            segs = planner.build_segments_from_items(nl, st.items, tile_bits=tile, final_perm=st.final_perm,
+                                                     preset=st.parts, reg_bits=4)
+            for rank in range(1 << p):
+                shard = np.ascontiguousarray(phys[rank << nl:(rank + 1) << nl])
+                run_segments_emulated(segs, shard, index_hi=rank, grid=2)
+                phys[rank << nl:(rank + 1) << nl] = shard
+            nplans += sum(1 for s in segs if s.kind == 'plan')
+        else:
+            k = len(st.rank_positions)
+            phys = _swap_index_bits(phys, [(nl + t, nl - k + i) for i, t in enumerate(st.rank_positions)])
+    assert nplans >= 1
+    shards = [phys[r << nl:(r + 1) << nl] for r in range(1 << p)]
+    got = sharded.gather_logical(shards, n, p, phys_of)
+    want = O.run_specs(specs, n, full.reshape([2] * n)).reshape(-1)
+    assert np.abs(got - want).max() < AMP_TOL
+
+
+def test_slice_variants_cover_the_state_like_one_full_launch():
+    """Pipelined remaps launch a sweep slice by slice: the variant generated for fix_mask (index bits outside the
+    sweep's tile) works on the amplitudes whose bits fix_mask equal the kernel parameter p_fix. Running the variant for
+    every value of the fixed bits must give what one full launch gives, and a single slice launch must leave every
+    other slice untouched."""
+    import plan_emulator as E
+    n, tile = 14, 9
+    specs = workloads.wb_gate_list(n, 5, 7)
+    segments = planner.build_segments(n, bitops_of(specs, n), tile_bits=tile, reg_bits=4)
+    rng = np.random.RandomState(3)
+    checked = 0
+    for seg in segments:
+        if seg.kind != 'plan':
+            continue
+        parsed = E.parse(seg.blob)
+        for i, sw in enumerate(parsed['sweeps'][:3]):
+            nontile = list(sw['hole'])          # index bits outside the sweep's tile
+            fix_bits = sorted(rng.choice(nontile, size=2, replace=False).tolist())
+            fix_mask = sum(1 << b for b in fix_bits)
+            start = rng.normal(size=1 << n) + 1j * rng.normal(size=1 << n)
+            full = start.copy()
+            ptx, coef, _, smem, groups = sweep_source(seg.blob, i)
+            PE.run_sweep(ptx, coef, full, grid=2, smem_bytes=smem, groups=groups)
+            vptx, vcoef, _, vsmem, vgroups = sweep_source(seg.blob, i, fix_mask)
+            sliced = start.copy()
+            idx = np.arange(1 << n)
+            for v in range(4):
+                value = sum(((v >> t) & 1) << b for t, b in enumerate(fix_bits))
+                before = sliced.copy()
+                PE.run_sweep(vptx, vcoef, sliced, fix_value=value, grid=2, smem_bytes=vsmem, groups=vgroups)
+                other = (idx & fix_mask) != value
+                assert np.array_equal(sliced[other], before[other])
+            assert np.abs(sliced - full).max() < 1e-13
+            checked += 1
+    assert checked >= 2
