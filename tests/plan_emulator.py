@@ -236,97 +236,114 @@ def conflict_degree(plan_round, M):
     return worst
 
 
+def _run_tile(plan, sweep, tile_id: int, state, index_hi: int, check_layout: bool) -> None:
+    """One tile of one sweep, in place on `state` (anything indexable by flat amplitude index: a numpy vector, or a
+    dict-backed sparse memory when only a few tiles of a large state are of interest)."""
+    nbits, M = plan['nbits'], plan['M']
+    T = 1 << (M - R)
+    gpos, spos, hole = sweep['gpos'], sweep['spos'], sweep['hole']
+    nrounds = len(sweep['rounds'])
+    gb = 0
+    for i, h in enumerate(hole):
+        gb |= ((tile_id >> i) & 1) << h
+    tile = np.zeros(1 << M, dtype=np.complex128)   # "shared memory", indexed by swizzled tile index
+    # asynchronous tile loader: tile-local index i <- state[gb | deposit(i through gpos)]
+    for i in range(1 << M):
+        g = 0
+        for j in range(M):
+            g |= ((i >> j) & 1) << gpos[j]
+        tile[swz(i)] = state[gb | g]
+    for rnd, rd in enumerate(sweep['rounds']):
+        regpos, thrpos = rd['regpos'], rd['thrpos']
+        assert sorted(regpos + thrpos) == list(range(M))
+        if check_layout and (rnd == 0 or rnd == nrounds - 1):
+            # edge rounds: lanes must walk the lowest index bits (coalesced 128-byte lines)
+            nlow = min(3, M - R)
+            if rnd == 0:
+                assert [gpos[thrpos[t]] for t in range(nlow)] == list(range(nlow)), 'uncoalesced load round'
+            if rnd == nrounds - 1:
+                assert [spos[thrpos[t]] for t in range(nlow)] == list(range(nlow)), 'uncoalesced store round'
+        regs_all = np.zeros((T, NE), dtype=np.complex128)
+        for tid in range(T):
+            tb = tg = 0
+            for t in range(M - R):
+                bit = (tid >> t) & 1
+                tb |= bit << thrpos[t]
+                tg |= bit << gpos[thrpos[t]]
+            a = np.zeros(NE, dtype=np.complex128)
+            for e in range(NE):
+                toff = goff = 0
+                for i in range(R):
+                    if (e >> i) & 1:
+                        toff |= 1 << regpos[i]
+                        goff |= 1 << gpos[regpos[i]]
+                a[e] = tile[swz(tb | toff)]
+            tfull = (index_hi << nbits) | gb | tg
+            scalar = 1.0 + 0j
+            for op in rd['ops']:
+                on = (tfull & op['idx_cmask']) == op['idx_cmask']
+                if op['type'] == 4:
+                    tbl = np.frombuffer(op['payload'], dtype=np.complex128, count=TABLE)
+                    for e in range(NE):
+                        if op['flag'] or (e & op['reg_cmask']):
+                            a[e] = tbl[e] * a[e]
+                elif op['type'] == 3:
+                    assert op['reg_cmask'] != 0 or rd['has_scalar'] == 1
+                    scalar = _apply_cph(a, op, on, scalar)
+                elif on:
+                    if op['type'] == 1:
+                        _apply_g1(a, op)
+                    else:
+                        _apply_g2(a, op)
+            if rd['has_scalar']:
+                a = a * scalar
+            else:
+                assert scalar == 1
+            regs_all[tid] = a
+        # all threads have read the tile before anyone writes it (the kernel's barriers)
+        staged = []
+        for tid in range(T):
+            tb = tg = 0
+            for t in range(M - R):
+                bit = (tid >> t) & 1
+                tb |= bit << thrpos[t]
+                tg |= bit << spos[thrpos[t]]       # only used by the final store: STORE positions
+            for e in range(NE):
+                toff = goff = 0
+                for i in range(R):
+                    if (e >> i) & 1:
+                        toff |= 1 << regpos[i]
+                        goff |= 1 << spos[regpos[i]]
+                if rnd + 1 < nrounds:
+                    tile[swz(tb | toff)] = regs_all[tid, e]
+                else:
+                    staged.append(((gb | tg | goff) ^ sweep['store_xor'], regs_all[tid, e]))
+        if rnd + 1 == nrounds:
+            # pending X flips: amplitude i lands at i ^ store_xor (all loads of the tile came first)
+            for addr, val in staged:
+                state[addr] = val
+
+
 def execute(blob: bytes, state: np.ndarray, index_hi: int = 0, check_layout: bool = True) -> np.ndarray:
     plan = parse(blob)
     nbits, M = plan['nbits'], plan['M']
     assert state.size == 1 << nbits
     state = np.array(state, dtype=np.complex128).reshape(-1)
-    T = 1 << (M - R)
     for sweep in plan['sweeps']:
-        gpos, spos, hole = sweep['gpos'], sweep['spos'], sweep['hole']
-        assert sorted(gpos + hole) == list(range(nbits))
-        nrounds = len(sweep['rounds'])
+        assert sorted(sweep['gpos'] + sweep['hole']) == list(range(nbits))
         for tile_id in range(1 << (nbits - M)):
-            gb = 0
-            for i, h in enumerate(hole):
-                gb |= ((tile_id >> i) & 1) << h
-            tile = np.zeros(1 << M, dtype=np.complex128)   # "shared memory", indexed by swizzled tile index
-            # asynchronous tile loader: tile-local index i <- state[gb | deposit(i through gpos)]
-            for i in range(1 << M):
-                g = 0
-                for j in range(M):
-                    g |= ((i >> j) & 1) << gpos[j]
-                tile[swz(i)] = state[gb | g]
-            for rnd, rd in enumerate(sweep['rounds']):
-                regpos, thrpos = rd['regpos'], rd['thrpos']
-                assert sorted(regpos + thrpos) == list(range(M))
-                if check_layout and (rnd == 0 or rnd == nrounds - 1):
-                    # edge rounds: lanes must walk the lowest index bits (coalesced 128-byte lines)
-                    nlow = min(3, M - R)
-                    if rnd == 0:
-                        assert [gpos[thrpos[t]] for t in range(nlow)] == list(range(nlow)), 'uncoalesced load round'
-                    if rnd == nrounds - 1:
-                        assert [spos[thrpos[t]] for t in range(nlow)] == list(range(nlow)), 'uncoalesced store round'
-                regs_all = np.zeros((T, NE), dtype=np.complex128)
-                for tid in range(T):
-                    tb = tg = 0
-                    for t in range(M - R):
-                        bit = (tid >> t) & 1
-                        tb |= bit << thrpos[t]
-                        tg |= bit << gpos[thrpos[t]]
-                    a = np.zeros(NE, dtype=np.complex128)
-                    for e in range(NE):
-                        toff = goff = 0
-                        for i in range(R):
-                            if (e >> i) & 1:
-                                toff |= 1 << regpos[i]
-                                goff |= 1 << gpos[regpos[i]]
-                        a[e] = tile[swz(tb | toff)]
-                    tfull = (index_hi << nbits) | gb | tg
-                    scalar = 1.0 + 0j
-                    for op in rd['ops']:
-                        on = (tfull & op['idx_cmask']) == op['idx_cmask']
-                        if op['type'] == 4:
-                            tbl = np.frombuffer(op['payload'], dtype=np.complex128, count=TABLE)
-                            for e in range(NE):
-                                if op['flag'] or (e & op['reg_cmask']):
-                                    a[e] = tbl[e] * a[e]
-                        elif op['type'] == 3:
-                            assert op['reg_cmask'] != 0 or rd['has_scalar'] == 1
-                            scalar = _apply_cph(a, op, on, scalar)
-                        elif on:
-                            if op['type'] == 1:
-                                _apply_g1(a, op)
-                            else:
-                                _apply_g2(a, op)
-                    if rd['has_scalar']:
-                        a = a * scalar
-                    else:
-                        assert scalar == 1
-                    regs_all[tid] = a
-                # all threads have read the tile before anyone writes it (the kernel's barriers)
-                staged = []
-                for tid in range(T):
-                    tb = tg = 0
-                    for t in range(M - R):
-                        bit = (tid >> t) & 1
-                        tb |= bit << thrpos[t]
-                        tg |= bit << spos[thrpos[t]]       # only used by the final store: STORE positions
-                    for e in range(NE):
-                        toff = goff = 0
-                        for i in range(R):
-                            if (e >> i) & 1:
-                                toff |= 1 << regpos[i]
-                                goff |= 1 << spos[regpos[i]]
-                        if rnd + 1 < nrounds:
-                            tile[swz(tb | toff)] = regs_all[tid, e]
-                        else:
-                            staged.append(((gb | tg | goff) ^ sweep['store_xor'], regs_all[tid, e]))
-                if rnd + 1 == nrounds:
-                    # pending X flips: amplitude i lands at i ^ store_xor (all loads of the tile came first)
-                    for addr, val in staged:
-                        state[addr] = val
+            _run_tile(plan, sweep, tile_id, state, index_hi, check_layout)
     return state
+
+
+def execute_tiles(blob: bytes, sweep_index: int, tile_ids, memory, index_hi: int = 0) -> None:
+    """The tiles `tile_ids` of sweep `sweep_index` only, in place on `memory` (flat amplitude index -> complex; a
+    mapping that returns 0 for absent keys works): what a few CTAs of the sweep's kernel do to a state that is too
+    large to emulate as a whole."""
+    plan = parse(blob)
+    sweep = plan['sweeps'][sweep_index]
+    for tile_id in tile_ids:
+        _run_tile(plan, sweep, int(tile_id), memory, index_hi, True)
 
 
 # ---------------------------------------------------------------------------------------------------------

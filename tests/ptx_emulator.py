@@ -410,22 +410,52 @@ class _Cta:
         return off >> 3
 
 
-def run_sweep(ptx: str, coef: np.ndarray, state: np.ndarray, index_hi: int = 0, fix_value: int = 0, grid: int = 2,
-              smem_bytes: int = 1 << 16, groups: int = 1) -> int:
-    """Execute one launch of a generated sweep kernel in place on `state` (complex128, 2^nbits amplitudes) with
-    `grid` CTAs, one after the other. index_hi: the rank bits of a sharded state (kernel parameter p_hi = index_hi <<
-    nbits); fix_value: the fixed index bits of a slice launch (p_fix). Returns the instructions executed."""
-    assert state.dtype == np.complex128 and state.flags['C_CONTIGUOUS']
-    nbits = int(state.size).bit_length() - 1
+class SparseState:
+    """The memory of a state that is too large to allocate (the 30-qubit benchmark: 16 GiB): amplitudes that were
+    never written read as 0. Indexed like the float64 view of the state vector (amplitude k = elements 2k, 2k+1), which
+    is what the emulator's loads and stores use; `amplitude` / `set_amplitude` for the test's side."""
+
+    def __init__(self, nbits: int):
+        self.nbits = nbits
+        self.size = 2 << nbits
+        self.data = {}
+
+    def __getitem__(self, idx):
+        get = self.data.get
+        return np.fromiter((get(int(i), 0.0) for i in np.asarray(idx).reshape(-1)), dtype=np.float64,
+                           count=np.asarray(idx).size)
+
+    def __setitem__(self, idx, values):
+        for i, v in zip(np.asarray(idx).reshape(-1).tolist(), np.asarray(values).reshape(-1).tolist()):
+            self.data[i] = v
+
+    def amplitude(self, k: int) -> complex:
+        return complex(self.data.get(2 * k, 0.0), self.data.get(2 * k + 1, 0.0))
+
+    def set_amplitude(self, k: int, value: complex) -> None:
+        self.data[2 * k], self.data[2 * k + 1] = float(value.real), float(value.imag)
+
+
+def run_sweep(ptx: str, coef: np.ndarray, state, index_hi: int = 0, fix_value: int = 0, grid: int = 2,
+              smem_bytes: int = 1 << 16, groups: int = 1, ctas=None) -> int:
+    """Execute one launch of a generated sweep kernel in place on `state` (complex128 vector of 2^nbits amplitudes, or a
+    SparseState) with `grid` CTAs, one after the other; `ctas`: run only these CTA indices of the grid (a few tiles of
+    a state too large to walk). index_hi: the rank bits of a sharded state (kernel parameter p_hi = index_hi << nbits);
+    fix_value: the fixed index bits of a slice launch (p_fix). Returns the instructions executed."""
+    if isinstance(state, SparseState):
+        nbits, g = state.nbits, state
+    else:
+        assert state.dtype == np.complex128 and state.flags['C_CONTIGUOUS']
+        nbits = int(state.size).bit_length() - 1
+        g = state.view(np.float64)
     kernel = Kernel(ptx)
     params = {'p_state': GLOBAL_BASE, 'p_hi': int(index_hi) << nbits, 'p_zero': 0, 'p_fix': int(fix_value)}
-    g = state.view(np.float64)
     coef = np.ascontiguousarray(coef, dtype=np.float64)
     if coef.size == 0:
         coef = np.zeros(2)
     total = 0
-    for cta in range(grid):
-        c = _Cta(kernel, g, coef, params, cta, grid, smem_bytes * max(1, groups))
+    for cta in (range(grid) if ctas is None else ctas):
+        c = _Cta(kernel, g, coef, params, int(cta), grid, smem_bytes * max(1, groups))
         c.run()
         total += c.executed
     return total

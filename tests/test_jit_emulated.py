@@ -204,3 +204,46 @@ def test_slice_variants_cover_the_state_like_one_full_launch():
             assert np.abs(sliced - full).max() < 1e-13
             checked += 1
     assert checked >= 2
+
+
+def test_the_benchmark_kernels_themselves_tile_by_tile():
+    """The 17 kernels the headline number is measured with (W-B, 30 qubits, depth 20, seed 0: the plan bench.py builds,
+    fingerprint in its JSON line), generated for the 30-bit state. The state cannot be walked on a CPU, a tile can: for
+    every sweep two CTAs of the grid (tile 0 and a random tile) run on the PTX emulator over a sparse memory that holds
+    random amplitudes in exactly those tiles, and the result is compared with the plan emulator's statement of the same
+    tiles (tests/plan_emulator.py, itself checked against the oracle on whole small states)."""
+    import collections
+    import plan_emulator as E
+    n = 30
+    specs = workloads.wb_gate_list(n, 20, 0)
+    segments = planner.build_segments(n, bitops_of(specs, n))
+    assert len(segments) == 1 and segments[0].kind == 'plan'
+    blob = segments[0].blob
+    import hashlib
+    # the plan every round-2 profile was measured with (bench.py prints the same fingerprint as plan.plan_sha256); a
+    # planner change that alters it is legitimate, but then the numbers in profiles/ describe another plan
+    assert hashlib.sha256(blob).hexdigest()[:16] == 'f29627fc01a7a6e8'
+    plan = E.parse(blob)
+    M = plan['M']
+    ntiles = 1 << (n - M)
+    rng = np.random.RandomState(30)
+    worst = 0.0
+    for i, sweep in enumerate(plan['sweeps']):
+        tiles = [0, int(rng.randint(1, ntiles))]
+        sparse = PE.SparseState(n)
+        memory = collections.defaultdict(complex)
+        for tile_id in tiles:
+            gb = sum(((tile_id >> j) & 1) << h for j, h in enumerate(sweep['hole']))
+            for local in range(1 << M):
+                addr = gb | sum(((local >> j) & 1) << sweep['gpos'][j] for j in range(M))
+                value = complex(rng.normal(), rng.normal())
+                memory[addr] = value
+                sparse.set_amplitude(addr, value)
+        E.execute_tiles(blob, i, tiles, memory)
+        ptx, coef, _, smem, groups = sweep_source(blob, i)
+        PE.run_sweep(ptx, coef, sparse, grid=ntiles, smem_bytes=smem, groups=groups, ctas=tiles)
+        touched = set(memory) | {k >> 1 for k in sparse.data}
+        assert len(touched) == len(tiles) << M          # both stayed inside the two tiles
+        worst = max(worst, max(abs(memory[a] - sparse.amplitude(a)) for a in touched))
+    assert len(plan['sweeps']) >= 15
+    assert worst < 1e-12, worst
