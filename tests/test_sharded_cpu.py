@@ -383,3 +383,65 @@ def test_stage_parts_skip_exactly_the_sweeps_the_pipelines_run():
     log.clear()
     runner._run_stage_part(a, None, 3, 2)          # nothing left between the two pipelines
     assert log == []
+
+
+@pytest.mark.parametrize('n,p', [(34, 1), (35, 2), (36, 3)])
+def test_overlapped_execution_launches_every_sweep_of_the_benchmark_schedules_exactly_once(n, p, monkeypatch):
+    """Dry run of ShardedCircuit._execute_overlapped on the schedules bench.py runs at 2 / 4 / 8 GPUs (33 qubits per
+    GPU), without a GPU: the real scheduler, stage plans and pipeline shapes (_pipeline_shape on the plans' own
+    non-tile masks), with recording stand-ins for the uploaded plans and for the device half of a pipelined remap.
+    Every sweep of every stage must be launched exactly once over the whole shard -- in one piece by _run_stage_part
+    or slice by slice (all 2^v values of the selector bits) inside a remap's pipeline -- in stage order, and every
+    remap must happen once."""
+    import plan_emulator as E
+    monkeypatch.delenv('QFB_REMAP_SLICE_BITS', raising=False)
+    monkeypatch.delenv('QFB_REMAP_CHAIN', raising=False)
+    specs = workloads.wb_gate_list(n, 20, 0)
+    runner = sharded.ShardedCircuit(None, n, 1 << p, 0, bitops=_bitops(specs, n))
+    log = []
+    stage_names = {}
+    for si, st in enumerate(s for s in runner.steps if isinstance(s, sharded.Stage)):
+        for gi, seg in enumerate(st.segments):
+            assert seg.kind == 'plan'
+            parsed = E.parse(seg.blob)
+            masks = [sum(1 << b for b in sw['hole']) for sw in parsed['sweeps']]
+            assert len(masks) == seg.nsweeps
+            name = 'stage{}.{}'.format(si, gi)
+            seg.uploaded = _FakePlan(masks, log, name)
+            stage_names[name] = seg.nsweeps
+    remaps = []
+    monkeypatch.setattr(runner, '_map_peers', lambda shard: None)
+    monkeypatch.setattr(runner, '_exchange_peer', lambda shard, pos: remaps.append(('whole', tuple(pos))))
+
+    def fake_pipeline(shard, prev, remap, nxt, bits, da, db):
+        a, b = prev.segments[-1].uploaded, nxt.segments[0].uploaded
+        assert all((a.nontile_mask(i) >> pos) & 1 for i in range(a.nsweeps - da, a.nsweeps) for pos in bits)
+        assert all((b.nontile_mask(i) >> pos) & 1 for i in range(db) for pos in bits)
+        k = len(remap.rank_positions)
+        assert all(12 <= pos < runner.nl - k - 1 for pos in bits) and bits == sorted(bits) and 1 <= len(bits) <= 3
+        mask = sum(1 << pos for pos in bits)
+        values = [sum(((sl >> t) & 1) << pos for t, pos in enumerate(bits)) for sl in range(1 << len(bits))]
+        for v in values:
+            a.launch_part(shard, a.nsweeps - da, da, fix_mask=mask, fix_value=v)
+        remaps.append(('pipelined', tuple(remap.rank_positions)))
+        for v in values:
+            b.launch_part(shard, 0, db, fix_mask=mask, fix_value=v)
+
+    monkeypatch.setattr(runner, '_remap_pipelined', fake_pipeline)
+    runner._execute_overlapped(None)
+    # coverage per sweep: 1.0 for a whole launch, 2^-v per slice launch
+    covered = {name: [0.0] * count for name, count in stage_names.items()}
+    order = []
+    for name, first, count, fix_mask, _value in log:
+        share = 1.0 / (1 << bin(fix_mask).count('1'))
+        for i in range(first, first + count):
+            covered[name][i] += share
+        order.append(name)
+    for name, shares in covered.items():
+        assert all(abs(s - 1.0) < 1e-12 for s in shares), (name, shares)
+    # stages run in order (a pipeline interleaves two neighbouring stages only)
+    stage_of = [int(name[5:].split('.')[0]) for name in order]
+    assert all(b >= a - 1 for a, b in zip(stage_of, stage_of[1:]))
+    assert len(remaps) == sum(isinstance(s, sharded.Remap) for s in runner.steps)
+    assert runner._remaps == len(remaps) and runner._executions == 1
+    print(n, p, 'remaps', remaps, 'sweeps inside pipelines', runner._pipelined_sweeps, 'of', sum(stage_names.values()))
