@@ -8,10 +8,15 @@ top qubits (weak scaling, BASELINE.json configs[4] shape).
 
 One step = one pass of the whole circuit over the state. Prints ONE JSON line (rank 0).
   value        device-timed (CUDA events on the launching stream, max over ranks), state resident in HBM
-  e2e          the same circuit through the public API (Circuit.run on a State built from a pinned HOST buffer,
-               result copied back to a pinned HOST buffer): host<->device copies inside the timed region
-  roofline     dominant kernel = sweep_kernel (one launch = one read + one write of the state = 32 B/amplitude)
+  e2e          the same circuit with HOST buffers, host<->device copies inside the timed region: one GPU =
+               Circuit.run_pipelined (pinned host states -> upload / sweeps / download on three streams -> pinned host
+               results); sharded = each rank's shard from / to host memory around ShardedCircuit.execute
+  e2e_reference_shaped   the reference's own call sequence, un-pipelined: qf.State(host numpy array) ->
+               Circuit.run -> qf.asarray (one GPU)
+  e2e_cold     first Circuit.run of a fresh process: planning + kernel generation / compilation + execution
+  roofline     dominant kernel = the sweep kernel (one launch = one read + one write of the state = 32 B/amplitude)
   cpu_baseline the C/OpenMP restatement of the reference's tensormul on the host cores, bounded sample
+  parity_max_abs (N > 1)  sharded path against the single-GPU engine on a 21-qubit-per-GPU circuit, inside the run
 --impl reference times the reference's own algorithm (np.einsum with the reference's subscripts, one thread --
 that is all numpy's einsum uses) on a bounded sample of the same workload.
 """
