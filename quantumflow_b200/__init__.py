@@ -2,8 +2,9 @@
 
 `import quantumflow_b200 as qf` gives the hot-path subset of the reference's flat namespace
 (quantumflow/__init__.py:5-23): states, gates, channels, circuits, programs, QAOA helpers and the closeness predicates,
-with `qf.backend` being the b200 tensor backend. Optional-dependency modules of the reference (forest,
-visualization, datasets, cvxpy-based measures) are out of scope and are not imported.
+with `qf.backend` being the b200 tensor backend. Optional-dependency modules of the reference (visualization,
+datasets, cvxpy-based measures, the pyQuil half of forest) are out of scope and are not imported; `qf.forest` holds
+the part of the reference's forest module that sits on the path: the QAM-shaped front of `Program.run`.
 """
 from . import backend                       # noqa: F401
 from .config import *                       # noqa: F401,F403
@@ -21,7 +22,7 @@ from .programs import *                     # noqa: F401,F403
 from .measures import *                     # noqa: F401,F403
 from .qaoa import *                         # noqa: F401,F403
 from .trajectories import StateBatch       # noqa: F401  (engine-only: batched stochastic trajectories)
-from . import utils, workloads, planner, engine, classify, stateio, trajectories   # noqa: F401
+from . import utils, workloads, planner, engine, classify, stateio, trajectories, forest   # noqa: F401
 
 from .config import version as __version__  # noqa: F401
 

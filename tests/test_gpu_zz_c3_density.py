@@ -42,3 +42,27 @@ def test_c3_density_14_qubits_full_matrix_against_c_oracle():
     mat = got.reshape(dim, dim)
     herm = max(float(np.abs(mat[lo:lo + 1024] - mat[:, lo:lo + 1024].conj().T).max()) for lo in range(0, dim, 4096))
     assert herm < 1e-12
+
+
+def test_qvm_front_of_program_run():
+    """forest.QuantumFlowQVM over Program.run on the device, as the reference's tests/test_forest.py:119-147 use it
+    (with Program objects instead of pyQuil programs): correlated outcomes of a measured Bell pair, and the
+    post-measurement wavefunction in pyQuil's amplitude order."""
+    import quantumflow_b200 as qf
+    from quantumflow_b200 import forest
+    ro = qf.Register('ro')
+    bell = qf.Program([qf.Declare('ro', 'BIT', 2), qf.H(0), qf.CNOT(0, 1), qf.Measure(0, ro[0]), qf.Measure(1, ro[1])])
+    qvm = forest.QuantumFlowQVM()
+    seen = set()
+    for _ in range(16):
+        res = qvm.load(bell).run().wait().read_from_memory_region(region_name='ro')
+        assert res[0] == res[1]
+        seen.add(res[0])
+    assert seen <= {0, 1}
+    prog = qf.Program([qf.Declare('ro', 'BIT', 1), qf.H(0), qf.CNOT(0, 1), qf.Measure(0, ro[0]), qf.H(0)])
+    qvm = forest.QuantumFlowQVM()
+    wf = qvm.load(prog).run().wait().wavefunction()
+    res = qvm.read_from_memory_region(region_name='ro')[0]
+    s = 0.70710678
+    expected = {0: np.array([s, s, 0, 0]), 1: np.array([0, 0, s, -s])}[res]
+    assert np.allclose(wf, expected, atol=1e-7)

@@ -183,3 +183,33 @@ def test_registers_and_addresses():
     assert qf.Register('c')[0] != 'foobar' and qf.Register('c')[0] < qf.Register('c')[1]
     with pytest.raises(TypeError):
         qf.Register('c')[0] < 'foobar'
+
+
+def test_qvm_state_machine_and_memory_readout():
+    """forest.QuantumFlowQVM (quantumflow/forest/__init__.py:372-447; the reference's tests/test_forest.py:119-193) on a
+    program of classical instructions only, run on the stand-in state: status transitions, read-out of a memory
+    region in the order its addresses entered the memory, the NotImplemented paths."""
+    from quantumflow_b200 import forest
+    prog = qf.Program([qf.Declare('ro', 'BIT', 2), qf.Move(qf.Register('ro')[1], 1), qf.Move(qf.Register('b')[0], 1)])
+    prog.run = lambda ket=None: run(prog)           # no amplitudes involved: interpret on the stand-in state
+    qvm = forest.QuantumFlowQVM()
+    assert qvm.status == 'connected'
+    with pytest.raises(NotImplementedError):
+        qvm.load('H 0')                              # Quil text needs pyQuil's parser
+    with pytest.raises(TypeError):
+        qvm.load(42)
+    assert qvm.load(prog) is qvm and qvm.status == 'loaded' and qvm.program is prog
+    with pytest.raises(AssertionError):
+        qvm.wait()                                   # nothing is running yet
+    with pytest.raises(NotImplementedError):
+        qvm.write_memory(region_name='ro')
+    assert qvm.run() is qvm and qvm.status == 'running'
+    with pytest.raises(AssertionError):
+        qvm.read_from_memory_region(region_name='ro')
+    assert qvm.wait().status == 'done'
+    assert qvm.read_from_memory_region(region_name='ro') == [0, 1]
+    assert qvm.read_from_memory_region(region_name='missing') == []
+    with pytest.raises(NotImplementedError):
+        qvm.read_from_memory_region(region_name='ro', offsets=[1])
+    # a finished machine takes the next program
+    assert qvm.load(prog).run().wait().read_from_memory_region(region_name='ro') == [0, 1]
