@@ -386,7 +386,7 @@ def test_stage_parts_skip_exactly_the_sweeps_the_pipelines_run():
 
 
 @pytest.mark.parametrize('n,p', [(34, 1), (35, 2), (36, 3)])
-def test_overlapped_execution_launches_every_sweep_of_the_benchmark_schedules_exactly_once(n, p, monkeypatch):
+def test_overlapped_execution_launches_every_sweep_of_the_benchmark_schedules_exactly_once(n, p, monkeypatch, tmp_path):
     """Dry run of ShardedCircuit._execute_overlapped on the schedules bench.py runs at 2 / 4 / 8 GPUs (33 qubits per
     GPU), without a GPU: the real scheduler, stage plans and pipeline shapes (_pipeline_shape on the plans' own
     non-tile masks), with recording stand-ins for the uploaded plans and for the device half of a pipelined remap.
@@ -413,8 +413,22 @@ def test_overlapped_execution_launches_every_sweep_of_the_benchmark_schedules_ex
     monkeypatch.setattr(runner, '_map_peers', lambda shard: None)
     monkeypatch.setattr(runner, '_exchange_peer', lambda shard, pos: remaps.append(('whole', tuple(pos))))
 
+    import shutil
+    import subprocess
+    from test_jit_emulated import sweep_source
+    ptxas = shutil.which('ptxas') or ('/usr/local/cuda/bin/ptxas' if os.path.exists('/usr/local/cuda/bin/ptxas') else None)
+    variants = []
+
     def fake_pipeline(shard, prev, remap, nxt, bits, da, db):
         a, b = prev.segments[-1].uploaded, nxt.segments[0].uploaded
+        # the slice variants this pipeline launches (compiled on first use on the device): generate them here and, where
+        # the toolkit's assembler is at hand, assemble them for sm_100a
+        fix = sum(1 << pos for pos in bits)
+        for seg, sweeps in ((prev.segments[-1], range(a.nsweeps - da, a.nsweeps)), (nxt.segments[0], range(db))):
+            for i in sweeps:
+                ptx = sweep_source(seg.blob, i, fix)[0]
+                assert 'p_fix' in ptx
+                variants.append(ptx)
         assert all((a.nontile_mask(i) >> pos) & 1 for i in range(a.nsweeps - da, a.nsweeps) for pos in bits)
         assert all((b.nontile_mask(i) >> pos) & 1 for i in range(db) for pos in bits)
         k = len(remap.rank_positions)
@@ -444,4 +458,14 @@ def test_overlapped_execution_launches_every_sweep_of_the_benchmark_schedules_ex
     assert all(b >= a - 1 for a, b in zip(stage_of, stage_of[1:]))
     assert len(remaps) == sum(isinstance(s, sharded.Remap) for s in runner.steps)
     assert runner._remaps == len(remaps) and runner._executions == 1
-    print(n, p, 'remaps', remaps, 'sweeps inside pipelines', runner._pipelined_sweeps, 'of', sum(stage_names.values()))
+    assert len(variants) == runner._pipelined_sweeps
+    if ptxas is not None:
+        for k, ptx in enumerate(variants):
+            path = os.path.join(str(tmp_path), 'variant{}.ptx'.format(k))
+            with open(path, 'w') as f:
+                f.write(ptx)
+            done = subprocess.run([ptxas, '-arch=sm_100a', '-O3', path, '-o', path + '.cubin'], capture_output=True,
+                                  text=True)
+            assert done.returncode == 0, done.stderr
+    print(n, p, 'remaps', remaps, 'sweeps inside pipelines', runner._pipelined_sweeps, 'of', sum(stage_names.values()),
+          '| slice variants assembled:', len(variants) if ptxas else 'no ptxas')
