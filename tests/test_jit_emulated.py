@@ -206,30 +206,19 @@ def test_slice_variants_cover_the_state_like_one_full_launch():
     assert checked >= 2
 
 
-def test_the_benchmark_kernels_themselves_tile_by_tile():
-    """The 17 kernels the headline number is measured with (W-B, 30 qubits, depth 20, seed 0: the plan bench.py builds,
-    fingerprint in its JSON line), generated for the 30-bit state. The state cannot be walked on a CPU, a tile can: for
-    every sweep two CTAs of the grid (tile 0 and a random tile) run on the PTX emulator over a sparse memory that holds
-    random amplitudes in exactly those tiles, and the result is compared with the plan emulator's statement of the same
-    tiles (tests/plan_emulator.py, itself checked against the oracle on whole small states)."""
+def check_plan_tiles(blob: bytes, rng, index_hi: int = 0, tiles_per_sweep: int = 2) -> float:
+    """Every sweep of a plan for a state too large to walk: `tiles_per_sweep` CTAs of the grid (tile 0 and random
+    tiles) run on the PTX emulator over a sparse memory that holds random amplitudes in exactly those tiles, compared
+    with the plan emulator's statement of the same tiles (tests/plan_emulator.py, itself checked against the oracle on
+    whole small states). Returns the largest difference."""
     import collections
     import plan_emulator as E
-    n = 30
-    specs = workloads.wb_gate_list(n, 20, 0)
-    segments = planner.build_segments(n, bitops_of(specs, n))
-    assert len(segments) == 1 and segments[0].kind == 'plan'
-    blob = segments[0].blob
-    import hashlib
-    # the plan every round-2 profile was measured with (bench.py prints the same fingerprint as plan.plan_sha256); a
-    # planner change that alters it is legitimate, but then the numbers in profiles/ describe another plan
-    assert hashlib.sha256(blob).hexdigest()[:16] == 'f29627fc01a7a6e8'
     plan = E.parse(blob)
-    M = plan['M']
+    n, M = plan['nbits'], plan['M']
     ntiles = 1 << (n - M)
-    rng = np.random.RandomState(30)
     worst = 0.0
     for i, sweep in enumerate(plan['sweeps']):
-        tiles = [0, int(rng.randint(1, ntiles))]
+        tiles = sorted({0} | {int(rng.randint(1, ntiles)) for _ in range(tiles_per_sweep - 1)})
         sparse = PE.SparseState(n)
         memory = collections.defaultdict(complex)
         for tile_id in tiles:
@@ -239,11 +228,47 @@ def test_the_benchmark_kernels_themselves_tile_by_tile():
                 value = complex(rng.normal(), rng.normal())
                 memory[addr] = value
                 sparse.set_amplitude(addr, value)
-        E.execute_tiles(blob, i, tiles, memory)
+        E.execute_tiles(blob, i, tiles, memory, index_hi)
         ptx, coef, _, smem, groups = sweep_source(blob, i)
-        PE.run_sweep(ptx, coef, sparse, grid=ntiles, smem_bytes=smem, groups=groups, ctas=tiles)
+        PE.run_sweep(ptx, coef, sparse, index_hi=index_hi, grid=ntiles, smem_bytes=smem, groups=groups, ctas=tiles)
         touched = set(memory) | {k >> 1 for k in sparse.data}
-        assert len(touched) == len(tiles) << M          # both stayed inside the two tiles
+        assert len(touched) == len(tiles) << M          # both stayed inside the chosen tiles
         worst = max(worst, max(abs(memory[a] - sparse.amplitude(a)) for a in touched))
-    assert len(plan['sweeps']) >= 15
+    return worst
+
+
+def test_the_benchmark_kernels_themselves_tile_by_tile():
+    """The 17 kernels the headline number is measured with (W-B, 30 qubits, depth 20, seed 0: the plan bench.py builds,
+    fingerprint in its JSON line), generated for the 30-bit state. The state cannot be walked on a CPU, a tile can
+    (check_plan_tiles)."""
+    import hashlib
+    n = 30
+    specs = workloads.wb_gate_list(n, 20, 0)
+    segments = planner.build_segments(n, bitops_of(specs, n))
+    assert len(segments) == 1 and segments[0].kind == 'plan' and segments[0].nsweeps >= 15
+    blob = segments[0].blob
+    # the plan every round-2 profile was measured with (bench.py prints the same fingerprint as plan.plan_sha256); a
+    # planner change that alters it is legitimate, but then the numbers in profiles/ describe another plan
+    assert hashlib.sha256(blob).hexdigest()[:16] == 'f29627fc01a7a6e8'
+    worst = check_plan_tiles(blob, np.random.RandomState(30))
+    assert worst < 1e-12, worst
+
+
+@pytest.mark.parametrize('n,p', [(34, 1), (35, 2), (36, 3)])
+def test_the_sharded_benchmark_kernels_tile_by_tile(n, p):
+    """The kernels of the multi-GPU benchmark (33 qubits per GPU: 128 GiB shards, byte offsets beyond 2^36; rank bits
+    as controls and phase bits through index_hi; the remaps' local permutations stored by the last sweep of a stage
+    or by a bare sweep): every sweep of every stage plan of the schedule bench.py runs, two tiles each, on a random
+    rank, PTX emulator against plan emulator."""
+    specs = workloads.wb_gate_list(n, 20, 0)
+    runner = sharded.ShardedCircuit(None, n, 1 << p, 0, bitops=bitops_of(specs, n))
+    rng = np.random.RandomState(n)
+    worst, nsweeps = 0.0, 0
+    for st in runner.steps:
+        if isinstance(st, sharded.Stage):
+            for seg in st.segments:
+                assert seg.kind == 'plan'
+                worst = max(worst, check_plan_tiles(seg.blob, rng, index_hi=int(rng.randint(0, 1 << p))))
+                nsweeps += seg.nsweeps
+    assert nsweeps >= 20
     assert worst < 1e-12, worst
