@@ -272,3 +272,62 @@ def test_the_sharded_benchmark_kernels_tile_by_tile(n, p):
                 nsweeps += seg.nsweeps
     assert nsweeps >= 20
     assert worst < 1e-12, worst
+
+
+def test_slice_variants_of_the_sharded_benchmark_kernels_tile_by_tile():
+    """The slice launches of the 36-qubit / 8-GPU benchmark's pipelined remaps (the variant of a sweep generated for
+    the selector bits ShardedCircuit._pipeline_shape picks, on a slice chosen through p_fix): one tile of a random slice
+    per launched sweep, PTX emulator against plan emulator."""
+    import collections
+    import plan_emulator as E
+    from test_sharded_cpu import _FakePlan
+    n, p = 36, 3
+    specs = workloads.wb_gate_list(n, 20, 0)
+    runner = sharded.ShardedCircuit(None, n, 1 << p, 0, bitops=bitops_of(specs, n))
+    stages = [st for st in runner.steps if isinstance(st, sharded.Stage)]
+    parsed = {}
+    for st in stages:
+        for seg in st.segments:
+            parsed[id(seg)] = E.parse(seg.blob)
+            seg.uploaded = _FakePlan([sum(1 << b for b in sw['hole']) for sw in parsed[id(seg)]['sweeps']], [], 'x')
+    rng = np.random.RandomState(36)
+    checked, worst = 0, 0.0
+    steps = runner.steps
+    for i, st in enumerate(steps):
+        if not (isinstance(st, sharded.Stage) and i + 2 < len(steps) and isinstance(steps[i + 1], sharded.Remap)):
+            continue
+        nxt = steps[i + 2]
+        shape = runner._pipeline_shape(st, steps[i + 1], nxt, 0, i + 3 < len(steps))
+        if shape is None:
+            continue
+        bits, da, db = shape
+        fix_mask = sum(1 << b for b in bits)
+        a_seg, b_seg = st.segments[-1], nxt.segments[0]
+        for seg, sweeps in ((a_seg, range(a_seg.nsweeps - da, a_seg.nsweeps)), (b_seg, range(db))):
+            plan = parsed[id(seg)]
+            nbits, M = plan['nbits'], plan['M']
+            for k in sweeps:
+                sweep = plan['sweeps'][k]
+                free = [h for h in sweep['hole'] if not (fix_mask >> h) & 1]      # bits the slice launch enumerates
+                cta = int(rng.randint(0, 1 << len(free)))
+                fix_value = sum(int(rng.randint(0, 2)) << b for b in bits)
+                gb = fix_value | sum(((cta >> j) & 1) << h for j, h in enumerate(free))
+                tile_id = sum(((gb >> h) & 1) << j for j, h in enumerate(sweep['hole']))
+                rank = int(rng.randint(0, 1 << p))
+                sparse = PE.SparseState(nbits)
+                memory = collections.defaultdict(complex)
+                for local in range(1 << M):
+                    addr = gb | sum(((local >> j) & 1) << sweep['gpos'][j] for j in range(M))
+                    value = complex(rng.normal(), rng.normal())
+                    memory[addr] = value
+                    sparse.set_amplitude(addr, value)
+                E.execute_tiles(seg.blob, k, [tile_id], memory, rank)
+                ptx, coef, _, smem, groups = sweep_source(seg.blob, k, fix_mask)
+                PE.run_sweep(ptx, coef, sparse, index_hi=rank, fix_value=fix_value, grid=1 << len(free),
+                             smem_bytes=smem, groups=groups, ctas=[cta])
+                touched = set(memory) | {a >> 1 for a in sparse.data}
+                assert len(touched) == 1 << M, 'the slice launch left its tile'
+                worst = max(worst, max(abs(memory[a] - sparse.amplitude(a)) for a in touched))
+                checked += 1
+    assert checked >= 8
+    assert worst < 1e-12, worst
