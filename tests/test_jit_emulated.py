@@ -331,3 +331,29 @@ def test_slice_variants_of_the_sharded_benchmark_kernels_tile_by_tile():
                 checked += 1
     assert checked >= 8
     assert worst < 1e-12, worst
+
+
+@pytest.mark.parametrize('depth', [4, 20])
+def test_the_density_benchmark_kernels_tile_by_tile(depth):
+    """Config C3 (14-qubit density evolution: rho as a 28-bit vector, depolarising channels as superoperators): the
+    kernels of `bench.py --config c3` (depth 20) and of the full-size GPU parity test (depth 4), planned from the same
+    operator list Circuit.evolve builds, two tiles per sweep."""
+    import quantumflow_b200 as qf
+    n = 14
+    circ = workloads.wd_circuit(qf, n, depth, 0, kraus=True)
+    qubits = tuple(sorted(circ.qubits))
+    ops = []
+    for elem in circ.elements:                      # circuits.py::Circuit.evolve, bitops()
+        where = [qubits.index(q) for q in elem.qubits]
+        ket = [2 * n - 1 - w for w in where]
+        bra = [n - 1 - w for w in where]
+        if isinstance(elem, qf.Gate):
+            mat = elem.matrix()
+            ops.append((mat, ket))
+            ops.append((mat.conj(), bra))
+        else:
+            ops.append((elem.superoperator_matrix(), ket + bra))
+    segments = planner.build_segments(2 * n, ops)
+    assert all(seg.kind == 'plan' for seg in segments)
+    rng = np.random.RandomState(depth)
+    assert max(check_plan_tiles(seg.blob, rng) for seg in segments) < 1e-12
