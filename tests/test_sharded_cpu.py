@@ -469,3 +469,64 @@ def test_overlapped_execution_launches_every_sweep_of_the_benchmark_schedules_ex
             assert done.returncode == 0, done.stderr
     print(n, p, 'remaps', remaps, 'sweeps inside pipelines', runner._pipelined_sweeps, 'of', sum(stage_names.values()),
           '| slice variants assembled:', len(variants) if ptxas else 'no ptxas')
+
+
+class _FakeShard:
+    """What ShardedCircuit._swap_runs reads of a shard tensor: size and a 'device address'."""
+
+    def __init__(self, base, numel):
+        self._base, self._numel = base, numel
+
+    def numel(self):
+        return self._numel
+
+    def data_ptr(self):
+        return self._base
+
+    def element_size(self):
+        return 16
+
+
+@pytest.mark.parametrize('p,nl,rank_positions', [(1, 6, [0]), (2, 7, [0, 1]), (2, 6, [1]), (3, 7, [0, 2]), (3, 8, [0, 1, 2])])
+def test_peer_exchange_runs_swap_exactly_the_remapped_blocks(p, nl, rank_positions):
+    """The address lists of the peer-memory exchange (ShardedCircuit._swap_runs -> qfb_remap_swap: of every pair's
+    block the lower rank swaps the first half, the higher rank the second half), executed on numpy shards for every
+    rank, equal the index-bit swap a remap stands for; the slice form (qfb_remap_swap_slice: only offsets of a run
+    whose selector bits equal the slice value) covers the same amplitudes once over all slice values."""
+    world = 1 << p
+    k = len(rank_positions)
+    rng = np.random.RandomState(p * 100 + nl)
+    full = rng.normal(size=1 << (nl + p)) + 1j * rng.normal(size=1 << (nl + p))
+    want = _swap_index_bits(full, [(nl + t, nl - k + i) for i, t in enumerate(rank_positions)])
+    stride = 1 << 40                                       # rank r's shard "lives" at r * stride
+
+    def runs_of(rank):
+        runner = sharded.ShardedCircuit.__new__(sharded.ShardedCircuit)
+        runner.rank, runner.world, runner._comm_bytes = rank, world, 0
+        runner._peers = [r * stride for r in range(world)]
+        return runner._swap_runs(_FakeShard(rank * stride, 1 << nl), rank_positions)
+
+    def swap(shards, local, remote, lo, hi):
+        (ra, oa), (rb, ob) = divmod(local, stride), divmod(remote, stride)
+        a = shards[ra][oa // 16 + lo: oa // 16 + hi].copy()
+        shards[ra][oa // 16 + lo: oa // 16 + hi] = shards[rb][ob // 16 + lo: ob // 16 + hi]
+        shards[rb][ob // 16 + lo: ob // 16 + hi] = a
+
+    whole = [full[r << nl:(r + 1) << nl].copy() for r in range(world)]
+    sliced = [s.copy() for s in whole]
+    selpos = [2, 3] if nl - k - 1 > 3 else [1]               # selector bits below the half-block split
+    total = 0
+    for rank in range(world):
+        local, remote, counts = runs_of(rank)
+        assert len(local) == (1 << k) - 1
+        for la, ra, n in zip(local, remote, counts):
+            assert la // stride == rank and ra // stride != rank
+            swap(whole, la, ra, 0, n)
+            total += n
+            for value in range(1 << len(selpos)):
+                for off in range(n):
+                    if all(((off >> pos) & 1) == ((value >> t) & 1) for t, pos in enumerate(selpos)):
+                        swap(sliced, la, ra, off, off + 1)
+    assert total == world * ((1 << nl) - (1 << (nl - k))) // 2        # every off-diagonal block once, half per rank
+    assert np.array_equal(np.concatenate(whole), want)
+    assert np.array_equal(np.concatenate(sliced), want)

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Time-boxed fuzz of the sweep-specialised kernels WITHOUT a GPU: random circuits (every standard gate kind the
 planner has a handler for, random sizes, tiles, register bits, grid sizes, density-style dense 2-bit operators, rank
-bits as controls) -> plan -> generated PTX of every sweep (qfb_jit_source) -> PTX emulator (tests/ptx_emulator.py)
+bits as controls, final bit permutations) -> plan -> generated PTX of every sweep (qfb_jit_source) -> PTX emulator (tests/ptx_emulator.py)
 -> compared with the numpy oracle. The GPU twin is tools/gpu_fuzz_jit.py.
 Usage: python tools/cpu_fuzz_jit.py [seconds=120] [seed=1]"""
 import os
@@ -79,7 +79,22 @@ while time.time() - t0 < budget:
     want = full.copy()
     for mat, bits in ops:
         want = O.tensormul_flat(np.asarray(mat, dtype=np.complex128), want, list(bits))
-    segments = planner.build_segments(n, ops, tile_bits=tile, reg_bits=reg_bits)
+    # a third of the cases end with an in-place bit permutation of the local index (the local half of a qubit remap:
+    # fused into the last sweep's store where its tile allows, bare sweeps otherwise)
+    perm = None
+    if rnd.random() < 0.33:
+        perm = list(range(n))
+        if rnd.random() < 0.5:
+            movers = rnd.sample(range(3, n), rnd.randint(1, 3))
+            perm = [b for b in range(n) if b not in movers] + movers
+        else:
+            rnd.shuffle(perm)
+        idx = np.arange(1 << total)
+        src = idx & ~((1 << n) - 1)                       # rank bits stay
+        for j in range(n):
+            src |= ((idx >> j) & 1) << perm[j]            # destination bit j <- source bit perm[j]
+        want = want[src]
+    segments = planner.build_segments(n, ops, tile_bits=tile, reg_bits=reg_bits, final_perm=perm)
     got = full.copy()
     for hi in range(1 << hi_bits):
         shard = np.ascontiguousarray(got[hi << n:(hi + 1) << n])
